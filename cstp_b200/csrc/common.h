@@ -1,0 +1,53 @@
+// Host-side helpers shared by every translation unit of libcstp_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/cstp_b200.h"
+
+namespace cstp {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline int fail_inval(const char* what) {
+  set_error("invalid argument: %s", what);
+  return CSTP_EINVAL;
+}
+
+#define CSTP_REQUIRE(cond)                                   \
+  do {                                                       \
+    if (!(cond)) return ::cstp::fail_inval(#cond);           \
+  } while (0)
+
+#define CSTP_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      ::cstp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return CSTP_ECUDA;                                                                         \
+    }                                                                                            \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define CSTP_LAUNCHED()                                 \
+  do {                                                  \
+    ::cstp::g_launches.fetch_add(1);                    \
+    CSTP_CUDA(cudaGetLastError());                      \
+  } while (0)
+
+// Encodes a tiled bf16 tensor map (128B swizzle, zero OOB fill) through the driver entry point obtained from
+// the runtime, so the library never links libcuda directly (it must dlopen on a box without a driver).
+int encode_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box);
+
+int num_sms();
+
+inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace cstp

@@ -1,0 +1,367 @@
+// Implicit-GEMM convolution (forward and dgrad) and linear layers on tcgen05 tensor cores.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 (one lane)  TMA producer: per K-block one 5-D box of activations (128 positions x 64 channels, the tap
+//                      shift folded into the box origin; out-of-range taps are zero-filled by TMA = conv padding)
+//                      and one 2-D box of packed weights (n_tile x 64).
+//   warp 1 (one lane)  tcgen05.mma issuer: D[128 x n_tile] fp32 in TMEM, double-buffered across tiles.
+//   warp 2             TMEM allocator.
+//   warps 4..7         epilogue: tcgen05.ld -> (+bias, +previous) -> bf16 / fp32 rows to global.
+// Replaces cuDNN conv3d fwd/dgrad and cuBLAS addmm behind models/pace/r21d_byol.py:81-97,236-253.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cstp {
+
+constexpr int kConvThreads = 256;
+constexpr uint32_t kABytes = 128 * 64 * 2;  // one A stage: 128 positions x 64 bf16 channels
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448;  // 227 KB
+
+struct ConvKParams {
+  CUtensorMap amap[CSTP_MAX_AMAPS];
+  CUtensorMap bmap;
+  int tiles_w, tiles_h, tiles_t, tiles_n, n_ntiles;
+  int bw, bh, bt, bn;
+  int Wt, Ht, Tt, Nt;
+  int n_taps, chunks_per_tap, last_ksteps;
+  int n_tile, Np;
+  int stages, tmem_cols;
+  uint32_t b_bytes, idesc;
+  int accumulate;
+  __nv_bfloat16* out;
+  float* out_f32;
+  const float* bias;
+  long long out_off, osw, osh, ost, osn;
+  cstp_tap taps[CSTP_MAX_TAPS];
+};
+
+struct TileCoord {
+  int w0, h0, t0, n0, ntile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord c;
+  c.ntile = tile % p.n_ntiles;
+  int pt = tile / p.n_ntiles;
+  c.w0 = (pt % p.tiles_w) * p.bw;
+  pt /= p.tiles_w;
+  c.h0 = (pt % p.tiles_h) * p.bh;
+  pt /= p.tiles_h;
+  c.t0 = (pt % p.tiles_t) * p.bt;
+  pt /= p.tiles_t;
+  c.n0 = pt * p.bn;
+  return c;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = kABytes + p.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.n_ntiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < CSTP_MAX_AMAPS; ++i) tma_prefetch_desc(&p.amap[i]);
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      for (int t = 0; t < p.n_taps; ++t) {
+        const cstp_tap tap = p.taps[t];
+        for (int c = 0; c < p.chunks_per_tap; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&full[stage], kABytes + p.b_bytes);
+          tma_load_5d(sa, &p.amap[tap.map_id], &full[stage], c * 64, tc.w0 + tap.dw, tc.h0 + tap.dh, tc.t0 + tap.dt,
+                      tc.n0);
+          tma_load_2d(sa + kABytes, &p.bmap, &full[stage], tap.k_off + c * 64, tc.ntile * p.n_tile);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const int kblocks = p.n_taps * p.chunks_per_tap;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      int kb = 0;
+      for (int t = 0; t < p.n_taps; ++t) {
+        for (int c = 0; c < p.chunks_per_tap; ++c, ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const int nk = (c == p.chunks_per_tap - 1) ? p.last_ksteps : 4;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (warp w owns TMEM lanes 32*(w%4)..)
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int rw = row % p.bw;
+    const int rh = (row / p.bw) % p.bh;
+    const int rt = (row / (p.bw * p.bh)) % p.bt;
+    const int rn = row / (p.bw * p.bh * p.bt);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const TileCoord tc = decode_tile(p, tile);
+      const int w = tc.w0 + rw, h = tc.h0 + rh, t = tc.t0 + rt, n = tc.n0 + rn;
+      const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
+      const int col0 = tc.ntile * p.n_tile;
+      const int ncols = min(p.n_tile, p.Np - col0);
+      const long long off = p.out_off + w * p.osw + h * p.osh + t * p.ost + n * p.osn + col0;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + col0 + c0 + i);
+          }
+          if (p.out != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+            if (p.accumulate) {
+              const uint4 o0 = dst[0], o1 = dst[1];
+              const uint32_t o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(o[i]);
+                f[2 * i + 1] += bf16_hi(o[i]);
+              }
+            }
+            uint4 s0, s1;
+            s0.x = pack_bf16x2(f[0], f[1]);
+            s0.y = pack_bf16x2(f[2], f[3]);
+            s0.z = pack_bf16x2(f[4], f[5]);
+            s0.w = pack_bf16x2(f[6], f[7]);
+            s1.x = pack_bf16x2(f[8], f[9]);
+            s1.y = pack_bf16x2(f[10], f[11]);
+            s1.z = pack_bf16x2(f[12], f[13]);
+            s1.w = pack_bf16x2(f[14], f[15]);
+            dst[0] = s0;
+            dst[1] = s1;
+          }
+          if (p.out_f32 != nullptr) {
+            float4* dstf = reinterpret_cast<float4*>(p.out_f32 + off + c0);
+            if (p.accumulate && p.out == nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 o = dstf[i];
+                f[4 * i] += o.x;
+                f[4 * i + 1] += o.y;
+                f[4 * i + 2] += o.z;
+                f[4 * i + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dstf[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+}  // namespace cstp
+
+struct cstp_conv_plan {
+  cstp::ConvKParams kp;
+  int grid;
+  int smem_bytes;
+};
+
+using namespace cstp;
+
+static int encode_tensor5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5]) {
+  uint64_t dims[5], strides[4];
+  for (int i = 0; i < 5; ++i) {
+    if (t.dims[i] <= 0) return fail_inval("tensor5 dim <= 0");
+    dims[i] = static_cast<uint64_t>(t.dims[i]);
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (t.strides[i] <= 0 || (t.strides[i] % 16) != 0) return fail_inval("tensor5 stride must be a positive multiple of 16 bytes");
+    strides[i] = static_cast<uint64_t>(t.strides[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(t.ptr) % 16) != 0 || t.ptr == nullptr) return fail_inval("tensor5 ptr must be 16B aligned");
+  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box);
+}
+
+extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** out_plan) {
+  CSTP_REQUIRE(d != nullptr && out_plan != nullptr);
+  CSTP_REQUIRE(d->n_amaps >= 1 && d->n_amaps <= CSTP_MAX_AMAPS);
+  CSTP_REQUIRE(d->n_taps >= 1 && d->n_taps <= CSTP_MAX_TAPS);
+  CSTP_REQUIRE(d->a_channels >= 16 && d->a_channels % 16 == 0);
+  CSTP_REQUIRE(d->Np >= 16 && d->Np % 16 == 0);
+  CSTP_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 256);
+  CSTP_REQUIRE(d->Ktot >= 64 && d->Ktot % 64 == 0);
+  CSTP_REQUIRE(d->bw >= 1 && d->bh >= 1 && d->bt >= 1 && d->bn >= 1);
+  CSTP_REQUIRE(d->bw * d->bh * d->bt * d->bn == 128);
+  CSTP_REQUIRE(d->bw <= 256 && d->bh <= 256 && d->bt <= 256 && d->bn <= 256);
+  CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
+  CSTP_REQUIRE(d->w_packed != nullptr);
+  CSTP_REQUIRE(d->out_bf16 != nullptr || d->out_f32 != nullptr);
+  CSTP_REQUIRE(d->osw % 8 == 0 && d->osh % 8 == 0 && d->ost % 8 == 0 && d->osn % 8 == 0 && d->out_off % 8 == 0);
+
+  cstp_conv_plan* plan = new (std::nothrow) cstp_conv_plan();
+  if (!plan) {
+    set_error("out of host memory");
+    return CSTP_ENOMEM;
+  }
+  ConvKParams& k = plan->kp;
+  memset(&k, 0, sizeof(k));
+  const uint32_t abox[5] = {64u, (uint32_t)d->bw, (uint32_t)d->bh, (uint32_t)d->bt, (uint32_t)d->bn};
+  for (int i = 0; i < CSTP_MAX_AMAPS; ++i) {
+    // Unused slots alias map 0 so the descriptor prefetch in the kernel always sees a valid descriptor.
+    const cstp_tensor5& t = d->amap[i < d->n_amaps ? i : 0];
+    int rc = encode_tensor5(&k.amap[i], t, abox);
+    if (rc != CSTP_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
+    const uint64_t strides[1] = {(uint64_t)d->Ktot * 2};
+    const uint32_t box[2] = {64u, (uint32_t)d->n_tile};
+    int rc = encode_tmap_bf16(&k.bmap, d->w_packed, 2, dims, strides, box);
+    if (rc != CSTP_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  k.tiles_w = ceil_div(d->Wt, d->bw);
+  k.tiles_h = ceil_div(d->Ht, d->bh);
+  k.tiles_t = ceil_div(d->Tt, d->bt);
+  k.tiles_n = ceil_div(d->Nt, d->bn);
+  k.n_ntiles = ceil_div(d->Np, d->n_tile);
+  k.bw = d->bw; k.bh = d->bh; k.bt = d->bt; k.bn = d->bn;
+  k.Wt = d->Wt; k.Ht = d->Ht; k.Tt = d->Tt; k.Nt = d->Nt;
+  k.n_taps = d->n_taps;
+  k.chunks_per_tap = ceil_div(d->a_channels, 64);
+  k.last_ksteps = ((d->a_channels - 1) % 64) / 16 + 1;
+  k.n_tile = d->n_tile;
+  k.Np = d->Np;
+  k.b_bytes = static_cast<uint32_t>(d->n_tile) * 128u;
+  k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 0, 0);
+  k.accumulate = d->accumulate;
+  k.out = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
+  k.out_f32 = d->out_f32;
+  k.bias = d->bias;
+  k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
+  for (int t = 0; t < d->n_taps; ++t) {
+    const cstp_tap& tp = d->taps[t];
+    if (tp.map_id < 0 || tp.map_id >= d->n_amaps || tp.k_off < 0 || tp.k_off % 64 != 0 ||
+        tp.k_off + k.chunks_per_tap * 64 > d->Ktot) {
+      delete plan;
+      return fail_inval("tap map_id / k_off out of range");
+    }
+    k.taps[t] = tp;
+  }
+  const uint32_t stage_bytes = kABytes + k.b_bytes;
+  const int bar_bytes = 256;
+  int stages = (kSmemLimit - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    delete plan;
+    return fail_inval("n_tile too large for the shared-memory pipeline");
+  }
+  k.stages = stages;
+  int cols = 32;
+  while (cols < 2 * d->n_tile) cols *= 2;
+  k.tmem_cols = cols;
+  plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
+  const long long total = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n * k.n_ntiles;
+  const int sms = num_sms();
+  plan->grid = static_cast<int>(total < sms ? total : sms);
+  *out_plan = plan;
+  return CSTP_OK;
+}
+
+extern "C" int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream) {
+  CSTP_REQUIRE(plan != nullptr);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSTP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  conv_gemm_kernel<<<plan->grid, kConvThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" void cstp_conv_plan_destroy(cstp_conv_plan* plan) { delete plan; }

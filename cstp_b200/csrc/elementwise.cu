@@ -1,0 +1,503 @@
+// HBM-bound kernels of the hot path: weight packing, stem im2col, training-mode BatchNorm (statistics,
+// finalize, apply + ReLU + residual, backward reduce / apply), average pooling, column sums and casts.
+// All activations are bf16 [rows][Cp] (NDHWC flattened), processed as 16-byte vectors of 8 channels.
+// Replaces ATen/cuDNN batch_norm, relu, add, adaptive_avg_pool3d behind models/pace/r21d_byol.py:83-97,141-148,210-223.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cstp {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------- weight packing
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int taps, int transpose,
+                                   __nv_bfloat16* __restrict__ packed, int Rp, int Kc) {
+  const long long total = static_cast<long long>(Rp) * taps * Kc;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Kc);
+    const int tap = static_cast<int>((i / Kc) % taps);
+    const int r = static_cast<int>(i / (static_cast<long long>(Kc) * taps));
+    float v = 0.f;
+    if (!transpose) {
+      if (r < cout && c < cin) v = w[(static_cast<long long>(r) * cin + c) * taps + tap];
+    } else {
+      if (r < cin && c < cout) v = w[(static_cast<long long>(c) * cin + r) * taps + tap];
+    }
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- stem im2col
+__global__ void stem_im2col_kernel(const float* __restrict__ x, int N, int T, int H, int W, __nv_bfloat16* __restrict__ col,
+                                   int ldk) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int nvec = ldk / 8;
+  const long long rows = static_cast<long long>(N) * T * Ho * Wo;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long m = i / nvec;
+    const int wo = static_cast<int>(m % Wo);
+    m /= Wo;
+    const int ho = static_cast<int>(m % Ho);
+    m /= Ho;
+    const int t = static_cast<int>(m % T);
+    const int n = static_cast<int>(m / T);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int ci = k / 49, rem = k % 49, kh = rem / 7, kw = rem % 7;
+        const int hi = 2 * ho + kh - 3, wi = 2 * wo + kw - 3;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+          val = __ldg(x + (((static_cast<long long>(n) * 3 + ci) * T + t) * H + hi) * W + wi);
+      }
+      f[j] = val;
+    }
+    reinterpret_cast<uint4*>(col)[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- BN statistics
+// Per-block partial sums.  grid = (nblocks, groups, channel segments of <=1024 channels).
+// partials layout: [nblocks][groups][2][Cp].
+constexpr int kSegVecs = 128;
+
+template <bool kBackward>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ act,
+                                                        const uint4* __restrict__ raw, long long rows_per_group, int Cp,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        float* __restrict__ partials) {
+  __shared__ float red[2][256 * 8];
+  const int nvec = Cp / 8;
+  const int g = blockIdx.y;
+  const int seg0 = blockIdx.z * kSegVecs;
+  const int seg_vecs = min(kSegVecs, nvec - seg0);
+  const int rows_per_pass = 256 / seg_vecs;
+  const int cv = threadIdx.x % seg_vecs;
+  const int rl = threadIdx.x / seg_vecs;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  if (rl < rows_per_pass) {
+    float mu[8], is[8];
+    if (kBackward) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mu[j] = mean[g * Cp + (seg0 + cv) * 8 + j];
+        is[j] = invstd[g * Cp + (seg0 + cv) * 8 + j];
+      }
+    }
+    const long long base = static_cast<long long>(g) * rows_per_group;
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + rl; r < rows_per_group;
+         r += static_cast<long long>(gridDim.x) * rows_per_pass) {
+      const long long idx = (base + r) * nvec + seg0 + cv;
+      float x[8];
+      if (!kBackward) {
+        unpack8(a[idx], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s0[j] += x[j];
+          s1[j] += x[j] * x[j];
+        }
+      } else {
+        float d[8];
+        unpack8(a[idx], d);
+        unpack8(raw[idx], x);
+        if (act != nullptr) {
+          float y[8];
+          unpack8(act[idx], y);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? d[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s0[j] += d[j];
+          s1[j] += d[j] * ((x[j] - mu[j]) * is[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x * 8 + j] = s0[j];
+    red[1][threadIdx.x * 8 + j] = s1[j];
+  }
+  __syncthreads();
+  // thread (rl, cv) data sits at ((rl*seg_vecs + cv)*8 + j); reduce over rl for each of seg_vecs*8 channels.
+  const int seg_ch = seg_vecs * 8;
+  for (int c = threadIdx.x; c < 2 * seg_ch; c += blockDim.x) {
+    const int q = c / seg_ch, ch = c % seg_ch;
+    float acc = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) acc += red[q][r * seg_ch + ch];
+    partials[((static_cast<long long>(blockIdx.x) * gridDim.y + g) * 2 + q) * Cp + seg0 * 8 + ch] = acc;
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups, long long rows_per_group,
+                                   int C, int Cp, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  for (int g = 0; g < groups; ++g) {
+    if (c >= C) {
+      scale[g * Cp + c] = 0.f;
+      shift[g * Cp + c] = 0.f;
+      mean_out[g * Cp + c] = 0.f;
+      invstd_out[g * Cp + c] = 0.f;
+      continue;
+    }
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += partials[((static_cast<long long>(b) * groups + g) * 2 + 0) * Cp + c];
+      ss += partials[((static_cast<long long>(b) * groups + g) * 2 + 1) * Cp + c];
+    }
+    const double n = static_cast<double>(rows_per_group);
+    const double mu = s / n;
+    double var = ss / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float istd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * istd;
+    scale[g * Cp + c] = sc;
+    shift[g * Cp + c] = beta[c] - static_cast<float>(mu) * sc;
+    mean_out[g * Cp + c] = static_cast<float>(mu);
+    invstd_out[g * Cp + c] = istd;
+    if (running_mean != nullptr) {
+      const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+  }
+}
+
+// out = act(raw*scale + shift + residual)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ raw, long long rows, int Cp,
+                                                       long long rows_per_group, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int relu, int res_mode,
+                                                       const uint4* __restrict__ res, const float* __restrict__ scale2,
+                                                       const float* __restrict__ shift2, uint4* __restrict__ out) {
+  const int nvec = Cp / 8;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % nvec);
+    const long long r = i / nvec;
+    const int g = static_cast<int>(r / rows_per_group);
+    const float4* sc = reinterpret_cast<const float4*>(scale + g * Cp + cv * 8);
+    const float4* sh = reinterpret_cast<const float4*>(shift + g * Cp + cv * 8);
+    const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+    const float s[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float t[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float x[8];
+    unpack8(raw[i], x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], s[j], t[j]);
+    if (res_mode == 1) {
+      float y[8];
+      unpack8(res[i], y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += y[j];
+    } else if (res_mode == 2) {
+      const float4* sc2 = reinterpret_cast<const float4*>(scale2 + g * Cp + cv * 8);
+      const float4* sh2 = reinterpret_cast<const float4*>(shift2 + g * Cp + cv * 8);
+      const float4 c0 = __ldg(sc2), c1 = __ldg(sc2 + 1), d0 = __ldg(sh2), d1 = __ldg(sh2 + 1);
+      const float s2[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float t2[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float y[8];
+      unpack8(res[i], y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += fmaf(y[j], s2[j], t2[j]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    out[i] = pack8(x);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
+                                       long long rows_per_group, int C, int Cp, const float* __restrict__ gamma,
+                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  double dg = 0.0, db = 0.0;
+  for (int g = 0; g < groups; ++g) {
+    float* cf = coef + static_cast<long long>(g) * 3 * Cp;
+    if (c >= C) {
+      cf[c] = 0.f;
+      cf[Cp + c] = 0.f;
+      cf[2 * Cp + c] = 0.f;
+      continue;
+    }
+    double s = 0.0, sx = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += partials[((static_cast<long long>(b) * groups + g) * 2 + 0) * Cp + c];
+      sx += partials[((static_cast<long long>(b) * groups + g) * 2 + 1) * Cp + c];
+    }
+    const double n = static_cast<double>(rows_per_group);
+    cf[c] = gamma[c] * invstd[g * Cp + c];
+    cf[Cp + c] = static_cast<float>(s / n);
+    cf[2 * Cp + c] = static_cast<float>(sx / n);
+    db += s;
+    dg += sx;
+  }
+  if (c < C && dgamma != nullptr) {
+    dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(dg) : static_cast<float>(dg);
+    dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(db) : static_cast<float>(db);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
+                                                           const uint4* __restrict__ raw, long long rows, int Cp,
+                                                           long long rows_per_group, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ coef, uint4* __restrict__ gout,
+                                                           uint4* __restrict__ dz) {
+  const int nvec = Cp / 8;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % nvec);
+    const long long r = i / nvec;
+    const int g = static_cast<int>(r / rows_per_group);
+    const int c0 = cv * 8;
+    const float* cf = coef + static_cast<long long>(g) * 3 * Cp;
+    float dy[8], x[8];
+    unpack8(d[i], dy);
+    unpack8(raw[i], x);
+    if (act != nullptr) {
+      float y[8];
+      unpack8(act[i], y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy[j] = y[j] > 0.f ? dy[j] : 0.f;
+    }
+    if (dz != nullptr) dz[i] = pack8(dy);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float xhat = (x[j] - __ldg(mean + g * Cp + c)) * __ldg(invstd + g * Cp + c);
+      o[j] = __ldg(cf + c) * (dy[j] - __ldg(cf + Cp + c) - xhat * __ldg(cf + 2 * Cp + c));
+    }
+    gout[i] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- pooling
+__global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, int P, int Cp, float* __restrict__ out_f32,
+                                   __nv_bfloat16* __restrict__ out_bf16) {
+  const int nvec = Cp / 8;
+  const int n = blockIdx.x;
+  for (int cv = threadIdx.x; cv < nvec; cv += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int p = 0; p < P; ++p) {
+      float f[8];
+      unpack8(x[(static_cast<long long>(n) * P + p) * nvec + cv], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    const float inv = 1.f / static_cast<float>(P);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] *= inv;
+      if (out_f32) out_f32[static_cast<long long>(n) * Cp + cv * 8 + j] = acc[j];
+    }
+    if (out_bf16) reinterpret_cast<uint4*>(out_bf16)[static_cast<long long>(n) * nvec + cv] = pack8(acc);
+  }
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, int P, int Cp, uint4* __restrict__ dx, long long total) {
+  const int nvec = Cp / 8;
+  const float inv = 1.f / static_cast<float>(P);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % nvec);
+    const long long n = i / nvec / P;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = dfeat[n * Cp + cv * 8 + j] * inv;
+    dx[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- misc
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int Cp, int C, float* __restrict__ out,
+                              int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (long long r = 0; r < rows; ++r) acc += __bfloat162float(x[r * Cp + c]);
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+__global__ void cast_pad_kernel(const float* __restrict__ x, long long rows, int cols, int ld_in,
+                                __nv_bfloat16* __restrict__ out, int ld_out, const float* __restrict__ scale_dev) {
+  const float s = scale_dev ? *scale_dev : 1.f;
+  const long long total = rows * ld_out;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ld_out);
+    const long long r = i / ld_out;
+    out[i] = __float2bfloat16_rn(c < cols ? x[r * ld_in + c] * s : 0.f);
+  }
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace cstp
+
+using namespace cstp;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int cstp_pack_weight(const float* w, int cout, int cin, int taps, int transpose, void* packed, int Rp, int Kc,
+                                void* stream) {
+  CSTP_REQUIRE(w && packed && cout > 0 && cin > 0 && taps > 0 && Rp > 0 && Kc > 0 && Kc % 64 == 0);
+  CSTP_REQUIRE(transpose ? (Rp >= cin && Kc >= cout) : (Rp >= cout && Kc >= cin));
+  const long long total = static_cast<long long>(Rp) * taps * Kc;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, cout, cin, taps, transpose,
+                                                                  reinterpret_cast<__nv_bfloat16*>(packed), Rp, Kc);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void* col, int ldk, void* stream) {
+  CSTP_REQUIRE(x && col && N > 0 && T > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
+  CSTP_REQUIRE(ldk >= 152 && ldk % 8 == 0);
+  const long long total = static_cast<long long>(N) * T * (H / 2) * (W / 2) * (ldk / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, N, T, H, W, reinterpret_cast<__nv_bfloat16*>(col), ldk);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_stats(const void* raw, int64_t rows, int Cp, int groups, float* partials, int nblocks,
+                             void* stream) {
+  CSTP_REQUIRE(raw && partials && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0 && nblocks > 0);
+  const dim3 grid(nblocks, groups, ceil_div(Cp / 8, kSegVecs));
+  bn_reduce_kernel<false><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(raw), nullptr, nullptr,
+                                                       rows / groups, Cp, nullptr, nullptr, partials);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C, int Cp,
+                                const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                                float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                void* stream) {
+  CSTP_REQUIRE(partials && gamma && beta && scale && shift && mean && invstd && C <= Cp);
+  bn_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma, beta,
+                                                               eps, momentum, running_mean, running_var, scale, shift,
+                                                               mean, invstd);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, const float* scale, const float* shift,
+                             int relu, int res_mode, const void* res, const float* scale2, const float* shift2,
+                             void* out, void* stream) {
+  CSTP_REQUIRE(raw && out && scale && shift && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
+  CSTP_REQUIRE(res_mode == 0 || res != nullptr);
+  CSTP_REQUIRE(res_mode != 2 || (scale2 && shift2));
+  const long long total = rows * (Cp / 8);
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(raw), rows, Cp, rows / groups, scale, shift, relu, res_mode,
+      reinterpret_cast<const uint4*>(res), scale2, shift2, reinterpret_cast<uint4*>(out));
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_bwd_reduce(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
+                                  const float* mean, const float* invstd, float* partials, int nblocks, void* stream) {
+  CSTP_REQUIRE(d && raw && mean && invstd && partials && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
+  const dim3 grid(nblocks, groups, ceil_div(Cp / 8, kSegVecs));
+  bn_reduce_kernel<true><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(d),
+                                                      reinterpret_cast<const uint4*>(act),
+                                                      reinterpret_cast<const uint4*>(raw), rows / groups, Cp, mean,
+                                                      invstd, partials);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_bwd_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C,
+                                    int Cp, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
+                                    int accumulate, float* coef, void* stream) {
+  CSTP_REQUIRE(partials && gamma && invstd && coef && C <= Cp);
+  bn_bwd_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma,
+                                                                   invstd, dgamma, dbeta, accumulate, coef);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
+                                 const float* mean, const float* invstd, const float* coef, void* g, void* dz,
+                                 void* stream) {
+  CSTP_REQUIRE(d && raw && mean && invstd && coef && g && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
+  const long long total = rows * (Cp / 8);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(d), reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint4*>(raw), rows,
+      Cp, rows / groups, mean, invstd, coef, reinterpret_cast<uint4*>(g), reinterpret_cast<uint4*>(dz));
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_avgpool_fwd(const void* x, int N, int P, int Cp, float* out_f32, void* out_bf16, void* stream) {
+  CSTP_REQUIRE(x && (out_f32 || out_bf16) && N > 0 && P > 0 && Cp % 16 == 0);
+  avgpool_fwd_kernel<<<N, 64, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(x), P, Cp, out_f32,
+                                              reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_avgpool_bwd(const float* dfeat, int N, int P, int Cp, void* dx, void* stream) {
+  CSTP_REQUIRE(dfeat && dx && N > 0 && P > 0 && Cp % 16 == 0);
+  const long long total = static_cast<long long>(N) * P * (Cp / 8);
+  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dfeat, P, Cp, reinterpret_cast<uint4*>(dx), total);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_colsum(const void* x, int64_t rows, int Cp, int C, float* out, int accumulate, void* stream) {
+  CSTP_REQUIRE(x && out && rows > 0 && C > 0 && C <= Cp);
+  colsum_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, Cp, C, out,
+                                                         accumulate);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_cast_pad(const float* x, int64_t rows, int cols, int ld_in, void* out, int ld_out,
+                             const float* scale_dev, void* stream) {
+  CSTP_REQUIRE(x && out && rows > 0 && cols > 0 && cols <= ld_in && cols <= ld_out);
+  const long long total = rows * ld_out;
+  cast_pad_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, rows, cols, ld_in,
+                                                               reinterpret_cast<__nv_bfloat16*>(out), ld_out, scale_dev);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}

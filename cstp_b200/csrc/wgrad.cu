@@ -1,0 +1,303 @@
+// Weight-gradient GEMM on tcgen05: P[m, n] = sum_pos X[pos + tap(m), c(m)] * G[pos, n].
+//
+// Both operands come straight out of NDHWC activations, so both are "MN-major" for the tensor core: the
+// reduction (K) axis is the position axis, channels are contiguous.  One K-block is a TMA box of 64 positions;
+// the M tile (128 rows) is two 64-channel chunks of X, each with its own tap shift, so that 3x3 / 3x1x1 taps of
+// narrow layers (Cin = 64) still fill the 128-row MMA.  Split-K over position tiles; fp32 partials are reduced in
+// fixed order by cstp_wgrad_finalize, which also scatters into the reference (Cout, Cin, kT, kH, kW) layout.
+// Replaces cuDNN conv3d wgrad / cuBLAS addmm wgrad behind main_byol.py:87.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cstp {
+
+constexpr int kWgThreads = 256;
+constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // 64 positions x 64 channels
+constexpr int kWgMaxStages = 8;
+constexpr int kWgSmemLimit = 232448;
+
+struct WgradKParams {
+  CUtensorMap amap[CSTP_MAX_AMAPS];
+  CUtensorMap gmap;
+  int tiles_w, tiles_h, tiles_t, tiles_n;
+  int bw, bh, bt, bn;
+  int n_mchunks, Np, n_tile, n_gboxes;
+  int total_kblocks, kblocks_per_split;
+  int stages, tmem_cols;
+  uint32_t idesc;
+  float* partials;
+  cstp_mchunk mchunks[CSTP_MAX_MCHUNKS];
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = 2 * kBoxBytes;
+  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.n_gboxes) * kBoxBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgMaxStages;
+  uint64_t* tfull = bars + 2 * kWgMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mtile = blockIdx.x, ntile = blockIdx.y, split = blockIdx.z;
+  const int chunk0 = mtile * 2;
+  const int nchunks = min(2, p.n_mchunks - chunk0);
+  const int kb_begin = split * p.kblocks_per_split;
+  const int kb_end = min(p.total_kblocks, kb_begin + p.kblocks_per_split);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < CSTP_MAX_AMAPS; ++i) tma_prefetch_desc(&p.amap[i]);
+    tma_prefetch_desc(&p.gmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const cstp_mchunk mc0 = p.mchunks[chunk0];
+    const cstp_mchunk mc1 = p.mchunks[nchunks > 1 ? chunk0 + 1 : chunk0];
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      int pt = kb;
+      const int w0 = (pt % p.tiles_w) * p.bw;
+      pt /= p.tiles_w;
+      const int h0 = (pt % p.tiles_h) * p.bh;
+      pt /= p.tiles_h;
+      const int t0 = (pt % p.tiles_t) * p.bt;
+      pt /= p.tiles_t;
+      const int n0 = pt * p.bn;
+      mbar_wait(&empty[stage], phase ^ 1u);
+      uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+      mbar_expect_tx(&full[stage], static_cast<uint32_t>(nchunks + p.n_gboxes) * kBoxBytes);
+      tma_load_5d(sa, &p.amap[mc0.map_id], &full[stage], mc0.c_off, w0 + mc0.dw, h0 + mc0.dh, t0 + mc0.dt, n0);
+      if (nchunks > 1)
+        tma_load_5d(sa + kBoxBytes, &p.amap[mc1.map_id], &full[stage], mc1.c_off, w0 + mc1.dw, h0 + mc1.dh,
+                    t0 + mc1.dt, n0);
+      for (int j = 0; j < p.n_gboxes; ++j)
+        tma_load_5d(sa + a_bytes + j * kBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+      const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // MN-major, 128B swizzle: 16 K-rows per step = 2048 B; LBO = next 64-channel chunk, SBO = next 8 K-rows.
+        const uint64_t da = umma_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
+        const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
+        umma_bf16(tmem_base, da, db, p.idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty[stage]);
+      if (kb == kb_end - 1) umma_commit(tfull);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const bool valid = (row >> 6) < nchunks;
+    const int col0 = ntile * p.n_tile;
+    const int ncols = min(p.n_tile, p.Np - col0);
+    const long long mtot = static_cast<long long>(p.n_mchunks) * 64;
+    float* dst = p.partials + (static_cast<long long>(split) * mtot + static_cast<long long>(mtile) * 128 + row) * p.Np + col0;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                              __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// dW[(co*cin + ci)*taps + tap] = sum_s P[s][chunk*64 + r][co], ci = c_off(chunk) + r.  One thread per (row, co).
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partials, int splits, int n_mchunks, int Np,
+                                      const int* __restrict__ chunk_tap, const int* __restrict__ chunk_coff, int cout,
+                                      int cin, int taps, float* __restrict__ dw, int accumulate) {
+  const long long mtot = static_cast<long long>(n_mchunks) * 64;
+  const long long total = mtot * cout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % cout);
+    const long long row = i / cout;
+    const int chunk = static_cast<int>(row >> 6);
+    const int ci = chunk_coff[chunk] + static_cast<int>(row & 63);
+    if (ci >= cin) continue;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partials[(static_cast<long long>(s) * mtot + row) * Np + co];
+    const long long o = (static_cast<long long>(co) * cin + ci) * taps + chunk_tap[chunk];
+    dw[o] = accumulate ? dw[o] + acc : acc;
+  }
+}
+
+}  // namespace cstp
+
+struct cstp_wgrad_plan {
+  cstp::WgradKParams kp;
+  dim3 grid;
+  int smem_bytes;
+  int splits;
+};
+
+using namespace cstp;
+
+static int encode_tensor5_w(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5]) {
+  uint64_t dims[5], strides[4];
+  for (int i = 0; i < 5; ++i) {
+    if (t.dims[i] <= 0) return fail_inval("tensor5 dim <= 0");
+    dims[i] = static_cast<uint64_t>(t.dims[i]);
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (t.strides[i] <= 0 || (t.strides[i] % 16) != 0) return fail_inval("tensor5 stride must be a positive multiple of 16 bytes");
+    strides[i] = static_cast<uint64_t>(t.strides[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(t.ptr) % 16) != 0 || t.ptr == nullptr) return fail_inval("tensor5 ptr must be 16B aligned");
+  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box);
+}
+
+extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan** out_plan) {
+  CSTP_REQUIRE(d != nullptr && out_plan != nullptr);
+  CSTP_REQUIRE(d->n_amaps >= 1 && d->n_amaps <= CSTP_MAX_AMAPS);
+  CSTP_REQUIRE(d->n_mchunks >= 1 && d->n_mchunks <= CSTP_MAX_MCHUNKS);
+  CSTP_REQUIRE(d->Np >= 16 && d->Np % 16 == 0);
+  CSTP_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 256);
+  CSTP_REQUIRE(d->Np <= d->n_tile || d->n_tile % 64 == 0);
+  CSTP_REQUIRE(d->bw >= 1 && d->bh >= 1 && d->bt >= 1 && d->bn >= 1);
+  CSTP_REQUIRE(d->bw * d->bh * d->bt * d->bn == 64);
+  CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
+  CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr);
+
+  cstp_wgrad_plan* plan = new (std::nothrow) cstp_wgrad_plan();
+  if (!plan) {
+    set_error("out of host memory");
+    return CSTP_ENOMEM;
+  }
+  WgradKParams& k = plan->kp;
+  memset(&k, 0, sizeof(k));
+  const uint32_t box[5] = {64u, (uint32_t)d->bw, (uint32_t)d->bh, (uint32_t)d->bt, (uint32_t)d->bn};
+  for (int i = 0; i < CSTP_MAX_AMAPS; ++i) {
+    int rc = encode_tensor5_w(&k.amap[i], d->amap[i < d->n_amaps ? i : 0], box);
+    if (rc != CSTP_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  {
+    int rc = encode_tensor5_w(&k.gmap, d->gmap, box);
+    if (rc != CSTP_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  k.tiles_w = ceil_div(d->Wt, d->bw);
+  k.tiles_h = ceil_div(d->Ht, d->bh);
+  k.tiles_t = ceil_div(d->Tt, d->bt);
+  k.tiles_n = ceil_div(d->Nt, d->bn);
+  k.bw = d->bw; k.bh = d->bh; k.bt = d->bt; k.bn = d->bn;
+  k.n_mchunks = d->n_mchunks;
+  k.Np = d->Np;
+  k.n_tile = d->n_tile;
+  k.n_gboxes = ceil_div(d->n_tile, 64);
+  k.total_kblocks = k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
+  int splits = d->splits < k.total_kblocks ? d->splits : k.total_kblocks;
+  k.kblocks_per_split = ceil_div(k.total_kblocks, splits);
+  splits = ceil_div(k.total_kblocks, k.kblocks_per_split);
+  plan->splits = splits;
+  k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 1, 1);
+  k.partials = d->partials;
+  for (int i = 0; i < d->n_mchunks; ++i) {
+    const cstp_mchunk& mc = d->mchunks[i];
+    if (mc.map_id < 0 || mc.map_id >= d->n_amaps || mc.c_off < 0 || mc.c_off % 8 != 0) {
+      delete plan;
+      return fail_inval("mchunk map_id / c_off out of range");
+    }
+    k.mchunks[i] = mc;
+  }
+  const uint32_t stage_bytes = (2u + static_cast<uint32_t>(k.n_gboxes)) * kBoxBytes;
+  const int bar_bytes = 256;
+  int stages = (kWgSmemLimit - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  k.stages = stages;
+  int cols = 32;
+  while (cols < d->n_tile) cols *= 2;
+  k.tmem_cols = cols;
+  plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  plan->grid = dim3(static_cast<unsigned>(ceil_div(d->n_mchunks, 2)), static_cast<unsigned>(ceil_div(d->Np, d->n_tile)),
+                    static_cast<unsigned>(splits));
+  *out_plan = plan;
+  return CSTP_OK;
+}
+
+extern "C" int cstp_wgrad_plan_splits(const cstp_wgrad_plan* plan) { return plan ? plan->splits : CSTP_EINVAL; }
+
+extern "C" int cstp_wgrad_plan_run(const cstp_wgrad_plan* plan, void* stream) {
+  CSTP_REQUIRE(plan != nullptr);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSTP_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
+    attr_set = true;
+  }
+  wgrad_gemm_kernel<<<plan->grid, kWgThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" void cstp_wgrad_plan_destroy(cstp_wgrad_plan* plan) { delete plan; }
+
+extern "C" int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np, const int32_t* chunk_tap,
+                                   const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
+                                   void* stream) {
+  CSTP_REQUIRE(partials && chunk_tap && chunk_coff && dw);
+  CSTP_REQUIRE(splits >= 1 && n_mchunks >= 1 && n_mchunks <= CSTP_MAX_MCHUNKS && cout <= Np);
+  // chunk_tap / chunk_coff are device pointers (tiny int arrays uploaded once by the host at plan time).
+  const long long total = static_cast<long long>(n_mchunks) * 64 * cout;
+  int blocks = ceil_div(total, 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  wgrad_finalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, n_mchunks, Np, chunk_tap,
+                                                                             chunk_coff, cout, cin, taps, dw, accumulate);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}

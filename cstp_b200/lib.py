@@ -1,0 +1,135 @@
+"""ctypes binding of libcstp_b200.so (the C ABI declared in include/cstp_b200.h).
+
+There is no CPU fallback: every compute entry point needs the CUDA library and a B200.  Importing this module
+only loads the shared object (which works without a GPU, e.g. to check the exported symbols).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+CSTP_MAX_AMAPS = 4
+CSTP_MAX_TAPS = 32
+CSTP_MAX_MCHUNKS = 96
+
+
+class Tensor5(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dims", C.c_int32 * 5), ("strides", C.c_int64 * 4)]
+
+
+class Tap(C.Structure):
+    _fields_ = [("map_id", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32), ("dt", C.c_int32), ("k_off", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("n_amaps", C.c_int32),
+        ("amap", Tensor5 * CSTP_MAX_AMAPS),
+        ("a_channels", C.c_int32),
+        ("n_taps", C.c_int32),
+        ("taps", Tap * CSTP_MAX_TAPS),
+        ("w_packed", C.c_void_p),
+        ("Np", C.c_int32),
+        ("Ktot", C.c_int32),
+        ("n_tile", C.c_int32),
+        ("Wt", C.c_int32), ("Ht", C.c_int32), ("Tt", C.c_int32), ("Nt", C.c_int32),
+        ("bw", C.c_int32), ("bh", C.c_int32), ("bt", C.c_int32), ("bn", C.c_int32),
+        ("out_bf16", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("out_off", C.c_int64),
+        ("osw", C.c_int64), ("osh", C.c_int64), ("ost", C.c_int64), ("osn", C.c_int64),
+        ("bias", C.c_void_p),
+        ("accumulate", C.c_int32),
+    ]
+
+
+class MChunk(C.Structure):
+    _fields_ = [("map_id", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32), ("dt", C.c_int32), ("c_off", C.c_int32)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("n_amaps", C.c_int32),
+        ("amap", Tensor5 * CSTP_MAX_AMAPS),
+        ("n_mchunks", C.c_int32),
+        ("mchunks", MChunk * CSTP_MAX_MCHUNKS),
+        ("gmap", Tensor5),
+        ("Np", C.c_int32),
+        ("n_tile", C.c_int32),
+        ("Wt", C.c_int32), ("Ht", C.c_int32), ("Tt", C.c_int32), ("Nt", C.c_int32),
+        ("bw", C.c_int32), ("bh", C.c_int32), ("bt", C.c_int32), ("bn", C.c_int32),
+        ("splits", C.c_int32),
+        ("partials", C.c_void_p),
+    ]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); the single source of truth for the symbols include/cstp_b200.h declares.
+SIGNATURES = {
+    "cstp_last_error": (C.c_char_p, []),
+    "cstp_version": (_i, []),
+    "cstp_launch_count": (C.c_longlong, []),
+    "cstp_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
+    "cstp_conv_plan_run": (_i, [_vp, _vp]),
+    "cstp_conv_plan_destroy": (None, [_vp]),
+    "cstp_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),
+    "cstp_wgrad_plan_splits": (_i, [_vp]),
+    "cstp_wgrad_plan_run": (_i, [_vp, _vp]),
+    "cstp_wgrad_plan_destroy": (None, [_vp]),
+    "cstp_wgrad_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "cstp_pack_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "cstp_stem_im2col": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "cstp_bn_stats": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
+    "cstp_bn_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cstp_bn_apply": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cstp_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "cstp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "cstp_bn_bwd_apply": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cstp_avgpool_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "cstp_avgpool_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "cstp_colsum": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
+    "cstp_cast_pad": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp, _vp]),
+    "cstp_byol_loss": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cstp_pretext_ce": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _vp, _vp, _vp]),
+    "cstp_ntxent": (_i, [_vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "cstp_ema_update": (_i, [_vp, _vp, _i64, _f, _f, _vp]),
+    "cstp_sgd_clip_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class CstpError(RuntimeError):
+    """A C-ABI call returned a CSTP_E* code (the message comes from cstp_last_error())."""
+
+
+def lib_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Loads (building first if needed) libcstp_b200.so and installs the argtypes of every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not path.exists():
+        if not build_if_missing:
+            raise CstpError(f"{path} is missing: run `python -m cstp_b200.build` (there is no CPU fallback)")
+        _build.build()
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().cstp_last_error().decode(errors="replace")
+        raise CstpError(f"cstp_b200 call failed (code {rc}): {msg}")

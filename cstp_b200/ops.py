@@ -1,0 +1,478 @@
+"""Host-side operator layer over the C ABI: builds implicit-GEMM plans (TMA views, tap lists, tile boxes) for the
+forward / dgrad / wgrad of the factorised R(2+1)D convolutions and linear layers, and wraps the elementwise,
+loss and optimiser kernels.  torch is used only for device memory and streams.
+
+Layout conventions: activations are bf16 (N, T, H, W, Cp) with Cp = channels padded to a multiple of 16;
+packed forward weights are bf16 [Np][taps*Kc] with Kc = Cp_in rounded up to 64.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from itertools import product
+
+import torch
+
+from . import lib as L
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise L.CstpError("cstp_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------ geometry
+def pick_box(W: int, H: int, T: int, N: int, rows: int) -> tuple[int, int, int, int]:
+    """Chooses the (bw, bh, bt, bn) box with bw*bh*bt*bn == rows that wastes the fewest positions."""
+    best = None
+    divs = [d for d in (1, 2, 4, 8, 16, 32, 64, 128) if d <= rows]
+    for bw in divs:
+        for bh in divs:
+            if bw * bh > rows:
+                continue
+            for bt in divs:
+                if bw * bh * bt > rows:
+                    continue
+                bn = rows // (bw * bh * bt)
+                if bw * bh * bt * bn != rows or bn > 256:
+                    continue
+                tiles = math.ceil(W / bw) * math.ceil(H / bh) * math.ceil(T / bt) * math.ceil(N / bn)
+                # tie-break: prefer wide inner boxes (fewer, longer TMA rows), then small bn
+                key = (tiles, -bw, -bh, bn)
+                if best is None or key < best[0]:
+                    best = (key, (bw, bh, bt, bn))
+    return best[1]
+
+
+def view5_geometry(shape, parity=(0, 0, 0), stride=(1, 1, 1)):
+    """(element offset, dims (C,W,H,T,N), element strides of W,H,T,N) of the stride-parity sub-lattice of an
+    (N, T, H, W, Cp) tensor.  Pure shape arithmetic (also interpreted by the CPU emulator in tests/)."""
+    N, T, H, W, Cp = shape
+    (rt, rh, rw), (st, sh, sw) = parity, stride
+    off = ((rt * H + rh) * W + rw) * Cp
+    dims = (Cp, (W - rw + sw - 1) // sw, (H - rh + sh - 1) // sh, (T - rt + st - 1) // st, N)
+    strides = (sw * Cp, sh * W * Cp, st * H * W * Cp, T * H * W * Cp)
+    return off, dims, strides
+
+
+def _view5(x: torch.Tensor, parity=(0, 0, 0), stride=(1, 1, 1)) -> L.Tensor5:
+    """TMA view (C, W, H, T, N) of the stride-parity sub-lattice of an (N, T, H, W, Cp) bf16 tensor."""
+    off, dims, strides = view5_geometry(tuple(x.shape), parity, stride)
+    t5 = L.Tensor5()
+    es = x.element_size()
+    t5.ptr = x.data_ptr() + off * es
+    for i, d in enumerate(dims):
+        t5.dims[i] = d
+    for i, s_ in enumerate(strides):
+        t5.strides[i] = s_ * es
+    return t5
+
+
+@dataclass
+class ConvGeom:
+    kernel: tuple[int, int, int]
+    stride: tuple[int, int, int] = (1, 1, 1)
+    pad: tuple[int, int, int] = (0, 0, 0)
+
+    @property
+    def taps(self) -> int:
+        return self.kernel[0] * self.kernel[1] * self.kernel[2]
+
+    def out_dims(self, T: int, H: int, W: int) -> tuple[int, int, int]:
+        (kt, kh, kw), (st, sh, sw), (pt, ph, pw) = self.kernel, self.stride, self.pad
+        return ((T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1)
+
+
+def fwd_taps(g: ConvGeom):
+    """Per tap (kt,kh,kw raster order): the stride-parity class it reads and the integer offset d such that
+    in = stride*(out + d) + parity.  Returns (parities, [(map_id, dw, dh, dt, tap_index)])."""
+    maps, taps = [], []
+    (kt, kh, kw), (st, sh, sw), (pt, ph, pw) = g.kernel, g.stride, g.pad
+    ti = 0
+    for a in range(kt):
+        for b in range(kh):
+            for c in range(kw):
+                q = (a - pt, b - ph, c - pw)
+                r = (q[0] % st, q[1] % sh, q[2] % sw)
+                d = ((q[0] - r[0]) // st, (q[1] - r[1]) // sh, (q[2] - r[2]) // sw)
+                if r not in maps:
+                    maps.append(r)
+                taps.append((maps.index(r), d[2], d[1], d[0], ti))
+                ti += 1
+    if len(maps) > L.CSTP_MAX_AMAPS:
+        raise L.CstpError("too many stride-parity views for one convolution")
+    return maps, taps
+
+
+def dgrad_classes(shape_dx, geom: ConvGeom):
+    """Stride-parity classes of dx for the transposed convolution.  For class c, dx[s*a + c] sums the taps k with
+    (c + p - k) % s == 0 read at g[a + (c + p - k)/s].  Yields dicts with taps (dw,dh,dt,tap_index), the tile space,
+    the element offset/strides of the class inside dx; classes without taps have taps == []."""
+    N, T, H, W, Ci = shape_dx
+    (kt, kh, kw), (st, sh, sw), (pt, ph, pw) = geom.kernel, geom.stride, geom.pad
+    out = []
+    for ct, ch, cw in product(range(st), range(sh), range(sw)):
+        taps = []
+        ti = 0
+        for a in range(kt):
+            for b in range(kh):
+                for c in range(kw):
+                    e = (ct + pt - a, ch + ph - b, cw + pw - c)
+                    if e[0] % st == 0 and e[1] % sh == 0 and e[2] % sw == 0:
+                        taps.append((e[2] // sw, e[1] // sh, e[0] // st, ti))
+                    ti += 1
+        space = ((W - cw + sw - 1) // sw, (H - ch + sh - 1) // sh, (T - ct + st - 1) // st, N)
+        if min(space) <= 0:
+            continue
+        out.append(dict(cls=(ct, ch, cw), taps=taps, space=space, off=((ct * H + ch) * W + cw) * Ci,
+                        ostrides=(sw * Ci, sh * W * Ci, st * H * W * Ci, T * H * W * Ci)))
+    return out
+
+
+def _fwd_taps(x: torch.Tensor, g: ConvGeom):
+    maps, taps = fwd_taps(g)
+    views = [_view5(x, r, g.stride) for r in maps]
+    return views, taps
+
+
+class _Plan:
+    """Owns a C plan handle plus references to every tensor whose address the plan baked in."""
+
+    def __init__(self, handle, destroy, keep):
+        self.handle, self._destroy, self._keep = handle, destroy, keep
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._destroy(self.handle)
+        except Exception:
+            pass
+
+
+class ConvPlan(_Plan):
+    def run(self):
+        L.check(L.load().cstp_conv_plan_run(self.handle, _stream()))
+
+
+class WgradPlan(_Plan):
+    splits: int = 1
+
+    def run(self):
+        L.check(L.load().cstp_wgrad_plan_run(self.handle, _stream()))
+
+
+def _default_n_tile(Np: int) -> int:
+    if Np <= 256:
+        return Np
+    # fewest tiles, each a multiple of 16 and <= 256, as even as possible
+    nt = math.ceil(Np / 256)
+    return pad16(math.ceil(Np / nt))
+
+
+def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out, out_f32, out_off, ostrides, bias,
+                    accumulate, n_tile, keep) -> ConvPlan:
+    lib = L.load()
+    d = L.ConvDesc()
+    d.n_amaps = len(views)
+    for i, v in enumerate(views):
+        d.amap[i] = v
+    d.a_channels = a_channels
+    d.n_taps = len(taps)
+    for i, (mid, dw, dh, dt, koff) in enumerate(taps):
+        d.taps[i] = L.Tap(mid, dw, dh, dt, koff)
+    d.w_packed = w_packed.data_ptr()
+    d.Np = Np
+    d.Ktot = w_packed.shape[1]
+    d.n_tile = n_tile or _default_n_tile(Np)
+    d.Wt, d.Ht, d.Tt, d.Nt = tile_space
+    d.bw, d.bh, d.bt, d.bn = box
+    d.out_bf16 = 0 if out is None else out.data_ptr()
+    d.out_f32 = 0 if out_f32 is None else out_f32.data_ptr()
+    d.out_off = out_off
+    d.osw, d.osh, d.ost, d.osn = ostrides
+    d.bias = 0 if bias is None else bias.data_ptr()
+    d.accumulate = int(accumulate)
+    h = C.c_void_p()
+    L.check(lib.cstp_conv_plan_create(C.byref(d), C.byref(h)))
+    return ConvPlan(h, lib.cstp_conv_plan_destroy, keep)
+
+
+def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None,
+                  box=None) -> ConvPlan:
+    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16."""
+    _require_cuda(x, w_packed, out, out_f32, bias)
+    N, T, H, W, Ca = x.shape
+    To, Ho, Wo = geom.out_dims(T, H, W)
+    ref = out if out is not None else out_f32
+    Np = ref.shape[-1]
+    assert tuple(ref.shape[:4]) == (N, To, Ho, Wo), (ref.shape, (N, To, Ho, Wo))
+    assert w_packed.shape[0] >= Np and w_packed.shape[1] == geom.taps * pad64(Ca), (w_packed.shape, Np, geom.taps, Ca)
+    views, taps = _fwd_taps(x, geom)
+    Kc = pad64(Ca)
+    taps = [(m, dw, dh, dt, ti * Kc) for (m, dw, dh, dt, ti) in taps]
+    box = box or pick_box(Wo, Ho, To, N, 128)
+    ostr = (Np, Wo * Np, Ho * Wo * Np, To * Ho * Wo * Np)
+    return _make_conv_plan(views, taps, Ca, w_packed, Np, (Wo, Ho, To, N), box, out, out_f32, 0, ostr, bias, accumulate,
+                           n_tile, (x, w_packed, out, out_f32, bias))
+
+
+def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False) -> tuple[list[ConvPlan], bool]:
+    """dx (N,T,H,W,Cp_in) = conv_transpose(g (N,To,Ho,Wo,Cp_out)); wt_packed [Cp_in][taps*pad64(Cp_out)] bf16.
+
+    One plan per stride-parity class of dx.  Returns (plans, covers_all): when covers_all is False some classes
+    receive no tap (1x1x1 strided conv) and dx must be zero-filled by the caller unless accumulating."""
+    _require_cuda(g, wt_packed, dx)
+    N, T, H, W, Ci = dx.shape
+    _, To, Ho, Wo, Co = g.shape
+    (kt, kh, kw), (st, sh, sw), (pt, ph, pw) = geom.kernel, geom.stride, geom.pad
+    Kc = pad64(Co)
+    assert wt_packed.shape[0] >= Ci and wt_packed.shape[1] == geom.taps * Kc
+    gview = _view5(g)
+    plans, covers_all = [], True
+    for cl in dgrad_classes(tuple(dx.shape), geom):
+        if not cl["taps"]:
+            covers_all = False
+            continue
+        taps = [(0, dw_, dh_, dt_, ti * Kc) for (dw_, dh_, dt_, ti) in cl["taps"]]
+        box = pick_box(*cl["space"], 128)
+        plans.append(_make_conv_plan([gview], taps, Co, wt_packed, Ci, cl["space"], box, dx, None, cl["off"],
+                                     cl["ostrides"], None, accumulate, None, (g, wt_packed, dx)))
+    return plans, covers_all
+
+
+def linear_plan(x, w_packed, out, *, out_f32=None, bias=None, accumulate=False) -> ConvPlan:
+    """out[B][Np] = x[B][Cp] @ w^T (+bias): a 1-tap implicit GEMM over a (B,1,1,1,Cp) tensor."""
+    B, Ca = x.shape
+    ref = out if out is not None else out_f32
+    Np = ref.shape[-1]
+    x5 = x.view(1, 1, 1, B, Ca)
+    o5 = None if out is None else out.view(1, 1, 1, B, Np)
+    of5 = None if out_f32 is None else out_f32.view(1, 1, 1, B, Np)
+    return conv_fwd_plan(x5, w_packed, o5, ConvGeom((1, 1, 1)), out_f32=of5, bias=bias, accumulate=accumulate,
+                         box=(128, 1, 1, 1))
+
+
+@dataclass
+class WgradSpec:
+    plan: WgradPlan
+    n_mchunks: int
+    Np: int
+    chunk_tap: torch.Tensor
+    chunk_coff: torch.Tensor
+    cout: int
+    cin: int
+    taps: int
+    partials: torch.Tensor
+
+    def run(self, dw: torch.Tensor, accumulate: bool = False):
+        self.plan.run()
+        L.check(L.load().cstp_wgrad_finalize(_ptr(self.partials), self.plan.splits, self.n_mchunks, self.Np,
+                                             _ptr(self.chunk_tap), _ptr(self.chunk_coff), self.cout, self.cin,
+                                             self.taps, _ptr(dw), int(accumulate), _stream()))
+
+
+def wgrad_partials_numel(x_channels: int, taps: int, Np: int, splits: int) -> int:
+    return splits * taps * (pad64(x_channels) // 64) * 64 * Np
+
+
+def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor, *, splits: int | None = None,
+               box=None, sms: int = 148) -> WgradSpec:
+    """dW (cout, cin, kt, kh, kw) from x (N,T,H,W,Cp_in) and g (N,To,Ho,Wo,Cp_out); `partials` is fp32 scratch."""
+    _require_cuda(x, g, partials)
+    lib = L.load()
+    N, T, H, W, Ca = x.shape
+    _, To, Ho, Wo, Np = g.shape
+    assert geom.out_dims(T, H, W) == (To, Ho, Wo)
+    views, taps = _fwd_taps(x, geom)
+    nchunk_c = pad64(Ca) // 64
+    mch, ctap, ccoff = [], [], []
+    for (m, dw_, dh_, dt_, ti) in taps:
+        for cc in range(nchunk_c):
+            mch.append((m, dw_, dh_, dt_, cc * 64))
+            ctap.append(ti)
+            ccoff.append(cc * 64)
+    if len(mch) > L.CSTP_MAX_MCHUNKS:
+        raise L.CstpError(f"wgrad needs {len(mch)} M chunks > {L.CSTP_MAX_MCHUNKS}")
+    box = box or pick_box(Wo, Ho, To, N, 64)
+    n_tile = Np if Np <= 256 else 256
+    kblocks = math.ceil(Wo / box[0]) * math.ceil(Ho / box[1]) * math.ceil(To / box[2]) * math.ceil(N / box[3])
+    base_ctas = math.ceil(len(mch) / 2) * math.ceil(Np / n_tile)
+    if splits is None:
+        splits = max(1, min(math.ceil(2 * sms / base_ctas), max(1, kblocks // 4)))
+    d = L.WgradDesc()
+    d.n_amaps = len(views)
+    for i, v in enumerate(views):
+        d.amap[i] = v
+    d.n_mchunks = len(mch)
+    for i, mc in enumerate(mch):
+        d.mchunks[i] = L.MChunk(*mc)
+    d.gmap = _view5(g)
+    d.Np, d.n_tile = Np, n_tile
+    d.Wt, d.Ht, d.Tt, d.Nt = Wo, Ho, To, N
+    d.bw, d.bh, d.bt, d.bn = box
+    d.splits = splits
+    need = splits * len(mch) * 64 * Np
+    if partials.numel() < need:
+        raise L.CstpError(f"wgrad partials scratch too small: {partials.numel()} < {need}")
+    d.partials = partials.data_ptr()
+    h = C.c_void_p()
+    L.check(lib.cstp_wgrad_plan_create(C.byref(d), C.byref(h)))
+    plan = WgradPlan(h, lib.cstp_wgrad_plan_destroy, (x, g, partials))
+    plan.splits = lib.cstp_wgrad_plan_splits(h)
+    dev = x.device
+    return WgradSpec(plan, len(mch), Np, torch.tensor(ctap, dtype=torch.int32, device=dev),
+                     torch.tensor(ccoff, dtype=torch.int32, device=dev), cout, cin, geom.taps, partials)
+
+
+# ------------------------------------------------------------------------------------------------ thin wrappers
+def pack_weight(w: torch.Tensor, packed: torch.Tensor, *, transpose: bool = False) -> None:
+    """fp32 (cout, cin, *kernel) -> bf16 packed [Rp][taps*Kc] (forward) or its dgrad transpose."""
+    _require_cuda(w, packed)
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (cout * cin)
+    Rp, Ktot = packed.shape
+    L.check(L.load().cstp_pack_weight(_ptr(w), cout, cin, taps, int(transpose), _ptr(packed), Rp, Ktot // taps, _stream()))
+
+
+def stem_im2col(x: torch.Tensor, col: torch.Tensor) -> None:
+    _require_cuda(x, col)
+    N, Cc, T, H, W = x.shape
+    assert Cc == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    L.check(L.load().cstp_stem_im2col(_ptr(x), N, T, H, W, _ptr(col), col.shape[-1], _stream()))
+
+
+def bn_nblocks(rows_per_group: int, Cp: int, sms: int = 148) -> int:
+    rows_per_pass = max(1, 256 // min(Cp // 8, 128))
+    return max(1, min(4 * sms, math.ceil(rows_per_group / (rows_per_pass * 8))))
+
+
+@dataclass
+class BNState:
+    """Per-call BatchNorm scratch: statistics partials, affine coefficients and saved mean/invstd."""
+    C: int
+    Cp: int
+    groups: int
+    nblocks: int
+    partials: torch.Tensor
+    scale: torch.Tensor
+    shift: torch.Tensor
+    mean: torch.Tensor
+    invstd: torch.Tensor
+    coef: torch.Tensor = field(default=None)
+
+    @staticmethod
+    def alloc(C_: int, Cp: int, groups: int, rows_per_group: int, device, backward: bool = True) -> "BNState":
+        nb = bn_nblocks(rows_per_group, Cp)
+        f = dict(dtype=torch.float32, device=device)
+        return BNState(C_, Cp, groups, nb, torch.empty(nb * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
+                       torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f),
+                       torch.empty(groups * 3 * Cp, **f) if backward else None)
+
+
+def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1) -> None:
+    rows = raw.numel() // st.Cp
+    lib = L.load()
+    L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
+    L.check(lib.cstp_bn_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp, _ptr(gamma),
+                                 _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var), _ptr(st.scale),
+                                 _ptr(st.shift), _ptr(st.mean), _ptr(st.invstd), _stream()))
+
+
+def bn_apply(raw, st: BNState, out, *, relu: bool, res=None, res_state: BNState | None = None) -> None:
+    rows = raw.numel() // st.Cp
+    mode = 0 if res is None else (2 if res_state is not None else 1)
+    L.check(L.load().cstp_bn_apply(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.scale), _ptr(st.shift), int(relu), mode,
+                                   _ptr(res), _ptr(res_state.scale if res_state else None),
+                                   _ptr(res_state.shift if res_state else None), _ptr(out), _stream()))
+
+
+def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False) -> None:
+    """g_out = dL/d(raw) given d = dL/d(act) (masked by act > 0 when act is given); fills dgamma/dbeta."""
+    rows = raw.numel() // st.Cp
+    lib = L.load()
+    L.check(lib.cstp_bn_bwd_reduce(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean),
+                                   _ptr(st.invstd), _ptr(st.partials), st.nblocks, _stream()))
+    L.check(lib.cstp_bn_bwd_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp,
+                                     _ptr(gamma), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta), int(accumulate),
+                                     _ptr(st.coef), _stream()))
+    L.check(lib.cstp_bn_bwd_apply(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean), _ptr(st.invstd),
+                                  _ptr(st.coef), _ptr(g_out), _ptr(dz), _stream()))
+
+
+def avgpool_fwd(x, out_f32, out_bf16) -> None:
+    N = x.shape[0]
+    Cp = x.shape[-1]
+    P = x.numel() // (N * Cp)
+    L.check(L.load().cstp_avgpool_fwd(_ptr(x), N, P, Cp, _ptr(out_f32), _ptr(out_bf16), _stream()))
+
+
+def avgpool_bwd(dfeat, dx) -> None:
+    N = dx.shape[0]
+    Cp = dx.shape[-1]
+    P = dx.numel() // (N * Cp)
+    L.check(L.load().cstp_avgpool_bwd(_ptr(dfeat), N, P, Cp, _ptr(dx), _stream()))
+
+
+def colsum(x, C_: int, out, accumulate=False) -> None:
+    rows, Cp = x.shape
+    L.check(L.load().cstp_colsum(_ptr(x), rows, Cp, C_, _ptr(out), int(accumulate), _stream()))
+
+
+def cast_pad(x, out, cols: int | None = None, scale_dev=None) -> None:
+    rows, ld_in = x.shape
+    L.check(L.load().cstp_cast_pad(_ptr(x), rows, cols or ld_in, ld_in, _ptr(out), out.shape[1], _ptr(scale_dev),
+                                   _stream()))
+
+
+def byol_loss(pred, tproj, B: int, D: int, loss_out, upstream=None, dpred=None) -> None:
+    L.check(L.load().cstp_byol_loss(_ptr(pred), _ptr(tproj), B, D, pred.shape[1], _ptr(loss_out), _ptr(upstream),
+                                    _ptr(dpred), _stream()))
+
+
+def pretext_ce(logits, labels, dlogits, B: int, n_cls: int, weights5, losses_out) -> None:
+    arr = C.c_void_p * 6
+    lg = arr(*[t.data_ptr() for t in logits])
+    lb = arr(*[t.data_ptr() for t in labels])
+    dl = arr(*[0 if t is None else t.data_ptr() for t in dlogits]) if dlogits is not None else None
+    L.check(L.load().cstp_pretext_ce(lg, lb, dl, B, n_cls, logits[0].shape[1], _ptr(weights5), _ptr(losses_out),
+                                     _stream()))
+
+
+def ntxent(z, temperature: float, use_cosine: bool, loss_out, dz, workspace) -> None:
+    rows, d = z.shape
+    L.check(L.load().cstp_ntxent(_ptr(z), rows, d, float(temperature), int(use_cosine), _ptr(loss_out), _ptr(dz),
+                                 _ptr(workspace), _stream()))
+
+
+def ema_update(k, q, m: float) -> None:
+    import numpy as np
+    L.check(L.load().cstp_ema_update(_ptr(k), _ptr(q), k.numel(), float(np.float32(m)), float(np.float32(1.0 - m)),
+                                     _stream()))
+
+
+def sgd_clip_step(p, g, mom, lr, momentum, wd, max_norm, do_clip, first_step, norm_out, workspace) -> None:
+    L.check(L.load().cstp_sgd_clip_step(_ptr(p), _ptr(g), _ptr(mom), p.numel(), float(lr), float(momentum), float(wd),
+                                        float(max_norm), int(do_clip), int(first_step), _ptr(norm_out), _ptr(workspace),
+                                        _stream()))
+
+
+def launch_count() -> int:
+    return int(L.load().cstp_launch_count())

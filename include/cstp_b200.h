@@ -1,0 +1,192 @@
+/*
+ * cstp_b200 C ABI -- the drop-in boundary of the B200-native CSTP `r21d_byol` pretraining hot path.
+ *
+ * The reference (KT27-A/CSTP) is pure Python/PyTorch and has no FFI of its own: every entry point below
+ * replaces a PyTorch library op that the reference invokes at the cited call site (paths relative to the
+ * reference repo).  Conventions:
+ *   - extern "C", plain pointers and sizes only; all tensors are caller-owned DEVICE pointers.
+ *   - every function returns 0 on success, <0 (CSTP_E*) on failure; cstp_last_error() gives the message
+ *     (thread-local).  No function synchronises the device; every launch goes to the `stream` argument
+ *     (a cudaStream_t passed as void*).
+ *   - "plans" hold host-encoded TMA descriptors and launch geometry; they own no device memory.
+ *   - activations are NDHWC bf16 with the channel count padded to a multiple of 16 ("Cp").
+ */
+#ifndef CSTP_B200_H_
+#define CSTP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSTP_OK 0
+#define CSTP_EINVAL (-1)  /* bad argument / unsupported geometry */
+#define CSTP_ECUDA (-2)   /* CUDA runtime / driver error */
+#define CSTP_ENOMEM (-3)
+
+#define CSTP_MAX_AMAPS 4
+#define CSTP_MAX_TAPS 32
+#define CSTP_MAX_MCHUNKS 96
+
+const char* cstp_last_error(void);
+int cstp_version(void);
+/* Number of kernels this library has launched since load (all entry points; for bench.py `gpu_launches`). */
+long long cstp_launch_count(void);
+
+/* A 5-D view (C, W, H, T, N) of an NDHWC bf16 tensor, possibly a stride-parity sub-lattice of it.
+ * dims[0] is the channel extent; strides[i] is the BYTE stride of dims[i+1]. */
+typedef struct {
+  const void* ptr;
+  int32_t dims[5];
+  int64_t strides[4];
+} cstp_tensor5;
+
+/* One filter tap of an implicit GEMM: which A view it reads, the (w,h,t) offset added to the tile origin,
+ * and the column (K) offset of its first 64-channel chunk inside the packed weight matrix. */
+typedef struct {
+  int32_t map_id;
+  int32_t dw, dh, dt;
+  int32_t k_off;
+} cstp_tap;
+
+/* ---- implicit-GEMM convolution / linear: forward and dgrad ---------------------------------------------
+ * Replaces nn.Conv3d forward (models/pace/r21d_byol.py:81-82,91-92,94-97) and its autograd dgrad
+ * (main_byol.py:87), and nn.Linear forward/dgrad (r21d_byol.py:236-239,250-253,276-291).
+ * D[m, n] = sum_taps sum_c A[pos(m)+tap, c] * Wp[n, tap.k_off + c]   (+ bias[n]) (+ previous out if accumulate)
+ * M tiles are boxes (bw,bh,bt,bn) of 128 positions in the (Wt,Ht,Tt,Nt) tile space; out-of-range taps read 0. */
+typedef struct {
+  int32_t n_amaps;
+  cstp_tensor5 amap[CSTP_MAX_AMAPS];
+  int32_t a_channels;           /* padded channel count of A (multiple of 16) */
+  int32_t n_taps;
+  cstp_tap taps[CSTP_MAX_TAPS];
+  const void* w_packed;         /* bf16 [Np][Ktot], K-major */
+  int32_t Np;                   /* padded output channels (multiple of 16) */
+  int32_t Ktot;                 /* packed K extent (multiple of 64) */
+  int32_t n_tile;               /* N per tile: multiple of 16, <= 256 */
+  int32_t Wt, Ht, Tt, Nt;       /* tile-space extents */
+  int32_t bw, bh, bt, bn;       /* box: bw*bh*bt*bn == 128 */
+  void* out_bf16;               /* may be NULL */
+  float* out_f32;               /* may be NULL */
+  int64_t out_off;              /* element offset of tile-space origin */
+  int64_t osw, osh, ost, osn;   /* element strides of the tile-space axes in `out` */
+  const float* bias;            /* fp32 [Np] or NULL */
+  int32_t accumulate;           /* 1: out += D (read-modify-write) */
+} cstp_conv_desc;
+
+typedef struct cstp_conv_plan cstp_conv_plan;
+int cstp_conv_plan_create(const cstp_conv_desc* desc, cstp_conv_plan** plan);
+int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream);
+void cstp_conv_plan_destroy(cstp_conv_plan* plan);
+
+/* ---- weight gradient ------------------------------------------------------------------------------------
+ * Replaces the autograd wgrad of nn.Conv3d / nn.Linear (main_byol.py:87).
+ * The M axis is a list of 64-row chunks, each one (tap, 64 input channels) of the conv input X; the N axis
+ * is the output-channel axis of G = dL/d(conv output); K runs over all output positions:
+ *   P[split][chunk*64 + r][n] = sum_{pos in split} X[pos + tap(chunk), c_off(chunk) + r] * G[pos, n]
+ * cstp_wgrad_finalize then reduces the splits in fixed order and scatters into the reference weight layout. */
+typedef struct {
+  int32_t map_id;
+  int32_t dw, dh, dt;
+  int32_t c_off;
+} cstp_mchunk;
+
+typedef struct {
+  int32_t n_amaps;
+  cstp_tensor5 amap[CSTP_MAX_AMAPS];   /* views of X */
+  int32_t n_mchunks;
+  cstp_mchunk mchunks[CSTP_MAX_MCHUNKS];
+  cstp_tensor5 gmap;                    /* view of G */
+  int32_t Np;                           /* padded G channels (multiple of 16) */
+  int32_t n_tile;                       /* multiple of 16, <= 256 */
+  int32_t Wt, Ht, Tt, Nt;               /* position space */
+  int32_t bw, bh, bt, bn;               /* box: product == 64 */
+  int32_t splits;                       /* requested split-K factor (>=1) */
+  float* partials;                      /* fp32 [splits_eff][n_mchunks*64][Np] */
+} cstp_wgrad_desc;
+
+typedef struct cstp_wgrad_plan cstp_wgrad_plan;
+int cstp_wgrad_plan_create(const cstp_wgrad_desc* desc, cstp_wgrad_plan** plan);
+int cstp_wgrad_plan_splits(const cstp_wgrad_plan* plan);      /* effective split count */
+int cstp_wgrad_plan_run(const cstp_wgrad_plan* plan, void* stream);
+void cstp_wgrad_plan_destroy(cstp_wgrad_plan* plan);
+/* dW[(co*cin + ci)*taps + tap] (+)= sum_s partials[s][row(chunk,ci)][co]; chunk_tap/chunk_coff are DEVICE int32
+ * arrays of length n_mchunks (tap index and first input channel of every 64-row chunk). */
+int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np, const int32_t* chunk_tap,
+                        const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
+                        void* stream);
+
+/* ---- packing / layout -----------------------------------------------------------------------------------
+ * fp32 reference-layout weight (rows_out, cin, taps) -> bf16 K-major packed [Rp][taps*Kc].
+ * transpose=0: packed[r=co][tap*Kc + ci] (forward);  transpose=1: packed[r=ci][tap*Kc + co] (dgrad). */
+int cstp_pack_weight(const float* w, int cout, int cin, int taps, int transpose, void* packed, int Rp, int Kc,
+                     void* stream);
+/* Stem: fp32 NCDHW clip (N,3,T,H,W) -> bf16 im2col rows [N*T*Ho*Wo][ldk] for the 1x7x7 s(1,2,2) p(0,3,3) conv
+ * (r21d_byol.py:198); column = ci*49 + kh*7 + kw, columns >= 147 are zero. */
+int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void* col, int ldk, void* stream);
+
+/* ---- BatchNorm (training mode), fused with ReLU / residual ---------------------------------------------
+ * Replaces nn.BatchNorm3d / BatchNorm1d forward+backward and the ReLU / residual adds around them
+ * (r21d_byol.py:83,95,126,133,138,141-148,199,216).  `groups` splits the rows evenly into independent
+ * statistics groups (the two views, which the reference pushes through the net one after the other). */
+int cstp_bn_stats(const void* raw, int64_t rows, int Cp, int groups, float* partials, int nblocks, void* stream);
+int cstp_bn_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C, int Cp,
+                     const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                     float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* out = act(raw*scale+shift + residual); res_mode 0 none, 1 bf16 tensor, 2 raw2*scale2+shift2. */
+int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, const float* scale, const float* shift,
+                  int relu, int res_mode, const void* res, const float* scale2, const float* shift2, void* out,
+                  void* stream);
+/* dy = d * (act > 0 if act else 1); partials of sum(dy), sum(dy*xhat) per (group, channel). */
+int cstp_bn_bwd_reduce(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
+                       const float* mean, const float* invstd, float* partials, int nblocks, void* stream);
+/* Reduces partials; writes dgamma/dbeta (summed over groups, optionally accumulated) and the apply coefficients
+ * coef[g][3][Cp] = {gamma*invstd, sum(dy)/n, sum(dy*xhat)/n}. */
+int cstp_bn_bwd_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C, int Cp,
+                         const float* gamma, const float* invstd, float* dgamma, float* dbeta, int accumulate,
+                         float* coef, void* stream);
+/* g = c0*(dy - c1 - xhat*c2) (bf16); optionally also writes dz = dy (masked upstream grad). */
+int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
+                      const float* mean, const float* invstd, const float* coef, void* g, void* dz, void* stream);
+
+/* AdaptiveAvgPool3d(1) over `P` positions (r21d_byol.py:210,222-223) and its backward broadcast. */
+int cstp_avgpool_fwd(const void* x, int N, int P, int Cp, float* out_f32, void* out_bf16, void* stream);
+int cstp_avgpool_bwd(const float* dfeat, int N, int P, int Cp, void* dx, void* stream);
+
+/* Column sums of a bf16 [rows][Cp] matrix into fp32 (bias gradients): out[c] (+)= sum_r x[r][c]. */
+int cstp_colsum(const void* x, int64_t rows, int Cp, int C, float* out, int accumulate, void* stream);
+/* fp32 [rows][ld_in] -> bf16 [rows][ld_out] (zero padded), optional scale read from a device scalar. */
+int cstp_cast_pad(const float* x, int64_t rows, int cols, int ld_in, void* out, int ld_out, const float* scale_dev,
+                  void* stream);
+
+/* ---- losses ---------------------------------------------------------------------------------------------
+ * BYOL regression loss (r21d_byol.py:346-355,382): pred/tproj are fp32 [2B][ld]; rows [0,B) view 1, [B,2B) view 2.
+ * loss_out[0] = mean_i[(2-2cos(p1_i,t2_i)) + (2-2cos(p2_i,t1_i))]; dpred = upstream * dloss/dpred
+ * (`upstream` is a device scalar, NULL = 1). */
+int cstp_byol_loss(const float* pred, const float* tproj, int B, int D, int ld, float* loss_out,
+                   const float* upstream, float* dpred, void* stream);
+/* Six nn.CrossEntropyLoss() (mean) over [B][ld] logits with 5 classes + the weighted sum of main_byol.py:63-73.
+ * logits[h], labels[h] (int64), dlogits[h] for h in spa, tem, pb1, pb2, rot1, rot2; weights[5] = --loss_weight.
+ * losses_out[0..5] = the six CE values, losses_out[6] = weighted sum of them (BYOL term excluded). */
+int cstp_pretext_ce(const float* const* logits, const int64_t* const* labels, float* const* dlogits, int B,
+                    int n_cls, int ld, const float* weights5, float* losses_out, void* stream);
+/* NT-Xent (loss/NTXent.py:46-62), closed form: z = cat(zjs, zis) [rows=2N][d] fp32;
+ * loss = mean_i[LSE_{j!=i}(cos_ij/tau) - cos_i,pos(i)/tau]; dz optional (NULL = forward only).
+ * workspace: fp32 [3*rows + rows*d]. use_cosine=0 uses raw dot products. */
+int cstp_ntxent(const float* z, int rows, int d, float temperature, int use_cosine, float* loss_out, float* dz,
+                float* workspace, void* stream);
+
+/* ---- optimiser side -------------------------------------------------------------------------------------
+ * EMA target update (r21d_byol.py:331-337): k = k*m + q*(1-m), bit-exact fp32 (two rounded products, one add). */
+int cstp_ema_update(float* k, const float* q, int64_t n, float m, float one_minus_m, void* stream);
+/* clip_grad_norm_(params, max_norm) + SGD(momentum, weight_decay) (main_byol.py:88-91,229-232) over flat buffers.
+ * norm_out[0] = total grad norm (before clipping), norm_out[1] = clip coefficient. first_step: buf = g. */
+int cstp_sgd_clip_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float wd,
+                       float max_norm, int do_clip, int first_step, float* norm_out, float* workspace,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSTP_B200_H_ */
