@@ -305,10 +305,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 }
 
 // ------------------------------------------------------------------------------------------- pooling
+// Sample n lands in output row n % rows_out at column offset (n / rows_out) * Cp of a row of ld_out elements:
+// rows_out == N gives the plain [N][Cp] layout, rows_out == N/2 the cat(feat1, feat2) layout of r21d_byol.py:374.
 __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, int P, int Cp, float* __restrict__ out_f32,
-                                   __nv_bfloat16* __restrict__ out_bf16) {
+                                   __nv_bfloat16* __restrict__ out_bf16, int rows_out, int ld_out) {
   const int nvec = Cp / 8;
   const int n = blockIdx.x;
+  const long long obase = static_cast<long long>(n % rows_out) * ld_out + static_cast<long long>(n / rows_out) * Cp;
   for (int cv = threadIdx.x; cv < nvec; cv += blockDim.x) {
     float acc[8];
 #pragma unroll
@@ -323,13 +326,15 @@ __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, int P, int Cp, f
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[j] *= inv;
-      if (out_f32) out_f32[static_cast<long long>(n) * Cp + cv * 8 + j] = acc[j];
+      if (out_f32) out_f32[obase + cv * 8 + j] = acc[j];
     }
-    if (out_bf16) reinterpret_cast<uint4*>(out_bf16)[static_cast<long long>(n) * nvec + cv] = pack8(acc);
+    if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + obase + cv * 8) = pack8(acc);
   }
 }
 
-__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, int P, int Cp, uint4* __restrict__ dx, long long total) {
+// dx[n][p][c] = (dfeat[n][c] + dcat[n % rows_cat][(n / rows_cat) * Cp + c]) / P   (dcat optional)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ dcat, int rows_cat,
+                                   int ld_cat, int P, int Cp, uint4* __restrict__ dx, long long total) {
   const int nvec = Cp / 8;
   const float inv = 1.f / static_cast<float>(P);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -338,7 +343,11 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, int P, int C
     const long long n = i / nvec / P;
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = dfeat[n * Cp + cv * 8 + j] * inv;
+    for (int j = 0; j < 8; ++j) {
+      float v = dfeat[n * Cp + cv * 8 + j];
+      if (dcat != nullptr) v += dcat[(n % rows_cat) * ld_cat + (n / rows_cat) * Cp + cv * 8 + j];
+      f[j] = v * inv;
+    }
     dx[i] = pack8(f);
   }
 }
@@ -468,18 +477,23 @@ extern "C" int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw
   return CSTP_OK;
 }
 
-extern "C" int cstp_avgpool_fwd(const void* x, int N, int P, int Cp, float* out_f32, void* out_bf16, void* stream) {
+extern "C" int cstp_avgpool_fwd(const void* x, int N, int P, int Cp, float* out_f32, void* out_bf16, int rows_out,
+                                int ld_out, void* stream) {
   CSTP_REQUIRE(x && (out_f32 || out_bf16) && N > 0 && P > 0 && Cp % 16 == 0);
+  CSTP_REQUIRE(rows_out > 0 && N % rows_out == 0 && ld_out >= (N / rows_out) * Cp && ld_out % 8 == 0);
   avgpool_fwd_kernel<<<N, 64, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(x), P, Cp, out_f32,
-                                              reinterpret_cast<__nv_bfloat16*>(out_bf16));
+                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), rows_out, ld_out);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
 
-extern "C" int cstp_avgpool_bwd(const float* dfeat, int N, int P, int Cp, void* dx, void* stream) {
+extern "C" int cstp_avgpool_bwd(const float* dfeat, const float* dcat, int rows_cat, int ld_cat, int N, int P, int Cp,
+                                void* dx, void* stream) {
   CSTP_REQUIRE(dfeat && dx && N > 0 && P > 0 && Cp % 16 == 0);
+  CSTP_REQUIRE(dcat == nullptr || (rows_cat > 0 && N % rows_cat == 0 && ld_cat >= (N / rows_cat) * Cp));
   const long long total = static_cast<long long>(N) * P * (Cp / 8);
-  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dfeat, P, Cp, reinterpret_cast<uint4*>(dx), total);
+  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dfeat, dcat, rows_cat > 0 ? rows_cat : 1, ld_cat, P, Cp,
+                                                                  reinterpret_cast<uint4*>(dx), total);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

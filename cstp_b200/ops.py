@@ -417,18 +417,20 @@ def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=Non
                                   _ptr(st.coef), _ptr(g_out), _ptr(dz), _stream()))
 
 
-def avgpool_fwd(x, out_f32, out_bf16) -> None:
+def avgpool_fwd(x, out_f32, out_bf16, rows_out: int | None = None, ld_out: int | None = None) -> None:
     N = x.shape[0]
     Cp = x.shape[-1]
     P = x.numel() // (N * Cp)
-    L.check(L.load().cstp_avgpool_fwd(_ptr(x), N, P, Cp, _ptr(out_f32), _ptr(out_bf16), _stream()))
+    L.check(L.load().cstp_avgpool_fwd(_ptr(x), N, P, Cp, _ptr(out_f32), _ptr(out_bf16), rows_out or N, ld_out or Cp,
+                                      _stream()))
 
 
-def avgpool_bwd(dfeat, dx) -> None:
+def avgpool_bwd(dfeat, dx, dcat=None) -> None:
     N = dx.shape[0]
     Cp = dx.shape[-1]
     P = dx.numel() // (N * Cp)
-    L.check(L.load().cstp_avgpool_bwd(_ptr(dfeat), N, P, Cp, _ptr(dx), _stream()))
+    rows_cat, ld_cat = (dcat.shape[0], dcat.shape[1]) if dcat is not None else (0, 0)
+    L.check(L.load().cstp_avgpool_bwd(_ptr(dfeat), _ptr(dcat), rows_cat, ld_cat, N, P, Cp, _ptr(dx), _stream()))
 
 
 def colsum(x, C_: int, out, accumulate=False) -> None:

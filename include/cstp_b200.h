@@ -150,9 +150,14 @@ int cstp_bn_bwd_finalize(const float* partials, int nblocks, int groups, int64_t
 int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
                       const float* mean, const float* invstd, const float* coef, void* g, void* dz, void* stream);
 
-/* AdaptiveAvgPool3d(1) over `P` positions (r21d_byol.py:210,222-223) and its backward broadcast. */
-int cstp_avgpool_fwd(const void* x, int N, int P, int Cp, float* out_f32, void* out_bf16, void* stream);
-int cstp_avgpool_bwd(const float* dfeat, int N, int P, int Cp, void* dx, void* stream);
+/* AdaptiveAvgPool3d(1) over `P` positions (r21d_byol.py:210,222-223) and its backward broadcast.
+ * Forward: sample n is written to row n % rows_out, column offset (n / rows_out)*Cp of a row of ld_out elements
+ * (rows_out == N: plain [N][Cp]; rows_out == N/2: the cat(feat1, feat2) layout of r21d_byol.py:374).
+ * Backward: dx[n][p][:] = (dfeat[n] + dcat[n % rows_cat][(n / rows_cat)*Cp ...]) / P, dcat optional. */
+int cstp_avgpool_fwd(const void* x, int N, int P, int Cp, float* out_f32, void* out_bf16, int rows_out, int ld_out,
+                     void* stream);
+int cstp_avgpool_bwd(const float* dfeat, const float* dcat, int rows_cat, int ld_cat, int N, int P, int Cp, void* dx,
+                     void* stream);
 
 /* Column sums of a bf16 [rows][Cp] matrix into fp32 (bias gradients): out[c] (+)= sum_r x[r][c]. */
 int cstp_colsum(const void* x, int64_t rows, int Cp, int C, float* out, int accumulate, void* stream);
