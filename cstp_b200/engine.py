@@ -1,0 +1,606 @@
+"""Static-shape step engine of the B200-native `r21d_byol` pretraining hot path.
+
+The engine owns every device buffer of one pretraining step for a fixed per-GPU batch `B` and clip size
+(T, H, W) and turns the reference step (main_byol.py:60-91 around R21DBYOL.forward(o_type="loss_com"),
+models/pace/r21d_byol.py:357-382) into three launch programs of hand-written sm_100a kernels:
+
+  forward   online_net(view1|view2) -> predictor -> EMA -> target_net(view1|view2) -> BYOL loss -> pretext heads
+  backward  heads / predictor / projector / backbone (BN-bwd, wgrad, dgrad per layer) into ONE flat fp32 grad buffer
+  update    (grad all-reduce) -> global-norm clip + SGD momentum on the flat buffers -> bf16 weight re-pack
+
+Data layout in HBM
+  * parameters: two flat fp32 buffers (trainable = online_net + predictor + 4 pretext heads; target_net), every
+    tensor in a 16-float aligned slot; gradients and SGD momentum mirror the trainable buffer.  The nn.Parameters of
+    the drop-in module are views into these buffers (reference shapes, state_dict compatible).
+  * activations: bf16 NDHWC, channels padded to 16, the two views concatenated along N (2B samples) and kept as two
+    BatchNorm statistics groups (the reference runs the views one after the other).
+  * weights for the tensor cores: bf16 K-major packed copies (forward and transposed-for-dgrad), refreshed after
+    every optimiser step / EMA update.
+
+Everything is launched on the current CUDA stream through the C ABI (cstp_b200.ops); torch is only used for
+memory, streams and torch.distributed.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .ops import ConvGeom, pad16, pad64
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+# Storage type of activations, activation gradients and packed weights.  The CUDA kernels only implement bf16; the
+# CPU emulator in tests/ also runs the orchestration in fp32 to separate wiring errors from rounding.
+ACT_DTYPE = torch.bfloat16
+
+
+def intermed_channels(cin: int, cout: int, k: tuple[int, int, int]) -> int:
+    """Channel count between the spatial and temporal halves -- models/pace/r21d_byol.py:74-76."""
+    kt, kh, kw = k
+    return int(math.floor((kt * kh * kw * cin * cout) / (kh * kw * cin + kt * cout)))
+
+
+# ---------------------------------------------------------------------------------------------- flat parameter store
+class FlatStore:
+    """name -> fp32 view registry over one flat buffer; every tensor sits in a 16-float aligned, zero-padded slot."""
+
+    def __init__(self, specs, device, dtype=torch.float32):
+        self.slots: dict[str, tuple[int, tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in specs:
+            n = int(math.prod(shape)) if len(shape) else 1
+            self.slots[name] = (off, tuple(shape))
+            off += (n + 15) // 16 * 16
+        self.numel = off
+        self.data = torch.zeros(max(off, 16), device=device, dtype=dtype)
+
+    def view(self, name: str, buf: torch.Tensor | None = None) -> torch.Tensor:
+        off, shape = self.slots[name]
+        n = int(math.prod(shape)) if len(shape) else 1
+        return (self.data if buf is None else buf)[off:off + n].view(shape)
+
+    def slot(self, name: str, buf: torch.Tensor | None = None, pad_to: int = 16) -> torch.Tensor:
+        """1-D view of the whole padded slot (bias vectors read up to the padded channel count)."""
+        off, shape = self.slots[name]
+        n = int(math.prod(shape)) if len(shape) else 1
+        return (self.data if buf is None else buf)[off:off + (n + pad_to - 1) // pad_to * pad_to]
+
+    def like(self) -> torch.Tensor:
+        return torch.zeros_like(self.data)
+
+
+# ---------------------------------------------------------------------------------------------- architecture tables
+def mlp_param_specs(prefix: str, cin: int, hidden: int, cout: int, i0="0", i1="1", i3="3"):
+    """Linear -> BatchNorm1d -> ReLU -> Linear (r21d_byol.py:232-257,276-291) in registration order."""
+    return [(f"{prefix}.{i0}.weight", (hidden, cin)), (f"{prefix}.{i0}.bias", (hidden,)),
+            (f"{prefix}.{i1}.weight", (hidden,)), (f"{prefix}.{i1}.bias", (hidden,)),
+            (f"{prefix}.{i3}.weight", (cout, hidden)), (f"{prefix}.{i3}.bias", (cout,))]
+
+
+def stconv_param_specs(prefix: str, cin: int, cout: int, k):
+    mid = intermed_channels(cin, cout, k)
+    return [(f"{prefix}.spatial_conv.weight", (mid, cin, 1, k[1], k[2])),
+            (f"{prefix}.bn.weight", (mid,)), (f"{prefix}.bn.bias", (mid,)),
+            (f"{prefix}.temporal_conv.weight", (cout, mid, k[0], 1, 1))]
+
+
+STAGES = (("conv2", 64, 64, False), ("conv3", 64, 128, True), ("conv4", 128, 256, True), ("conv5", 256, 512, True))
+
+
+def backbone_param_specs(prefix: str, project: bool = True):
+    """R2Plus1DNet((1,1,1,1)) parameters in registration order (r21d_byol.py:184-213,113-139)."""
+    s = stconv_param_specs(f"{prefix}.conv1", 3, 64, (3, 7, 7))
+    s += [(f"{prefix}.bn1.weight", (64,)), (f"{prefix}.bn1.bias", (64,))]
+    for stage, cin, cout, down in STAGES:
+        b = f"{prefix}.{stage}.block1"
+        if down:
+            s += stconv_param_specs(b + ".downsampleconv", cin, cout, (1, 1, 1))
+            s += [(b + ".downsamplebn.weight", (cout,)), (b + ".downsamplebn.bias", (cout,))]
+        s += stconv_param_specs(b + ".conv1", cin, cout, (3, 3, 3))
+        s += [(b + ".bn1.weight", (cout,)), (b + ".bn1.bias", (cout,))]
+        s += stconv_param_specs(b + ".conv2", cout, cout, (3, 3, 3))
+        s += [(b + ".bn2.weight", (cout,)), (b + ".bn2.bias", (cout,))]
+    if project:
+        s += mlp_param_specs(f"{prefix}.project.net", 512, 4096, 512)
+    return s
+
+
+def trainable_param_specs():
+    s = backbone_param_specs("online_net")
+    s += mlp_param_specs("predictor.net", 512, 4096, 512)
+    s += mlp_param_specs("overlap_spa", 1024, 1024, 5)
+    s += mlp_param_specs("overlap_tem", 1024, 1024, 5)
+    s += mlp_param_specs("pb_cls", 512, 512, 5)
+    s += mlp_param_specs("rotate_cls", 512, 512, 5)
+    return s
+
+
+def bn_buffer_specs(param_specs):
+    """running_mean / running_var for every BatchNorm (a 1-D `.weight` whose sibling `.bias` is also 1-D and whose
+    module is not a Linear: identified by the absence of a 2-D/5-D weight under the same module name)."""
+    shapes = dict(param_specs)
+    out = []
+    for name, shape in param_specs:
+        if name.endswith(".weight") and len(shape) == 1:
+            mod = name[:-len(".weight")]
+            out += [(mod + ".running_mean", shape), (mod + ".running_var", shape)]
+    del shapes
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- engine
+@dataclass
+class _Site:
+    """One BatchNorm call site: parameters, running buffers and per-step statistics scratch."""
+    name: str
+    C: int
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    rm: torch.Tensor
+    rv: torch.Tensor
+    st: "ops.BNState"
+    dgamma: torch.Tensor | None = None
+    dbeta: torch.Tensor | None = None
+
+
+class _Timed:
+    """A group of tensor-core launches with its algorithmic FLOPs; records CUDA events around the group while the
+    engine is in profiling mode (bench.py roofline), otherwise just launches."""
+
+    def __init__(self, eng, kind: str, flops: float, plans):
+        self.eng, self.kind, self.flops, self.plans = eng, kind, flops, list(plans)
+
+    def run(self, *args):
+        prof = self.eng._prof
+        if prof is None:
+            for p in self.plans:
+                p.run(*args)
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for p in self.plans:
+            p.run(*args)
+        b.record()
+        prof.append((self.kind, self.flops, len(self.plans), a, b))
+
+
+class StepEngine:
+    """See the module docstring.  `B` is the per-GPU batch (samples; each sample is two views)."""
+
+    def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", momentum_ema: float = 0.996,
+                 record: bool = False):
+        if H % 2 or W % 2:
+            raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
+        self.B, self.T, self.H, self.W = B, T, H, W
+        self.N = 2 * B
+        self.device = torch.device(device)
+        self.momentum_ema = momentum_ema
+        self.record = record
+        self.named: dict[str, torch.Tensor] = {}      # name -> activation / gradient tensors (parity tests)
+        self._prof = None                             # list of (kind, flops, launches, ev0, ev1) while profiling
+        f32 = dict(device=self.device, dtype=torch.float32)
+
+        # ---- flat parameter / gradient / momentum / buffer stores
+        tspecs = trainable_param_specs()
+        self.train = FlatStore(tspecs, self.device)
+        self.grad = self.train.like()
+        self.mom = self.train.like()
+        self.target = FlatStore(backbone_param_specs("target_net"), self.device)
+        self.online_numel = FlatStore(backbone_param_specs("online_net"), "meta").numel
+        assert self.online_numel == self.target.numel
+        self.bufs = FlatStore(bn_buffer_specs(tspecs) + bn_buffer_specs(backbone_param_specs("target_net")), self.device)
+        for name in self.bufs.slots:
+            if name.endswith("running_var"):
+                self.bufs.view(name).fill_(1.0)
+        self.first_step = True
+
+        # ---- scratch shared by all layers
+        self._g_numel = 0            # bf16 d(raw) scratch, sized while building
+        self._wg_numel = 0           # fp32 wgrad split-K partials scratch
+        self._deferred = []          # closures that need the scratch buffers (run after allocation)
+        self._dbufs: dict[int, torch.Tensor] = {}
+        self._pack_jobs_online = []  # (param view, packed fwd, packed dgrad or None)
+        self._pack_jobs_target = []
+
+        self.fwd_online: list = []
+        self.fwd_target: list = []
+        self.fwd_heads: list = []
+        self.bwd: list = []          # executed in order (already reversed while building)
+
+        # ---- inputs
+        Ho, Wo = H // 2, W // 2
+        self.col = torch.zeros(self.N * T * Ho * Wo, 160, device=self.device, dtype=ACT_DTYPE)
+        self.weights5 = torch.tensor([0.1, 1.0, 1.0, 1.0, 1.0], **f32)
+        self.losses = torch.zeros(8, **f32)       # [0..5] CE, [6] weighted CE sum, [7] BYOL loss
+        self.norm_out = torch.zeros(2, **f32)
+        self.sgd_ws = torch.zeros(2048, **f32)
+
+        self._build()
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _act(self, *shape) -> torch.Tensor:
+        return torch.zeros(*shape, device=self.device, dtype=ACT_DTYPE)
+
+    def _dbuf(self, t: torch.Tensor) -> torch.Tensor:
+        """Gradient buffer of an activation tensor (keyed by storage address so views share it)."""
+        k = t.data_ptr()
+        if k not in self._dbufs:
+            self._dbufs[k] = torch.zeros_like(t)
+        return self._dbufs[k].view(t.shape)
+
+    def _rec(self, name: str, t: torch.Tensor) -> None:
+        if self.record:
+            self.named[name] = t
+
+    def _site(self, store: FlatStore, grads: bool, name: str, C: int, groups: int, rows_per_group: int) -> _Site:
+        st = ops.BNState.alloc(C, pad16(C), groups, rows_per_group, self.device, backward=grads)
+        return _Site(name, C, store.view(name + ".weight"), store.view(name + ".bias"),
+                     self.bufs.view(name + ".running_mean"), self.bufs.view(name + ".running_var"), st,
+                     store.view(name + ".weight", self.grad) if grads else None,
+                     store.view(name + ".bias", self.grad) if grads else None)
+
+    def _packed(self, store: FlatStore, name: str, grads: bool, rows_pad: int | None = None, as_2d: bool = False):
+        """bf16 packed forward (and dgrad-transposed) copies of a conv / linear weight; registers the re-pack job.
+        as_2d flattens (Cout, Cin, kT, kH, kW) to (Cout, Cin*taps): the stem runs as a GEMM over im2col rows."""
+        w = store.view(name)
+        if as_2d:
+            w = w.view(w.shape[0], -1)
+        cout, cin = w.shape[0], w.shape[1]
+        taps = w.numel() // (cout * cin)
+        wp = torch.zeros(rows_pad or pad16(cout), taps * pad64(pad16(cin)), device=self.device, dtype=ACT_DTYPE)
+        wt = None
+        if grads:
+            wt = torch.zeros(pad16(cin), taps * pad64(pad16(cout)), device=self.device, dtype=ACT_DTYPE)
+        (self._pack_jobs_online if store is self.train else self._pack_jobs_target).append((w, wp, wt))
+        return wp, wt
+
+    # ------------------------------------------------------------------------------------------ conv + BN unit
+    def _conv_bn(self, prog, store, grads, x, wname, bnname, geom: ConvGeom, cin, cout, *, relu=True, res=None,
+                 res_site=None, apply=True, tag="", skip_dgrad=False, x_is_col=False):
+        """raw = conv(x); BN statistics; act = [relu](bn(raw) [+ res]).  Returns (raw, act, site) and, when `grads`,
+        appends this unit's backward closure to self._units (run in reverse by _finish_backward)."""
+        N, T, H, W, _ = x.shape
+        To, Ho, Wo = geom.out_dims(T, H, W)
+        Cop = pad16(cout)
+        raw = self._act(N, To, Ho, Wo, Cop)
+        act = self._act(N, To, Ho, Wo, Cop) if apply else None
+        wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
+        rows = N * To * Ho * Wo
+        flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
+        plan = _Timed(self, "conv_fwd", flops, [ops.conv_fwd_plan(x, wp, raw, geom)])
+        site = self._site(store, grads, bnname, cout, 2, rows // 2)
+
+        def fwd():
+            plan.run()
+            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM)
+            if apply:
+                ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_site.st if res_site else None)
+        prog.append(fwd)
+        self._rec(tag + ".raw", raw)
+        if act is not None:
+            self._rec(tag + ".act", act)
+        unit = dict(x=x, raw=raw, act=act, site=site, relu=relu, geom=geom, wname=wname, cin=cin, cout=cout, wt=wt,
+                    skip_dgrad=skip_dgrad, tag=tag, flops=flops)
+        self._g_numel = max(self._g_numel, raw.numel())
+        return raw, act, site, unit
+
+    def _unit_backward(self, unit, d_out, *, act_for_mask, dz=None, dx_accumulate=False):
+        """Backward closure of one conv+BN unit: BN backward -> wgrad -> dgrad (see _conv_bn)."""
+        x, raw, site, geom = unit["x"], unit["raw"], unit["site"], unit["geom"]
+        dw = self.train.view(unit["wname"], self.grad)
+        holder = {}
+
+        def prepare():
+            g = self._g[:raw.numel()].view(raw.shape)
+            holder["g"] = g
+            holder["wg"] = _Timed(self, "wgrad", unit["flops"], [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg)])
+            if not unit["skip_dgrad"]:
+                dx = self._dbuf(x)
+                plans, covers = ops.conv_dgrad_plans(g, unit["wt"], dx, geom, accumulate=dx_accumulate)
+                holder["dg"] = _Timed(self, "conv_dgrad", unit["flops"], plans)
+                holder["zero"], holder["dx"] = (not covers and not dx_accumulate), dx
+                self._rec(unit["tag"] + ".dx", dx)
+        self._deferred.append(prepare)
+        self._wg_numel = max(self._wg_numel, self._wgrad_need(x, raw, geom))
+
+        def bwd():
+            g = holder["g"]
+            ops.bn_backward(d_out, act_for_mask, raw, site.st, site.gamma, site.dgamma, site.dbeta, g, dz=dz)
+            holder["wg"].run(dw)
+            if not unit["skip_dgrad"]:
+                if holder["zero"]:
+                    holder["dx"].zero_()
+                holder["dg"].run()
+        return bwd
+
+    @staticmethod
+    def _wgrad_need(x, raw, geom, sms: int = 148) -> int:
+        """Upper bound of the split-K partials (floats) ops.wgrad_plan will need for this layer."""
+        Ca, Np = x.shape[-1], raw.shape[-1]
+        nch = geom.taps * (pad64(Ca) // 64)
+        n_tile = Np if Np <= 256 else 256
+        base = math.ceil(nch / 2) * math.ceil(Np / n_tile)
+        splits = max(1, math.ceil(2 * sms / base))
+        return splits * nch * 64 * Np
+
+    # ------------------------------------------------------------------------------------------ backbone
+    def _backbone(self, prog, store, prefix, grads, tag):
+        """R2Plus1DNet.forward (r21d_byol.py:215-229) over both views.  Returns (last block act, backward closures in
+        forward order)."""
+        N, T = self.N, self.T
+        Ho, Wo = self.H // 2, self.W // 2
+        bw: list = []
+        col5 = self.col.view(1, 1, 1, self.col.shape[0], 160)
+        # stem spatial 1x7x7 s(1,2,2): a GEMM over the im2col rows (K = 147 padded to 160)
+        raw5, act5, site, u = self._conv_bn(prog, store, grads, col5, f"{prefix}.conv1.spatial_conv.weight",
+                                            f"{prefix}.conv1.bn", ConvGeom((1, 1, 1)), 147, 83, tag=f"{tag}.conv1.spatial",
+                                            skip_dgrad=True, x_is_col=True)
+        a0 = act5.view(N, T, Ho, Wo, act5.shape[-1])
+        if grads:
+            bw.append(self._unit_backward(u, self._dbuf(a0).view(act5.shape), act_for_mask=act5))
+        raw, x, site, u = self._conv_bn(prog, store, grads, a0, f"{prefix}.conv1.temporal_conv.weight", f"{prefix}.bn1",
+                                        ConvGeom((3, 1, 1), (1, 1, 1), (1, 0, 0)), 83, 64, tag=f"{tag}.conv1.temporal")
+        if grads:
+            bw.append(self._unit_backward(u, self._dbuf(x), act_for_mask=x))
+        for stage, cin, cout, down in STAGES:
+            x = self._block(prog, store, f"{prefix}.{stage}.block1", grads, x, cin, cout, down, bw,
+                            f"{tag}.{stage}.block1")
+        return x, bw
+
+    def _block(self, prog, store, pre, grads, xin, cin, cout, down, bw, tag):
+        """SpatioTemporalResBlock.forward (r21d_byol.py:141-148)."""
+        s = 2 if down else 1
+        mid1 = intermed_channels(cin, cout, (3, 3, 3))
+        mid2 = intermed_channels(cout, cout, (3, 3, 3))
+        sp = lambda st: ConvGeom((1, 3, 3), (1, st, st), (0, 1, 1))
+        tp = lambda st: ConvGeom((3, 1, 1), (st, 1, 1), (1, 0, 0))
+        _, a, _, u1 = self._conv_bn(prog, store, grads, xin, f"{pre}.conv1.spatial_conv.weight", f"{pre}.conv1.bn", sp(s),
+                                    cin, mid1, tag=f"{tag}.conv1.spatial")
+        _, b, _, u2 = self._conv_bn(prog, store, grads, a, f"{pre}.conv1.temporal_conv.weight", f"{pre}.bn1", tp(s),
+                                    mid1, cout, tag=f"{tag}.conv1.temporal")
+        _, c, _, u3 = self._conv_bn(prog, store, grads, b, f"{pre}.conv2.spatial_conv.weight", f"{pre}.conv2.bn", sp(1),
+                                    cout, mid2, tag=f"{tag}.conv2.spatial")
+        if down:
+            midd = intermed_channels(cin, cout, (1, 1, 1))
+            _, d1, _, u5 = self._conv_bn(prog, store, grads, xin, f"{pre}.downsampleconv.spatial_conv.weight",
+                                         f"{pre}.downsampleconv.bn", ConvGeom((1, 1, 1), (1, 2, 2)), cin, midd,
+                                         tag=f"{tag}.downsampleconv.spatial")
+            raw_ds, _, site_ds, u6 = self._conv_bn(prog, store, grads, d1, f"{pre}.downsampleconv.temporal_conv.weight",
+                                                   f"{pre}.downsamplebn", ConvGeom((1, 1, 1), (2, 1, 1)), midd, cout,
+                                                   relu=False, apply=False, tag=f"{tag}.downsampleconv.temporal")
+            _, out, _, u4 = self._conv_bn(prog, store, grads, c, f"{pre}.conv2.temporal_conv.weight", f"{pre}.bn2", tp(1),
+                                          mid2, cout, relu=True, res=raw_ds, res_site=site_ds,
+                                          tag=f"{tag}.conv2.temporal")
+        else:
+            _, out, _, u4 = self._conv_bn(prog, store, grads, c, f"{pre}.conv2.temporal_conv.weight", f"{pre}.bn2", tp(1),
+                                          mid2, cout, relu=True, res=xin, tag=f"{tag}.conv2.temporal")
+        self._rec(tag + ".out", out)
+        if grads:
+            d_out = self._dbuf(out)
+            if down:
+                dz = self._act(*out.shape)          # masked upstream gradient, shared by bn2 and downsamplebn
+                self._rec(tag + ".dz", dz)
+                # forward order: u1 u2 u3 u5 u6 u4  -> reversed at run time
+                bw.append(self._unit_backward(u1, self._dbuf(a), act_for_mask=a))                 # writes d(xin)
+                bw.append(self._unit_backward(u2, self._dbuf(b), act_for_mask=b))
+                bw.append(self._unit_backward(u3, self._dbuf(c), act_for_mask=c))
+                # run order is reversed, so u5/u6 must come BEFORE u1 in the list to run AFTER it: they accumulate
+                # into d(xin) that u1 has overwritten.  Insert them ahead of u1.
+                k = len(bw) - 3
+                bw.insert(k, self._unit_backward(u5, self._dbuf(d1), act_for_mask=d1, dx_accumulate=True))
+                bw.insert(k + 1, self._unit_backward(u6, dz, act_for_mask=None))
+                bw.append(self._unit_backward(u4, d_out, act_for_mask=out, dz=dz))
+            else:
+                # bn2 backward writes the masked upstream gradient straight into d(xin) (identity shortcut); the conv1
+                # spatial dgrad then accumulates into it.
+                bw.append(self._unit_backward(u1, self._dbuf(a), act_for_mask=a, dx_accumulate=True))
+                bw.append(self._unit_backward(u2, self._dbuf(b), act_for_mask=b))
+                bw.append(self._unit_backward(u3, self._dbuf(c), act_for_mask=c))
+                bw.append(self._unit_backward(u4, d_out, act_for_mask=out, dz=self._dbuf(xin)))
+        return out
+
+    # ------------------------------------------------------------------------------------------ MLP heads
+    def _mlp(self, prog, store, grads, x, pre, cin, hidden, cout, groups, *, names=("0", "1", "3"), out_bf16=False,
+             tag=""):
+        """Linear -> BatchNorm1d -> ReLU -> Linear.  x: bf16 [rows][pad16(cin)].  Returns dict with out_f32 [rows][Op]
+        (+ out_bf16) and, when `grads`, a backward factory taking (d_out fp32 [rows][Op], scale_dev, dx_f32, accumulate)."""
+        i0, i1, i3 = names
+        rows = x.shape[0]
+        Hp, Op = pad16(hidden), pad16(cout)
+        raw = self._act(rows, Hp)
+        h = self._act(rows, Hp)
+        outf = torch.zeros(rows, Op, device=self.device, dtype=torch.float32)
+        outb = self._act(rows, Op) if out_bf16 else None
+        w0, w0t = self._packed(store, f"{pre}.{i0}.weight", grads)
+        w3, w3t = self._packed(store, f"{pre}.{i3}.weight", grads)
+        b0 = store.slot(f"{pre}.{i0}.bias")
+        b3 = store.slot(f"{pre}.{i3}.bias")
+        p0 = ops.linear_plan(x, w0, raw, bias=b0)
+        p3 = ops.linear_plan(h, w3, outb, out_f32=outf, bias=b3)
+        site = self._site(store, grads, f"{pre}.{i1}", hidden, groups, rows // groups)
+
+        def fwd():
+            p0.run()
+            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM)
+            ops.bn_apply(raw, site.st, h, relu=True)
+            p3.run()
+        prog.append(fwd)
+        self._rec(tag + ".raw", raw)
+        self._rec(tag + ".h", h)
+        self._rec(tag + ".out", outf)
+        res = dict(out_f32=outf, out_bf16=outb)
+        if not grads:
+            return res
+        g_out = self._act(rows, Op)
+        d_h = self._act(rows, Hp)
+        g_h = self._act(rows, Hp)
+        dW0 = store.view(f"{pre}.{i0}.weight", self.grad)
+        dW3 = store.view(f"{pre}.{i3}.weight", self.grad)
+        db0 = store.view(f"{pre}.{i0}.bias", self.grad)
+        db3 = store.view(f"{pre}.{i3}.bias", self.grad)
+        g1 = ConvGeom((1, 1, 1))
+        x5, h5 = x.view(1, 1, 1, rows, -1), h.view(1, 1, 1, rows, Hp)
+        go5, gh5 = g_out.view(1, 1, 1, rows, Op), g_h.view(1, 1, 1, rows, Hp)
+        self._wg_numel = max(self._wg_numel, self._wgrad_need(h5, go5, g1), self._wgrad_need(x5, gh5, g1))
+        holder = {}
+
+        def make_backward(d_out, scale_dev, dx_f32, accumulate):
+            """d_out fp32 [rows][Op] (optionally scaled by the device scalar) -> parameter grads and dx_f32 [rows][Cip]."""
+            pd_h = ops.linear_plan(g_out, w3t, d_h)
+            pd_x = ops.linear_plan(g_h, w0t, None, out_f32=dx_f32, accumulate=accumulate) if dx_f32 is not None else None
+
+            def prepare():
+                holder["wg3"] = ops.wgrad_plan(h5, go5, g1, cout, hidden, self._wg)
+                holder["wg0"] = ops.wgrad_plan(x5, gh5, g1, hidden, cin, self._wg)
+            self._deferred.append(prepare)
+
+            def bwd():
+                ops.cast_pad(d_out, g_out, cols=cout, scale_dev=scale_dev)
+                ops.colsum(g_out, cout, db3)
+                holder["wg3"].run(dW3)
+                pd_h.run()
+                ops.bn_backward(d_h, h, raw, site.st, site.gamma, site.dgamma, site.dbeta, g_h)
+                ops.colsum(g_h, hidden, db0)
+                holder["wg0"].run(dW0)
+                if pd_x is not None:
+                    pd_x.run()
+            return bwd
+        res["make_backward"] = make_backward
+        return res
+
+    # ------------------------------------------------------------------------------------------ build
+    def _build(self):
+        B, N = self.B, self.N
+        f32 = dict(device=self.device, dtype=torch.float32)
+        # ---------------- online network + projector + predictor
+        x5, bw_backbone = self._backbone(self.fwd_online, self.train, "online_net", True, "online")
+        P = x5.shape[1] * x5.shape[2] * x5.shape[3]
+        self.feat = torch.zeros(N, 512, **f32)                 # rows [0,B) view 1, [B,2B) view 2
+        self.feat_bf = self._act(N, 512)
+        self.feat_cat = self._act(B, 1024)                     # cat(feat1, feat2) (r21d_byol.py:374)
+        self.fwd_online.append(lambda: (ops.avgpool_fwd(x5, self.feat, self.feat_bf),
+                                        ops.avgpool_fwd(x5, None, self.feat_cat, rows_out=B, ld_out=1024)))
+        self._rec("online.feat", self.feat)
+        proj = self._mlp(self.fwd_online, self.train, True, self.feat_bf, "online_net.project.net", 512, 4096, 512, 2,
+                         out_bf16=True, tag="online.project")
+        pred = self._mlp(self.fwd_online, self.train, True, proj["out_bf16"], "predictor.net", 512, 4096, 512, 2,
+                         tag="predictor")
+        self.pred = pred["out_f32"]
+        # ---------------- target network (no gradients; its own activations are scratch)
+        t5, _ = self._backbone(self.fwd_target, self.target, "target_net", False, "target")
+        self.tfeat_bf = self._act(N, 512)
+        self.fwd_target.append(lambda: ops.avgpool_fwd(t5, None, self.tfeat_bf))
+        tproj = self._mlp(self.fwd_target, self.target, False, self.tfeat_bf, "target_net.project.net", 512, 4096, 512, 2,
+                          tag="target.project")
+        self.tproj = tproj["out_f32"]
+        # ---------------- pretext heads (r21d_byol.py:374-380)
+        spa = self._mlp(self.fwd_heads, self.train, True, self.feat_cat, "overlap_spa", 1024, 1024, 5, 1, tag="overlap_spa")
+        tem = self._mlp(self.fwd_heads, self.train, True, self.feat_cat, "overlap_tem", 1024, 1024, 5, 1, tag="overlap_tem")
+        pb = self._mlp(self.fwd_heads, self.train, True, self.feat_bf, "pb_cls", 512, 512, 5, 2, tag="pb_cls")
+        rot = self._mlp(self.fwd_heads, self.train, True, self.feat_bf, "rotate_cls", 512, 512, 5, 2, tag="rotate_cls")
+        self.logit_bufs = (spa["out_f32"], tem["out_f32"], pb["out_f32"], rot["out_f32"])
+        # views in the reference's return order: spa, tem, pb1, pb2, rot1, rot2 (each [B][16], 5 valid columns)
+        self.logits6 = (spa["out_f32"], tem["out_f32"], pb["out_f32"][:B], pb["out_f32"][B:], rot["out_f32"][:B],
+                        rot["out_f32"][B:])
+        self.dlogit_bufs = tuple(torch.zeros_like(t) for t in self.logit_bufs)
+        d = self.dlogit_bufs
+        self.dlogits6 = (d[0], d[1], d[2][:B], d[2][B:], d[3][:B], d[3][B:])
+        # ---------------- backward program
+        self.dpred = torch.zeros(N, 512, **f32)      # dL_byol/dpred for upstream 1 (scaled inside cast_pad)
+        self.dproj = torch.zeros(N, 512, **f32)
+        self.dfeat = torch.zeros(N, 512, **f32)
+        self.dcat = torch.zeros(B, 1024, **f32)
+        self.byol_scale = torch.ones(1, **f32)       # d(total)/d(loss_byol) (= loss_weight[0] on the fused path)
+        bw = self.bwd
+        bw.append(pred["make_backward"](self.dpred, self.byol_scale, self.dproj, False))
+        bw.append(proj["make_backward"](self.dproj, None, self.dfeat, False))
+        bw.append(pb["make_backward"](d[2], None, self.dfeat, True))
+        bw.append(rot["make_backward"](d[3], None, self.dfeat, True))
+        bw.append(spa["make_backward"](d[0], None, self.dcat, False))
+        bw.append(tem["make_backward"](d[1], None, self.dcat, True))
+        d_x5 = self._dbuf(x5)
+        bw.append(lambda: ops.avgpool_bwd(self.dfeat, d_x5, dcat=self.dcat))
+        bw.extend(reversed(bw_backbone))
+        # ---------------- shared scratch + deferred plan creation
+        self._g = self._act(self._g_numel)
+        self._wg = torch.zeros(self._wg_numel, **f32)
+        for fn in self._deferred:
+            fn()
+        self._deferred.clear()
+
+    # ------------------------------------------------------------------------------------------ programs
+    def pack_online(self):
+        for w, wp, wt in self._pack_jobs_online:
+            ops.pack_weight(w, wp)
+            if wt is not None:
+                ops.pack_weight(w, wt, transpose=True)
+
+    def pack_target(self):
+        for w, wp, _ in self._pack_jobs_target:
+            ops.pack_weight(w, wp)
+
+    def load_clips(self, x1: torch.Tensor, x2: torch.Tensor):
+        """fp32 NCDHW clips (B,3,T,H,W) -> bf16 im2col rows of the stem (shared by the online and target nets)."""
+        rows = self.col.shape[0] // 2
+        ops.stem_im2col(x1, self.col[:rows])
+        ops.stem_im2col(x2, self.col[rows:])
+
+    def ema(self):
+        """R21DBYOL._update_target_net (r21d_byol.py:331-337) over the flat buffers, then re-pack the target weights."""
+        ops.ema_update(self.target.data[:self.target.numel], self.train.data[:self.online_numel], self.momentum_ema)
+        self.pack_target()
+
+    def forward(self, x1, x2, repack_online: bool = False):
+        """R21DBYOL.forward(o_type='loss_com') -- r21d_byol.py:357-382.  Fills self.losses[7] (BYOL), self.logits6 and
+        self.dpred (gradient of the BYOL loss w.r.t. the predictor output for upstream 1)."""
+        if repack_online:
+            self.pack_online()
+        self.load_clips(x1, x2)
+        for op in self.fwd_online:
+            op()
+        self.ema()
+        for op in self.fwd_target:
+            op()
+        ops.byol_loss(self.pred, self.tproj, self.B, 512, self.losses[7:8], None, self.dpred)
+        for op in self.fwd_heads:
+            op()
+
+    def pretext_losses(self, labels5):
+        """Six CrossEntropyLoss terms + the --loss_weight sum (main_byol.py:62-73); writes dlogits for backward."""
+        spa, tem, pb, r1, r2 = labels5
+        ops.pretext_ce(self.logits6, (spa, tem, pb, pb, r1, r2), self.dlogits6, self.B, 5, self.weights5, self.losses)
+
+    def backward(self):
+        for op in self.bwd:
+            op()
+
+    def optimizer_step(self, lr, momentum=0.9, wd=5e-4, max_norm=18.0, clip=True):
+        """clip_grad_norm_ + SGD.step (main_byol.py:88-91,229-232) on the flat buffers, then re-pack the bf16 weights."""
+        n = self.train.numel
+        ops.sgd_clip_step(self.train.data[:n], self.grad[:n], self.mom[:n], lr, momentum, wd, max_norm, clip,
+                          self.first_step, self.norm_out, self.sgd_ws)
+        self.first_step = False
+        self.pack_online()
+
+    def profile_tensor_launches(self, x1, x2):
+        """Runs one forward + backward with CUDA events around every backbone tensor-core launch group.
+        Returns {kind: (ms, algorithmic FLOPs, launches)} for kind in conv_fwd / conv_dgrad / wgrad."""
+        self._prof = []
+        try:
+            self.forward(x1, x2)
+            self.backward()
+            torch.cuda.synchronize()
+            out: dict = {}
+            for kind, flops, n, a, b in self._prof:
+                ms, fl, cnt = out.get(kind, (0.0, 0.0, 0))
+                out[kind] = (ms + a.elapsed_time(b), fl + flops, cnt + n)
+        finally:
+            self._prof = None
+        return out
+
+    def set_loss_weight(self, w5):
+        self.weights5.copy_(torch.tensor([float(v) for v in w5], dtype=torch.float32))
+        self.byol_scale.copy_(self.weights5[0:1])

@@ -39,6 +39,11 @@ def _require_cuda(*tensors) -> None:
             raise L.CstpError("cstp_b200 ops need CUDA tensors: there is no CPU fallback")
 
 
+def require_device(*tensors) -> None:
+    """Public guard used by the module layer: the product path only accepts CUDA tensors."""
+    _require_cuda(*tensors)
+
+
 # ------------------------------------------------------------------------------------------------ geometry
 def pick_box(W: int, H: int, T: int, N: int, rows: int) -> tuple[int, int, int, int]:
     """Chooses the (bw, bh, bt, bn) box with bw*bh*bt*bn == rows that wastes the fewest positions."""

@@ -9,6 +9,8 @@ SGD lr 0.03 momentum 0.9 wd 5e-4, clip_grad_norm_ 18, two steps.  Stored per bat
   * scalars: losses, grad-norm, parameter checksums before/after, label vectors
   * per hooked module call: (mean, std, l2) + 512 sampled values of the output and of its gradient
   * per trainable parameter: gradient l2 norm + 256 sampled values; post-step sampled values
+`step_struct_b4.pt` repeats the protocol on the video-like clips of oracle.structured_batch (B=4, with layers): the
+fixture the bf16 per-layer comparison uses (i.i.d. noise clips make every small-batch BatchNorm ill-conditioned).
 and NT-Xent anchors (loss + gradient samples) from loss/NTXent.py for rows in {64, 256, 1024}.
 """
 from __future__ import annotations
@@ -23,7 +25,7 @@ import torch.nn as nn
 REF = os.environ.get("CSTP_REFERENCE", "/root/reference")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.cstp_oracle import synthetic_batch  # noqa: E402
+from oracle.cstp_oracle import structured_batch, synthetic_batch  # noqa: E402
 
 N_ACT_SAMPLES = 512
 N_GRAD_SAMPLES = 256
@@ -40,14 +42,14 @@ def summarize(t: torch.Tensor, k: int) -> dict:
                 l2=f.norm().item(), samples=f[sample_idx(f.numel(), k)].clone())
 
 
-def run_reference(B: int, steps: int, with_layers: bool) -> dict:
+def run_reference(B: int, steps: int, with_layers: bool, batch_fn=synthetic_batch) -> dict:
     sys.path.insert(0, REF)
     from models.pace import r21d_byol as ref_mod  # the reference, unmodified
 
     torch.manual_seed(1)
     model = ref_mod.R21DBYOL(pretrain=True)
     model.train()
-    x1, x2, labels = synthetic_batch(B, 0)
+    x1, x2, labels = batch_fn(B, 0)
     w = [0.1, 1.0, 1.0, 1.0, 1.0]
     crit = nn.CrossEntropyLoss()
     params = list(model.parameters())
@@ -146,7 +148,13 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
-    torch.save(run_ntxent(), os.path.join(gold, "ntxent_ref.pt"))
-    torch.save(run_reference(2, 2, True), os.path.join(gold, "step_b2.pt"))
-    torch.save(run_reference(4, 2, False), os.path.join(gold, "step_b4.pt"))
+    which = sys.argv[1:] or ["ntxent", "b2", "b4", "struct_b4"]
+    if "ntxent" in which:
+        torch.save(run_ntxent(), os.path.join(gold, "ntxent_ref.pt"))
+    if "b2" in which:
+        torch.save(run_reference(2, 2, True), os.path.join(gold, "step_b2.pt"))
+    if "b4" in which:
+        torch.save(run_reference(4, 2, False), os.path.join(gold, "step_b4.pt"))
+    if "struct_b4" in which:       # video-like clips (oracle.structured_batch): the bf16 per-layer parity fixture
+        torch.save(run_reference(4, 2, True, structured_batch), os.path.join(gold, "step_struct_b4.pt"))
     print("golden fixtures written to", gold)

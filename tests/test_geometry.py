@@ -1,0 +1,80 @@
+"""Host-side implicit-GEMM geometry (tap lists, stride-parity views, dgrad classes, wgrad chunks, tile boxes) checked
+against torch's convolution functions through the descriptor interpreter in tests/emulate.py.  CPU only."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cstp_b200 import ops
+from cstp_b200.ops import ConvGeom
+from tests import emulate as E
+
+CASES = [
+    # kernel, stride, pad, (N, T, H, W)  -- every conv geometry of R2Plus1DNet plus degenerate extents
+    ((1, 3, 3), (1, 1, 1), (0, 1, 1), (2, 3, 8, 8)),
+    ((1, 3, 3), (1, 2, 2), (0, 1, 1), (2, 2, 8, 8)),
+    ((1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 7, 7)),
+    ((3, 1, 1), (1, 1, 1), (1, 0, 0), (2, 4, 3, 3)),
+    ((3, 1, 1), (2, 1, 1), (1, 0, 0), (2, 4, 4, 4)),
+    ((3, 1, 1), (2, 1, 1), (1, 0, 0), (2, 1, 4, 4)),
+    ((1, 1, 1), (1, 2, 2), (0, 0, 0), (2, 2, 8, 8)),
+    ((1, 1, 1), (2, 1, 1), (0, 0, 0), (2, 4, 4, 4)),
+    ((1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1, 9)),
+]
+
+
+@pytest.mark.parametrize("k,s,p,shape", CASES)
+def test_descriptor_semantics_match_torch(k, s, p, shape):
+    torch.manual_seed(0)
+    N, T, H, W = shape
+    g = ConvGeom(k, s, p)
+    ci, co = 5, 7
+    x = torch.randn(N, T, H, W, ci)
+    w = torch.randn(co, ci, *k)
+    xr = x.permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xr, w, stride=s, padding=p).permute(0, 2, 3, 4, 1)
+    assert tuple(ref.shape[1:4]) == g.out_dims(T, H, W)
+    torch.testing.assert_close(E.emulate_fwd(x, w, g), ref, rtol=1e-4, atol=1e-4)
+    gg = torch.randn_like(ref)
+    gr = gg.permute(0, 4, 1, 2, 3)
+    dref = torch.nn.grad.conv3d_input((N, ci, T, H, W), w, gr, stride=s, padding=p).permute(0, 2, 3, 4, 1)
+    dx, covers = E.emulate_dgrad(gg, w, g, (N, T, H, W, ci))
+    torch.testing.assert_close(dx, dref, rtol=1e-4, atol=1e-4)
+    # a class without taps exists exactly when some input position is never read by the conv
+    never_read = any(all((c + pp - a) % st != 0 for a in range(kk)) for kk, st, pp, ext in zip(k, s, p, (T, H, W))
+                     for c in range(min(st, ext)))
+    assert covers == (not never_read)
+    wref = torch.nn.grad.conv3d_weight(xr, w.shape, gr, stride=s, padding=p)
+    torch.testing.assert_close(E.emulate_wgrad(x, gg, g, co, ci), wref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("space,rows", [((56, 56, 16, 120), 128), ((7, 7, 2, 8), 128), ((1, 1, 1, 60), 128),
+                                        ((28, 28, 8, 3), 64), ((14, 14, 4, 1), 64), ((6021120, 1, 1, 1), 128)])
+def test_pick_box(space, rows):
+    bw, bh, bt, bn = ops.pick_box(*space, rows)
+    assert bw * bh * bt * bn == rows and max(bw, bh, bt, bn) <= 256
+    tiles = math.prod(math.ceil(d / b) for d, b in zip(space, (bw, bh, bt, bn)))
+    # never worse than the trivial row-major box
+    trivial = math.ceil(space[0] / rows) * space[1] * space[2] * space[3]
+    assert tiles <= trivial
+
+
+def test_view5_geometry_matches_strided_slicing():
+    x = torch.arange(2 * 5 * 6 * 7 * 16).view(2, 5, 6, 7, 16)
+    for parity, stride in [((0, 0, 0), (1, 1, 1)), ((1, 0, 1), (2, 1, 2)), ((0, 1, 1), (1, 2, 2)), ((1, 1, 1), (2, 2, 2))]:
+        off, dims, strides = ops.view5_geometry(tuple(x.shape), parity, stride)
+        sub = x[:, parity[0]::stride[0], parity[1]::stride[1], parity[2]::stride[2], :]
+        assert dims == (16, sub.shape[3], sub.shape[2], sub.shape[1], sub.shape[0])
+        v = torch.as_strided(x.reshape(-1), (dims[4], dims[3], dims[2], dims[1], dims[0]),
+                             (strides[3], strides[2], strides[1], strides[0], 1), off)
+        assert torch.equal(v, sub)
+
+
+def test_intermediate_channels_table():
+    """SURVEY.md A.1 / r21d_byol.py:74-76: the odd mid-channel counts of every factorised conv."""
+    from cstp_b200.engine import intermed_channels as ic
+    assert ic(3, 64, (3, 7, 7)) == 83
+    assert [ic(64, 64, (3, 3, 3)), ic(64, 128, (3, 3, 3)), ic(128, 128, (3, 3, 3))] == [144, 230, 288]
+    assert [ic(128, 256, (3, 3, 3)), ic(256, 256, (3, 3, 3)), ic(256, 512, (3, 3, 3)), ic(512, 512, (3, 3, 3))] == [460, 576, 921, 1152]
+    assert [ic(64, 128, (1, 1, 1)), ic(128, 256, (1, 1, 1)), ic(256, 512, (1, 1, 1))] == [42, 85, 170]
