@@ -84,6 +84,7 @@ template <bool kBackward>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ act,
                                                         const uint4* __restrict__ raw, long long rows_per_group, int Cp,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ mscale, const float* __restrict__ mshift,
                                                         float* __restrict__ partials) {
   __shared__ float red[2][256 * 8];
   const int nvec = Cp / 8;
@@ -97,12 +98,16 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
   if (rl < rows_per_pass) {
-    float mu[8], is[8];
+    float mu[8], is[8], ms[8], mb[8];
     if (kBackward) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         mu[j] = mean[g * Cp + (seg0 + cv) * 8 + j];
         is[j] = invstd[g * Cp + (seg0 + cv) * 8 + j];
+        if (mscale != nullptr) {
+          ms[j] = mscale[g * Cp + (seg0 + cv) * 8 + j];
+          mb[j] = mshift[g * Cp + (seg0 + cv) * 8 + j];
+        }
       }
     }
     const long long base = static_cast<long long>(g) * rows_per_group;
@@ -126,6 +131,9 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
           unpack8(act[idx], y);
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? d[j] : 0.f;
+        } else if (mscale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = fmaf(x[j], ms[j], mb[j]) > 0.f ? d[j] : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -151,25 +159,57 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
   }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups, long long rows_per_group,
-                                   int C, int Cp, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cp) return;
+// Deterministic tree over the per-block partials: 8 warps x 32 channels per CTA, warp w sums blocks w, w+8, ... in
+// double, the 8 warp sums are combined in fixed order.  partials: [nblocks][groups][2][Cp].
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nblocks, int groups, int g, int Cp,
+                                                int c, bool active, double (*red)[2][32], double& s, double& ss) {
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+  double a0 = 0.0, a1 = 0.0;
+  if (active) {
+    for (int b = ty; b < nblocks; b += 8) {
+      const float* p = partials + ((static_cast<long long>(b) * groups + g) * 2) * Cp + c;
+      a0 += static_cast<double>(p[0]);
+      a1 += static_cast<double>(p[Cp]);
+    }
+  }
+  __syncthreads();
+  red[ty][0][tx] = a0;
+  red[ty][1][tx] = a1;
+  __syncthreads();
+  s = 0.0;
+  ss = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    s += red[w][0][tx];
+    ss += red[w][1][tx];
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
+                                                          long long rows_per_group, int C, int Cp,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, float momentum, float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var, float* __restrict__ scale,
+                                                          float* __restrict__ shift, float* __restrict__ mean_out,
+                                                          float* __restrict__ invstd_out) {
+  __shared__ double red[8][2][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < Cp;
+  float rm = 0.f, rv = 0.f;
+  if (lead && c < C && running_mean != nullptr) {
+    rm = running_mean[c];
+    rv = running_var[c];
+  }
   for (int g = 0; g < groups; ++g) {
+    double s, ss;
+    reduce_partials(partials, nblocks, groups, g, Cp, c, c < C, red, s, ss);
+    if (!lead) continue;
     if (c >= C) {
       scale[g * Cp + c] = 0.f;
       shift[g * Cp + c] = 0.f;
       mean_out[g * Cp + c] = 0.f;
       invstd_out[g * Cp + c] = 0.f;
       continue;
-    }
-    double s = 0.0, ss = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += partials[((static_cast<long long>(b) * groups + g) * 2 + 0) * Cp + c];
-      ss += partials[((static_cast<long long>(b) * groups + g) * 2 + 1) * Cp + c];
     }
     const double n = static_cast<double>(rows_per_group);
     const double mu = s / n;
@@ -181,51 +221,76 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nbloc
     shift[g * Cp + c] = beta[c] - static_cast<float>(mu) * sc;
     mean_out[g * Cp + c] = static_cast<float>(mu);
     invstd_out[g * Cp + c] = istd;
-    if (running_mean != nullptr) {
-      const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
-    }
+    // the views pass through the module one after the other: the running statistics advance once per group
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * static_cast<float>(mu);
+    rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
+  }
+  if (lead && c < C && running_mean != nullptr) {
+    running_mean[c] = rm;
+    running_var[c] = rv;
   }
 }
 
-// out = act(raw*scale + shift + residual)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ raw, long long rows, int Cp,
-                                                       long long rows_per_group, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, int relu, int res_mode,
-                                                       const uint4* __restrict__ res, const float* __restrict__ scale2,
-                                                       const float* __restrict__ shift2, uint4* __restrict__ out) {
+// Shared row/channel geometry of the BatchNorm streaming kernels: grid = (row blocks, groups, channel segments of
+// <= 1024 channels); every thread owns ONE 8-channel vector (its per-channel coefficients live in registers) and
+// walks the rows of its group.
+struct BnThread {
+  int g, cvec, rl, rows_per_pass;
+  bool active;
+};
+__device__ __forceinline__ BnThread bn_thread(int Cp) {
+  BnThread t;
   const int nvec = Cp / 8;
-  const long long total = rows * nvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % nvec);
-    const long long r = i / nvec;
-    const int g = static_cast<int>(r / rows_per_group);
-    const float4* sc = reinterpret_cast<const float4*>(scale + g * Cp + cv * 8);
-    const float4* sh = reinterpret_cast<const float4*>(shift + g * Cp + cv * 8);
-    const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
-    const float s[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float t[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const int seg0 = blockIdx.z * kSegVecs;
+  const int seg_vecs = min(kSegVecs, nvec - seg0);
+  t.rows_per_pass = 256 / seg_vecs;
+  t.cvec = seg0 + static_cast<int>(threadIdx.x) % seg_vecs;
+  t.rl = static_cast<int>(threadIdx.x) / seg_vecs;
+  t.g = blockIdx.y;
+  t.active = t.rl < t.rows_per_pass;
+  return t;
+}
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// out = act(raw*scale + shift + residual)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ raw, int Cp, long long rows_per_group,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       int relu, int res_mode, const uint4* __restrict__ res,
+                                                       const float* __restrict__ scale2, const float* __restrict__ shift2,
+                                                       uint4* __restrict__ out) {
+  const BnThread t = bn_thread(Cp);
+  if (!t.active) return;
+  const int nvec = Cp / 8;
+  float s[8], b[8], s2[8], b2[8];
+  load8(scale + t.g * Cp + t.cvec * 8, s);
+  load8(shift + t.g * Cp + t.cvec * 8, b);
+  if (res_mode == 2) {
+    load8(scale2 + t.g * Cp + t.cvec * 8, s2);
+    load8(shift2 + t.g * Cp + t.cvec * 8, b2);
+  }
+  const long long base = static_cast<long long>(t.g) * rows_per_group;
+  for (long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl; r < rows_per_group;
+       r += static_cast<long long>(gridDim.x) * t.rows_per_pass) {
+    const long long i = (base + r) * nvec + t.cvec;
     float x[8];
     unpack8(raw[i], x);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], s[j], t[j]);
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], s[j], b[j]);
     if (res_mode == 1) {
       float y[8];
       unpack8(res[i], y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] += y[j];
     } else if (res_mode == 2) {
-      const float4* sc2 = reinterpret_cast<const float4*>(scale2 + g * Cp + cv * 8);
-      const float4* sh2 = reinterpret_cast<const float4*>(shift2 + g * Cp + cv * 8);
-      const float4 c0 = __ldg(sc2), c1 = __ldg(sc2 + 1), d0 = __ldg(sh2), d1 = __ldg(sh2 + 1);
-      const float s2[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      const float t2[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
       float y[8];
       unpack8(res[i], y);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] += fmaf(y[j], s2[j], t2[j]);
+      for (int j = 0; j < 8; ++j) x[j] += fmaf(y[j], s2[j], b2[j]);
     }
     if (relu) {
 #pragma unroll
@@ -235,25 +300,26 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
-                                       long long rows_per_group, int C, int Cp, const float* __restrict__ gamma,
-                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cp) return;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
+                                                              long long rows_per_group, int C, int Cp,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, int accumulate,
+                                                              float* __restrict__ coef) {
+  __shared__ double red[8][2][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < Cp;
   double dg = 0.0, db = 0.0;
   for (int g = 0; g < groups; ++g) {
+    double s, sx;
+    reduce_partials(partials, nblocks, groups, g, Cp, c, c < C, red, s, sx);
+    if (!lead) continue;
     float* cf = coef + static_cast<long long>(g) * 3 * Cp;
     if (c >= C) {
       cf[c] = 0.f;
       cf[Cp + c] = 0.f;
       cf[2 * Cp + c] = 0.f;
       continue;
-    }
-    double s = 0.0, sx = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += partials[((static_cast<long long>(b) * groups + g) * 2 + 0) * Cp + c];
-      sx += partials[((static_cast<long long>(b) * groups + g) * 2 + 1) * Cp + c];
     }
     const double n = static_cast<double>(rows_per_group);
     cf[c] = gamma[c] * invstd[g * Cp + c];
@@ -262,27 +328,40 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
     db += s;
     dg += sx;
   }
-  if (c < C && dgamma != nullptr) {
+  if (lead && c < C && dgamma != nullptr) {
     dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(dg) : static_cast<float>(dg);
     dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(db) : static_cast<float>(db);
   }
 }
 
+// g = c0*(dy - c1 - xhat*c2) with dy = d masked by the ReLU of the forward pass:
+//   act != NULL            mask = act > 0            (block outputs: the pre-activation includes the residual)
+//   mscale != NULL         mask = raw*mscale + mshift > 0, the same fmaf the forward apply evaluated (saves the act read)
+//   neither                no ReLU behind this BatchNorm
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
-                                                           const uint4* __restrict__ raw, long long rows, int Cp,
-                                                           long long rows_per_group, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd,
-                                                           const float* __restrict__ coef, uint4* __restrict__ gout,
+                                                           const uint4* __restrict__ raw, int Cp, long long rows_per_group,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ coef, const float* __restrict__ mscale,
+                                                           const float* __restrict__ mshift, uint4* __restrict__ gout,
                                                            uint4* __restrict__ dz) {
+  const BnThread t = bn_thread(Cp);
+  if (!t.active) return;
   const int nvec = Cp / 8;
-  const long long total = rows * nvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % nvec);
-    const long long r = i / nvec;
-    const int g = static_cast<int>(r / rows_per_group);
-    const int c0 = cv * 8;
-    const float* cf = coef + static_cast<long long>(g) * 3 * Cp;
+  const int co = t.g * Cp + t.cvec * 8;
+  float mu[8], is[8], c0[8], c1[8], c2[8], ms[8], mb[8];
+  load8(mean + co, mu);
+  load8(invstd + co, is);
+  load8(coef + static_cast<long long>(t.g) * 3 * Cp + t.cvec * 8, c0);
+  load8(coef + static_cast<long long>(t.g) * 3 * Cp + Cp + t.cvec * 8, c1);
+  load8(coef + static_cast<long long>(t.g) * 3 * Cp + 2 * Cp + t.cvec * 8, c2);
+  if (mscale != nullptr) {
+    load8(mscale + co, ms);
+    load8(mshift + co, mb);
+  }
+  const long long base = static_cast<long long>(t.g) * rows_per_group;
+  for (long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl; r < rows_per_group;
+       r += static_cast<long long>(gridDim.x) * t.rows_per_pass) {
+    const long long i = (base + r) * nvec + t.cvec;
     float dy[8], x[8];
     unpack8(d[i], dy);
     unpack8(raw[i], x);
@@ -291,14 +370,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
       unpack8(act[i], y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dy[j] = y[j] > 0.f ? dy[j] : 0.f;
+    } else if (mscale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy[j] = fmaf(x[j], ms[j], mb[j]) > 0.f ? dy[j] : 0.f;
     }
     if (dz != nullptr) dz[i] = pack8(dy);
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float xhat = (x[j] - __ldg(mean + g * Cp + c)) * __ldg(invstd + g * Cp + c);
-      o[j] = __ldg(cf + c) * (dy[j] - __ldg(cf + Cp + c) - xhat * __ldg(cf + 2 * Cp + c));
+      const float xhat = (x[j] - mu[j]) * is[j];
+      o[j] = c0[j] * (dy[j] - c1[j] - xhat * c2[j]);
     }
     gout[i] = pack8(o);
   }
@@ -374,6 +455,19 @@ __global__ void cast_pad_kernel(const float* __restrict__ x, long long rows, int
   }
 }
 
+// Row-block count of the BatchNorm streaming kernels (see bn_thread): enough CTAs to fill the machine a few times.
+static inline dim3 bn_grid(long long rows_per_group, int Cp, int groups) {
+  const int nvec = Cp / 8;
+  const int segs = ceil_div(nvec, kSegVecs);
+  const int seg_vecs = nvec < kSegVecs ? nvec : kSegVecs;
+  const int rows_per_pass = 256 / seg_vecs;
+  long long want = (static_cast<long long>(num_sms()) * 8 + groups * segs - 1) / (groups * segs);
+  long long have = (rows_per_group + rows_per_pass - 1) / rows_per_pass;
+  if (want > have) want = have;
+  if (want < 1) want = 1;
+  return dim3(static_cast<unsigned>(want), static_cast<unsigned>(groups), static_cast<unsigned>(segs));
+}
+
 static inline int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -412,7 +506,7 @@ extern "C" int cstp_bn_stats(const void* raw, int64_t rows, int Cp, int groups, 
   CSTP_REQUIRE(raw && partials && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0 && nblocks > 0);
   const dim3 grid(nblocks, groups, ceil_div(Cp / 8, kSegVecs));
   bn_reduce_kernel<false><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(raw), nullptr, nullptr,
-                                                       rows / groups, Cp, nullptr, nullptr, partials);
+                                                       rows / groups, Cp, nullptr, nullptr, nullptr, nullptr, partials);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
@@ -422,7 +516,7 @@ extern "C" int cstp_bn_finalize(const float* partials, int nblocks, int groups, 
                                 float* running_var, float* scale, float* shift, float* mean, float* invstd,
                                 void* stream) {
   CSTP_REQUIRE(partials && gamma && beta && scale && shift && mean && invstd && C <= Cp);
-  bn_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma, beta,
+  bn_finalize_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma, beta,
                                                                eps, momentum, running_mean, running_var, scale, shift,
                                                                mean, invstd);
   CSTP_LAUNCHED();
@@ -435,22 +529,24 @@ extern "C" int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, 
   CSTP_REQUIRE(raw && out && scale && shift && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
   CSTP_REQUIRE(res_mode == 0 || res != nullptr);
   CSTP_REQUIRE(res_mode != 2 || (scale2 && shift2));
-  const long long total = rows * (Cp / 8);
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
-      reinterpret_cast<const uint4*>(raw), rows, Cp, rows / groups, scale, shift, relu, res_mode,
+  bn_apply_kernel<<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(raw), Cp, rows / groups, scale, shift, relu, res_mode,
       reinterpret_cast<const uint4*>(res), scale2, shift2, reinterpret_cast<uint4*>(out));
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
 
 extern "C" int cstp_bn_bwd_reduce(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
-                                  const float* mean, const float* invstd, float* partials, int nblocks, void* stream) {
+                                  const float* mean, const float* invstd, const float* mask_scale,
+                                  const float* mask_shift, float* partials, int nblocks, void* stream) {
   CSTP_REQUIRE(d && raw && mean && invstd && partials && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
+  CSTP_REQUIRE((mask_scale == nullptr) == (mask_shift == nullptr));
+  CSTP_REQUIRE(act == nullptr || mask_scale == nullptr);
   const dim3 grid(nblocks, groups, ceil_div(Cp / 8, kSegVecs));
   bn_reduce_kernel<true><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(d),
                                                       reinterpret_cast<const uint4*>(act),
                                                       reinterpret_cast<const uint4*>(raw), rows / groups, Cp, mean,
-                                                      invstd, partials);
+                                                      invstd, mask_scale, mask_shift, partials);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
@@ -459,20 +555,22 @@ extern "C" int cstp_bn_bwd_finalize(const float* partials, int nblocks, int grou
                                     int Cp, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
                                     int accumulate, float* coef, void* stream) {
   CSTP_REQUIRE(partials && gamma && invstd && coef && C <= Cp);
-  bn_bwd_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma,
+  bn_bwd_finalize_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma,
                                                                    invstd, dgamma, dbeta, accumulate, coef);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
 
 extern "C" int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
-                                 const float* mean, const float* invstd, const float* coef, void* g, void* dz,
-                                 void* stream) {
+                                 const float* mean, const float* invstd, const float* coef, const float* mask_scale,
+                                 const float* mask_shift, void* g, void* dz, void* stream) {
   CSTP_REQUIRE(d && raw && mean && invstd && coef && g && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
-  const long long total = rows * (Cp / 8);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
-      reinterpret_cast<const uint4*>(d), reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint4*>(raw), rows,
-      Cp, rows / groups, mean, invstd, coef, reinterpret_cast<uint4*>(g), reinterpret_cast<uint4*>(dz));
+  CSTP_REQUIRE((mask_scale == nullptr) == (mask_shift == nullptr));
+  CSTP_REQUIRE(act == nullptr || mask_scale == nullptr);
+  bn_bwd_apply_kernel<<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(d), reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint4*>(raw), Cp,
+      rows / groups, mean, invstd, coef, mask_scale, mask_shift, reinterpret_cast<uint4*>(g),
+      reinterpret_cast<uint4*>(dz));
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -180,6 +180,7 @@ class StepEngine:
         self.momentum_ema = momentum_ema
         self.record = record
         self.named: dict[str, torch.Tensor] = {}      # name -> activation / gradient tensors (parity tests)
+        self.units: list[dict] = []                   # every conv+BN unit in build order (parity tests, profiling)
         self._prof = None                             # list of (kind, flops, launches, ev0, ev1) while profiling
         f32 = dict(device=self.device, dtype=torch.float32)
 
@@ -283,7 +284,9 @@ class StepEngine:
         if act is not None:
             self._rec(tag + ".act", act)
         unit = dict(x=x, raw=raw, act=act, site=site, relu=relu, geom=geom, wname=wname, cin=cin, cout=cout, wt=wt,
-                    skip_dgrad=skip_dgrad, tag=tag, flops=flops)
+                    skip_dgrad=skip_dgrad, tag=tag, flops=flops, bnname=bnname, res=res, res_site=res_site,
+                    x_is_col=x_is_col, grads=grads)
+        self.units.append(unit)
         self._g_numel = max(self._g_numel, raw.numel())
         return raw, act, site, unit
 
@@ -306,9 +309,16 @@ class StepEngine:
         self._deferred.append(prepare)
         self._wg_numel = max(self._wg_numel, self._wgrad_need(x, raw, geom))
 
+        self._rec(unit["tag"] + ".d_out", d_out)
+        # plain BN -> ReLU units recompute the mask from raw; block outputs (residual in the pre-activation) read act
+        from_raw = act_for_mask is not None and unit["relu"] and unit["res"] is None
+
         def bwd():
             g = holder["g"]
-            ops.bn_backward(d_out, act_for_mask, raw, site.st, site.gamma, site.dgamma, site.dbeta, g, dz=dz)
+            ops.bn_backward(d_out, act_for_mask, raw, site.st, site.gamma, site.dgamma, site.dbeta, g, dz=dz,
+                            mask_from_raw=from_raw)
+            if self.record:      # parity tests: the shared d(raw) scratch is overwritten by the next unit
+                self.named[unit["tag"] + ".g"] = g.clone()
             holder["wg"].run(dw)
             if not unit["skip_dgrad"]:
                 if holder["zero"]:
@@ -428,10 +438,11 @@ class StepEngine:
             ops.bn_apply(raw, site.st, h, relu=True)
             p3.run()
         prog.append(fwd)
+        self._rec(tag + ".x", x)
         self._rec(tag + ".raw", raw)
         self._rec(tag + ".h", h)
         self._rec(tag + ".out", outf)
-        res = dict(out_f32=outf, out_bf16=outb)
+        res = dict(out_f32=outf, out_bf16=outb, site=site)
         if not grads:
             return res
         g_out = self._act(rows, Op)
@@ -444,6 +455,9 @@ class StepEngine:
         g1 = ConvGeom((1, 1, 1))
         x5, h5 = x.view(1, 1, 1, rows, -1), h.view(1, 1, 1, rows, Hp)
         go5, gh5 = g_out.view(1, 1, 1, rows, Op), g_h.view(1, 1, 1, rows, Hp)
+        self._rec(tag + ".g_out", g_out)
+        self._rec(tag + ".d_h", d_h)
+        self._rec(tag + ".g_h", g_h)
         self._wg_numel = max(self._wg_numel, self._wgrad_need(h5, go5, g1), self._wgrad_need(x5, gh5, g1))
         holder = {}
 
@@ -457,12 +471,15 @@ class StepEngine:
                 holder["wg0"] = ops.wgrad_plan(x5, gh5, g1, hidden, cin, self._wg)
             self._deferred.append(prepare)
 
+            self._rec(tag + ".dx", dx_f32)
+            self._rec(tag + ".dx_accumulate", accumulate)
+
             def bwd():
                 ops.cast_pad(d_out, g_out, cols=cout, scale_dev=scale_dev)
                 ops.colsum(g_out, cout, db3)
                 holder["wg3"].run(dW3)
                 pd_h.run()
-                ops.bn_backward(d_h, h, raw, site.st, site.gamma, site.dgamma, site.dbeta, g_h)
+                ops.bn_backward(d_h, h, raw, site.st, site.gamma, site.dgamma, site.dbeta, g_h, mask_from_raw=True)
                 ops.colsum(g_h, hidden, db0)
                 holder["wg0"].run(dW0)
                 if pd_x is not None:

@@ -85,9 +85,9 @@ SIGNATURES = {
     "cstp_bn_stats": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
     "cstp_bn_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cstp_bn_apply": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "cstp_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "cstp_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "cstp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
-    "cstp_bn_bwd_apply": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cstp_bn_bwd_apply": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cstp_avgpool_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "cstp_avgpool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "cstp_colsum": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),

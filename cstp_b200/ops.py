@@ -409,17 +409,23 @@ def bn_apply(raw, st: BNState, out, *, relu: bool, res=None, res_state: BNState 
                                    _ptr(res_state.shift if res_state else None), _ptr(out), _stream()))
 
 
-def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False) -> None:
-    """g_out = dL/d(raw) given d = dL/d(act) (masked by act > 0 when act is given); fills dgamma/dbeta."""
+def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False,
+                mask_from_raw: bool = False) -> None:
+    """g_out = dL/d(raw) given d = dL/d(act); fills dgamma/dbeta.  The ReLU mask is `act > 0` when act is given, or --
+    with mask_from_raw -- recomputed as raw*scale + shift > 0 from the forward coefficients kept in `st` (the same fmaf
+    the forward apply evaluated; saves reading act twice)."""
     rows = raw.numel() // st.Cp
     lib = L.load()
+    ms, mb = (st.scale, st.shift) if mask_from_raw else (None, None)
+    if mask_from_raw:
+        act = None
     L.check(lib.cstp_bn_bwd_reduce(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean),
-                                   _ptr(st.invstd), _ptr(st.partials), st.nblocks, _stream()))
+                                   _ptr(st.invstd), _ptr(ms), _ptr(mb), _ptr(st.partials), st.nblocks, _stream()))
     L.check(lib.cstp_bn_bwd_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp,
                                      _ptr(gamma), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta), int(accumulate),
                                      _ptr(st.coef), _stream()))
     L.check(lib.cstp_bn_bwd_apply(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean), _ptr(st.invstd),
-                                  _ptr(st.coef), _ptr(g_out), _ptr(dz), _stream()))
+                                  _ptr(st.coef), _ptr(ms), _ptr(mb), _ptr(g_out), _ptr(dz), _stream()))
 
 
 def avgpool_fwd(x, out_f32, out_bf16, rows_out: int | None = None, ld_out: int | None = None) -> None:

@@ -138,17 +138,21 @@ int cstp_bn_finalize(const float* partials, int nblocks, int groups, int64_t row
 int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, const float* scale, const float* shift,
                   int relu, int res_mode, const void* res, const float* scale2, const float* shift2, void* out,
                   void* stream);
-/* dy = d * (act > 0 if act else 1); partials of sum(dy), sum(dy*xhat) per (group, channel). */
+/* dy = d masked by the forward ReLU; partials of sum(dy), sum(dy*xhat) per (group, channel).  The mask is
+ * act > 0 when `act` is given (block outputs, whose pre-activation includes the residual), else
+ * raw*mask_scale + mask_shift > 0 when the forward affine coefficients are given (no read of act), else none. */
 int cstp_bn_bwd_reduce(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
-                       const float* mean, const float* invstd, float* partials, int nblocks, void* stream);
+                       const float* mean, const float* invstd, const float* mask_scale, const float* mask_shift,
+                       float* partials, int nblocks, void* stream);
 /* Reduces partials; writes dgamma/dbeta (summed over groups, optionally accumulated) and the apply coefficients
  * coef[g][3][Cp] = {gamma*invstd, sum(dy)/n, sum(dy*xhat)/n}. */
 int cstp_bn_bwd_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C, int Cp,
                          const float* gamma, const float* invstd, float* dgamma, float* dbeta, int accumulate,
                          float* coef, void* stream);
-/* g = c0*(dy - c1 - xhat*c2) (bf16); optionally also writes dz = dy (masked upstream grad). */
+/* g = c0*(dy - c1 - xhat*c2) (bf16), same masking as cstp_bn_bwd_reduce; optionally also writes dz = dy. */
 int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
-                      const float* mean, const float* invstd, const float* coef, void* g, void* dz, void* stream);
+                      const float* mean, const float* invstd, const float* coef, const float* mask_scale,
+                      const float* mask_shift, void* g, void* dz, void* stream);
 
 /* AdaptiveAvgPool3d(1) over `P` positions (r21d_byol.py:210,222-223) and its backward broadcast.
  * Forward: sample n is written to row n % rows_out, column offset (n / rows_out)*Cp of a row of ld_out elements

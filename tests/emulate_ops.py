@@ -214,11 +214,16 @@ def bn_apply(raw, st: BNState, out, *, relu, res=None, res_state=None):
     out.copy_(y.reshape(out.shape).to(out.dtype))
 
 
-def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False):
+def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False,
+                mask_from_raw=False):
     _count(3)
     G, C, Cp = st.groups, st.C, st.Cp
     dy = _group_view(d, G).float()
-    if act is not None:
+    if mask_from_raw:
+        # the very expression bn_apply evaluated in the forward pass (the kernels use the same fmaf in both places)
+        pre = _group_view(raw, G).float() * st.scale.view(G, 1, Cp) + st.shift.view(G, 1, Cp)
+        dy = dy * (pre > 0)
+    elif act is not None:
         dy = dy * (_group_view(act, G).float() > 0)
     if dz is not None:
         dz.copy_(dy.reshape(dz.shape).to(dz.dtype))

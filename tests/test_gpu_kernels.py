@@ -1,0 +1,75 @@
+"""Kernel-family parity through the C ABI on a B200: implicit-GEMM conv forward / dgrad / wgrad at the layer shapes of
+R2Plus1DNet, linear layers, BatchNorm forward/backward, stem im2col, EMA (bit-exact), clip + SGD, BYOL
+and pretext cross-entropy losses -- each against the fp32 torch operator on identical (bf16-rounded) inputs.
+The case bodies live in tools/gpu_kernel_check.py (also usable as a stand-alone bring-up harness)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_reference():
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _cases(kind):
+    from tools.gpu_kernel_check import CASES
+    return [n for n, (k, _) in CASES.items() if k == kind]
+
+
+@pytest.mark.parametrize("name", _cases("conv"))
+def test_conv_forward_dgrad_wgrad(name):
+    from tools.gpu_kernel_check import run_case
+    r = run_case(name)
+    assert r["fwd_nan"] == 0 and r["fwd_pad_zero"]
+    assert r["fwd_rel"] < 4e-3, r            # bf16 output rounding of an fp32-accumulated sum: ~2^-9 RMS
+    assert r["dgrad_nan"] == 0 and r["dgrad_rel"] < 4e-3, r
+    assert r["wgrad_nan"] == 0 and r["wgrad_rel"] < 2e-4, r      # fp32 output, deterministic split-K
+
+
+@pytest.mark.parametrize("name", _cases("linear"))
+def test_linear(name):
+    from tools.gpu_kernel_check import run_case
+    r = run_case(name)
+    assert r["nan"] == 0 and r["bf16_rel"] < 4e-3 and r["f32_rel"] < 1e-5, r
+
+
+def test_elementwise_bn_im2col_ema_sgd():
+    from tools.gpu_kernel_check import run_case
+    r = run_case("elementwise")
+    for C in (144, 4096, 83):
+        assert r[f"bn{C}_fwd_rel"] < 4e-3 and r[f"bn{C}_dx_rel"] < 4e-3, r
+        assert r[f"bn{C}_rm_rel"] < 1e-5 and r[f"bn{C}_rv_rel"] < 1e-5, r
+        assert r[f"bn{C}_dgamma_rel"] < 1e-5 and r[f"bn{C}_dbeta_rel"] < 1e-5, r
+    assert r["im2col_rel"] < 1e-6 and r["im2col_padzero"]
+    assert r["ema_bitexact"]                                       # r21d_byol.py:331-337: exact fp32 arithmetic
+    assert r["sgd_rel"] < 1e-6
+    assert abs(r["sgd_norm"][0] - r["sgd_norm"][1]) < 1e-4 * r["sgd_norm"][1]
+
+
+def test_losses_byol_ce_ntxent():
+    from tools.gpu_kernel_check import run_case
+    r = run_case("losses")
+    assert r["byol_loss_rel"] < 1e-5 and r["byol_grad_rel"] < 1e-5, r
+    assert r["ce_loss_rel"] < 1e-5 and r["ce_total_rel"] < 1e-5 and r["ce_grad_rel"] < 1e-5, r
+    for rows in (256, 1024, 200):
+        assert r[f"ntxent{rows}_loss_rel"] < 1e-5 and r[f"ntxent{rows}_grad_rel"] < 1e-4, r
+
+
+def test_ragged_and_tiny_geometries():
+    """Edge cases: batch 1, odd sizes that leave partial tiles in every tile-space axis, channel counts that are not
+    multiples of 16, a single 128-row tile."""
+    from tools.gpu_kernel_check import case_conv
+    for kw in (dict(N=1, T=3, H=10, W=6, cin=42, cout=85, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1)),
+               dict(N=1, T=5, H=6, W=10, cin=85, cout=42, kernel=(3, 1, 1), stride=(2, 1, 1), pad=(1, 0, 0)),
+               dict(N=3, T=2, H=14, W=14, cin=170, cout=21, kernel=(1, 3, 3), stride=(1, 2, 2), pad=(0, 1, 1)),
+               dict(N=1, T=1, H=2, W=2, cin=16, cout=16, kernel=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0))):
+        r = case_conv(**kw)
+        assert r["fwd_nan"] == 0 and r["fwd_pad_zero"] and r["fwd_rel"] < 4e-3, (kw, r)
+        assert r["dgrad_nan"] == 0 and r["dgrad_rel"] < 4e-3, (kw, r)
+        assert r["wgrad_nan"] == 0 and r["wgrad_rel"] < 2e-4, (kw, r)

@@ -1,0 +1,71 @@
+"""NTXentLoss drop-in (cstp_b200/loss/NTXent.py -> cstp_ntxent) against the reference's golden outputs
+(tests/golden/ntxent_ref.pt, produced by loss/NTXent.py) and the closed-form oracle at the BASELINE sweep sizes."""
+import pytest
+import torch
+
+from tests.parity import load_golden, rel, sample_idx
+
+pytestmark = pytest.mark.gpu
+
+
+def _z(key, g):
+    if isinstance(key, int):
+        return torch.nn.functional.normalize(torch.randn(g["rows"], g["d"], generator=torch.Generator().manual_seed(key)), dim=1), True
+    return torch.randn(128, 48, generator=torch.Generator().manual_seed(7)) * 0.7, key.endswith("1")
+
+
+@pytest.mark.parametrize("key", [64, 256, 1024, "raw_cos1", "raw_cos0"])
+def test_matches_reference_golden(key):
+    from cstp_b200.loss.NTXent import NTXentLoss
+    g = load_golden("ntxent_ref.pt")[key]
+    z, use_cos = _z(key, g)
+    n = g["rows"] // 2
+    zis, zjs = z[n:].cuda().requires_grad_(True), z[:n].cuda().requires_grad_(True)
+    crit = NTXentLoss("cuda", n, g["tau"], use_cos)
+    loss = crit(zis, zjs)
+    loss.backward()
+    assert abs(loss.item() - g["loss"]) < 1e-5 * abs(g["loss"])          # north star: loss within 1e-3
+    dz = torch.cat([zjs.grad, zis.grad], 0).reshape(-1).cpu()
+    assert rel(dz[sample_idx(dz.numel(), 512)], g["dz"]["samples"]) < 1e-4
+    assert abs(dz.abs().sum().item() - g["dz_abs_sum"]) < 1e-4 * g["dz_abs_sum"]
+    assert torch.equal(crit.positive_index(), (torch.arange(2 * n) + n) % (2 * n))      # integer index map
+
+
+@pytest.mark.parametrize("rows", [2, 6, 200, 2048, 4096, 8192])
+def test_matches_closed_form_oracle(rows):
+    """BASELINE config 2 sizes (the reference itself needs 51 GB at rows=4096 and cannot run 8192);
+    plus the smallest and a ragged (not a multiple of the 64-row tile) size."""
+    from cstp_b200.loss.NTXent import NTXentLoss
+    from oracle import cstp_oracle as O
+    d, tau = 128, 0.1
+    z = torch.nn.functional.normalize(torch.randn(rows, d, generator=torch.Generator().manual_seed(rows)), dim=1)
+    n = rows // 2
+    a, b = z[n:].clone().requires_grad_(True), z[:n].clone().requires_grad_(True)
+    ref = O.ntxent_closed_form(a.double(), b.double(), tau)
+    ref.backward()
+    zis, zjs = z[n:].cuda().requires_grad_(True), z[:n].cuda().requires_grad_(True)
+    loss = NTXentLoss("cuda", n, tau, True)(zis, zjs)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7, (loss.item(), ref.item())
+    dz, dref = torch.cat([zjs.grad, zis.grad]).cpu(), torch.cat([b.grad, a.grad]).float()
+    assert (dz - dref).norm() <= 1e-4 * dref.norm() + 1e-7
+    if rows in (256, 1024, 2048, 4096):       # SURVEY.md A.3 anchors
+        anchor = {256: 5.915076, 1024: 7.327291, 2048: 8.046678, 4096: 8.733852}[rows]
+        assert abs(loss.item() - anchor) < 1e-5 * anchor
+
+
+def test_properties_and_errors():
+    from cstp_b200.loss.NTXent import NTXentLoss
+    from cstp_b200.lib import CstpError
+    z = torch.randn(64, 32, device="cuda")
+    crit = NTXentLoss("cuda", 32, 0.5, True)
+    a = crit(z[32:], z[:32])
+    # swapping the two views permutes rows of cat(zjs, zis) consistently: the loss is symmetric
+    assert abs(a.item() - crit(z[:32], z[32:]).item()) < 1e-6 * abs(a.item())
+    # cosine similarity is scale invariant per row
+    s = torch.rand(64, 1, device="cuda") + 0.5
+    assert abs(a.item() - crit((z * s)[32:], (z * s)[:32]).item()) < 1e-5 * abs(a.item())
+    with pytest.raises(RuntimeError):
+        crit(z[:16], z[16:32])                 # batch-size mismatch (the reference's mask has a fixed size)
+    with pytest.raises(CstpError):
+        crit(z[32:].cpu(), z[:32].cpu())       # no CPU fallback
