@@ -150,8 +150,8 @@ class _Timed:
     """A group of tensor-core launches with its algorithmic FLOPs; records CUDA events around the group while the
     engine is in profiling mode (bench.py roofline), otherwise just launches."""
 
-    def __init__(self, eng, kind: str, flops: float, plans):
-        self.eng, self.kind, self.flops, self.plans = eng, kind, flops, list(plans)
+    def __init__(self, eng, kind: str, flops: float, plans, tag: str = ""):
+        self.eng, self.kind, self.flops, self.plans, self.tag = eng, kind, flops, list(plans), tag
 
     def run(self, *args):
         prof = self.eng._prof
@@ -164,7 +164,7 @@ class _Timed:
         for p in self.plans:
             p.run(*args)
         b.record()
-        prof.append((self.kind, self.flops, len(self.plans), a, b))
+        prof.append((self.kind, self.flops, len(self.plans), a, b, self.tag))
 
 
 class StepEngine:
@@ -271,7 +271,7 @@ class StepEngine:
         wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
         rows = N * To * Ho * Wo
         flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
-        plan = _Timed(self, "conv_fwd", flops, [ops.conv_fwd_plan(x, wp, raw, geom)])
+        plan = _Timed(self, "conv_fwd", flops, [ops.conv_fwd_plan(x, wp, raw, geom)], tag)
         site = self._site(store, grads, bnname, cout, 2, rows // 2)
 
         def fwd():
@@ -299,11 +299,12 @@ class StepEngine:
         def prepare():
             g = self._g[:raw.numel()].view(raw.shape)
             holder["g"] = g
-            holder["wg"] = _Timed(self, "wgrad", unit["flops"], [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg)])
+            holder["wg"] = _Timed(self, "wgrad", unit["flops"],
+                                  [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg)], unit["tag"])
             if not unit["skip_dgrad"]:
                 dx = self._dbuf(x)
                 plans, covers = ops.conv_dgrad_plans(g, unit["wt"], dx, geom, accumulate=dx_accumulate)
-                holder["dg"] = _Timed(self, "conv_dgrad", unit["flops"], plans)
+                holder["dg"] = _Timed(self, "conv_dgrad", unit["flops"], plans, unit["tag"])
                 holder["zero"], holder["dx"] = (not covers and not dx_accumulate), dx
                 self._rec(unit["tag"] + ".dx", dx)
         self._deferred.append(prepare)
@@ -611,9 +612,11 @@ class StepEngine:
             self.backward()
             torch.cuda.synchronize()
             out: dict = {}
-            for kind, flops, n, a, b in self._prof:
+            self.last_profile = []          # per launch group: (kind, tag, ms, flops, launches)
+            for kind, flops, n, a, b, tag in self._prof:
                 ms, fl, cnt = out.get(kind, (0.0, 0.0, 0))
                 out[kind] = (ms + a.elapsed_time(b), fl + flops, cnt + n)
+                self.last_profile.append((kind, tag, a.elapsed_time(b), flops, n))
         finally:
             self._prof = None
         return out

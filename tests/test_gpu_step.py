@@ -120,7 +120,7 @@ def test_end_to_end_matches_bf16_restatement(run):
     assert sorted(errs.values())[len(errs) // 2] < 1.5e-2
     assert worst[1] < 5e-2, worst
     assert rel(gpu["feat"], emu["feat"]) < 2e-2
-    assert abs(gpu["norm"][0] - emu["norm"][0]) / emu["norm"][0] < 1e-2
+    assert abs(gpu["norm"][0] - emu["norm"][0]) / emu["norm"][0] < 5e-2
     gerr = {}
     for n, (off, shape) in run["slots"].items():
         cnt = max(1, int(torch.tensor(shape).prod())) if len(shape) else 1
