@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
       }
     }
     const long long base = static_cast<long long>(g) * rows_per_group;
+#pragma unroll 2
     for (long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + rl; r < rows_per_group;
          r += static_cast<long long>(gridDim.x) * rows_per_pass) {
       const long long idx = (base + r) * nvec + seg0 + cv;
@@ -159,17 +160,35 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
   }
 }
 
-// Deterministic tree over the per-block partials: 8 warps x 32 channels per CTA, warp w sums blocks w, w+8, ... in
-// double, the 8 warp sums are combined in fixed order.  partials: [nblocks][groups][2][Cp].
+// Deterministic tree over the per-block partials: 8 warps x 32 channels per CTA; warp w owns blocks w, w+8, ... and
+// keeps 8 independent loads of both quantities in flight (the loop is latency bound: a serial version of it cost
+// 130 us per launch), the 8 warp sums are then combined in fixed order in double.  partials: [nblocks][groups][2][Cp].
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nblocks, int groups, int g, int Cp,
                                                 int c, bool active, double (*red)[2][32], double& s, double& ss) {
   const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
   double a0 = 0.0, a1 = 0.0;
   if (active) {
-    for (int b = ty; b < nblocks; b += 8) {
-      const float* p = partials + ((static_cast<long long>(b) * groups + g) * 2) * Cp + c;
-      a0 += static_cast<double>(p[0]);
-      a1 += static_cast<double>(p[Cp]);
+    const long long bstride = static_cast<long long>(groups) * 2 * Cp;
+    const float* base = partials + static_cast<long long>(g) * 2 * Cp + c;
+    int b = ty;
+    for (; b + 56 < nblocks; b += 64) {
+      float v0[8], v1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* p = base + (b + 8 * j) * bstride;
+        v0[j] = __ldg(p);
+        v1[j] = __ldg(p + Cp);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0 += static_cast<double>(v0[j]);
+        a1 += static_cast<double>(v1[j]);
+      }
+    }
+    for (; b < nblocks; b += 8) {
+      const float* p = base + b * bstride;
+      a0 += static_cast<double>(__ldg(p));
+      a1 += static_cast<double>(__ldg(p + Cp));
     }
   }
   __syncthreads();
@@ -348,19 +367,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
   if (!t.active) return;
   const int nvec = Cp / 8;
   const int co = t.g * Cp + t.cvec * 8;
-  float mu[8], is[8], c0[8], c1[8], c2[8], ms[8], mb[8];
-  load8(mean + co, mu);
-  load8(invstd + co, is);
-  load8(coef + static_cast<long long>(t.g) * 3 * Cp + t.cvec * 8, c0);
-  load8(coef + static_cast<long long>(t.g) * 3 * Cp + Cp + t.cvec * 8, c1);
-  load8(coef + static_cast<long long>(t.g) * 3 * Cp + 2 * Cp + t.cvec * 8, c2);
+  float mu[8], A[8], Bc[8], Cc[8], ms[8], mb[8];
+  {
+    // g = c0*(dy - c1 - (x - mu)*istd*c2) = A*dy + Bc*(x - mu) + Cc
+    float is[8], c1[8], c2[8];
+    load8(mean + co, mu);
+    load8(invstd + co, is);
+    load8(coef + static_cast<long long>(t.g) * 3 * Cp + t.cvec * 8, A);
+    load8(coef + static_cast<long long>(t.g) * 3 * Cp + Cp + t.cvec * 8, c1);
+    load8(coef + static_cast<long long>(t.g) * 3 * Cp + 2 * Cp + t.cvec * 8, c2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      Bc[j] = -A[j] * c2[j] * is[j];
+      Cc[j] = -A[j] * c1[j];
+    }
+  }
   if (mscale != nullptr) {
     load8(mscale + co, ms);
     load8(mshift + co, mb);
   }
   const long long base = static_cast<long long>(t.g) * rows_per_group;
-  for (long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl; r < rows_per_group;
-       r += static_cast<long long>(gridDim.x) * t.rows_per_pass) {
+  const long long rstep = static_cast<long long>(gridDim.x) * t.rows_per_pass;
+#pragma unroll 2
+  for (long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl; r < rows_per_group; r += rstep) {
     const long long i = (base + r) * nvec + t.cvec;
     float dy[8], x[8];
     unpack8(d[i], dy);
@@ -377,10 +406,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     if (dz != nullptr) dz[i] = pack8(dy);
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xhat = (x[j] - mu[j]) * is[j];
-      o[j] = c0[j] * (dy[j] - c1[j] - xhat * c2[j]);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dy[j], fmaf(Bc[j], x[j] - mu[j], Cc[j]));
     gout[i] = pack8(o);
   }
 }

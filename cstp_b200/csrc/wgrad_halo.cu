@@ -1,0 +1,308 @@
+// Weight-gradient GEMM for the wide, shallow layers (stride-1 1x3x3 / 3x1x1 convs of conv1..conv3): every CTA computes
+// ALL taps of dW for its slice of the position (K) axis.
+//
+//   P[split][chunk*64 + r][n] = sum_{pos in split} X[pos + tap(chunk), c_off(chunk) + r] * G[pos, n]
+//
+// wgrad.cu gives every (tap, 64-channel chunk) pair of X its own CTA column, so the same activations are fetched once
+// per tap and G once per M tile: those layers (K = 6M positions, 64..144 channels) ran at 150-380 TFLOP/s, bound by the
+// L2->SM feed.  Here one K-block of 64 positions is staged ONCE: X as a box with a halo along the tap axis (the taps
+// of that axis are the same shared-memory rows, shifted by a multiple of 8 rows, i.e. whole 128B-swizzle atoms), G as
+// plain boxes; the tcgen05 issuer then runs one 128 x n_tile MMA per pair of (tap, chunk) row blocks into its own
+// TMEM accumulator (n_mtiles * n_tile <= 512 columns).  Taps along the fastest axis (kw) cannot be expressed as an
+// aligned row shift and are staged as separately shifted boxes ("groups").
+// Replaces cuDNN conv3d wgrad behind main_byol.py:87 for models/pace/r21d_byol.py:81-92 layers with stride 1.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cstp {
+
+constexpr int kWhThreads = 256;
+constexpr int kWhMaxStages = 8;
+constexpr int kWhSmemLimit = 232448;
+constexpr int kWhMaxMtiles = 16;
+constexpr int kWhMaxBoxes = 16;      // (group, channel chunk) X boxes per stage
+constexpr uint32_t kGBoxBytes = 64 * 64 * 2;
+
+struct WhXBox {
+  int c_off, dw, dh, dt;  // channel offset and tile-origin offset of this staged box
+};
+struct WhMtile {
+  uint32_t a_off;  // byte offset (inside a stage) of the first 64-row block
+  uint32_t lbo;    // byte distance to the second 64-row block (== 0: single block, upper 64 lanes unused)
+};
+
+struct WgradHaloKParams {
+  CUtensorMap xmap;
+  CUtensorMap gmap;
+  int tiles_w, tiles_h, tiles_t, tiles_n;
+  int bw, bh, bt, bn;
+  int n_xboxes, n_mtiles, n_chunks, Np, n_tile, n_gboxes;
+  int total_kblocks, kblocks_per_split;
+  int stages, tmem_cols;
+  uint32_t xbox_bytes, stage_bytes, idesc;
+  float* partials;
+  WhXBox xboxes[kWhMaxBoxes];
+  WhMtile mtiles[kWhMaxMtiles];
+};
+
+__global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWhMaxStages;
+  uint64_t* tfull = bars + 2 * kWhMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWhMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntile = blockIdx.x, split = blockIdx.y;
+  const int kb_begin = split * p.kblocks_per_split;
+  const int kb_end = min(p.total_kblocks, kb_begin + p.kblocks_per_split);
+  const uint32_t x_bytes = static_cast<uint32_t>(p.n_xboxes) * p.xbox_bytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.xmap);
+    tma_prefetch_desc(&p.gmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      int pt = kb;
+      const int w0 = (pt % p.tiles_w) * p.bw;
+      pt /= p.tiles_w;
+      const int h0 = (pt % p.tiles_h) * p.bh;
+      pt /= p.tiles_h;
+      const int t0 = (pt % p.tiles_t) * p.bt;
+      pt /= p.tiles_t;
+      const int n0 = pt * p.bn;
+      mbar_wait(&empty[stage], phase ^ 1u);
+      uint8_t* st = smem + static_cast<size_t>(stage) * p.stage_bytes;
+      mbar_expect_tx(&full[stage], x_bytes + static_cast<uint32_t>(p.n_gboxes) * kGBoxBytes);
+      for (int b = 0; b < p.n_xboxes; ++b) {
+        const WhXBox xb = p.xboxes[b];
+        tma_load_5d(st + static_cast<size_t>(b) * p.xbox_bytes, &p.xmap, &full[stage], xb.c_off, w0 + xb.dw, h0 + xb.dh,
+                    t0 + xb.dt, n0);
+      }
+      for (int j = 0; j < p.n_gboxes; ++j)
+        tma_load_5d(st + x_bytes + j * kGBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer: n_mtiles accumulators per K-block
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t s_addr = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+      const uint32_t b_addr = s_addr + x_bytes;
+      const uint32_t acc = kb > kb_begin ? 1u : 0u;
+      for (int mt = 0; mt < p.n_mtiles; ++mt) {
+        const WhMtile m = p.mtiles[mt];
+        const uint32_t lbo = m.lbo != 0 ? m.lbo : 1024u;   // single block: the upper 64 rows are never read back
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // MN-major, 128B swizzle: 16 K-rows (positions) per step = 2048 B; LBO = next 64-channel block of the M
+          // (resp. N) axis, SBO = next 8 K-rows.
+          const uint64_t da = umma_smem_desc(s_addr + m.a_off + k * 2048, lbo, 1024);
+          const uint64_t db = umma_smem_desc(b_addr + k * 2048, kGBoxBytes, 1024);
+          umma_bf16(d_tmem, da, db, p.idesc, (acc | (k > 0 ? 1u : 0u)));
+        }
+      }
+      umma_commit(&empty[stage]);
+      if (kb == kb_end - 1) umma_commit(tfull);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: TMEM -> fp32 partials
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int col0 = ntile * p.n_tile;
+    const int ncols = min(p.n_tile, p.Np - col0);
+    const long long mtot = static_cast<long long>(p.n_chunks) * 64;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    for (int mt = 0; mt < p.n_mtiles; ++mt) {
+      const bool valid = (mt * 2 + (row >> 6)) < p.n_chunks;
+      float* dst = p.partials + (static_cast<long long>(split) * mtot + static_cast<long long>(mt) * 128 + row) * p.Np + col0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * p.n_tile);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                __uint_as_float(v[4 * i + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+}  // namespace cstp
+
+struct cstp_wgrad_halo_plan {
+  cstp::WgradHaloKParams kp;
+  dim3 grid;
+  int smem_bytes;
+  int splits;
+};
+
+using namespace cstp;
+
+static int encode5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5]) {
+  uint64_t dims[5], strides[4];
+  for (int i = 0; i < 5; ++i) {
+    if (t.dims[i] <= 0) return fail_inval("tensor5 dim <= 0");
+    dims[i] = static_cast<uint64_t>(t.dims[i]);
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (t.strides[i] <= 0 || (t.strides[i] % 16) != 0) return fail_inval("tensor5 stride must be a positive multiple of 16 bytes");
+    strides[i] = static_cast<uint64_t>(t.strides[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(t.ptr) % 16) != 0 || t.ptr == nullptr) return fail_inval("tensor5 ptr must be 16B aligned");
+  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box);
+}
+
+extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_wgrad_halo_plan** out_plan) {
+  CSTP_REQUIRE(d != nullptr && out_plan != nullptr);
+  CSTP_REQUIRE(d->n_chunks >= 1 && d->n_chunks <= 2 * kWhMaxMtiles);
+  CSTP_REQUIRE(d->n_xboxes >= 1 && d->n_xboxes <= kWhMaxBoxes);
+  CSTP_REQUIRE(d->Np >= 16 && d->Np % 16 == 0);
+  CSTP_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 256);
+  CSTP_REQUIRE(d->bw >= 1 && d->bh >= 1 && d->bt >= 1 && d->bn >= 1 && d->bw * d->bh * d->bt * d->bn == 64);
+  CSTP_REQUIRE(d->halo_w >= 0 && d->halo_h >= 0 && d->halo_t >= 0);
+  CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
+  CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr);
+  const int n_mtiles = (d->n_chunks + 1) / 2;
+  CSTP_REQUIRE(n_mtiles * d->n_tile <= 512);
+  const int xrows = (d->bw + d->halo_w) * (d->bh + d->halo_h) * (d->bt + d->halo_t) * d->bn;
+  CSTP_REQUIRE(xrows % 8 == 0 && d->bw + d->halo_w <= 256 && d->bh + d->halo_h <= 256 && d->bt + d->halo_t <= 256);
+
+  cstp_wgrad_halo_plan* plan = new (std::nothrow) cstp_wgrad_halo_plan();
+  if (!plan) {
+    set_error("out of host memory");
+    return CSTP_ENOMEM;
+  }
+  WgradHaloKParams& k = plan->kp;
+  memset(&k, 0, sizeof(k));
+  const uint32_t xbox[5] = {64u, (uint32_t)(d->bw + d->halo_w), (uint32_t)(d->bh + d->halo_h),
+                            (uint32_t)(d->bt + d->halo_t), (uint32_t)d->bn};
+  const uint32_t gbox[5] = {64u, (uint32_t)d->bw, (uint32_t)d->bh, (uint32_t)d->bt, (uint32_t)d->bn};
+  int rc = encode5(&k.xmap, d->xmap, xbox);
+  if (rc == CSTP_OK) rc = encode5(&k.gmap, d->gmap, gbox);
+  if (rc != CSTP_OK) {
+    delete plan;
+    return rc;
+  }
+  k.tiles_w = ceil_div(d->Wt, d->bw);
+  k.tiles_h = ceil_div(d->Ht, d->bh);
+  k.tiles_t = ceil_div(d->Tt, d->bt);
+  k.tiles_n = ceil_div(d->Nt, d->bn);
+  k.bw = d->bw; k.bh = d->bh; k.bt = d->bt; k.bn = d->bn;
+  k.n_xboxes = d->n_xboxes;
+  k.n_chunks = d->n_chunks;
+  k.n_mtiles = n_mtiles;
+  k.Np = d->Np;
+  k.n_tile = d->n_tile;
+  k.n_gboxes = ceil_div(d->n_tile, 64);
+  k.xbox_bytes = static_cast<uint32_t>(xrows) * 128u;
+  k.stage_bytes = static_cast<uint32_t>(d->n_xboxes) * k.xbox_bytes + static_cast<uint32_t>(k.n_gboxes) * kGBoxBytes;
+  k.total_kblocks = k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
+  int splits = d->splits < k.total_kblocks ? d->splits : k.total_kblocks;
+  k.kblocks_per_split = ceil_div(k.total_kblocks, splits);
+  splits = ceil_div(k.total_kblocks, k.kblocks_per_split);
+  plan->splits = splits;
+  k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 1, 1);
+  k.partials = d->partials;
+  for (int i = 0; i < d->n_xboxes; ++i) {
+    const cstp_xbox& b = d->xboxes[i];
+    if (b.c_off < 0 || b.c_off % 8 != 0) {
+      delete plan;
+      return fail_inval("xbox c_off");
+    }
+    k.xboxes[i] = WhXBox{b.c_off, b.dw, b.dh, b.dt};
+  }
+  // chunk i = 64 rows starting at stage byte offset chunk_off[i] (a row shift of a staged X box); consecutive chunks
+  // are paired into one 128-row MMA, so offsets must ascend inside a pair and keep 1024-byte (8-row) alignment.
+  const uint32_t x_bytes = static_cast<uint32_t>(d->n_xboxes) * k.xbox_bytes;
+  for (int mt = 0; mt < n_mtiles; ++mt) {
+    const uint32_t a = d->chunk_off[2 * mt];
+    const bool two = 2 * mt + 1 < d->n_chunks;
+    const uint32_t b = two ? d->chunk_off[2 * mt + 1] : a;
+    if (a % 1024 != 0 || b % 1024 != 0 || (two && b <= a) || b + kGBoxBytes > x_bytes || (b - a) / 16 >= (1u << 14)) {
+      delete plan;
+      return fail_inval("chunk_off must be 1024-aligned, ascending within a pair and inside the staged X boxes");
+    }
+    k.mtiles[mt] = WhMtile{a, two ? b - a : 0u};
+  }
+  const int bar_bytes = 256;
+  int stages = (kWhSmemLimit - 1024 - bar_bytes) / static_cast<int>(k.stage_bytes);
+  if (stages > kWhMaxStages) stages = kWhMaxStages;
+  if (stages < 2) {
+    delete plan;
+    return fail_inval("stage too large for the shared-memory pipeline");
+  }
+  k.stages = stages;
+  int cols = 32;
+  while (cols < n_mtiles * d->n_tile) cols *= 2;
+  k.tmem_cols = cols;
+  plan->smem_bytes = 1024 + stages * static_cast<int>(k.stage_bytes) + bar_bytes;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;   // one CTA per SM (TMEM ownership)
+  plan->grid = dim3(static_cast<unsigned>(ceil_div(d->Np, d->n_tile)), static_cast<unsigned>(splits), 1);
+  *out_plan = plan;
+  return CSTP_OK;
+}
+
+extern "C" int cstp_wgrad_halo_plan_splits(const cstp_wgrad_halo_plan* plan) { return plan ? plan->splits : CSTP_EINVAL; }
+
+extern "C" int cstp_wgrad_halo_plan_run(const cstp_wgrad_halo_plan* plan, void* stream) {
+  CSTP_REQUIRE(plan != nullptr);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSTP_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmemLimit));
+    attr_set = true;
+  }
+  wgrad_halo_kernel<<<plan->grid, kWhThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" void cstp_wgrad_halo_plan_destroy(cstp_wgrad_halo_plan* plan) { delete plan; }

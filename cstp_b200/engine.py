@@ -328,14 +328,9 @@ class StepEngine:
         return bwd
 
     @staticmethod
-    def _wgrad_need(x, raw, geom, sms: int = 148) -> int:
+    def _wgrad_need(x, raw, geom) -> int:
         """Upper bound of the split-K partials (floats) ops.wgrad_plan will need for this layer."""
-        Ca, Np = x.shape[-1], raw.shape[-1]
-        nch = geom.taps * (pad64(Ca) // 64)
-        n_tile = Np if Np <= 256 else 256
-        base = math.ceil(nch / 2) * math.ceil(Np / n_tile)
-        splits = max(1, math.ceil(2 * sms / base))
-        return splits * nch * 64 * Np
+        return ops.wgrad_partials_need(tuple(x.shape), tuple(raw.shape), geom)
 
     # ------------------------------------------------------------------------------------------ backbone
     def _backbone(self, prog, store, prefix, grads, tag):

@@ -65,6 +65,26 @@ class WgradDesc(C.Structure):
     ]
 
 
+class XBox(C.Structure):
+    _fields_ = [("c_off", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32), ("dt", C.c_int32)]
+
+
+class WgradHaloDesc(C.Structure):
+    _fields_ = [
+        ("xmap", Tensor5), ("gmap", Tensor5),
+        ("n_xboxes", C.c_int32),
+        ("xboxes", XBox * 16),
+        ("n_chunks", C.c_int32),
+        ("chunk_off", C.c_uint32 * 32),
+        ("Np", C.c_int32), ("n_tile", C.c_int32),
+        ("Wt", C.c_int32), ("Ht", C.c_int32), ("Tt", C.c_int32), ("Nt", C.c_int32),
+        ("bw", C.c_int32), ("bh", C.c_int32), ("bt", C.c_int32), ("bn", C.c_int32),
+        ("halo_w", C.c_int32), ("halo_h", C.c_int32), ("halo_t", C.c_int32),
+        ("splits", C.c_int32),
+        ("partials", C.c_void_p),
+    ]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); the single source of truth for the symbols include/cstp_b200.h declares.
@@ -79,6 +99,10 @@ SIGNATURES = {
     "cstp_wgrad_plan_splits": (_i, [_vp]),
     "cstp_wgrad_plan_run": (_i, [_vp, _vp]),
     "cstp_wgrad_plan_destroy": (None, [_vp]),
+    "cstp_wgrad_halo_plan_create": (_i, [C.POINTER(WgradHaloDesc), C.POINTER(_vp)]),
+    "cstp_wgrad_halo_plan_splits": (_i, [_vp]),
+    "cstp_wgrad_halo_plan_run": (_i, [_vp, _vp]),
+    "cstp_wgrad_halo_plan_destroy": (None, [_vp]),
     "cstp_wgrad_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "cstp_pack_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "cstp_stem_im2col": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),

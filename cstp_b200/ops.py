@@ -294,18 +294,128 @@ class WgradSpec:
                                              self.taps, _ptr(dw), int(accumulate), _stream()))
 
 
-def wgrad_partials_numel(x_channels: int, taps: int, Np: int, splits: int) -> int:
-    return splits * taps * (pad64(x_channels) // 64) * 64 * Np
+class WgradHaloPlan(_Plan):
+    splits: int = 1
+
+    def run(self):
+        L.check(L.load().cstp_wgrad_halo_plan_run(self.handle, _stream()))
+
+
+def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
+    """Geometry of the all-taps-per-CTA weight-gradient kernel (csrc/wgrad_halo.cu) for a stride-1 1xkxk / kx1x1
+    convolution, or None when the layer does not qualify (then csrc/wgrad.cu is used).  Pure shape arithmetic.
+
+    Returns dict(box, halo, xboxes [(c_off, dw, dh, dt)], chunks [(stage byte offset, tap index, c_off)] sorted by
+    offset, xbox_bytes, n_tile, n_ntiles, splits, need (floats of split-K partials))."""
+    (kt, kh, kw), (pt, ph, pw) = geom.kernel, geom.pad
+    if tuple(geom.stride) != (1, 1, 1) or geom.taps == 1 or (kt > 1 and (kh > 1 or kw > 1)):
+        return None
+    N, T, H, W, Ca = x_shape
+    _, To, Ho, Wo, Np = g_shape
+    n_cc = pad64(Ca) // 64
+    n_chunks = geom.taps * n_cc
+    if n_chunks > 32:
+        return None
+    n_mtiles = (n_chunks + 1) // 2
+    n_tile = min(Np, 256, (512 // n_mtiles) // 16 * 16)
+    if n_tile < 16:
+        return None
+    n_ntiles = math.ceil(Np / n_tile)
+    if n_ntiles > 2:                      # X is re-staged once per N tile
+        return None
+    temporal = kt > 1
+    best = None
+    for bw in (8, 16, 32, 64):
+        for bh in (1, 2, 4, 8):
+            for bt in ((1, 2, 4, 8) if temporal else (1,)):
+                if bw * bh * bt != 64:
+                    continue
+                halo = (0, 0, kt - 1) if temporal else (0, kh - 1, 0)
+                tiles = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt)
+                staged = tiles * (bw + halo[0]) * (bh + halo[1]) * (bt + halo[2]) * (1 if temporal else kw)
+                key = (staged, -bw)
+                if best is None or key < best[0]:
+                    best = (key, (bw, bh, bt, 1), halo)
+    _, box, halo = best
+    bw, bh, bt, _ = box
+    xrows = (bw + halo[0]) * (bh + halo[1]) * (bt + halo[2])
+    xbox_bytes = xrows * 128
+    xboxes, chunks = [], []
+    if temporal:
+        for cc in range(n_cc):
+            xboxes.append((cc * 64, 0, 0, -pt))
+        for a in range(kt):
+            for cc in range(n_cc):
+                chunks.append((cc * xbox_bytes + a * (bw * bh) * 128, a, cc * 64))
+    else:
+        for c in range(kw):
+            for cc in range(n_cc):
+                xboxes.append((cc * 64, c - pw, -ph, 0))
+        for b_ in range(kh):
+            for c in range(kw):
+                for cc in range(n_cc):
+                    chunks.append(((c * n_cc + cc) * xbox_bytes + b_ * bw * 128, b_ * kw + c, cc * 64))
+    if len(xboxes) > 16:
+        return None
+    chunks.sort()
+    n_gboxes = math.ceil(n_tile / 64)
+    stage = len(xboxes) * xbox_bytes + n_gboxes * 8192
+    if 2 * stage + 1280 > 232448:
+        return None
+    splits = max(1, sms // n_ntiles)
+    kblocks = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt) * N
+    splits = min(splits, kblocks)
+    return dict(box=box, halo=halo, xboxes=xboxes, chunks=chunks, xbox_bytes=xbox_bytes, n_tile=n_tile,
+                n_ntiles=n_ntiles, splits=splits, need=splits * n_chunks * 64 * Np)
+
+
+def wgrad_partials_need(x_shape, g_shape, geom: ConvGeom, sms: int = 148) -> int:
+    """Upper bound (floats) of the split-K scratch wgrad_plan needs for this layer."""
+    lay = wgrad_halo_layout(x_shape, g_shape, geom, sms)
+    if lay is not None:
+        return lay["need"]
+    Ca, Np = x_shape[-1], g_shape[-1]
+    nch = geom.taps * (pad64(Ca) // 64)
+    n_tile = Np if Np <= 256 else 256
+    base = math.ceil(nch / 2) * math.ceil(Np / n_tile)
+    return max(1, math.ceil(2 * sms / base)) * nch * 64 * Np
 
 
 def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor, *, splits: int | None = None,
-               box=None, sms: int = 148) -> WgradSpec:
+               box=None, sms: int = 148, allow_halo: bool = True) -> WgradSpec:
     """dW (cout, cin, kt, kh, kw) from x (N,T,H,W,Cp_in) and g (N,To,Ho,Wo,Cp_out); `partials` is fp32 scratch."""
     _require_cuda(x, g, partials)
     lib = L.load()
     N, T, H, W, Ca = x.shape
     _, To, Ho, Wo, Np = g.shape
     assert geom.out_dims(T, H, W) == (To, Ho, Wo)
+    dev = x.device
+    lay = wgrad_halo_layout(tuple(x.shape), tuple(g.shape), geom, sms) if (allow_halo and splits is None and box is None) else None
+    if lay is not None:
+        d = L.WgradHaloDesc()
+        d.xmap, d.gmap = _view5(x), _view5(g)
+        d.n_xboxes = len(lay["xboxes"])
+        for i, xb in enumerate(lay["xboxes"]):
+            d.xboxes[i] = L.XBox(*xb)
+        d.n_chunks = len(lay["chunks"])
+        for i, (off, _, _) in enumerate(lay["chunks"]):
+            d.chunk_off[i] = off
+        d.Np, d.n_tile = Np, lay["n_tile"]
+        d.Wt, d.Ht, d.Tt, d.Nt = Wo, Ho, To, N
+        d.bw, d.bh, d.bt, d.bn = lay["box"]
+        d.halo_w, d.halo_h, d.halo_t = lay["halo"]
+        d.splits = lay["splits"]
+        if partials.numel() < lay["need"]:
+            raise L.CstpError(f"wgrad partials scratch too small: {partials.numel()} < {lay['need']}")
+        d.partials = partials.data_ptr()
+        h = C.c_void_p()
+        L.check(lib.cstp_wgrad_halo_plan_create(C.byref(d), C.byref(h)))
+        plan = WgradHaloPlan(h, lib.cstp_wgrad_halo_plan_destroy, (x, g, partials))
+        plan.splits = lib.cstp_wgrad_halo_plan_splits(h)
+        return WgradSpec(plan, len(lay["chunks"]), Np,
+                         torch.tensor([c[1] for c in lay["chunks"]], dtype=torch.int32, device=dev),
+                         torch.tensor([c[2] for c in lay["chunks"]], dtype=torch.int32, device=dev), cout, cin, geom.taps,
+                         partials)
     views, taps = _fwd_taps(x, geom)
     nchunk_c = pad64(Ca) // 64
     mch, ctap, ccoff = [], [], []
@@ -342,7 +452,6 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
     L.check(lib.cstp_wgrad_plan_create(C.byref(d), C.byref(h)))
     plan = WgradPlan(h, lib.cstp_wgrad_plan_destroy, (x, g, partials))
     plan.splits = lib.cstp_wgrad_plan_splits(h)
-    dev = x.device
     return WgradSpec(plan, len(mch), Np, torch.tensor(ctap, dtype=torch.int32, device=dev),
                      torch.tensor(ccoff, dtype=torch.int32, device=dev), cout, cin, geom.taps, partials)
 
@@ -366,7 +475,7 @@ def stem_im2col(x: torch.Tensor, col: torch.Tensor) -> None:
 
 def bn_nblocks(rows_per_group: int, Cp: int, sms: int = 148) -> int:
     rows_per_pass = max(1, 256 // min(Cp // 8, 128))
-    return max(1, min(4 * sms, math.ceil(rows_per_group / (rows_per_pass * 8))))
+    return max(1, min(2 * sms, math.ceil(rows_per_group / (rows_per_pass * 8))))
 
 
 @dataclass

@@ -117,6 +117,38 @@ int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np
                         const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
                         void* stream);
 
+/* Weight gradient of the wide, shallow stride-1 layers: every CTA computes all taps for its slice of positions.
+ * One K-block (box of 64 positions) stages `n_xboxes` boxes of X, each 64 channels wide and extended by
+ * (halo_w, halo_h, halo_t) positions so that the taps of one axis are row shifts of the same shared-memory box, and
+ * the G boxes of one N tile.  chunk i of the M axis is the 64 rows found `chunk_off[i]` bytes into the staged X
+ * region (1024-byte aligned: whole 8-row swizzle atoms); chunks are paired into 128-row MMAs.  Output partials have
+ * the layout of cstp_wgrad_desc (chunk-major rows), so cstp_wgrad_finalize applies unchanged. */
+typedef struct {
+  int32_t c_off;        /* first channel of the box */
+  int32_t dw, dh, dt;   /* offset of the box origin from the K-block origin */
+} cstp_xbox;
+
+typedef struct {
+  cstp_tensor5 xmap;
+  cstp_tensor5 gmap;
+  int32_t n_xboxes;
+  cstp_xbox xboxes[16];
+  int32_t n_chunks;                     /* <= 32 */
+  uint32_t chunk_off[32];
+  int32_t Np, n_tile;                   /* ceil(n_chunks/2) * n_tile <= 512 TMEM columns */
+  int32_t Wt, Ht, Tt, Nt;
+  int32_t bw, bh, bt, bn;               /* product == 64 */
+  int32_t halo_w, halo_h, halo_t;
+  int32_t splits;
+  float* partials;                      /* fp32 [splits_eff][n_chunks*64][Np] */
+} cstp_wgrad_halo_desc;
+
+typedef struct cstp_wgrad_halo_plan cstp_wgrad_halo_plan;
+int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* desc, cstp_wgrad_halo_plan** plan);
+int cstp_wgrad_halo_plan_splits(const cstp_wgrad_halo_plan* plan);
+int cstp_wgrad_halo_plan_run(const cstp_wgrad_halo_plan* plan, void* stream);
+void cstp_wgrad_halo_plan_destroy(cstp_wgrad_halo_plan* plan);
+
 /* ---- packing / layout -----------------------------------------------------------------------------------
  * fp32 reference-layout weight (rows_out, cin, taps) -> bf16 K-major packed [Rp][taps*Kc].
  * transpose=0: packed[r=co][tap*Kc + ci] (forward);  transpose=1: packed[r=ci][tap*Kc + co] (dgrad). */

@@ -13,7 +13,8 @@ import torch.nn.functional as F
 
 from cstp_b200 import lib as L  # noqa: F401  (engine reaches CstpError through ops.L)
 from cstp_b200 import ops as real
-from cstp_b200.ops import BNState, ConvGeom, pad16, pad64, fwd_taps, dgrad_classes, bn_nblocks, pick_box  # noqa: F401
+from cstp_b200.ops import (BNState, ConvGeom, pad16, pad64, fwd_taps, dgrad_classes, bn_nblocks, pick_box,  # noqa: F401
+                           wgrad_partials_need, wgrad_halo_layout)
 
 from .emulate import _gather
 

@@ -78,3 +78,65 @@ def test_intermediate_channels_table():
     assert [ic(64, 64, (3, 3, 3)), ic(64, 128, (3, 3, 3)), ic(128, 128, (3, 3, 3))] == [144, 230, 288]
     assert [ic(128, 256, (3, 3, 3)), ic(256, 256, (3, 3, 3)), ic(256, 512, (3, 3, 3)), ic(512, 512, (3, 3, 3))] == [460, 576, 921, 1152]
     assert [ic(64, 128, (1, 1, 1)), ic(128, 256, (1, 1, 1)), ic(256, 512, (1, 1, 1))] == [42, 85, 170]
+
+
+@pytest.mark.parametrize("k,p,shape,cin,cout", [
+    ((1, 3, 3), (0, 1, 1), (2, 3, 16, 24), 64, 144),      # conv2 spatial (two N tiles)
+    ((3, 1, 1), (1, 0, 0), (1, 8, 8, 16), 144, 64),       # conv2 temporal (3 channel chunks, last one 16 wide)
+    ((3, 1, 1), (1, 0, 0), (2, 4, 6, 8), 83, 64),         # stem temporal, ragged tiles
+    ((1, 3, 3), (0, 1, 1), (1, 2, 10, 12), 128, 32),
+])
+def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
+    """Interprets ops.wgrad_halo_layout exactly as csrc/wgrad_halo.cu does (staged X boxes with halo, chunks as row
+    shifts, zero OOB fill, chunk -> (tap, channel) scatter of cstp_wgrad_finalize) and compares with torch's wgrad."""
+    import torch.nn.functional as F  # noqa: F401
+    from cstp_b200.ops import wgrad_halo_layout, pad16
+    N, T, H, W = shape
+    geom = ConvGeom(k, (1, 1, 1), p)
+    Ca, Np = pad16(cin), pad16(cout)
+    g_ = torch.Generator().manual_seed(3)
+    x = torch.zeros(N, T, H, W, Ca)
+    x[..., :cin] = torch.randn(N, T, H, W, cin, generator=g_)
+    gr = torch.zeros(N, T, H, W, Np)
+    gr[..., :cout] = torch.randn(N, T, H, W, cout, generator=g_)
+    lay = wgrad_halo_layout(tuple(x.shape), tuple(gr.shape), geom)
+    assert lay is not None
+    bw, bh, bt, bn = lay["box"]
+    hw, hh, ht = lay["halo"]
+    assert all(off % 1024 == 0 for off, _, _ in lay["chunks"])
+    offs = [c[0] for c in lay["chunks"]]
+    assert all(offs[i] < offs[i + 1] for i in range(len(offs) - 1))
+
+    def fetch(t, c0, w0, h0, t0, n0, ew, eh, et):
+        """TMA box (64 ch, ew, eh, et, 1) at the given origin with zero fill outside the tensor -> [rows][64]."""
+        out = torch.zeros(et, eh, ew, 64)
+        for a in range(et):
+            for b in range(eh):
+                for c in range(ew):
+                    tt, hh_, ww = t0 + a, h0 + b, w0 + c
+                    if 0 <= tt < t.shape[1] and 0 <= hh_ < t.shape[2] and 0 <= ww < t.shape[3] and n0 < t.shape[0]:
+                        ce = min(64, t.shape[-1] - c0)
+                        if ce > 0:
+                            out[a, b, c, :ce] = t[n0, tt, hh_, ww, c0:c0 + ce]
+        return out.reshape(-1, 64)
+
+    n_chunks = len(lay["chunks"])
+    P = torch.zeros(n_chunks * 64, Np)
+    for n0 in range(N):
+        for t0 in range(0, T, bt):
+            for h0 in range(0, H, bh):
+                for w0 in range(0, W, bw):
+                    staged = torch.cat([fetch(x, c0, w0 + dw, h0 + dh, t0 + dt, n0, bw + hw, bh + hh, bt + ht)
+                                        for (c0, dw, dh, dt) in lay["xboxes"]], 0)          # rows of 128 bytes
+                    G = torch.cat([fetch(gr, c0, w0, h0, t0, n0, bw, bh, bt) for c0 in range(0, Np, 64)], 1)[:, :Np]
+                    for i, (off, _, _) in enumerate(lay["chunks"]):
+                        rows = staged[off // 128: off // 128 + 64]
+                        P[i * 64:(i + 1) * 64] += rows.t() @ G
+    dw_ = torch.zeros(cout, cin, geom.taps)
+    for i, (_, tap, c0) in enumerate(lay["chunks"]):
+        for r in range(64):
+            if c0 + r < cin:
+                dw_[:, c0 + r, tap] = P[i * 64 + r, :cout]
+    ref = torch.nn.grad.conv3d_weight(x[..., :cin].permute(0, 4, 1, 2, 3), (cout, cin, *k),
+                                      gr[..., :cout].permute(0, 4, 1, 2, 3), stride=1, padding=p)
+    assert torch.allclose(dw_.reshape(ref.shape), ref, rtol=1e-4, atol=1e-3)
