@@ -1,0 +1,422 @@
+// Implicit-GEMM convolution (forward and dgrad) for the stride-1 1x3x3 / 3x1x1 layers with a large spatial extent
+// (conv1.temporal, conv2.*, conv3.block1.conv2.*), where conv_gemm.cu is bound by the L2->SM feed, not by the tensor
+// pipe: it stages one 128-position activation box PER FILTER TAP (9x / 3x the same data) and one weight tile per tap
+// for every output tile.  Here
+//   * the activation box is staged once per "load group" with a HALO along the tap axis; the taps of that axis are the
+//     same shared-memory rows shifted by a multiple of 8 rows (whole 128B-swizzle atoms), i.e. just another UMMA
+//     descriptor start address.  Taps along the fastest axis (kw) are separate groups (a one-row shift is not
+//     atom aligned);
+//   * when all weight K-blocks of one N tile fit next to the activation pipeline they are loaded ONCE per CTA
+//     ("resident B"); every CTA then keeps its N tile for its whole life (blockIdx.y) and walks M tiles only.
+// Same math, epilogue and output layout as conv_gemm.cu.
+// Replaces cuDNN conv3d fwd/dgrad behind models/pace/r21d_byol.py:81-97 (main_byol.py:87 for the dgrad).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cstp {
+
+constexpr int kHcThreads = 256;
+constexpr int kHcMaxStages = 8;
+constexpr int kHcSmemLimit = 232448;
+constexpr int kHcMaxGroups = 4;
+constexpr int kHcMaxTaps = 16;
+
+struct HcGroup {
+  int dw, dh, dt;       // origin offset of the staged (halo) box from the tile origin
+  int first_tap, n_taps;
+};
+struct HcTap {
+  uint32_t a_shift;     // byte offset of this tap's first row inside the staged box (multiple of 1024)
+  int k_off;            // column of its first 64-channel chunk in the packed weight matrix
+};
+
+struct ConvHaloKParams {
+  CUtensorMap amap;
+  CUtensorMap bmap;
+  int tiles_w, tiles_h, tiles_t, tiles_n;
+  int bw, bh, bt, bn;
+  int Wt, Ht, Tt, Nt;
+  int n_groups, n_taps, chunks, last_ksteps;
+  int n_tile, Np;
+  int stages, tmem_cols, resident;
+  uint32_t a_bytes, b_bytes, stage_bytes, res_bytes, idesc;
+  int accumulate;
+  __nv_bfloat16* out;
+  float* out_f32;
+  const float* bias;
+  long long out_off, osw, osh, ost, osn;
+  HcGroup groups[kHcMaxGroups];
+  HcTap taps[kHcMaxTaps];
+};
+
+__global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_constant__ ConvHaloKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage0 = smem + p.res_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kHcMaxStages;
+  uint64_t* tfull = bars + 2 * kHcMaxStages;
+  uint64_t* tempty = bars + 2 * kHcMaxStages + 2;
+  uint64_t* bfull = bars + 2 * kHcMaxStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHcMaxStages + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntile = blockIdx.y;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.amap);
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    mbar_init(bfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (p.resident) {
+      mbar_expect_tx(bfull, p.res_bytes);
+      for (int t = 0; t < p.n_taps; ++t)
+        for (int c = 0; c < p.chunks; ++c)
+          tma_load_2d(smem + static_cast<size_t>(t * p.chunks + c) * p.b_bytes, &p.bmap, bfull, p.taps[t].k_off + c * 64,
+                      ntile * p.n_tile);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      int pt = tile;
+      const int w0 = (pt % p.tiles_w) * p.bw;
+      pt /= p.tiles_w;
+      const int h0 = (pt % p.tiles_h) * p.bh;
+      pt /= p.tiles_h;
+      const int t0 = (pt % p.tiles_t) * p.bt;
+      pt /= p.tiles_t;
+      const int n0 = pt * p.bn;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const HcGroup gr = p.groups[g];
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* st = stage0 + static_cast<size_t>(stage) * p.stage_bytes;
+          mbar_expect_tx(&full[stage], p.a_bytes + (p.resident ? 0u : static_cast<uint32_t>(gr.n_taps) * p.b_bytes));
+          tma_load_5d(st, &p.amap, &full[stage], c * 64, w0 + gr.dw, h0 + gr.dh, t0 + gr.dt, n0);
+          if (!p.resident) {
+            for (int j = 0; j < gr.n_taps; ++j)
+              tma_load_2d(st + p.a_bytes + static_cast<size_t>(j) * p.b_bytes, &p.bmap, &full[stage],
+                          p.taps[gr.first_tap + j].k_off + c * 64, ntile * p.n_tile);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    if (p.resident) {
+      mbar_wait(bfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t res_addr = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      uint32_t first = 1;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const HcGroup gr = p.groups[g];
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t s_addr = smem_u32(stage0 + static_cast<size_t>(stage) * p.stage_bytes);
+          const int nk = (c == p.chunks - 1) ? p.last_ksteps : 4;
+          for (int j = 0; j < gr.n_taps; ++j) {
+            const int t = gr.first_tap + j;
+            const uint32_t a_addr = s_addr + p.taps[t].a_shift;
+            const uint32_t b_addr = p.resident ? res_addr + static_cast<uint32_t>(t * p.chunks + c) * p.b_bytes
+                                               : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (g == p.n_groups - 1 && c == p.chunks - 1) umma_commit(&tfull[as]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (warp w owns TMEM lanes 32*(w%4)..)
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int rw = row % p.bw;
+    const int rh = (row / p.bw) % p.bh;
+    const int rt = (row / (p.bw * p.bh)) % p.bt;
+    const int rn = row / (p.bw * p.bh * p.bt);
+    const int col0 = ntile * p.n_tile;
+    const int ncols = min(p.n_tile, p.Np - col0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      int pt = tile;
+      const int w = (pt % p.tiles_w) * p.bw + rw;
+      pt /= p.tiles_w;
+      const int h = (pt % p.tiles_h) * p.bh + rh;
+      pt /= p.tiles_h;
+      const int t = (pt % p.tiles_t) * p.bt + rt;
+      pt /= p.tiles_t;
+      const int n = pt * p.bn + rn;
+      const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
+      const long long off = p.out_off + w * p.osw + h * p.osh + t * p.ost + n * p.osn + col0;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + col0 + c0 + i);
+          }
+          if (p.out != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+            if (p.accumulate) {
+              const uint4 o0 = dst[0], o1 = dst[1];
+              const uint32_t o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(o[i]);
+                f[2 * i + 1] += bf16_hi(o[i]);
+              }
+            }
+            uint4 s0, s1;
+            s0.x = pack_bf16x2(f[0], f[1]);
+            s0.y = pack_bf16x2(f[2], f[3]);
+            s0.z = pack_bf16x2(f[4], f[5]);
+            s0.w = pack_bf16x2(f[6], f[7]);
+            s1.x = pack_bf16x2(f[8], f[9]);
+            s1.y = pack_bf16x2(f[10], f[11]);
+            s1.z = pack_bf16x2(f[12], f[13]);
+            s1.w = pack_bf16x2(f[14], f[15]);
+            dst[0] = s0;
+            dst[1] = s1;
+          }
+          if (p.out_f32 != nullptr) {
+            float4* dstf = reinterpret_cast<float4*>(p.out_f32 + off + c0);
+            if (p.accumulate && p.out == nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 o = dstf[i];
+                f[4 * i] += o.x;
+                f[4 * i + 1] += o.y;
+                f[4 * i + 2] += o.z;
+                f[4 * i + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dstf[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+}  // namespace cstp
+
+struct cstp_conv_halo_plan {
+  cstp::ConvHaloKParams kp;
+  dim3 grid;
+  int smem_bytes;
+};
+
+using namespace cstp;
+
+extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_conv_halo_plan** out_plan) {
+  CSTP_REQUIRE(d != nullptr && out_plan != nullptr);
+  CSTP_REQUIRE(d->n_groups >= 1 && d->n_groups <= kHcMaxGroups);
+  CSTP_REQUIRE(d->n_taps >= 1 && d->n_taps <= kHcMaxTaps);
+  CSTP_REQUIRE(d->a_channels >= 16 && d->a_channels % 16 == 0);
+  CSTP_REQUIRE(d->Np >= 16 && d->Np % 16 == 0);
+  CSTP_REQUIRE(d->n_tile >= 16 && d->n_tile % 16 == 0 && d->n_tile <= 256);
+  CSTP_REQUIRE(d->Ktot >= 64 && d->Ktot % 64 == 0);
+  CSTP_REQUIRE(d->bw >= 1 && d->bh >= 1 && d->bt >= 1 && d->bn >= 1 && d->bw * d->bh * d->bt * d->bn == 128);
+  CSTP_REQUIRE(d->halo_w >= 0 && d->halo_h >= 0 && d->halo_t >= 0);
+  CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
+  CSTP_REQUIRE(d->w_packed != nullptr && (d->out_bf16 != nullptr || d->out_f32 != nullptr));
+  CSTP_REQUIRE(d->osw % 8 == 0 && d->osh % 8 == 0 && d->ost % 8 == 0 && d->osn % 8 == 0 && d->out_off % 8 == 0);
+  const int xrows = (d->bw + d->halo_w) * (d->bh + d->halo_h) * (d->bt + d->halo_t) * d->bn;
+  CSTP_REQUIRE(xrows % 8 == 0 && d->bw + d->halo_w <= 256 && d->bh + d->halo_h <= 256 && d->bt + d->halo_t <= 256);
+
+  cstp_conv_halo_plan* plan = new (std::nothrow) cstp_conv_halo_plan();
+  if (!plan) {
+    set_error("out of host memory");
+    return CSTP_ENOMEM;
+  }
+  ConvHaloKParams& k = plan->kp;
+  memset(&k, 0, sizeof(k));
+  {
+    uint64_t dims[5], strides[4];
+    for (int i = 0; i < 5; ++i) dims[i] = static_cast<uint64_t>(d->amap.dims[i]);
+    for (int i = 0; i < 4; ++i) strides[i] = static_cast<uint64_t>(d->amap.strides[i]);
+    bool ok = d->amap.ptr != nullptr && (reinterpret_cast<uintptr_t>(d->amap.ptr) % 16) == 0;
+    for (int i = 0; i < 5; ++i) ok = ok && d->amap.dims[i] > 0;
+    for (int i = 0; i < 4; ++i) ok = ok && d->amap.strides[i] > 0 && d->amap.strides[i] % 16 == 0;
+    if (!ok) {
+      delete plan;
+      return fail_inval("amap: dims > 0, strides positive multiples of 16 bytes, ptr 16B aligned");
+    }
+    const uint32_t abox[5] = {64u, (uint32_t)(d->bw + d->halo_w), (uint32_t)(d->bh + d->halo_h),
+                              (uint32_t)(d->bt + d->halo_t), (uint32_t)d->bn};
+    int rc = encode_tmap_bf16(&k.amap, d->amap.ptr, 5, dims, strides, abox);
+    if (rc == CSTP_OK) {
+      const uint64_t bdims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
+      const uint64_t bstr[1] = {(uint64_t)d->Ktot * 2};
+      const uint32_t bbox[2] = {64u, (uint32_t)d->n_tile};
+      rc = encode_tmap_bf16(&k.bmap, d->w_packed, 2, bdims, bstr, bbox);
+    }
+    if (rc != CSTP_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  k.tiles_w = ceil_div(d->Wt, d->bw);
+  k.tiles_h = ceil_div(d->Ht, d->bh);
+  k.tiles_t = ceil_div(d->Tt, d->bt);
+  k.tiles_n = ceil_div(d->Nt, d->bn);
+  k.bw = d->bw; k.bh = d->bh; k.bt = d->bt; k.bn = d->bn;
+  k.Wt = d->Wt; k.Ht = d->Ht; k.Tt = d->Tt; k.Nt = d->Nt;
+  k.n_groups = d->n_groups;
+  k.n_taps = d->n_taps;
+  k.chunks = ceil_div(d->a_channels, 64);
+  k.last_ksteps = ((d->a_channels - 1) % 64) / 16 + 1;
+  k.n_tile = d->n_tile;
+  k.Np = d->Np;
+  k.a_bytes = static_cast<uint32_t>(xrows) * 128u;
+  k.b_bytes = static_cast<uint32_t>(d->n_tile) * 128u;
+  k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 0, 0);
+  k.accumulate = d->accumulate;
+  k.out = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
+  k.out_f32 = d->out_f32;
+  k.bias = d->bias;
+  k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
+  int max_group_taps = 0, seen = 0;
+  for (int g = 0; g < d->n_groups; ++g) {
+    const cstp_halo_group& gr = d->groups[g];
+    if (gr.n_taps < 1 || gr.first_tap != seen) {
+      delete plan;
+      return fail_inval("groups must partition the tap list in order");
+    }
+    seen += gr.n_taps;
+    if (gr.n_taps > max_group_taps) max_group_taps = gr.n_taps;
+    k.groups[g] = HcGroup{gr.dw, gr.dh, gr.dt, gr.first_tap, gr.n_taps};
+  }
+  if (seen != d->n_taps) {
+    delete plan;
+    return fail_inval("groups must cover every tap");
+  }
+  for (int t = 0; t < d->n_taps; ++t) {
+    const cstp_halo_tap& tp = d->taps[t];
+    if (tp.a_shift % 1024 != 0 || tp.a_shift + 128u * 128u > k.a_bytes || tp.k_off < 0 || tp.k_off % 64 != 0 ||
+        tp.k_off + k.chunks * 64 > d->Ktot) {
+      delete plan;
+      return fail_inval("tap a_shift (1024-aligned, 128 rows inside the staged box) / k_off out of range");
+    }
+    k.taps[t] = HcTap{tp.a_shift, tp.k_off};
+  }
+  // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
+  const int bar_bytes = 256;
+  const long long res_all = 1LL * d->n_taps * k.chunks * k.b_bytes;
+  const long long budget = kHcSmemLimit - 1024 - bar_bytes;
+  if (d->allow_resident && res_all + 3LL * k.a_bytes <= budget) {
+    k.resident = 1;
+    k.res_bytes = static_cast<uint32_t>(res_all);
+    k.stage_bytes = k.a_bytes;
+  } else {
+    k.resident = 0;
+    k.res_bytes = 0;
+    k.stage_bytes = k.a_bytes + static_cast<uint32_t>(max_group_taps) * k.b_bytes;
+  }
+  int stages = static_cast<int>((budget - k.res_bytes) / k.stage_bytes);
+  if (stages > kHcMaxStages) stages = kHcMaxStages;
+  if (stages < 2) {
+    delete plan;
+    return fail_inval("stage too large for the shared-memory pipeline");
+  }
+  k.stages = stages;
+  int cols = 32;
+  while (cols < 2 * d->n_tile) cols *= 2;
+  k.tmem_cols = cols;
+  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) + bar_bytes;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
+  const int n_ntiles = ceil_div(d->Np, d->n_tile);
+  const long long m_tiles = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
+  long long gx = num_sms() / n_ntiles;
+  if (gx < 1) gx = 1;
+  if (gx > m_tiles) gx = m_tiles;
+  plan->grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_ntiles), 1);
+  *out_plan = plan;
+  return CSTP_OK;
+}
+
+extern "C" int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan) { return plan ? plan->kp.resident : CSTP_EINVAL; }
+
+extern "C" int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream) {
+  CSTP_REQUIRE(plan != nullptr);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    attr_set = true;
+  }
+  conv_halo_kernel<<<plan->grid, kHcThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" void cstp_conv_halo_plan_destroy(cstp_conv_halo_plan* plan) { delete plan; }

@@ -65,6 +65,37 @@ class WgradDesc(C.Structure):
     ]
 
 
+class HaloGroup(C.Structure):
+    _fields_ = [("dw", C.c_int32), ("dh", C.c_int32), ("dt", C.c_int32), ("first_tap", C.c_int32), ("n_taps", C.c_int32)]
+
+
+class HaloTap(C.Structure):
+    _fields_ = [("a_shift", C.c_uint32), ("k_off", C.c_int32)]
+
+
+class ConvHaloDesc(C.Structure):
+    _fields_ = [
+        ("amap", Tensor5),
+        ("a_channels", C.c_int32),
+        ("n_groups", C.c_int32),
+        ("groups", HaloGroup * 4),
+        ("n_taps", C.c_int32),
+        ("taps", HaloTap * 16),
+        ("w_packed", C.c_void_p),
+        ("Np", C.c_int32), ("Ktot", C.c_int32), ("n_tile", C.c_int32),
+        ("Wt", C.c_int32), ("Ht", C.c_int32), ("Tt", C.c_int32), ("Nt", C.c_int32),
+        ("bw", C.c_int32), ("bh", C.c_int32), ("bt", C.c_int32), ("bn", C.c_int32),
+        ("halo_w", C.c_int32), ("halo_h", C.c_int32), ("halo_t", C.c_int32),
+        ("out_bf16", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("out_off", C.c_int64),
+        ("osw", C.c_int64), ("osh", C.c_int64), ("ost", C.c_int64), ("osn", C.c_int64),
+        ("bias", C.c_void_p),
+        ("accumulate", C.c_int32),
+        ("allow_resident", C.c_int32),
+    ]
+
+
 class XBox(C.Structure):
     _fields_ = [("c_off", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32), ("dt", C.c_int32)]
 
@@ -95,6 +126,10 @@ SIGNATURES = {
     "cstp_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
     "cstp_conv_plan_run": (_i, [_vp, _vp]),
     "cstp_conv_plan_destroy": (None, [_vp]),
+    "cstp_conv_halo_plan_create": (_i, [C.POINTER(ConvHaloDesc), C.POINTER(_vp)]),
+    "cstp_conv_halo_plan_resident": (_i, [_vp]),
+    "cstp_conv_halo_plan_run": (_i, [_vp, _vp]),
+    "cstp_conv_halo_plan_destroy": (None, [_vp]),
     "cstp_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),
     "cstp_wgrad_plan_splits": (_i, [_vp]),
     "cstp_wgrad_plan_run": (_i, [_vp, _vp]),

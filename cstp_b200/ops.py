@@ -220,8 +220,114 @@ def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out,
     return ConvPlan(h, lib.cstp_conv_plan_destroy, keep)
 
 
+class ConvHaloPlan(_Plan):
+    resident: bool = False
+
+    def run(self):
+        L.check(L.load().cstp_conv_halo_plan_run(self.handle, _stream()))
+
+
+SMEM_BUDGET = 232448 - 1024 - 256
+
+
+def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
+    """Geometry of csrc/conv_halo.cu for a single-view (stride-1) tap list [(dw, dh, dt, k_off)], or None when the
+    layer does not qualify (then csrc/conv_gemm.cu is used).  Pure shape arithmetic.
+
+    The taps must vary along t only (3x1x1: one load group, halo along t) or along h and w only (1x3x3: one load group
+    per dw, halo along h).  Returns dict(box, halo, groups [(dw, dh, dt, first_tap, n_taps)], taps [(a_shift, k_off)]
+    in group order, n_tile, a_bytes, resident)."""
+    Wt, Ht, Tt, Nt = tile_space
+    if len(taps) < 2 or len(taps) > 16:
+        return None
+    dws, dhs, dts = sorted({t[0] for t in taps}), sorted({t[1] for t in taps}), sorted({t[2] for t in taps})
+    temporal = len(dws) == 1 and len(dhs) == 1 and len(dts) > 1
+    spatial = len(dts) == 1 and len(dhs) > 1
+    if not (temporal or spatial) or len(dws) > 4:
+        return None
+    if temporal and (dws[0] != 0 or dhs[0] != 0):
+        return None
+    span = (dts[-1] - dts[0]) if temporal else (dhs[-1] - dhs[0])
+    best = None
+    for bw in (4, 8, 16, 32, 64, 128):
+        for bh in (1, 2, 4, 8, 16, 32):
+            for bt in ((1, 2, 4, 8, 16, 32) if temporal else (1,)):
+                if bw * bh * bt != 128:
+                    continue
+                unit = bw * bh if temporal else bw          # rows per step of the halo axis
+                if unit % 8:
+                    continue
+                tiles = math.ceil(Wt / bw) * math.ceil(Ht / bh) * math.ceil(Tt / bt)
+                rows = (bw * bh * (bt + span)) if temporal else (bw * (bh + span))
+                key = (tiles, tiles * rows * (1 if temporal else len(dws)), -bw)
+                if best is None or key < best[0]:
+                    best = (key, (bw, bh, bt, 1), rows, unit)
+    if best is None:
+        return None
+    _, box, rows, unit = best
+    halo = (0, 0, span) if temporal else (0, span, 0)
+    groups, out_taps = [], []
+    if temporal:
+        groups.append((0, 0, dts[0], 0, len(taps)))
+        for (dw, dh, dt, k_off) in sorted(taps, key=lambda t: t[2]):
+            out_taps.append(((dt - dts[0]) * unit * 128, k_off))
+    else:
+        for dw in dws:
+            mine = sorted([t for t in taps if t[0] == dw], key=lambda t: t[1])
+            groups.append((dw, dhs[0], dts[0], len(out_taps), len(mine)))
+            for (_, dh, _, k_off) in mine:
+                out_taps.append(((dh - dhs[0]) * unit * 128, k_off))
+    a_bytes = rows * 128
+    chunks = pad64(a_channels) // 64
+    # N tile: keep all weight K-blocks resident when they fit beside 3 activation stages, splitting N in two if needed
+    n_tile, resident = (Np if Np <= 256 else _default_n_tile(Np)), False
+    for cand in ([Np] if Np <= 256 else []) + ([pad16(math.ceil(Np / 2))] if Np > 64 else []):
+        if cand <= 256 and len(taps) * chunks * cand * 128 + 3 * a_bytes <= SMEM_BUDGET:
+            n_tile, resident = cand, True
+            break
+    if not resident:
+        per_stage = a_bytes + max(g[4] for g in groups) * n_tile * 128
+        if 2 * per_stage > SMEM_BUDGET:
+            return None
+    return dict(box=box, halo=halo, groups=groups, taps=out_taps, n_tile=n_tile, a_bytes=a_bytes, resident=resident)
+
+
+def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
+                         accumulate, keep) -> ConvHaloPlan:
+    lib = L.load()
+    d = L.ConvHaloDesc()
+    d.amap = view
+    d.a_channels = a_channels
+    d.n_groups = len(lay["groups"])
+    for i, g in enumerate(lay["groups"]):
+        d.groups[i] = L.HaloGroup(*g)
+    d.n_taps = len(lay["taps"])
+    for i, (shift, k_off) in enumerate(lay["taps"]):
+        d.taps[i] = L.HaloTap(shift, k_off)
+    d.w_packed = w_packed.data_ptr()
+    d.Np, d.Ktot, d.n_tile = Np, w_packed.shape[1], lay["n_tile"]
+    d.Wt, d.Ht, d.Tt, d.Nt = tile_space
+    d.bw, d.bh, d.bt, d.bn = lay["box"]
+    d.halo_w, d.halo_h, d.halo_t = lay["halo"]
+    d.out_bf16 = 0 if out is None else out.data_ptr()
+    d.out_f32 = 0 if out_f32 is None else out_f32.data_ptr()
+    d.out_off = out_off
+    d.osw, d.osh, d.ost, d.osn = ostrides
+    d.bias = 0 if bias is None else bias.data_ptr()
+    d.accumulate = int(accumulate)
+    d.allow_resident = int(lay["resident"])
+    h = C.c_void_p()
+    L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
+    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep)
+    plan.resident = bool(lib.cstp_conv_halo_plan_resident(h))
+    return plan
+
+
+HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
+
+
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None,
-                  box=None) -> ConvPlan:
+                  box=None, allow_halo: bool = True) -> ConvPlan:
     """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16."""
     _require_cuda(x, w_packed, out, out_f32, bias)
     N, T, H, W, Ca = x.shape
@@ -233,13 +339,18 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
     views, taps = _fwd_taps(x, geom)
     Kc = pad64(Ca)
     taps = [(m, dw, dh, dt, ti * Kc) for (m, dw, dh, dt, ti) in taps]
-    box = box or pick_box(Wo, Ho, To, N, 128)
     ostr = (Np, Wo * Np, Ho * Wo * Np, To * Ho * Wo * Np)
+    if allow_halo and box is None and n_tile is None and len(views) == 1 and Ho * Wo >= HALO_MIN_POSITIONS:
+        lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np)
+        if lay is not None:
+            return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, out_f32, 0, ostr, bias,
+                                        accumulate, (x, w_packed, out, out_f32, bias))
+    box = box or pick_box(Wo, Ho, To, N, 128)
     return _make_conv_plan(views, taps, Ca, w_packed, Np, (Wo, Ho, To, N), box, out, out_f32, 0, ostr, bias, accumulate,
                            n_tile, (x, w_packed, out, out_f32, bias))
 
 
-def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False) -> tuple[list[ConvPlan], bool]:
+def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False, allow_halo: bool = True) -> tuple[list[ConvPlan], bool]:
     """dx (N,T,H,W,Cp_in) = conv_transpose(g (N,To,Ho,Wo,Cp_out)); wt_packed [Cp_in][taps*pad64(Cp_out)] bf16.
 
     One plan per stride-parity class of dx.  Returns (plans, covers_all): when covers_all is False some classes
@@ -257,6 +368,12 @@ def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False) -> t
             covers_all = False
             continue
         taps = [(0, dw_, dh_, dt_, ti * Kc) for (dw_, dh_, dt_, ti) in cl["taps"]]
+        if allow_halo and tuple(geom.stride) == (1, 1, 1) and H * W >= HALO_MIN_POSITIONS:
+            lay = conv_halo_layout(cl["space"], [t[1:] for t in taps], Co, Ci)
+            if lay is not None:
+                plans.append(_make_conv_halo_plan(gview, lay, Co, wt_packed, Ci, cl["space"], dx, None, cl["off"],
+                                                  cl["ostrides"], None, accumulate, (g, wt_packed, dx)))
+                continue
         box = pick_box(*cl["space"], 128)
         plans.append(_make_conv_plan([gview], taps, Co, wt_packed, Ci, cl["space"], box, dx, None, cl["off"],
                                      cl["ostrides"], None, accumulate, None, (g, wt_packed, dx)))

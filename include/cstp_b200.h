@@ -80,6 +80,47 @@ int cstp_conv_plan_create(const cstp_conv_desc* desc, cstp_conv_plan** plan);
 int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream);
 void cstp_conv_plan_destroy(cstp_conv_plan* plan);
 
+/* Stride-1 1xkxk / kx1x1 convolutions with a large spatial extent: the activation box is staged once per "load group"
+ * with a halo along the tap axis and every tap of the group is a row shift (`a_shift` bytes, whole 8-row swizzle
+ * atoms) of that box; weights stay resident in shared memory when they fit (csrc/conv_halo.cu).  Same math and
+ * output conventions as cstp_conv_desc; taps must be listed group by group. */
+typedef struct {
+  int32_t dw, dh, dt;          /* origin of the staged box relative to the tile origin */
+  int32_t first_tap, n_taps;
+} cstp_halo_group;
+
+typedef struct {
+  uint32_t a_shift;
+  int32_t k_off;
+} cstp_halo_tap;
+
+typedef struct {
+  cstp_tensor5 amap;
+  int32_t a_channels;
+  int32_t n_groups;
+  cstp_halo_group groups[4];
+  int32_t n_taps;
+  cstp_halo_tap taps[16];
+  const void* w_packed;
+  int32_t Np, Ktot, n_tile;
+  int32_t Wt, Ht, Tt, Nt;
+  int32_t bw, bh, bt, bn;       /* product == 128 */
+  int32_t halo_w, halo_h, halo_t;
+  void* out_bf16;
+  float* out_f32;
+  int64_t out_off;
+  int64_t osw, osh, ost, osn;
+  const float* bias;
+  int32_t accumulate;
+  int32_t allow_resident;
+} cstp_conv_halo_desc;
+
+typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;
+int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* desc, cstp_conv_halo_plan** plan);
+int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan);   /* 1 when the weights are kept in shared memory */
+int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream);
+void cstp_conv_halo_plan_destroy(cstp_conv_halo_plan* plan);
+
 /* ---- weight gradient ------------------------------------------------------------------------------------
  * Replaces the autograd wgrad of nn.Conv3d / nn.Linear (main_byol.py:87).
  * The M axis is a list of 64-row chunks, each one (tap, 64 input channels) of the conv input X; the N axis

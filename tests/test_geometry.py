@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from cstp_b200 import ops
-from cstp_b200.ops import ConvGeom
+from cstp_b200.ops import ConvGeom, fwd_taps
 from tests import emulate as E
 
 CASES = [
@@ -140,3 +140,74 @@ def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
     ref = torch.nn.grad.conv3d_weight(x[..., :cin].permute(0, 4, 1, 2, 3), (cout, cin, *k),
                                       gr[..., :cout].permute(0, 4, 1, 2, 3), stride=1, padding=p)
     assert torch.allclose(dw_.reshape(ref.shape), ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("k,p,shape,cin,cout,dgrad", [
+    ((1, 3, 3), (0, 1, 1), (2, 2, 20, 12), 64, 144, False),
+    ((3, 1, 1), (1, 0, 0), (1, 20, 8, 8), 144, 64, False),
+    ((1, 3, 3), (0, 1, 1), (1, 1, 18, 40), 144, 64, True),
+    ((3, 1, 1), (1, 0, 0), (2, 5, 4, 12), 64, 144, True),
+])
+def test_conv_halo_layout_semantics(k, p, shape, cin, cout, dgrad):
+    """Interprets ops.conv_halo_layout exactly as csrc/conv_halo.cu does (one staged halo box per load group and
+    channel chunk, taps as row shifts, zero OOB fill) and compares with torch conv3d / its input gradient."""
+    import torch.nn.functional as F
+    from cstp_b200.ops import conv_halo_layout, dgrad_classes, pad16, pad64
+    N, T, H, W = shape
+    geom = ConvGeom(k, (1, 1, 1), p)
+    gen = torch.Generator().manual_seed(5)
+    w = torch.randn(cout, cin, *k, generator=gen)
+    if not dgrad:
+        a_c, n_c = cin, cout
+        _, taps = fwd_taps(geom)
+        taps = [(dw, dh, dt, ti) for (_, dw, dh, dt, ti) in taps]
+        wmat = lambda ti: w.reshape(cout, cin, -1)[:, :, ti]                     # [n][c]   # noqa: E731
+    else:
+        a_c, n_c = cout, cin
+        (cl,) = dgrad_classes((N, T, H, W, pad16(cin)), geom)
+        taps = cl["taps"]
+        wmat = lambda ti: w.reshape(cout, cin, -1)[:, :, ti].t()                 # [n = ci][c = co]  # noqa: E731
+    Ca, Np = pad16(a_c), pad16(n_c)
+    a = torch.zeros(N, T, H, W, Ca)
+    a[..., :a_c] = torch.randn(N, T, H, W, a_c, generator=gen)
+    lay = conv_halo_layout((W, H, T, N), [(dw, dh, dt, ti * pad64(Ca)) for (dw, dh, dt, ti) in taps], Ca, Np)
+    assert lay is not None
+    bw, bh, bt, bn = lay["box"]
+    hw, hh, ht = lay["halo"]
+    assert bw * bh * bt * bn == 128 and all(s_ % 1024 == 0 for s_, _ in lay["taps"])
+    out = torch.zeros(N, T, H, W, n_c)
+    tap_of_koff = {ti * pad64(Ca): ti for (_, _, _, ti) in taps}
+
+    def fetch(c0, w0, h0, t0, n0):
+        box = torch.zeros(bt + ht, bh + hh, bw + hw, 64)
+        for aa in range(bt + ht):
+            for bb in range(bh + hh):
+                for cc in range(bw + hw):
+                    tt, hh_, ww = t0 + aa, h0 + bb, w0 + cc
+                    if 0 <= tt < T and 0 <= hh_ < H and 0 <= ww < W:
+                        ce = min(64, Ca - c0)
+                        box[aa, bb, cc, :ce] = a[n0, tt, hh_, ww, c0:c0 + ce]
+        return box.reshape(-1, 64)
+
+    for n0 in range(N):
+        for t0 in range(0, T, bt):
+            for h0 in range(0, H, bh):
+                for w0 in range(0, W, bw):
+                    acc = torch.zeros(128, n_c)
+                    for (gdw, gdh, gdt, first, cnt) in lay["groups"]:
+                        for c0 in range(0, Ca, 64):
+                            staged = fetch(c0, w0 + gdw, h0 + gdh, t0 + gdt, n0)
+                            for (shift, k_off) in lay["taps"][first:first + cnt]:
+                                rows = staged[shift // 128: shift // 128 + 128]
+                                wm = wmat(tap_of_koff[k_off])[:, c0:c0 + 64]
+                                acc += rows[:, :wm.shape[1]] @ wm.t()
+                    for r in range(128):
+                        ww, hh_, tt = w0 + r % bw, h0 + (r // bw) % bh, t0 + r // (bw * bh)
+                        if ww < W and hh_ < H and tt < T:
+                            out[n0, tt, hh_, ww] = acc[r]
+    x5 = a[..., :a_c].permute(0, 4, 1, 2, 3)
+    if not dgrad:
+        ref = F.conv3d(x5, w, None, 1, p)
+    else:
+        ref = torch.nn.grad.conv3d_input((N, cin, T, H, W), w, x5, stride=1, padding=p)
+    assert torch.allclose(out.permute(0, 4, 1, 2, 3), ref, rtol=1e-4, atol=1e-3)
