@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t phase = 0;
     int it = 0;
     const int kblocks = p.n_taps * p.chunks_per_tap;
+    const uint32_t smem_addr0 = smem_u32(smem);
+    const uint64_t dhi = umma_desc_hi(16, 1024);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -132,13 +134,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int c = 0; c < p.chunks_per_tap; ++c, ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
-          const int nk = (c == p.chunks_per_tap - 1) ? p.last_ksteps : 4;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+          const uint64_t da = umma_desc_at(dhi, a_addr);
+          const uint64_t db = umma_desc_at(dhi, a_addr + kABytes);
+          umma_bf16(d_tmem, da, db, p.idesc, kb != 0 ? 1u : 0u);
+          if (c != p.chunks_per_tap - 1 || p.last_ksteps == 4) {
+            umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
+            umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
+            umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
+          } else {
+            for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
           }
           umma_commit(&empty[stage]);
           if (kb == kblocks - 1) umma_commit(&tfull[as]);

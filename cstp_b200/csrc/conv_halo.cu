@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       tc_fence_after();
     }
     const uint32_t res_addr = smem_u32(smem);
+    const uint32_t stage_addr0 = smem_u32(stage0);
+    const uint64_t dhi = umma_desc_hi(16, 1024);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -152,18 +154,21 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t s_addr = smem_u32(stage0 + static_cast<size_t>(stage) * p.stage_bytes);
-          const int nk = (c == p.chunks - 1) ? p.last_ksteps : 4;
+          const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const bool full_chunk = (c != p.chunks - 1) || p.last_ksteps == 4;
           for (int j = 0; j < gr.n_taps; ++j) {
             const int t = gr.first_tap + j;
-            const uint32_t a_addr = s_addr + p.taps[t].a_shift;
-            const uint32_t b_addr = p.resident ? res_addr + static_cast<uint32_t>(t * p.chunks + c) * p.b_bytes
-                                               : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes;
-            for (int k = 0; k < nk; ++k) {
-              const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
-              first = 0;
+            const uint64_t da = umma_desc_at(dhi, s_addr + p.taps[t].a_shift);
+            const uint64_t db = umma_desc_at(dhi, p.resident ? res_addr + static_cast<uint32_t>(t * p.chunks + c) * p.b_bytes
+                                                             : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes);
+            umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
+            first = 0;
+            if (full_chunk) {
+              umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
+              umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
+              umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
+            } else {
+              for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
             }
           }
           umma_commit(&empty[stage]);

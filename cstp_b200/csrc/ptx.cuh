@@ -159,6 +159,33 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// The tcgen05 issuer is ONE thread: every ALU instruction between two MMAs is exposed latency (a 128x64x16 MMA keeps
+// the tensor pipe busy for only 32 cycles).  The constant upper bits of a descriptor are therefore built once and the
+// 14-bit start-address field is advanced by plain adds: +2 per 32-byte K step (K-major), +128 per 2048-byte K step
+// (MN-major).  Shared-memory addresses are < 256 KB, so the field never carries into its neighbours.
+__device__ __forceinline__ uint64_t umma_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t hi, uint32_t saddr) {
+  return hi | static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+}
+// D[tmem] += A * B (accumulate unconditionally).
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4

@@ -100,18 +100,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   } else if (warp == 1 && lane == 0) {
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t smem_addr0 = smem_u32(smem);
+    const uint64_t dhi = umma_desc_hi(kBoxBytes, 1024);
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-      const uint32_t b_addr = a_addr + a_bytes;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // MN-major, 128B swizzle: 16 K-rows per step = 2048 B; LBO = next 64-channel chunk, SBO = next 8 K-rows.
-        const uint64_t da = umma_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
-        const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
-        umma_bf16(tmem_base, da, db, p.idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-      }
+      const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+      // MN-major, 128B swizzle: 16 K-rows per step = 2048 B (+128 in the address field); LBO = next 64-channel chunk,
+      // SBO = next 8 K-rows.
+      const uint64_t da = umma_desc_at(dhi, a_addr);
+      const uint64_t db = umma_desc_at(dhi, a_addr + a_bytes);
+      umma_bf16(tmem_base, da, db, p.idesc, kb > kb_begin ? 1u : 0u);
+      umma_bf16_acc(tmem_base, da + 128, db + 128, p.idesc);
+      umma_bf16_acc(tmem_base, da + 256, db + 256, p.idesc);
+      umma_bf16_acc(tmem_base, da + 384, db + 384, p.idesc);
       umma_commit(&empty[stage]);
       if (kb == kb_end - 1) umma_commit(tfull);
       if (++stage == p.stages) {

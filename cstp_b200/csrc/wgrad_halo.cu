@@ -112,25 +112,36 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer: n_mtiles accumulators per K-block
+    const uint32_t smem_addr0 = smem_u32(smem);
+    const uint64_t dhi_b = umma_desc_hi(kGBoxBytes, 1024);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      const uint32_t s_addr = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
-      const uint32_t b_addr = s_addr + x_bytes;
-      const uint32_t acc = kb > kb_begin ? 1u : 0u;
-      for (int mt = 0; mt < p.n_mtiles; ++mt) {
-        const WhMtile m = p.mtiles[mt];
-        const uint32_t lbo = m.lbo != 0 ? m.lbo : 1024u;   // single block: the upper 64 rows are never read back
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // MN-major, 128B swizzle: 16 K-rows (positions) per step = 2048 B; LBO = next 64-channel block of the M
-          // (resp. N) axis, SBO = next 8 K-rows.
-          const uint64_t da = umma_smem_desc(s_addr + m.a_off + k * 2048, lbo, 1024);
-          const uint64_t db = umma_smem_desc(b_addr + k * 2048, kGBoxBytes, 1024);
-          umma_bf16(d_tmem, da, db, p.idesc, (acc | (k > 0 ? 1u : 0u)));
+      const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
+      const uint64_t db = umma_desc_at(dhi_b, s_addr + x_bytes);
+      // MN-major, 128B swizzle: 16 K-rows (positions) per step = 2048 B (+128 in the address field); LBO = next
+      // 64-channel block of the M (resp. N) axis, SBO = next 8 K-rows.
+      if (kb > kb_begin) {
+        for (int mt = 0; mt < p.n_mtiles; ++mt) {
+          const WhMtile m = p.mtiles[mt];
+          const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, 1024), s_addr + m.a_off);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
+          umma_bf16_acc(d_tmem, da, db, p.idesc);
+          umma_bf16_acc(d_tmem, da + 128, db + 128, p.idesc);
+          umma_bf16_acc(d_tmem, da + 256, db + 256, p.idesc);
+          umma_bf16_acc(d_tmem, da + 384, db + 384, p.idesc);
+        }
+      } else {
+        for (int mt = 0; mt < p.n_mtiles; ++mt) {
+          const WhMtile m = p.mtiles[mt];
+          const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, 1024), s_addr + m.a_off);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
+          umma_bf16(d_tmem, da, db, p.idesc, 0u);
+          umma_bf16_acc(d_tmem, da + 128, db + 128, p.idesc);
+          umma_bf16_acc(d_tmem, da + 256, db + 256, p.idesc);
+          umma_bf16_acc(d_tmem, da + 384, db + 384, p.idesc);
         }
       }
       umma_commit(&empty[stage]);
