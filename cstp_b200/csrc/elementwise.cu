@@ -42,36 +42,47 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 }
 
 // ------------------------------------------------------------------------------------------- stem im2col
-__global__ void stem_im2col_kernel(const float* __restrict__ x, int N, int T, int H, int W, __nv_bfloat16* __restrict__ col,
-                                   int ldk) {
+// One CTA per (n, t, ho): the 3 x 7 input rows this output row needs are staged in shared memory with coalesced
+// float4 loads (zero rows / columns for the padding), then every thread assembles 16-byte vectors of 8 consecutive
+// K columns (k = ci*49 + kh*7 + kw) for the 56 output positions.  The first version gathered straight from global
+// memory and ran at 0.85 TB/s.
+constexpr int kStemMaxW = 256;
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, int N, int T, int H, int W,
+                                                          __nv_bfloat16* __restrict__ col, int ldk) {
+  __shared__ float rows[3 * 7][kStemMaxW + 8];       // [ci*7 + kh][3 + wi], 3 zero columns of left padding
   const int Ho = H / 2, Wo = W / 2;
+  int b = blockIdx.x;
+  const int ho = b % Ho;
+  b /= Ho;
+  const int t = b % T;
+  const int n = b / T;
+  const int wpad = W + 8;
+  for (int i = threadIdx.x; i < 21 * wpad; i += blockDim.x) {
+    const int r = i / wpad, c = i % wpad;
+    const int ci = r / 7, kh = r % 7;
+    const int hi = 2 * ho + kh - 3, wi = c - 3;
+    float v = 0.f;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      v = __ldg(x + (((static_cast<long long>(n) * 3 + ci) * T + t) * H + hi) * W + wi);
+    rows[r][c] = v;
+  }
+  __syncthreads();
   const int nvec = ldk / 8;
-  const long long rows = static_cast<long long>(N) * T * Ho * Wo;
-  const long long total = rows * nvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % nvec);
-    long long m = i / nvec;
-    const int wo = static_cast<int>(m % Wo);
-    m /= Wo;
-    const int ho = static_cast<int>(m % Ho);
-    m /= Ho;
-    const int t = static_cast<int>(m % T);
-    const int n = static_cast<int>(m / T);
+  uint4* dst = reinterpret_cast<uint4*>(col) + ((static_cast<long long>(n) * T + t) * Ho + ho) * Wo * nvec;
+  for (int i = threadIdx.x; i < Wo * nvec; i += blockDim.x) {
+    const int v = i % nvec, wo = i / nvec;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = v * 8 + j;
       float val = 0.f;
       if (k < 147) {
-        const int ci = k / 49, rem = k % 49, kh = rem / 7, kw = rem % 7;
-        const int hi = 2 * ho + kh - 3, wi = 2 * wo + kw - 3;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-          val = __ldg(x + (((static_cast<long long>(n) * 3 + ci) * T + t) * H + hi) * W + wi);
+        const int r = k / 7, kw = k % 7;          // r = ci*7 + kh
+        val = rows[r][2 * wo + kw];               // wi + 3 = 2*wo + kw - 3 + 3
       }
       f[j] = val;
     }
-    reinterpret_cast<uint4*>(col)[i] = pack8(f);
+    dst[i] = pack8(f);
   }
 }
 
@@ -80,8 +91,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, int N, int T, in
 // partials layout: [nblocks][groups][2][Cp].
 constexpr int kSegVecs = 128;
 
+// Backward flavour: s0 = sum(dy), s1 = sum(dy * x) over RAW x; bn_bwd_finalize converts to sum(dy * xhat) =
+// invstd * (s1 - mean * s0) in double, so the streaming loop carries no per-channel statistics (registers ->
+// occupancy -> bytes in flight: this kernel ran at 45% of HBM peak with mean/invstd held per thread).
 template <bool kBackward>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(256, 4) bn_reduce_kernel(const uint4* __restrict__ a, const uint4* __restrict__ act,
                                                         const uint4* __restrict__ raw, long long rows_per_group, int Cp,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ mscale, const float* __restrict__ mshift,
@@ -98,16 +112,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
   if (rl < rows_per_pass) {
-    float mu[8], is[8], ms[8], mb[8];
-    if (kBackward) {
+    float ms[8], mb[8];
+    if (kBackward && mscale != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        mu[j] = mean[g * Cp + (seg0 + cv) * 8 + j];
-        is[j] = invstd[g * Cp + (seg0 + cv) * 8 + j];
-        if (mscale != nullptr) {
-          ms[j] = mscale[g * Cp + (seg0 + cv) * 8 + j];
-          mb[j] = mshift[g * Cp + (seg0 + cv) * 8 + j];
-        }
+        ms[j] = mscale[g * Cp + (seg0 + cv) * 8 + j];
+        mb[j] = mshift[g * Cp + (seg0 + cv) * 8 + j];
       }
     }
     const long long base = static_cast<long long>(g) * rows_per_group;
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s0[j] += d[j];
-          s1[j] += d[j] * ((x[j] - mu[j]) * is[j]);
+          s1[j] = fmaf(d[j], x[j], s1[j]);
         }
       }
     }
@@ -322,6 +332,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
                                                               long long rows_per_group, int C, int Cp,
                                                               const float* __restrict__ gamma,
+                                                              const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, int accumulate,
                                                               float* __restrict__ coef) {
@@ -340,6 +351,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
       cf[2 * Cp + c] = 0.f;
       continue;
     }
+    // partials hold sum(dy * x) over raw x: sum(dy * xhat) = invstd * (sum(dy*x) - mean * sum(dy))
+    sx = static_cast<double>(invstd[g * Cp + c]) * (sx - static_cast<double>(mean[g * Cp + c]) * s);
     const double n = static_cast<double>(rows_per_group);
     cf[c] = gamma[c] * invstd[g * Cp + c];
     cf[Cp + c] = static_cast<float>(s / n);
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 //   act != NULL            mask = act > 0            (block outputs: the pre-activation includes the residual)
 //   mscale != NULL         mask = raw*mscale + mshift > 0, the same fmaf the forward apply evaluated (saves the act read)
 //   neither                no ReLU behind this BatchNorm
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
                                                            const uint4* __restrict__ raw, int Cp, long long rows_per_group,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ coef, const float* __restrict__ mscale,
@@ -367,10 +380,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
   if (!t.active) return;
   const int nvec = Cp / 8;
   const int co = t.g * Cp + t.cvec * 8;
-  float mu[8], A[8], Bc[8], Cc[8], ms[8], mb[8];
+  float A[8], Bc[8], Cc[8], ms[8], mb[8];
   {
-    // g = c0*(dy - c1 - (x - mu)*istd*c2) = A*dy + Bc*(x - mu) + Cc
-    float is[8], c1[8], c2[8];
+    // g = c0*(dy - c1 - (x - mu)*istd*c2) = A*dy + Bc*x + Cc with Bc = -c0*c2*istd, Cc = -c0*c1 - Bc*mu
+    float mu[8], is[8], c1[8], c2[8];
     load8(mean + co, mu);
     load8(invstd + co, is);
     load8(coef + static_cast<long long>(t.g) * 3 * Cp + t.cvec * 8, A);
@@ -379,7 +392,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       Bc[j] = -A[j] * c2[j] * is[j];
-      Cc[j] = -A[j] * c1[j];
+      Cc[j] = -A[j] * c1[j] - Bc[j] * mu[j];
     }
   }
   if (mscale != nullptr) {
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     if (dz != nullptr) dz[i] = pack8(dy);
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dy[j], fmaf(Bc[j], x[j] - mu[j], Cc[j]));
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dy[j], fmaf(Bc[j], x[j], Cc[j]));
     gout[i] = pack8(o);
   }
 }
@@ -520,9 +533,11 @@ extern "C" int cstp_pack_weight(const float* w, int cout, int cin, int taps, int
 
 extern "C" int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void* col, int ldk, void* stream) {
   CSTP_REQUIRE(x && col && N > 0 && T > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
-  CSTP_REQUIRE(ldk >= 152 && ldk % 8 == 0);
-  const long long total = static_cast<long long>(N) * T * (H / 2) * (W / 2) * (ldk / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, N, T, H, W, reinterpret_cast<__nv_bfloat16*>(col), ldk);
+  CSTP_REQUIRE(ldk >= 152 && ldk % 8 == 0 && W <= kStemMaxW);
+  const long long blocks = static_cast<long long>(N) * T * (H / 2);
+  CSTP_REQUIRE(blocks < (1LL << 31));
+  stem_im2col_kernel<<<static_cast<unsigned>(blocks), 256, 0, ST(stream)>>>(x, N, T, H, W,
+                                                                           reinterpret_cast<__nv_bfloat16*>(col), ldk);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
@@ -578,11 +593,11 @@ extern "C" int cstp_bn_bwd_reduce(const void* d, const void* act, const void* ra
 }
 
 extern "C" int cstp_bn_bwd_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C,
-                                    int Cp, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
-                                    int accumulate, float* coef, void* stream) {
-  CSTP_REQUIRE(partials && gamma && invstd && coef && C <= Cp);
+                                    int Cp, const float* gamma, const float* mean, const float* invstd, float* dgamma,
+                                    float* dbeta, int accumulate, float* coef, void* stream) {
+  CSTP_REQUIRE(partials && gamma && mean && invstd && coef && C <= Cp);
   bn_bwd_finalize_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma,
-                                                                   invstd, dgamma, dbeta, accumulate, coef);
+                                                                  mean, invstd, dgamma, dbeta, accumulate, coef);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

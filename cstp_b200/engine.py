@@ -271,12 +271,15 @@ class StepEngine:
         wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
         rows = N * To * Ho * Wo
         flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
-        plan = _Timed(self, "conv_fwd", flops, [ops.conv_fwd_plan(x, wp, raw, geom)], tag)
         site = self._site(store, grads, bnname, cout, 2, rows // 2)
+        cplan = ops.conv_fwd_plan(x, wp, raw, geom, stats=site.st)
+        plan = _Timed(self, "conv_fwd", flops, [cplan], tag)
+        fused = cplan.stat_blocks       # > 0: the conv epilogue already produced the BatchNorm statistics partials
 
         def fwd():
             plan.run()
-            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM)
+            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
+                                 fused_blocks=fused)
             if apply:
                 ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_site.st if res_site else None)
         prog.append(fwd)

@@ -93,6 +93,7 @@ class ConvHaloDesc(C.Structure):
         ("bias", C.c_void_p),
         ("accumulate", C.c_int32),
         ("allow_resident", C.c_int32),
+        ("stats_partials", C.c_void_p),
     ]
 
 
@@ -128,6 +129,7 @@ SIGNATURES = {
     "cstp_conv_plan_destroy": (None, [_vp]),
     "cstp_conv_halo_plan_create": (_i, [C.POINTER(ConvHaloDesc), C.POINTER(_vp)]),
     "cstp_conv_halo_plan_resident": (_i, [_vp]),
+    "cstp_conv_halo_plan_stat_blocks": (_i, [_vp]),
     "cstp_conv_halo_plan_run": (_i, [_vp, _vp]),
     "cstp_conv_halo_plan_destroy": (None, [_vp]),
     "cstp_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),
@@ -145,7 +147,7 @@ SIGNATURES = {
     "cstp_bn_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cstp_bn_apply": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cstp_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "cstp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "cstp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "cstp_bn_bwd_apply": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cstp_avgpool_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "cstp_avgpool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

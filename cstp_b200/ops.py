@@ -173,6 +173,8 @@ class _Plan:
 
 
 class ConvPlan(_Plan):
+    stat_blocks: int = 0         # > 0: the kernel also produced BatchNorm statistics partials (that many blocks)
+
     def run(self):
         L.check(L.load().cstp_conv_plan_run(self.handle, _stream()))
 
@@ -222,6 +224,7 @@ def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out,
 
 class ConvHaloPlan(_Plan):
     resident: bool = False
+    stat_blocks: int = 0
 
     def run(self):
         L.check(L.load().cstp_conv_halo_plan_run(self.handle, _stream()))
@@ -230,7 +233,7 @@ class ConvHaloPlan(_Plan):
 SMEM_BUDGET = 232448 - 1024 - 256
 
 
-def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
+def conv_halo_layout(tile_space, taps, a_channels: int, Np: int, stats: bool = False):
     """Geometry of csrc/conv_halo.cu for a single-view (stride-1) tap list [(dw, dh, dt, k_off)], or None when the
     layer does not qualify (then csrc/conv_gemm.cu is used).  Pure shape arithmetic.
 
@@ -281,19 +284,20 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
     chunks = pad64(a_channels) // 64
     # N tile: keep all weight K-blocks resident when they fit beside 3 activation stages, splitting N in two if needed
     n_tile, resident = (Np if Np <= 256 else _default_n_tile(Np)), False
+    sb = 64 if stats else 0                  # fused-statistics accumulators: 64 bytes per output column of the N tile
     for cand in ([Np] if Np <= 256 else []) + ([pad16(math.ceil(Np / 2))] if Np > 64 else []):
-        if cand <= 256 and len(taps) * chunks * cand * 128 + 3 * a_bytes <= SMEM_BUDGET:
+        if cand <= 256 and len(taps) * chunks * cand * 128 + 3 * a_bytes + sb * cand <= SMEM_BUDGET:
             n_tile, resident = cand, True
             break
     if not resident:
         per_stage = a_bytes + max(g[4] for g in groups) * n_tile * 128
-        if 2 * per_stage > SMEM_BUDGET:
+        if 2 * per_stage + sb * n_tile > SMEM_BUDGET:
             return None
     return dict(box=box, halo=halo, groups=groups, taps=out_taps, n_tile=n_tile, a_bytes=a_bytes, resident=resident)
 
 
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
-                         accumulate, keep) -> ConvHaloPlan:
+                         accumulate, keep, stats=None) -> ConvHaloPlan:
     lib = L.load()
     d = L.ConvHaloDesc()
     d.amap = view
@@ -316,10 +320,15 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     d.bias = 0 if bias is None else bias.data_ptr()
     d.accumulate = int(accumulate)
     d.allow_resident = int(lay["resident"])
+    d.stats_partials = 0 if stats is None else stats.partials.data_ptr()
     h = C.c_void_p()
     L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
-    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep)
+    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep + ((stats.partials,) if stats is not None else ()))
     plan.resident = bool(lib.cstp_conv_halo_plan_resident(h))
+    if stats is not None:
+        plan.stat_blocks = lib.cstp_conv_halo_plan_stat_blocks(h)
+        if plan.stat_blocks * stats.groups * 2 * stats.Cp > stats.partials.numel():
+            raise L.CstpError("BatchNorm partials buffer too small for the fused statistics")
     return plan
 
 
@@ -327,8 +336,10 @@ HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill
 
 
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None,
-                  box=None, allow_halo: bool = True) -> ConvPlan:
-    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16."""
+                  box=None, allow_halo: bool = True, stats: "BNState | None" = None) -> ConvPlan:
+    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16.
+    With `stats` (two view groups) the kernel may also emit the BatchNorm statistics partials of `out`
+    (plan.stat_blocks > 0 tells the caller to skip the separate statistics pass)."""
     _require_cuda(x, w_packed, out, out_f32, bias)
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
@@ -341,10 +352,11 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
     taps = [(m, dw, dh, dt, ti * Kc) for (m, dw, dh, dt, ti) in taps]
     ostr = (Np, Wo * Np, Ho * Wo * Np, To * Ho * Wo * Np)
     if allow_halo and box is None and n_tile is None and len(views) == 1 and Ho * Wo >= HALO_MIN_POSITIONS:
-        lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np)
+        fuse = stats is not None and stats.groups == 2 and N % 2 == 0 and out is not None and not accumulate
+        lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np, stats=fuse)
         if lay is not None:
             return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, out_f32, 0, ostr, bias,
-                                        accumulate, (x, w_packed, out, out_f32, bias))
+                                        accumulate, (x, w_packed, out, out_f32, bias), stats=stats if fuse else None)
     box = box or pick_box(Wo, Ho, To, N, 128)
     return _make_conv_plan(views, taps, Ca, w_packed, Np, (Wo, Ho, To, N), box, out, out_f32, 0, ostr, bias, accumulate,
                            n_tile, (x, w_packed, out, out_f32, bias))
@@ -613,16 +625,22 @@ class BNState:
     def alloc(C_: int, Cp: int, groups: int, rows_per_group: int, device, backward: bool = True) -> "BNState":
         nb = bn_nblocks(rows_per_group, Cp)
         f = dict(dtype=torch.float32, device=device)
-        return BNState(C_, Cp, groups, nb, torch.empty(nb * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
+        # room for the fused-statistics path too: one partial row per CTA of a persistent conv kernel (<= 148)
+        return BNState(C_, Cp, groups, nb, torch.empty(max(nb, 160) * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * 3 * Cp, **f) if backward else None)
 
 
-def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1) -> None:
+def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1,
+                     fused_blocks: int = 0) -> None:
+    """Batch statistics of raw -> scale/shift/mean/invstd (+ running buffers).  fused_blocks > 0: the producing conv
+    kernel already wrote that many partial rows into st.partials (no statistics pass over raw)."""
     rows = raw.numel() // st.Cp
     lib = L.load()
-    L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
-    L.check(lib.cstp_bn_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp, _ptr(gamma),
+    nblocks = fused_blocks or st.nblocks
+    if not fused_blocks:
+        L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
+    L.check(lib.cstp_bn_finalize(_ptr(st.partials), nblocks, st.groups, rows // st.groups, st.C, st.Cp, _ptr(gamma),
                                  _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var), _ptr(st.scale),
                                  _ptr(st.shift), _ptr(st.mean), _ptr(st.invstd), _stream()))
 
@@ -648,7 +666,7 @@ def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=Non
     L.check(lib.cstp_bn_bwd_reduce(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean),
                                    _ptr(st.invstd), _ptr(ms), _ptr(mb), _ptr(st.partials), st.nblocks, _stream()))
     L.check(lib.cstp_bn_bwd_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp,
-                                     _ptr(gamma), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta), int(accumulate),
+                                     _ptr(gamma), _ptr(st.mean), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta), int(accumulate),
                                      _ptr(st.coef), _stream()))
     L.check(lib.cstp_bn_bwd_apply(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean), _ptr(st.invstd),
                                   _ptr(st.coef), _ptr(ms), _ptr(mb), _ptr(g_out), _ptr(dz), _stream()))

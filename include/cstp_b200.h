@@ -113,11 +113,16 @@ typedef struct {
   const float* bias;
   int32_t accumulate;
   int32_t allow_resident;
+  /* Optional fused BatchNorm statistics of the stored (bf16-rounded) output, two groups = the two halves of the N axis:
+   * fp32 [stat_blocks][2 groups][2: sum, sum of squares][Np], the partials layout cstp_bn_finalize consumes
+   * (nblocks = cstp_conv_halo_plan_stat_blocks).  Replaces a cstp_bn_stats pass over the output. */
+  float* stats_partials;
 } cstp_conv_halo_desc;
 
 typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;
 int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* desc, cstp_conv_halo_plan** plan);
 int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan);   /* 1 when the weights are kept in shared memory */
+int cstp_conv_halo_plan_stat_blocks(const cstp_conv_halo_plan* plan);
 int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream);
 void cstp_conv_halo_plan_destroy(cstp_conv_halo_plan* plan);
 
@@ -211,7 +216,8 @@ int cstp_bn_finalize(const float* partials, int nblocks, int groups, int64_t row
 int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, const float* scale, const float* shift,
                   int relu, int res_mode, const void* res, const float* scale2, const float* shift2, void* out,
                   void* stream);
-/* dy = d masked by the forward ReLU; partials of sum(dy), sum(dy*xhat) per (group, channel).  The mask is
+/* dy = d masked by the forward ReLU; partials of sum(dy), sum(dy*raw) per (group, channel) (cstp_bn_bwd_finalize turns
+ * the second into sum(dy*xhat)).  The mask is
  * act > 0 when `act` is given (block outputs, whose pre-activation includes the residual), else
  * raw*mask_scale + mask_shift > 0 when the forward affine coefficients are given (no read of act), else none. */
 int cstp_bn_bwd_reduce(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
@@ -220,8 +226,8 @@ int cstp_bn_bwd_reduce(const void* d, const void* act, const void* raw, int64_t 
 /* Reduces partials; writes dgamma/dbeta (summed over groups, optionally accumulated) and the apply coefficients
  * coef[g][3][Cp] = {gamma*invstd, sum(dy)/n, sum(dy*xhat)/n}. */
 int cstp_bn_bwd_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C, int Cp,
-                         const float* gamma, const float* invstd, float* dgamma, float* dbeta, int accumulate,
-                         float* coef, void* stream);
+                         const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                         int accumulate, float* coef, void* stream);
 /* g = c0*(dy - c1 - xhat*c2) (bf16), same masking as cstp_bn_bwd_reduce; optionally also writes dz = dy. */
 int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw, int64_t rows, int Cp, int groups,
                       const float* mean, const float* invstd, const float* coef, const float* mask_scale,
