@@ -332,6 +332,10 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     return plan
 
 
+# Fused BatchNorm statistics in the halo-conv epilogue (csrc/conv_halo.cu).  Measured at B=60: it removes 2.3 ms of
+# bn_reduce passes but the shuffle reduction makes the N=64 tiles epilogue-bound (+5 ms of conv time), so it stays
+# off until the epilogue reduction is restructured (profiles/README.md).
+FUSE_BN_STATS = False
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
 
 
@@ -352,7 +356,8 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
     taps = [(m, dw, dh, dt, ti * Kc) for (m, dw, dh, dt, ti) in taps]
     ostr = (Np, Wo * Np, Ho * Wo * Np, To * Ho * Wo * Np)
     if allow_halo and box is None and n_tile is None and len(views) == 1 and Ho * Wo >= HALO_MIN_POSITIONS:
-        fuse = stats is not None and stats.groups == 2 and N % 2 == 0 and out is not None and not accumulate
+        fuse = (FUSE_BN_STATS and stats is not None and stats.groups == 2 and N % 2 == 0 and out is not None
+                and not accumulate)
         lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np, stats=fuse)
         if lay is not None:
             return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, out_f32, 0, ostr, bias,
