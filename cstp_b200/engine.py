@@ -164,14 +164,14 @@ class _Timed:
         for p in self.plans:
             p.run(*args)
         b.record()
-        prof.append((self.kind, self.flops, len(self.plans), a, b, self.tag))
+        prof.append((self.kind, self.flops, len(self.plans), a, b, self.tag, ops.kernel_name(self.plans[0])))
 
 
 class StepEngine:
     """See the module docstring.  `B` is the per-GPU batch (samples; each sample is two views)."""
 
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", momentum_ema: float = 0.996,
-                 record: bool = False):
+                 record: bool = False, overlap: bool = True):
         if H % 2 or W % 2:
             raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
         self.B, self.T, self.H, self.W = B, T, H, W
@@ -179,6 +179,15 @@ class StepEngine:
         self.device = torch.device(device)
         self.momentum_ema = momentum_ema
         self.record = record
+        # Two-stream schedule (CUDA only): the target network's forward runs beside the online network's, and every
+        # weight-gradient GEMM runs beside the BatchNorm-backward streaming kernels of the next unit, so HBM-bound and
+        # tensor-bound kernels share the machine.  Results are unchanged (same kernels, same reduction orders).
+        self.overlap = bool(overlap) and self.device.type == "cuda"
+        if self.overlap:
+            self._s2 = torch.cuda.Stream(device=self.device)
+            self._ev_fwd, self._ev_tgt = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_g = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_wg = [torch.cuda.Event(), torch.cuda.Event()]
         self.named: dict[str, torch.Tensor] = {}      # name -> activation / gradient tensors (parity tests)
         self.units: list[dict] = []                   # every conv+BN unit in build order (parity tests, profiling)
         self._prof = None                             # list of (kind, flops, launches, ev0, ev1) while profiling
@@ -300,7 +309,7 @@ class StepEngine:
         holder = {}
 
         def prepare():
-            g = self._g[:raw.numel()].view(raw.shape)
+            g = self._gbufs[holder["gbuf"]][:raw.numel()].view(raw.shape)
             holder["g"] = g
             holder["wg"] = _Timed(self, "wgrad", unit["flops"],
                                   [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg)], unit["tag"])
@@ -319,15 +328,28 @@ class StepEngine:
 
         def bwd():
             g = holder["g"]
+            if self.overlap and self._prof is None:
+                # the weight-gradient GEMM that last read this d(raw) buffer (two units ago) must have finished
+                torch.cuda.current_stream().wait_event(self._ev_wg[holder["gbuf"]])
             ops.bn_backward(d_out, act_for_mask, raw, site.st, site.gamma, site.dgamma, site.dbeta, g, dz=dz,
                             mask_from_raw=from_raw)
-            if self.record:      # parity tests: the shared d(raw) scratch is overwritten by the next unit
+            if self.record:      # parity tests: the shared d(raw) scratch is overwritten by a later unit
                 self.named[unit["tag"] + ".g"] = g.clone()
-            holder["wg"].run(dw)
+            if self.overlap and self._prof is None:
+                b = holder["gbuf"]
+                main = torch.cuda.current_stream()
+                self._ev_g[b].record(main)
+                with torch.cuda.stream(self._s2):
+                    self._s2.wait_event(self._ev_g[b])
+                    holder["wg"].run(dw)
+                    self._ev_wg[b].record(self._s2)
+            else:
+                holder["wg"].run(dw)
             if not unit["skip_dgrad"]:
                 if holder["zero"]:
                     holder["dx"].zero_()
                 holder["dg"].run()
+        bwd.holder = holder
         return bwd
 
     @staticmethod
@@ -541,7 +563,16 @@ class StepEngine:
         bw.append(lambda: ops.avgpool_bwd(self.dfeat, d_x5, dcat=self.dcat))
         bw.extend(reversed(bw_backbone))
         # ---------------- shared scratch + deferred plan creation
-        self._g = self._act(self._g_numel)
+        # d(raw) scratch: two buffers, alternating in RUN order, so that a unit's weight-gradient GEMM (side stream) can
+        # still read its d(raw) while the next unit's BatchNorm backward writes the other buffer
+        turn = 0
+        for op in self.bwd:
+            h = getattr(op, "holder", None)
+            if h is not None:
+                h["gbuf"] = turn
+                turn ^= 1 if self.overlap else 0
+        self._gbufs = [self._act(self._g_numel)]
+        self._gbufs.append(self._act(self._g_numel) if self.overlap else self._gbufs[0])
         self._wg = torch.zeros(self._wg_numel, **f32)
         for fn in self._deferred:
             fn()
@@ -575,11 +606,24 @@ class StepEngine:
         if repack_online:
             self.pack_online()
         self.load_clips(x1, x2)
-        for op in self.fwd_online:
-            op()
-        self.ema()
-        for op in self.fwd_target:
-            op()
+        if self.overlap and self._prof is None:
+            main = torch.cuda.current_stream()
+            self._ev_fwd.record(main)
+            with torch.cuda.stream(self._s2):
+                self._s2.wait_event(self._ev_fwd)
+                self.ema()                       # reads the online weights, which nothing writes during the forward
+                for op in self.fwd_target:
+                    op()
+                self._ev_tgt.record(self._s2)
+            for op in self.fwd_online:
+                op()
+            main.wait_event(self._ev_tgt)
+        else:
+            for op in self.fwd_online:
+                op()
+            self.ema()
+            for op in self.fwd_target:
+                op()
         ops.byol_loss(self.pred, self.tproj, self.B, 512, self.losses[7:8], None, self.dpred)
         for op in self.fwd_heads:
             op()
@@ -592,6 +636,10 @@ class StepEngine:
     def backward(self):
         for op in self.bwd:
             op()
+        if self.overlap and self._prof is None:
+            main = torch.cuda.current_stream()
+            main.wait_event(self._ev_wg[0])
+            main.wait_event(self._ev_wg[1])
 
     def optimizer_step(self, lr, momentum=0.9, wd=5e-4, max_norm=18.0, clip=True):
         """clip_grad_norm_ + SGD.step (main_byol.py:88-91,229-232) on the flat buffers, then re-pack the bf16 weights."""
@@ -603,7 +651,8 @@ class StepEngine:
 
     def profile_tensor_launches(self, x1, x2):
         """Runs one forward + backward with CUDA events around every backbone tensor-core launch group.
-        Returns {kind: (ms, algorithmic FLOPs, launches)} for kind in conv_fwd / conv_dgrad / wgrad."""
+        Returns {kind: (ms, algorithmic FLOPs, launches)} for kind in conv_fwd / conv_dgrad / wgrad; the per-group
+        records (kind, layer tag, ms, FLOPs, launches, kernel name) are kept in self.last_profile."""
         self._prof = []
         try:
             self.forward(x1, x2)
@@ -611,10 +660,10 @@ class StepEngine:
             torch.cuda.synchronize()
             out: dict = {}
             self.last_profile = []          # per launch group: (kind, tag, ms, flops, launches)
-            for kind, flops, n, a, b, tag in self._prof:
+            for kind, flops, n, a, b, tag, kernel in self._prof:
                 ms, fl, cnt = out.get(kind, (0.0, 0.0, 0))
                 out[kind] = (ms + a.elapsed_time(b), fl + flops, cnt + n)
-                self.last_profile.append((kind, tag, a.elapsed_time(b), flops, n))
+                self.last_profile.append((kind, tag, a.elapsed_time(b), flops, n, kernel))
         finally:
             self._prof = None
         return out

@@ -736,5 +736,12 @@ def sgd_clip_step(p, g, mom, lr, momentum, wd, max_norm, do_clip, first_step, no
                                         _stream()))
 
 
+def kernel_name(plan) -> str:
+    """CUDA kernel a plan object launches (for profiles and the bench roofline)."""
+    inner = getattr(plan, "plan", plan)          # WgradSpec wraps its plan
+    return {ConvHaloPlan: "conv_halo_kernel", ConvPlan: "conv_gemm_kernel", WgradHaloPlan: "wgrad_halo_kernel",
+            WgradPlan: "wgrad_gemm_kernel"}.get(type(inner), type(inner).__name__)
+
+
 def launch_count() -> int:
     return int(L.load().cstp_launch_count())

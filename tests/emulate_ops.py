@@ -34,6 +34,10 @@ def launch_count():
     return _launches
 
 
+def kernel_name(plan):
+    return "emulated"
+
+
 class _Plan:
     stat_blocks = 0
 

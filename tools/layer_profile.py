@@ -19,8 +19,8 @@ torch.cuda.synchronize()
 eng = m._engine
 eng.profile_tensor_launches(x1, x2)
 tot = {}
-for kind, tag, ms, fl, n in eng.last_profile:
-    print(f"{kind:11s} {tag:45s} {ms:8.3f} ms {fl / ms / 1e9:8.1f} TF/s  x{n}")
+for kind, tag, ms, fl, n, kern in eng.last_profile:
+    print(f"{kind:11s} {tag:45s} {ms:8.3f} ms {fl / ms / 1e9:8.1f} TF/s  x{n} {kern}")
     k = tot.setdefault(kind, [0.0, 0.0])
     k[0] += ms
     k[1] += fl
