@@ -93,8 +93,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // Roles run warp-converged with one elected issuing lane (see conv_halo.cu: a single-lane branch makes every
+  // UTCHMMA pay an ELECT / R2UR round trip).
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -103,11 +106,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const cstp_tap tap = p.taps[t];
         for (int c = 0; c < p.chunks_per_tap; ++c) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          mbar_expect_tx(&full[stage], kABytes + p.b_bytes);
-          tma_load_5d(sa, &p.amap[tap.map_id], &full[stage], c * 64, tc.w0 + tap.dw, tc.h0 + tap.dh, tc.t0 + tap.dt,
-                      tc.n0);
-          tma_load_2d(sa + kABytes, &p.bmap, &full[stage], tap.k_off + c * 64, tc.ntile * p.n_tile);
+          if (leader) {
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            mbar_expect_tx(&full[stage], kABytes + p.b_bytes);
+            tma_load_5d(sa, &p.amap[tap.map_id], &full[stage], c * 64, tc.w0 + tap.dw, tc.h0 + tap.dh, tc.t0 + tap.dt,
+                        tc.n0);
+            tma_load_2d(sa + kABytes, &p.bmap, &full[stage], tap.k_off + c * 64, tc.ntile * p.n_tile);
+          }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -115,8 +121,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -134,19 +141,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int c = 0; c < p.chunks_per_tap; ++c, ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
-          const uint64_t da = umma_desc_at(dhi, a_addr);
-          const uint64_t db = umma_desc_at(dhi, a_addr + kABytes);
-          umma_bf16(d_tmem, da, db, p.idesc, kb != 0 ? 1u : 0u);
-          if (c != p.chunks_per_tap - 1 || p.last_ksteps == 4) {
-            umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
-            umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
-            umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
-          } else {
-            for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
+          if (leader) {
+            const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+            const uint64_t da = umma_desc_at(dhi, a_addr);
+            const uint64_t db = umma_desc_at(dhi, a_addr + kABytes);
+            umma_bf16(d_tmem, da, db, p.idesc, kb != 0 ? 1u : 0u);
+            if (c != p.chunks_per_tap - 1 || p.last_ksteps == 4) {
+              umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
+              umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
+              umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
+            } else {
+              for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
+            }
+            umma_commit(&empty[stage]);
+            if (kb == kblocks - 1) umma_commit(&tfull[as]);
           }
-          umma_commit(&empty[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;

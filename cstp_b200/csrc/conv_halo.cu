@@ -94,9 +94,14 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // Roles run WARP-CONVERGED: all 32 lanes walk the loops and poll the mbarriers, one elected lane issues the TMA /
+  // tcgen05 instructions.  (With a single-lane branch the compiler cannot keep descriptors and addresses in uniform
+  // registers and wraps every UTCHMMA in an ELECT / R2UR loop: the issuer then ran at ~25 cycles per instruction and
+  // the N=64 layers sat at 19% tensor-pipe activity, ncu r01_conv_halo.)
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (p.resident) {
+    const bool leader = elect_one();
+    if (p.resident && leader) {
       mbar_expect_tx(bfull, p.res_bytes);
       for (int t = 0; t < p.n_taps; ++t)
         for (int c = 0; c < p.chunks; ++c)
@@ -118,14 +123,17 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
         const HcGroup gr = p.groups[g];
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          uint8_t* st = stage0 + static_cast<size_t>(stage) * p.stage_bytes;
-          mbar_expect_tx(&full[stage], p.a_bytes + (p.resident ? 0u : static_cast<uint32_t>(gr.n_taps) * p.b_bytes));
-          tma_load_5d(st, &p.amap, &full[stage], c * 64, w0 + gr.dw, h0 + gr.dh, t0 + gr.dt, n0);
-          if (!p.resident) {
-            for (int j = 0; j < gr.n_taps; ++j)
-              tma_load_2d(st + p.a_bytes + static_cast<size_t>(j) * p.b_bytes, &p.bmap, &full[stage],
-                          p.taps[gr.first_tap + j].k_off + c * 64, ntile * p.n_tile);
+          if (leader) {
+            uint8_t* st = stage0 + static_cast<size_t>(stage) * p.stage_bytes;
+            mbar_expect_tx(&full[stage], p.a_bytes + (p.resident ? 0u : static_cast<uint32_t>(gr.n_taps) * p.b_bytes));
+            tma_load_5d(st, &p.amap, &full[stage], c * 64, w0 + gr.dw, h0 + gr.dh, t0 + gr.dt, n0);
+            if (!p.resident) {
+              for (int j = 0; j < gr.n_taps; ++j)
+                tma_load_2d(st + p.a_bytes + static_cast<size_t>(j) * p.b_bytes, &p.bmap, &full[stage],
+                            p.taps[gr.first_tap + j].k_off + c * 64, ntile * p.n_tile);
+            }
           }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -133,8 +141,9 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
     if (p.resident) {
       mbar_wait(bfull, 0);
       tc_fence_after();
@@ -157,25 +166,30 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const bool full_chunk = (c != p.chunks - 1) || p.last_ksteps == 4;
-          for (int j = 0; j < gr.n_taps; ++j) {
-            const int t = gr.first_tap + j;
-            const uint64_t da = umma_desc_at(dhi, s_addr + p.taps[t].a_shift);
-            const uint64_t db = umma_desc_at(dhi, p.resident ? res_addr + static_cast<uint32_t>(t * p.chunks + c) * p.b_bytes
-                                                             : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes);
-            umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
-            first = 0;
-            if (full_chunk) {
-              umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
-              umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
-              umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
-            } else {
-              for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
+          if (leader) {
+            const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
+            const bool full_chunk = (c != p.chunks - 1) || p.last_ksteps == 4;
+            for (int j = 0; j < gr.n_taps; ++j) {
+              const int t = gr.first_tap + j;
+              const uint64_t da = umma_desc_at(dhi, s_addr + p.taps[t].a_shift);
+              const uint64_t db =
+                  umma_desc_at(dhi, p.resident ? res_addr + static_cast<uint32_t>(t * p.chunks + c) * p.b_bytes
+                                               : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes);
+              umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
+              first = 0;
+              if (full_chunk) {
+                umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
+                umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
+                umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
+              } else {
+                for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
+              }
             }
+            umma_commit(&empty[stage]);
+            if (g == p.n_groups - 1 && c == p.chunks - 1) umma_commit(&tfull[as]);
           }
-          umma_commit(&empty[stage]);
-          if (g == p.n_groups - 1 && c == p.chunks - 1) umma_commit(&tfull[as]);
+          first = 0;
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;

@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // Roles run warp-converged with one elected issuing lane (see conv_halo.cu).
+  if (warp == 0) {
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     const cstp_mchunk mc0 = p.mchunks[chunk0];
@@ -84,20 +86,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
       pt /= p.tiles_t;
       const int n0 = pt * p.bn;
       mbar_wait(&empty[stage], phase ^ 1u);
-      uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-      mbar_expect_tx(&full[stage], static_cast<uint32_t>(nchunks + p.n_gboxes) * kBoxBytes);
-      tma_load_5d(sa, &p.amap[mc0.map_id], &full[stage], mc0.c_off, w0 + mc0.dw, h0 + mc0.dh, t0 + mc0.dt, n0);
-      if (nchunks > 1)
-        tma_load_5d(sa + kBoxBytes, &p.amap[mc1.map_id], &full[stage], mc1.c_off, w0 + mc1.dw, h0 + mc1.dh,
-                    t0 + mc1.dt, n0);
-      for (int j = 0; j < p.n_gboxes; ++j)
-        tma_load_5d(sa + a_bytes + j * kBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
+      if (leader) {
+        uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+        mbar_expect_tx(&full[stage], static_cast<uint32_t>(nchunks + p.n_gboxes) * kBoxBytes);
+        tma_load_5d(sa, &p.amap[mc0.map_id], &full[stage], mc0.c_off, w0 + mc0.dw, h0 + mc0.dh, t0 + mc0.dt, n0);
+        if (nchunks > 1)
+          tma_load_5d(sa + kBoxBytes, &p.amap[mc1.map_id], &full[stage], mc1.c_off, w0 + mc1.dw, h0 + mc1.dh,
+                      t0 + mc1.dt, n0);
+        for (int j = 0; j < p.n_gboxes; ++j)
+          tma_load_5d(sa + a_bytes + j * kBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
+      }
+      __syncwarp();
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1u;
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t smem_addr0 = smem_u32(smem);
@@ -105,17 +111,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
-      // MN-major, 128B swizzle: 16 K-rows per step = 2048 B (+128 in the address field); LBO = next 64-channel chunk,
-      // SBO = next 8 K-rows.
-      const uint64_t da = umma_desc_at(dhi, a_addr);
-      const uint64_t db = umma_desc_at(dhi, a_addr + a_bytes);
-      umma_bf16(tmem_base, da, db, p.idesc, kb > kb_begin ? 1u : 0u);
-      umma_bf16_acc(tmem_base, da + 128, db + 128, p.idesc);
-      umma_bf16_acc(tmem_base, da + 256, db + 256, p.idesc);
-      umma_bf16_acc(tmem_base, da + 384, db + 384, p.idesc);
-      umma_commit(&empty[stage]);
-      if (kb == kb_end - 1) umma_commit(tfull);
+      if (leader) {
+        const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+        // MN-major, 128B swizzle: 16 K-rows per step = 2048 B (+128 in the address field); LBO = next 64-channel
+        // chunk, SBO = next 8 K-rows.
+        const uint64_t da = umma_desc_at(dhi, a_addr);
+        const uint64_t db = umma_desc_at(dhi, a_addr + a_bytes);
+        umma_bf16(tmem_base, da, db, p.idesc, kb > kb_begin ? 1u : 0u);
+        umma_bf16_acc(tmem_base, da + 128, db + 128, p.idesc);
+        umma_bf16_acc(tmem_base, da + 256, db + 256, p.idesc);
+        umma_bf16_acc(tmem_base, da + 384, db + 384, p.idesc);
+        umma_commit(&empty[stage]);
+        if (kb == kb_end - 1) umma_commit(tfull);
+      }
+      __syncwarp();
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1u;

@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // Roles run warp-converged with one elected issuing lane (see conv_halo.cu).
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -96,22 +98,26 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
       pt /= p.tiles_t;
       const int n0 = pt * p.bn;
       mbar_wait(&empty[stage], phase ^ 1u);
-      uint8_t* st = smem + static_cast<size_t>(stage) * p.stage_bytes;
-      mbar_expect_tx(&full[stage], x_bytes + static_cast<uint32_t>(p.n_gboxes) * kGBoxBytes);
-      for (int b = 0; b < p.n_xboxes; ++b) {
-        const WhXBox xb = p.xboxes[b];
-        tma_load_5d(st + static_cast<size_t>(b) * p.xbox_bytes, &p.xmap, &full[stage], xb.c_off, w0 + xb.dw, h0 + xb.dh,
-                    t0 + xb.dt, n0);
+      if (leader) {
+        uint8_t* st = smem + static_cast<size_t>(stage) * p.stage_bytes;
+        mbar_expect_tx(&full[stage], x_bytes + static_cast<uint32_t>(p.n_gboxes) * kGBoxBytes);
+        for (int b = 0; b < p.n_xboxes; ++b) {
+          const WhXBox xb = p.xboxes[b];
+          tma_load_5d(st + static_cast<size_t>(b) * p.xbox_bytes, &p.xmap, &full[stage], xb.c_off, w0 + xb.dw, h0 + xb.dh,
+                      t0 + xb.dt, n0);
+        }
+        for (int j = 0; j < p.n_gboxes; ++j)
+          tma_load_5d(st + x_bytes + j * kGBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
       }
-      for (int j = 0; j < p.n_gboxes; ++j)
-        tma_load_5d(st + x_bytes + j * kGBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
+      __syncwarp();
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1u;
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: n_mtiles accumulators per K-block
+    const bool leader = elect_one();
     const uint32_t smem_addr0 = smem_u32(smem);
     const uint64_t dhi_b = umma_desc_hi(kGBoxBytes, 1024);
     int stage = 0;
@@ -119,33 +125,25 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
-      const uint64_t db = umma_desc_at(dhi_b, s_addr + x_bytes);
-      // MN-major, 128B swizzle: 16 K-rows (positions) per step = 2048 B (+128 in the address field); LBO = next
-      // 64-channel block of the M (resp. N) axis, SBO = next 8 K-rows.
-      if (kb > kb_begin) {
+      if (leader) {
+        const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
+        const uint64_t db = umma_desc_at(dhi_b, s_addr + x_bytes);
+        // MN-major, 128B swizzle: 16 K-rows (positions) per step = 2048 B (+128 in the address field); LBO = next
+        // 64-channel block of the M (resp. N) axis, SBO = next 8 K-rows.
+        const uint32_t acc = kb > kb_begin ? 1u : 0u;
         for (int mt = 0; mt < p.n_mtiles; ++mt) {
           const WhMtile m = p.mtiles[mt];
           const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, 1024), s_addr + m.a_off);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
-          umma_bf16_acc(d_tmem, da, db, p.idesc);
+          umma_bf16(d_tmem, da, db, p.idesc, acc);
           umma_bf16_acc(d_tmem, da + 128, db + 128, p.idesc);
           umma_bf16_acc(d_tmem, da + 256, db + 256, p.idesc);
           umma_bf16_acc(d_tmem, da + 384, db + 384, p.idesc);
         }
-      } else {
-        for (int mt = 0; mt < p.n_mtiles; ++mt) {
-          const WhMtile m = p.mtiles[mt];
-          const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, 1024), s_addr + m.a_off);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
-          umma_bf16(d_tmem, da, db, p.idesc, 0u);
-          umma_bf16_acc(d_tmem, da + 128, db + 128, p.idesc);
-          umma_bf16_acc(d_tmem, da + 256, db + 256, p.idesc);
-          umma_bf16_acc(d_tmem, da + 384, db + 384, p.idesc);
-        }
+        umma_commit(&empty[stage]);
+        if (kb == kb_end - 1) umma_commit(tfull);
       }
-      umma_commit(&empty[stage]);
-      if (kb == kb_end - 1) umma_commit(tfull);
+      __syncwarp();
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1u;
