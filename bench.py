@@ -80,6 +80,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_config(B: int, world: int) -> dict:
+    """`config` of the JSON line -- identical for the native and the reference arm."""
+    return {"workload": f"r21d_byol UCF-101-shaped pretrain step (UcfRepreBYOLSpPre shape), batch {B}/GPU, "
+                        "2 views x 3x16x112x112, loss_weight 0.1 1 1 1 1, SGD lr 0.03 m 0.9 wd 5e-4 clip 18",
+            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "bn": "per-GPU (reference semantics)"}
+
+
 def run_reference(args, rank: int):
     """The reference's CPU implementation of the step (its algorithm restated in oracle/cstp_oracle.py -- the Python
     reference itself is not installable and does not travel to the GPU box), all host threads, bounded sample."""
@@ -110,7 +118,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": v, "unit": "clips/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"r21d_byol UCF-101-shaped pretrain step, batch {args.batch}/GPU, 16x112x112 (CPU sample batch {Bs})"},
+        "config": workload_config(args.batch, args.gpus),
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -273,11 +281,9 @@ def main():
         "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"r21d_byol UCF-101-shaped pretrain step (UcfRepreBYOLSpPre shape), batch {B}/GPU, "
-                               "2 views x 3x16x112x112, loss_weight 0.1 1 1 1 1, SGD lr 0.03 m 0.9 wd 5e-4 clip 18",
-                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "bn": "per-GPU (reference semantics)",
+        "config": {**workload_config(B, world),
                    "l2_policy": "inputs and activations far larger than the 126 MB L2 (clips alone 2x%.0f MB)" % (x1.numel() * 4 / 1e6),
-                   "views_per_s": 2 * value},
+                   "views_per_s": 2 * value, "schedule": "two streams (target fwd || online fwd, wgrad || BN backward)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
