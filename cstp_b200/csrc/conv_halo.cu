@@ -15,8 +15,7 @@
 
 namespace cstp {
 
-constexpr int kHcThreads = 384;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
-constexpr int kHcEpiWarps = 8;
+constexpr int kHcThreads = 256;
 constexpr int kHcMaxStages = 8;
 constexpr int kHcSmemLimit = 232448;
 constexpr int kHcMaxGroups = 4;
@@ -47,7 +46,7 @@ struct ConvHaloKParams {
   const float* bias;
   long long out_off, osw, osh, ost, osn;
   float* stats;            // optional fused BatchNorm statistics: partials [gridDim.x][2 groups][2][Np]
-  uint32_t stats_bytes;    // shared-memory accumulators [8 warps][2 groups][2][n_tile] floats (0 = disabled)
+  uint32_t stats_bytes;    // shared-memory accumulators [4 warps][2 groups][2][n_tile] floats (0 = disabled)
   HcGroup groups[kHcMaxGroups];
   HcTap taps[kHcMaxTaps];
 };
@@ -81,7 +80,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], kHcEpiWarps);
+      mbar_init(&tempty[a], 4);
     }
     mbar_init(bfull, 1);
     fence_mbar_init();
@@ -199,10 +198,8 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: 8 warps.  Warp e owns TMEM lanes
-    // 32*(e%4).. (one output row per lane) and the 32-column chunks k with k % 2 == e / 4.
-    const int e = warp - 4;
-    const int q = e & 3, hc = e >> 2;
+    // ------------------------------------------------------------ epilogue (warp w owns TMEM lanes 32*(w%4)..)
+    const int q = warp - 4;
     const int row = q * 32 + lane;
     const int rw = row % p.bw;
     const int rh = (row / p.bw) % p.bh;
@@ -210,8 +207,8 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     const int rn = row / (p.bw * p.bh * p.bt);
     const int col0 = ntile * p.n_tile;
     const int ncols = min(p.n_tile, p.Np - col0);
-    // fused BatchNorm statistics: this warp's accumulators [group][sum | sumsq][n_tile] (only its own columns are used)
-    float* wacc = sacc + static_cast<size_t>(e) * 4 * p.n_tile;
+    // fused BatchNorm statistics: this warp's accumulators [group][sum | sumsq][n_tile]; lane l owns column c0 + (l>>1)
+    float* wacc = sacc + static_cast<size_t>(q) * 4 * p.n_tile;
     if (p.stats != nullptr) {
       for (int i = lane; i < 4 * p.n_tile; i += 32) wacc[i] = 0.f;
       __syncwarp();
@@ -235,97 +232,83 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
-      for (int c0 = hc * 32; c0 < ncols; c0 += 64) {
-        const int width = min(32, ncols - c0);          // 32, or 16 for the tail of an N tile that is 16 mod 32
-        uint32_t v[32];
-        if (width == 32) {
-          tmem_ld32(taddr + c0, v);
-        } else {
-          uint32_t v16[16];
-          tmem_ld16(taddr + c0, v16);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (p.stats != nullptr) {
+          // per-column sum / sum of squares over this warp's 32 rows of the values AS STORED (bf16-rounded), by a
+          // reduce-scatter butterfly: 16 -> 8 -> 4 -> 2 -> 1 columns per lane, then the lane pair is combined
+          float a[16], b[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            v[i] = v16[i];
-            v[i + 16] = 0u;
+            const float r = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
+            a[i] = r;
+            b[i] = r * r;
+          }
+#pragma unroll
+          for (int half = 8, m = 16; half >= 1; half >>= 1, m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+              const float sa = up ? a[i] : a[i + half], ka = up ? a[i + half] : a[i];
+              const float sb = up ? b[i] : b[i + half], kb = up ? b[i + half] : b[i];
+              a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, m);
+              b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, m);
+            }
+          }
+          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+          b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
+          if ((lane & 1) == 0) {
+            gacc[c0 + (lane >> 1)] += a[0];
+            gacc[p.n_tile + c0 + (lane >> 1)] += b[0];
           }
         }
-        tmem_ld_wait();
-        float f[32];
+        if (valid) {
+          float f[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias != nullptr) {
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < width) f[i] += __ldg(p.bias + col0 + c0 + i);
-        }
-        if (p.out != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
-          if (p.accumulate && valid) {
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + col0 + c0 + i);
+          }
+          if (p.out != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+            if (p.accumulate) {
+              const uint4 o0 = dst[0], o1 = dst[1];
+              const uint32_t o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (i * 8 < width) {
-                const uint4 o = dst[i];
-                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  f[i * 8 + 2 * j] += bf16_lo(ow[j]);
-                  f[i * 8 + 2 * j + 1] += bf16_hi(ow[j]);
-                }
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += bf16_lo(o[i]);
+                f[2 * i + 1] += bf16_hi(o[i]);
               }
             }
+            uint4 s0, s1;
+            s0.x = pack_bf16x2(f[0], f[1]);
+            s0.y = pack_bf16x2(f[2], f[3]);
+            s0.z = pack_bf16x2(f[4], f[5]);
+            s0.w = pack_bf16x2(f[6], f[7]);
+            s1.x = pack_bf16x2(f[8], f[9]);
+            s1.y = pack_bf16x2(f[10], f[11]);
+            s1.z = pack_bf16x2(f[12], f[13]);
+            s1.w = pack_bf16x2(f[14], f[15]);
+            dst[0] = s0;
+            dst[1] = s1;
           }
-          uint32_t pk[16];
+          if (p.out_f32 != nullptr) {
+            float4* dstf = reinterpret_cast<float4*>(p.out_f32 + off + c0);
+            if (p.accumulate && p.out == nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i * 8 < width) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          }
-          if (p.stats != nullptr) {
-            // Per-column sum / sum of squares over this warp's 32 rows of the values AS STORED (bf16-rounded), by a
-            // reduce-scatter butterfly: 32 -> 16 -> 8 -> 4 -> 2 -> 1 columns per lane; lane l ends with column c0 + l.
-            float a[32], b[32];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float lo = valid ? bf16_lo(pk[i]) : 0.f, hi = valid ? bf16_hi(pk[i]) : 0.f;
-              a[2 * i] = lo;
-              a[2 * i + 1] = hi;
-              b[2 * i] = lo * lo;
-              b[2 * i + 1] = hi * hi;
-            }
-#pragma unroll
-            for (int half = 16, m = 16; half >= 1; half >>= 1, m >>= 1) {
-              const bool up = (lane & m) != 0;
-#pragma unroll
-              for (int i = 0; i < half; ++i) {
-                const float sa = up ? a[i] : a[i + half], ka = up ? a[i + half] : a[i];
-                const float sb = up ? b[i] : b[i + half], kb = up ? b[i + half] : b[i];
-                a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, m);
-                b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, m);
+              for (int i = 0; i < 4; ++i) {
+                const float4 o = dstf[i];
+                f[4 * i] += o.x;
+                f[4 * i + 1] += o.y;
+                f[4 * i + 2] += o.z;
+                f[4 * i + 3] += o.w;
               }
             }
-            if (lane < width) {
-              gacc[c0 + lane] += a[0];
-              gacc[p.n_tile + c0 + lane] += b[0];
-            }
-          }
-        }
-        if (p.out_f32 != nullptr && valid) {
-          float4* dstf = reinterpret_cast<float4*>(p.out_f32 + off + c0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i * 4 < width) {
-              float4 o = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-              if (p.accumulate && p.out == nullptr) {
-                const float4 prev = dstf[i];
-                o.x += prev.x;
-                o.y += prev.y;
-                o.z += prev.z;
-                o.w += prev.w;
-              }
-              dstf[i] = o;
-            }
+            for (int i = 0; i < 4; ++i) dstf[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           }
         }
       }
@@ -334,17 +317,15 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
     if (p.stats != nullptr) {
-      // combine the warps of the four lane quadrants in fixed order and publish this CTA's partial row (deterministic)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int eid = e * 32 + lane;
-      for (int c = eid; c < ncols; c += 256) {
-        const int owner_half = (c >> 5) & 1;              // which half of the epilogue warps accumulated column c
+      // combine the four warps in fixed order and publish this CTA's partial row (deterministic, no atomics)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = q * 32 + lane;
+      for (int c = e; c < ncols; c += 128) {
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {                  // gq = group*2 + (0: sum, 1: sum of squares)
+        for (int gq = 0; gq < 4; ++gq) {      // gq = group*2 + (0: sum, 1: sum of squares)
           float sum = 0.f;
 #pragma unroll
-          for (int wq = 0; wq < 4; ++wq)
-            sum += sacc[(static_cast<size_t>(owner_half * 4 + wq) * 4 + gq) * p.n_tile + c];
+          for (int wq = 0; wq < 4; ++wq) sum += sacc[(static_cast<size_t>(wq) * 4 + gq) * p.n_tile + c];
           p.stats[(static_cast<long long>(blockIdx.x) * 4 + gq) * p.Np + col0 + c] = sum;
         }
       }
@@ -438,7 +419,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.bias = d->bias;
   k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
   k.stats = d->stats_partials;
-  k.stats_bytes = d->stats_partials != nullptr ? 128u * static_cast<uint32_t>(d->n_tile) : 0u;
+  k.stats_bytes = d->stats_partials != nullptr ? 64u * static_cast<uint32_t>(d->n_tile) : 0u;
   if (d->stats_partials != nullptr && (d->bn != 1 || d->Nt % 2 != 0)) {
     delete plan;
     return fail_inval("fused statistics need bn == 1 and an even N (two views)");

@@ -285,7 +285,7 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int, stats: bool = F
     chunks = pad64(a_channels) // 64
     # N tile: keep all weight K-blocks resident when they fit beside 3 activation stages, splitting N in two if needed
     n_tile, resident = (Np if Np <= 256 else _default_n_tile(Np)), False
-    sb = 128 if stats else 0                 # fused-statistics accumulators: 128 bytes per output column of the N tile
+    sb = 64 if stats else 0                  # fused-statistics accumulators: 64 bytes per output column of the N tile
     for cand in ([Np] if Np <= 256 else []) + ([pad16(math.ceil(Np / 2))] if Np > 64 else []):
         if cand <= 256 and len(taps) * chunks * cand * 128 + 3 * a_bytes + sb * cand <= SMEM_BUDGET:
             n_tile, resident = cand, True
@@ -333,9 +333,10 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     return plan
 
 
-# Fused BatchNorm statistics in the halo-conv epilogue (csrc/conv_halo.cu).  Measured at B=60: it removes 2.3 ms of
-# bn_reduce passes but the shuffle reduction makes the N=64 tiles epilogue-bound (+5 ms of conv time), so it stays
-# off until the epilogue reduction is restructured (profiles/README.md).
+# Fused BatchNorm statistics in the halo-conv epilogue (csrc/conv_halo.cu), opt-in with CSTP_FUSE_BN_STATS=1.
+# Measured at B=60 (two variants: 4 epilogue warps / 16-column loads, and 8 warps / 32-column loads): it removes 2.3 ms
+# of bn_reduce passes but costs more than that in the conv kernels (shuffle reduction in the epilogue, and the
+# accumulators push the 64->144 spatial conv out of its resident-weights configuration), so it is off by default.
 FUSE_BN_STATS = os.environ.get("CSTP_FUSE_BN_STATS", "0") == "1"
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
 
