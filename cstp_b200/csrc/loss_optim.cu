@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, co
   }
 }
 
+int ntxent_tensor_path(const float* zn, int rows, int d, float temperature, bool backward, float* row_loss, float* ws,
+                       float** dzn_out, cudaStream_t stream);
+
 static inline int grid_cap(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 8;
@@ -433,9 +436,12 @@ extern "C" int cstp_pretext_ce(const float* const* logits, const int64_t* const*
   return CSTP_OK;
 }
 
+extern "C" long long cstp_ntxent_workspace_floats(int rows, int d);
+
 extern "C" int cstp_ntxent(const float* z, int rows, int d, float temperature, int use_cosine, float* loss_out,
-                           float* dz, float* workspace, void* stream) {
+                           float* dz, float* workspace, long long workspace_floats, void* stream) {
   CSTP_REQUIRE(z && loss_out && workspace && rows >= 2 && rows % 2 == 0 && d > 0 && temperature > 0.f);
+  CSTP_REQUIRE(workspace_floats >= 3LL * rows + static_cast<long long>(rows) * d);
   float* norms = workspace;
   float* lse = workspace + rows;
   float* row_loss = workspace + 2 * static_cast<long long>(rows);
@@ -444,6 +450,24 @@ extern "C" int cstp_ntxent(const float* z, int rows, int d, float temperature, i
   ntxent_normalize_kernel<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, ST(stream)>>>(z, rows, d, use_cosine,
                                                                                                   zn, norms);
   CSTP_LAUNCHED();
+  // Tensor-core path (ntxent_tc.cu) when the shape allows and the caller provided its larger workspace; the SIMT
+  // kernels below serve small / odd shapes (rows < 256, d not a multiple of 64).
+  if (rows >= 256 && d % 64 == 0 && d <= 256 && workspace_floats >= cstp_ntxent_workspace_floats(rows, d) &&
+      (reinterpret_cast<uintptr_t>(workspace) % 16) == 0) {
+    float* dzn = nullptr;
+    float* tc_ws = zn + static_cast<long long>(rows) * d;
+    tc_ws += (4 - (reinterpret_cast<uintptr_t>(tc_ws) / 4) % 4) % 4;        // 16-byte alignment
+    int rc = ntxent_tensor_path(zn, rows, d, temperature, dz != nullptr, row_loss, tc_ws, &dzn, ST(stream));
+    if (rc != CSTP_OK) return rc;
+    ntxent_loss_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_loss, rows, loss_out);
+    CSTP_LAUNCHED();
+    if (dz != nullptr) {
+      ntxent_bwd_norm_kernel<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, ST(stream)>>>(
+          zn, norms, dzn, rows, d, use_cosine, dz);
+      CSTP_LAUNCHED();
+    }
+    return CSTP_OK;
+  }
   ntxent_fwd_kernel<<<ceil_div(rows, kNtBM), 256, 0, ST(stream)>>>(zn, rows, d, inv_tau, lse, row_loss);
   CSTP_LAUNCHED();
   ntxent_loss_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_loss, rows, loss_out);

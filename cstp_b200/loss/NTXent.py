@@ -22,7 +22,7 @@ class _NTXentFn(torch.autograd.Function):
         rows, d = z.shape
         loss = torch.zeros(1, device=z.device, dtype=torch.float32)
         dz = torch.empty_like(z) if z.requires_grad else None
-        ws = torch.empty(3 * rows + rows * d, device=z.device, dtype=torch.float32)
+        ws = torch.empty(ops.ntxent_workspace_floats(rows, d), device=z.device, dtype=torch.float32)
         ops.ntxent(z, temperature, use_cosine, loss, dz, ws)
         ctx.dz = dz
         return loss[0]

@@ -720,10 +720,15 @@ def pretext_ce(logits, labels, dlogits, B: int, n_cls: int, weights5, losses_out
                                      _stream()))
 
 
+def ntxent_workspace_floats(rows: int, d: int) -> int:
+    """Scratch size (fp32 elements) that lets cstp_ntxent use its tensor-core path."""
+    return max(int(L.load().cstp_ntxent_workspace_floats(rows, d)), 3 * rows + rows * d)
+
+
 def ntxent(z, temperature: float, use_cosine: bool, loss_out, dz, workspace) -> None:
     rows, d = z.shape
     L.check(L.load().cstp_ntxent(_ptr(z), rows, d, float(temperature), int(use_cosine), _ptr(loss_out), _ptr(dz),
-                                 _ptr(workspace), _stream()))
+                                 _ptr(workspace), workspace.numel(), _stream()))
 
 
 def ema_update(k, q, m: float) -> None:

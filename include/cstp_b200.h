@@ -261,9 +261,12 @@ int cstp_pretext_ce(const float* const* logits, const int64_t* const* labels, fl
                     int n_cls, int ld, const float* weights5, float* losses_out, void* stream);
 /* NT-Xent (loss/NTXent.py:46-62), closed form: z = cat(zjs, zis) [rows=2N][d] fp32;
  * loss = mean_i[LSE_{j!=i}(cos_ij/tau) - cos_i,pos(i)/tau]; dz optional (NULL = forward only).
- * workspace: fp32 [3*rows + rows*d]. use_cosine=0 uses raw dot products. */
+ * use_cosine=0 uses raw dot products.  workspace: 16-byte aligned fp32 scratch of `workspace_floats` elements, at
+ * least 3*rows + rows*d; with cstp_ntxent_workspace_floats(rows, d) elements (and rows >= 256, d a multiple of 64,
+ * d <= 256) the similarity matrix runs on the tensor cores (bf16 operands, fp32 accumulation and softmax). */
+long long cstp_ntxent_workspace_floats(int rows, int d);
 int cstp_ntxent(const float* z, int rows, int d, float temperature, int use_cosine, float* loss_out, float* dz,
-                float* workspace, void* stream);
+                float* workspace, long long workspace_floats, void* stream);
 
 /* ---- optimiser side -------------------------------------------------------------------------------------
  * EMA target update (r21d_byol.py:331-337): k = k*m + q*(1-m), bit-exact fp32 (two rounded products, one add). */

@@ -47,7 +47,7 @@ def test_invalid_arguments_fail_loudly():
     w = L.WgradDesc()
     assert lib.cstp_wgrad_plan_create(C.byref(w), C.byref(h)) == -1
     assert lib.cstp_ema_update(None, None, 0, 0.5, 0.5, None) == -1
-    assert lib.cstp_ntxent(None, 3, 8, 0.1, 1, None, None, None, None) == -1
+    assert lib.cstp_ntxent(None, 3, 8, 0.1, 1, None, None, None, 0, None) == -1
 
 
 def test_product_path_rejects_cpu_tensors():

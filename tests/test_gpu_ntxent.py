@@ -1,5 +1,16 @@
 """NTXentLoss drop-in (cstp_b200/loss/NTXent.py -> cstp_ntxent) against the reference's golden outputs
-(tests/golden/ntxent_ref.pt, produced by loss/NTXent.py) and the closed-form oracle at the BASELINE sweep sizes."""
+(tests/golden/ntxent_ref.pt, produced by loss/NTXent.py) and the closed-form oracle at the BASELINE sweep sizes.
+
+Two code paths behind the one entry point: rows >= 256 with d a multiple of 64 runs the similarity matrix on the tensor
+cores (bf16 operands, fp32 accumulate / softmax): loss within 1e-4 relative (north star: 1e-3), gradient within 1e-2;
+everything else runs the fp32 SIMT kernels: loss 1e-5, gradient 1e-4."""
+
+TC = dict(loss=1e-4, grad=1e-2)
+SIMT = dict(loss=1e-5, grad=1e-4)
+
+
+def _tol(rows, d):
+    return TC if rows >= 256 and d % 64 == 0 and d <= 256 else SIMT
 import pytest
 import torch
 
@@ -24,14 +35,15 @@ def test_matches_reference_golden(key):
     crit = NTXentLoss("cuda", n, g["tau"], use_cos)
     loss = crit(zis, zjs)
     loss.backward()
-    assert abs(loss.item() - g["loss"]) < 1e-5 * abs(g["loss"])          # north star: loss within 1e-3
+    tol = _tol(g["rows"], g["d"])
+    assert abs(loss.item() - g["loss"]) < tol["loss"] * abs(g["loss"])          # north star: loss within 1e-3
     dz = torch.cat([zjs.grad, zis.grad], 0).reshape(-1).cpu()
-    assert rel(dz[sample_idx(dz.numel(), 512)], g["dz"]["samples"]) < 1e-4
-    assert abs(dz.abs().sum().item() - g["dz_abs_sum"]) < 1e-4 * g["dz_abs_sum"]
+    assert rel(dz[sample_idx(dz.numel(), 512)], g["dz"]["samples"]) < tol["grad"]
+    assert abs(dz.abs().sum().item() - g["dz_abs_sum"]) < max(tol["grad"], 1e-4) * g["dz_abs_sum"]
     assert torch.equal(crit.positive_index(), (torch.arange(2 * n) + n) % (2 * n))      # integer index map
 
 
-@pytest.mark.parametrize("rows", [2, 6, 200, 2048, 4096, 8192])
+@pytest.mark.parametrize("rows", [2, 6, 200, 256, 300, 2048, 4096, 8192])
 def test_matches_closed_form_oracle(rows):
     """BASELINE config 2 sizes (the reference itself needs 51 GB at rows=4096 and cannot run 8192, SURVEY.md 0.8);
     plus the smallest and a ragged (not a multiple of the 64-row tile) size."""
@@ -46,12 +58,13 @@ def test_matches_closed_form_oracle(rows):
     zis, zjs = z[n:].cuda().requires_grad_(True), z[:n].cuda().requires_grad_(True)
     loss = NTXentLoss("cuda", n, tau, True)(zis, zjs)
     loss.backward()
-    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7, (loss.item(), ref.item())
+    tol = _tol(rows, d)
+    assert abs(loss.item() - ref.item()) <= tol["loss"] * abs(ref.item()) + 1e-7, (loss.item(), ref.item())
     dz, dref = torch.cat([zjs.grad, zis.grad]).cpu(), torch.cat([b.grad, a.grad]).float()
-    assert (dz - dref).norm() <= 1e-4 * dref.norm() + 1e-7
+    assert (dz - dref).norm() <= tol["grad"] * dref.norm() + 1e-7
     if rows in (256, 1024, 2048, 4096):       # SURVEY.md A.3 anchors
         anchor = {256: 5.915076, 1024: 7.327291, 2048: 8.046678, 4096: 8.733852}[rows]
-        assert abs(loss.item() - anchor) < 1e-5 * anchor
+        assert abs(loss.item() - anchor) < tol["loss"] * anchor
 
 
 def test_properties_and_errors():

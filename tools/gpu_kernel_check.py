@@ -260,7 +260,7 @@ def case_losses():
         lref.backward()
         lo = torch.zeros(1, device=dev)
         dz = torch.empty_like(z)
-        ws = torch.empty(3 * rows + rows * d, device=dev)
+        ws = torch.empty(3 * rows + rows * d, device=dev)          # small workspace: the fp32 SIMT path
         ops.ntxent(z, tau, True, lo, dz, ws)
         torch.cuda.synchronize()
         res[f"ntxent{rows}_loss_rel"] = abs(lo.item() - lref.item()) / lref.item()

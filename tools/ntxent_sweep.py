@@ -31,7 +31,7 @@ for rows in (256, 512, 1024, 2048, 4096, 8192):
     # kernel-only timing through the C ABI (no autograd / cat overhead)
     zc = torch.cat([zjs, zis]).detach().float().contiguous()
     lo, dz = torch.zeros(1, device="cuda"), torch.empty_like(zc)
-    ws = torch.empty(3 * rows + rows * d, device="cuda")
+    ws = torch.empty(ops.ntxent_workspace_floats(rows, d), device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 20
     e0.record()
@@ -47,6 +47,16 @@ for rows in (256, 512, 1024, 2048, 4096, 8192):
     torch.cuda.synchronize()
     m_ms = e0.elapsed_time(e1) / iters
     flops = 6.0 * rows * rows * d          # fwd 2*rows^2*d + bwd 4*rows^2*d (S recomputed + W.Z), SURVEY.md 8(d)
+    # the SIMT fp32 path of the same entry point (small workspace) for comparison
+    ws0 = torch.empty(3 * rows + rows * d, device="cuda")
+    ops.ntxent(zc, tau, True, lo, dz, ws0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        ops.ntxent(zc, tau, True, lo, dz, ws0)
+    e1.record()
+    torch.cuda.synchronize()
+    simt_ms = e0.elapsed_time(e1) / 5
     print(json.dumps({"rows": rows, "d": d, "tau": tau, "loss": loss.item(), "anchor": ANCHOR.get(rows),
-                      "kernel_ms_fwd_bwd": k_ms, "module_ms_fwd_bwd": m_ms, "tflops_fp32": flops / k_ms / 1e9,
-                      "pairs_per_s": n / (k_ms * 1e-3)}), flush=True)
+                      "kernel_ms_fwd_bwd": k_ms, "module_ms_fwd_bwd": m_ms, "tflops": flops / k_ms / 1e9,
+                      "simt_fp32_ms_fwd_bwd": simt_ms, "pairs_per_s": n / (k_ms * 1e-3)}), flush=True)
