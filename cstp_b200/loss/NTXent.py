@@ -18,18 +18,17 @@ from .. import ops
 
 class _NTXentFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, temperature, use_cosine):
+    def forward(ctx, z, temperature, use_cosine, ws):
         rows, d = z.shape
         loss = torch.zeros(1, device=z.device, dtype=torch.float32)
         dz = torch.empty_like(z) if z.requires_grad else None
-        ws = torch.empty(ops.ntxent_workspace_floats(rows, d), device=z.device, dtype=torch.float32)
         ops.ntxent(z, temperature, use_cosine, loss, dz, ws)
         ctx.dz = dz
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        return (ctx.dz * g if ctx.dz is not None else None), None, None
+        return (ctx.dz * g if ctx.dz is not None else None), None, None, None
 
 
 class NTXentLoss(torch.nn.Module):
@@ -55,4 +54,8 @@ class NTXentLoss(torch.nn.Module):
         if not zis.is_cuda:
             raise ops.L.CstpError("cstp_b200 NTXentLoss runs on CUDA tensors only: there is no CPU fallback")
         z = torch.cat([zjs, zis], dim=0).float().contiguous()
-        return _NTXentFn.apply(z, float(self.temperature), self.use_cosine_similarity)
+        key = (z.shape[0], z.shape[1], z.device)
+        if getattr(self, "_ws_key", None) != key:          # scratch of the kernel, kept across calls
+            self._ws = torch.empty(ops.ntxent_workspace_floats(z.shape[0], z.shape[1]), device=z.device, dtype=torch.float32)
+            self._ws_key = key
+        return _NTXentFn.apply(z, float(self.temperature), self.use_cosine_similarity, self._ws)
