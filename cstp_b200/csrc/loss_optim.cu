@@ -106,6 +106,96 @@ __global__ void __launch_bounds__(1024) pretext_ce_kernel(CeArgs a, int B, int n
   }
 }
 
+// ------------------------------------------------------------------------------------------- finetune head
+// F.normalize(feat, p=2, dim=1) of the finetune / test branch (models/pace/r21d_byol.py:394-399): y = x / max(|x|, eps),
+// written as bf16 rows for the BatchNorm1d / Linear kernels; the norms are kept for the backward.
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, int rows, int d, int ld, float eps,
+                                  __nv_bfloat16* __restrict__ y, int ld_y, float* __restrict__ norms) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + static_cast<long long>(warp) * ld;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) ss += xr[c] * xr[c];
+  ss = warp_sum(ss);
+  const float n = fmaxf(sqrtf(ss), eps);
+  for (int c = lane; c < ld_y; c += 32) y[static_cast<long long>(warp) * ld_y + c] = __float2bfloat16_rn(c < d ? xr[c] / n : 0.f);
+  if (lane == 0) norms[warp] = n;
+}
+
+// dx = (g - y (y . g)) / norm with y = x / norm (rows whose norm was clamped to eps pass g / eps, as torch does).
+__global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ norms,
+                                  const __nv_bfloat16* __restrict__ g, int rows, int d, int ld, int ld_g,
+                                  float* __restrict__ dx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + static_cast<long long>(warp) * ld;
+  const __nv_bfloat16* gr = g + static_cast<long long>(warp) * ld_g;
+  const float inv = 1.f / norms[warp];
+  float dot = 0.f, ss = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    dot += xr[c] * inv * __bfloat162float(gr[c]);
+    ss += xr[c] * xr[c];
+  }
+  dot = warp_sum(dot);
+  ss = warp_sum(ss);
+  const bool clamped = sqrtf(ss) < norms[warp];        // |x| < eps: the forward divided by the constant eps
+  for (int c = lane; c < ld; c += 32) {
+    float v = 0.f;
+    if (c < d) v = clamped ? __bfloat162float(gr[c]) * inv : (__bfloat162float(gr[c]) - xr[c] * inv * dot) * inv;
+    dx[static_cast<long long>(warp) * ld + c] = v;
+  }
+}
+
+// nn.CrossEntropyLoss() (mean) over [B][ld] logits with n_cls classes (main_ft_mp.py:188,203) + gradient.
+// One block; warp w handles rows w, w + nwarps, ...; the row losses are summed in row order.
+__global__ void __launch_bounds__(1024) ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                       int B, int n_cls, int ld, float* __restrict__ loss_out,
+                                                       float* __restrict__ dlogits, float* __restrict__ row_loss) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < B; i += nwarps) {
+    const float* l = logits + static_cast<long long>(i) * ld;
+    const int y = static_cast<int>(labels[i]);
+    float m = -INFINITY;
+    for (int c = lane; c < n_cls; c += 32) m = fmaxf(m, l[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < n_cls; c += 32) s += expf(l[c] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    if (lane == 0) row_loss[i] = lse - l[y];
+    if (dlogits != nullptr) {
+      float* dr = dlogits + static_cast<long long>(i) * ld;
+      const float k = 1.f / static_cast<float>(B);
+      for (int c = lane; c < ld; c += 32) dr[c] = c < n_cls ? k * (expf(l[c] - lse) - (c == y ? 1.f : 0.f)) : 0.f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < B; ++i) t += row_loss[i];
+    loss_out[0] = t / static_cast<float>(B);
+  }
+}
+
+// Eval-mode BatchNorm as an affine map: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale
+// (model.eval() in main_ft_mp.py:281-289 / test.py:76-93); the forward then only needs cstp_bn_apply.
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, int C, int Cp, int groups,
+                                      float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  float sc = 0.f, sh = 0.f;
+  if (c < C) {
+    sc = gamma[c] / sqrtf(rv[c] + eps);
+    sh = beta[c] - rm[c] * sc;
+  }
+  for (int g = 0; g < groups; ++g) {
+    scale[g * Cp + c] = sc;
+    shift[g * Cp + c] = sh;
+  }
+}
+
 // ------------------------------------------------------------------------------------------- NT-Xent
 // loss/NTXent.py:46-62 in closed form: no rows x rows matrix is ever materialised.
 constexpr int kNtBM = 64, kNtBN = 64, kNtBK = 32;
@@ -432,6 +522,42 @@ extern "C" int cstp_pretext_ce(const float* const* logits, const int64_t* const*
     a.dlogits[h] = dlogits ? dlogits[h] : nullptr;
   }
   pretext_ce_kernel<<<1, 1024, 0, ST(stream)>>>(a, B, n_cls, ld, weights5, losses_out);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_l2norm_fwd(const float* x, int rows, int d, int ld, float eps, void* y_bf16, int ld_y, float* norms,
+                               void* stream) {
+  CSTP_REQUIRE(x && y_bf16 && norms && rows > 0 && d > 0 && d <= ld && d <= ld_y);
+  l2norm_fwd_kernel<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, ST(stream)>>>(
+      x, rows, d, ld, eps, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_y, norms);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_l2norm_bwd(const float* x, const float* norms, const void* g_bf16, int rows, int d, int ld, int ld_g,
+                               float* dx, void* stream) {
+  CSTP_REQUIRE(x && norms && g_bf16 && dx && rows > 0 && d > 0 && d <= ld && d <= ld_g);
+  l2norm_bwd_kernel<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, ST(stream)>>>(
+      x, norms, reinterpret_cast<const __nv_bfloat16*>(g_bf16), rows, d, ld, ld_g, dx);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_ce_loss(const float* logits, const int64_t* labels, int B, int n_cls, int ld, float* loss_out,
+                            float* dlogits, float* workspace, void* stream) {
+  CSTP_REQUIRE(logits && labels && loss_out && workspace && B > 0 && n_cls > 0 && n_cls <= ld);
+  ce_loss_kernel<<<1, 1024, 0, ST(stream)>>>(logits, labels, B, n_cls, ld, loss_out, dlogits, workspace);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                                   const float* running_var, int C, int Cp, int groups, float eps, float* scale,
+                                   float* shift, void* stream) {
+  CSTP_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && C > 0 && C <= Cp && groups > 0);
+  bn_eval_coeffs_kernel<<<ceil_div(Cp, 128), 128, 0, ST(stream)>>>(gamma, beta, running_mean, running_var, C, Cp, groups,
+                                                                  eps, scale, shift);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -170,15 +170,18 @@ class _Timed:
 class StepEngine:
     """See the module docstring.  `B` is the per-GPU batch (samples; each sample is two views)."""
 
+    VIEWS = 2          # clips per sample pushed through the backbone = BatchNorm statistics groups
+
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", momentum_ema: float = 0.996,
                  record: bool = False, overlap: bool = True):
         if H % 2 or W % 2:
             raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
         self.B, self.T, self.H, self.W = B, T, H, W
-        self.N = 2 * B
+        self.N = self.VIEWS * B
         self.device = torch.device(device)
         self.momentum_ema = momentum_ema
         self.record = record
+        self.eval_mode = False       # True: BatchNorm uses its running statistics (finetune validation / test)
         # Two-stream schedule (CUDA only): the target network's forward runs beside the online network's, and every
         # weight-gradient GEMM runs beside the BatchNorm-backward streaming kernels of the next unit, so HBM-bound and
         # tensor-bound kernels share the machine.  Results are unchanged (same kernels, same reduction orders).
@@ -193,18 +196,7 @@ class StepEngine:
         self._prof = None                             # list of (kind, flops, launches, ev0, ev1) while profiling
         f32 = dict(device=self.device, dtype=torch.float32)
 
-        # ---- flat parameter / gradient / momentum / buffer stores
-        tspecs = trainable_param_specs()
-        self.train = FlatStore(tspecs, self.device)
-        self.grad = self.train.like()
-        self.mom = self.train.like()
-        self.target = FlatStore(backbone_param_specs("target_net"), self.device)
-        self.online_numel = FlatStore(backbone_param_specs("online_net"), "meta").numel
-        assert self.online_numel == self.target.numel
-        self.bufs = FlatStore(bn_buffer_specs(tspecs) + bn_buffer_specs(backbone_param_specs("target_net")), self.device)
-        for name in self.bufs.slots:
-            if name.endswith("running_var"):
-                self.bufs.view(name).fill_(1.0)
+        self._make_stores()
         self.first_step = True
 
         # ---- scratch shared by all layers
@@ -229,6 +221,20 @@ class StepEngine:
         self.sgd_ws = torch.zeros(2048, **f32)
 
         self._build()
+
+    def _make_stores(self):
+        """Flat parameter / gradient / momentum / buffer stores (overridden by the finetune engine)."""
+        tspecs = trainable_param_specs()
+        self.train = FlatStore(tspecs, self.device)
+        self.grad = self.train.like()
+        self.mom = self.train.like()
+        self.target = FlatStore(backbone_param_specs("target_net"), self.device)
+        self.online_numel = FlatStore(backbone_param_specs("online_net"), "meta").numel
+        assert self.online_numel == self.target.numel
+        self.bufs = FlatStore(bn_buffer_specs(tspecs) + bn_buffer_specs(backbone_param_specs("target_net")), self.device)
+        for name in self.bufs.slots:
+            if name.endswith("running_var"):
+                self.bufs.view(name).fill_(1.0)
 
     # ------------------------------------------------------------------------------------------ helpers
     def _act(self, *shape) -> torch.Tensor:
@@ -280,15 +286,18 @@ class StepEngine:
         wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
         rows = N * To * Ho * Wo
         flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
-        site = self._site(store, grads, bnname, cout, 2, rows // 2)
+        site = self._site(store, grads, bnname, cout, self.VIEWS, rows // self.VIEWS)
         cplan = ops.conv_fwd_plan(x, wp, raw, geom, stats=site.st)
         plan = _Timed(self, "conv_fwd", flops, [cplan], tag)
         fused = cplan.stat_blocks       # > 0: the conv epilogue already produced the BatchNorm statistics partials
 
         def fwd():
             plan.run()
-            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
-                                 fused_blocks=fused)
+            if self.eval_mode:       # model.eval(): running statistics as an affine map, nothing is updated
+                ops.bn_eval_coeffs(site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS)
+            else:
+                ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
+                                     fused_blocks=fused)
             if apply:
                 ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_site.st if res_site else None)
         prog.append(fwd)
@@ -563,6 +572,11 @@ class StepEngine:
         bw.append(lambda: ops.avgpool_bwd(self.dfeat, d_x5, dcat=self.dcat))
         bw.extend(reversed(bw_backbone))
         # ---------------- shared scratch + deferred plan creation
+        self._finish_build()
+
+    def _finish_build(self):
+        """Shared scratch + deferred plan creation, once every forward / backward closure exists."""
+        f32 = dict(device=self.device, dtype=torch.float32)
         # d(raw) scratch: two buffers, alternating in RUN order, so that a unit's weight-gradient GEMM (side stream) can
         # still read its d(raw) while the next unit's BatchNorm backward writes the other buffer
         turn = 0

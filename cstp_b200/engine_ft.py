@@ -1,0 +1,138 @@
+"""Finetune / test engine: the `ft_fc` / `ft_all` / `test` branch of R21DBYOL.forward (models/pace/r21d_byol.py:394-399)
+driven by main_ft_mp.py:179-289 (train / validation) and test.py:76-93 (multi-clip inference).
+
+    logits = classify(cls_bn(F.normalize(online_net(x), p=2, dim=1)))            R21DBYOL(pretrain=False, num_classes, cls_bn)
+
+Reuses the backbone program builder and every kernel of the pretraining engine (cstp_b200.engine.StepEngine) with ONE
+view per sample (one BatchNorm statistics group) and no target network; adds the L2-normalise / BatchNorm1d / Linear
+head, the n-way cross-entropy, and an eval mode in which every BatchNorm is the affine map of its running statistics
+(model.eval()): forward only, no statistics kernels, nothing updated.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine as E
+from .engine import FlatStore, StepEngine, backbone_param_specs, bn_buffer_specs, pad16
+
+
+def finetune_param_specs(num_classes: int, cls_bn: bool):
+    """Parameters of R21DBYOL(pretrain=False) in registration order (r21d_byol.py:293-299)."""
+    s = backbone_param_specs("online_net", project=False)
+    s += [("classify.weight", (num_classes, 512)), ("classify.bias", (num_classes,))]
+    if cls_bn:
+        s += [("cls_bn.weight", (512,)), ("cls_bn.bias", (512,))]
+    return s
+
+
+class FinetuneEngine(StepEngine):
+    VIEWS = 1
+
+    def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", num_classes: int = 101,
+                 cls_bn: bool = True, record: bool = False, overlap: bool = True, backbone_grads: bool = True):
+        self.num_classes, self.cls_bn, self.backbone_grads = num_classes, bool(cls_bn), backbone_grads
+        super().__init__(B, T, H, W, device=device, record=record, overlap=overlap)
+
+    def _make_stores(self):
+        specs = finetune_param_specs(self.num_classes, self.cls_bn)
+        self.train = FlatStore(specs, self.device)
+        self.grad = self.train.like()
+        self.mom = self.train.like()
+        self.target = None
+        self.bufs = FlatStore(bn_buffer_specs(specs), self.device)
+        for name in self.bufs.slots:
+            if name.endswith("running_var"):
+                self.bufs.view(name).fill_(1.0)
+
+    # ------------------------------------------------------------------------------------------ build
+    def _build(self):
+        ops = E.ops
+        B = self.B
+        f32 = dict(device=self.device, dtype=torch.float32)
+        x5, bw_backbone = self._backbone(self.fwd_online, self.train, "online_net", self.backbone_grads, "online")
+        C = self.num_classes
+        Cp = pad16(C)
+        self.feat = torch.zeros(B, 512, **f32)
+        self.norms = torch.zeros(B, **f32)
+        self.nfeat = self._act(B, 512)                     # F.normalize(feat) as bf16 rows
+        self.hfeat = self._act(B, 512) if self.cls_bn else self.nfeat
+        self.logits = torch.zeros(B, Cp, **f32)
+        self.dlogits = torch.zeros(B, Cp, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.ce_ws = torch.zeros(max(B, 16), **f32)
+        wc, wct = self._packed(self.train, "classify.weight", True)
+        bias = self.train.slot("classify.bias")
+        p_cls = ops.linear_plan(self.hfeat, wc, None, out_f32=self.logits, bias=bias)
+        site = self._site(self.train, True, "cls_bn", 512, 1, B) if self.cls_bn else None
+        self._rec("head.feat", self.feat)
+        self._rec("head.nfeat", self.nfeat)
+        self._rec("head.hfeat", self.hfeat)
+        self._rec("head.logits", self.logits)
+
+        def head_fwd():
+            ops.avgpool_fwd(x5, self.feat, None)
+            ops.l2norm_fwd(self.feat, self.nfeat, self.norms, 512)
+            if site is not None:
+                if self.eval_mode:
+                    ops.bn_eval_coeffs(site.st, site.gamma, site.beta, site.rm, site.rv, E.BN_EPS)
+                else:
+                    ops.bn_forward_stats(self.nfeat, site.st, site.gamma, site.beta, site.rm, site.rv, E.BN_EPS,
+                                         E.BN_MOMENTUM)
+                ops.bn_apply(self.nfeat, site.st, self.hfeat, relu=False)
+            p_cls.run()
+        self.fwd_online.append(head_fwd)
+
+        # ---------------- backward program: head -> pool -> backbone
+        g_out = self._act(B, Cp)
+        d_h = self._act(B, 512)
+        g_n = self._act(B, 512) if self.cls_bn else d_h
+        self.dfeat = torch.zeros(B, 512, **f32)
+        dWc = self.train.view("classify.weight", self.grad)
+        dbc = self.train.view("classify.bias", self.grad)
+        g1 = ops.ConvGeom((1, 1, 1))
+        h5, go5 = self.hfeat.view(1, 1, 1, B, 512), g_out.view(1, 1, 1, B, Cp)
+        self._wg_numel = max(self._wg_numel, self._wgrad_need(h5, go5, g1))
+        pd_h = ops.linear_plan(g_out, wct, d_h)
+        holder = {}
+        self._deferred.append(lambda: holder.__setitem__("wg", ops.wgrad_plan(h5, go5, g1, C, 512, self._wg)))
+        self._rec("head.g_out", g_out)
+        self._rec("head.d_h", d_h)
+        self._rec("head.g_n", g_n)
+        self._rec("head.dfeat", self.dfeat)
+        d_x5 = self._dbuf(x5)
+
+        def head_bwd():
+            ops.cast_pad(self.dlogits, g_out, cols=C)
+            ops.colsum(g_out, C, dbc)
+            holder["wg"].run(dWc)
+            if not self.backbone_grads:
+                return
+            pd_h.run()
+            if site is not None:
+                ops.bn_backward(d_h, None, self.nfeat, site.st, site.gamma, site.dgamma, site.dbeta, g_n)
+            ops.l2norm_bwd(self.feat, self.norms, g_n, self.dfeat, 512)
+            ops.avgpool_bwd(self.dfeat, d_x5)
+        self.bwd.append(head_bwd)
+        if self.backbone_grads:
+            self.bwd.extend(reversed(bw_backbone))
+        self._finish_build()
+
+    # ------------------------------------------------------------------------------------------ programs
+    def load_clip(self, x: torch.Tensor):
+        E.ops.stem_im2col(x, self.col)
+
+    def forward(self, x, repack: bool = False):
+        """logits (device fp32 [B][pad16(num_classes)], the first num_classes columns are valid)."""
+        if repack:
+            self.pack_online()
+        self.load_clip(x)
+        for op in self.fwd_online:
+            op()
+        return self.logits
+
+    def cross_entropy(self, labels):
+        """nn.CrossEntropyLoss() of main_ft_mp.py:188,203 on the current logits; fills self.loss and self.dlogits."""
+        E.ops.ce_loss(self.logits, labels, self.num_classes, self.loss, self.dlogits, self.ce_ws)
+
+    def optimizer_step(self, lr, momentum=0.9, wd=1e-3, max_norm=0.0, clip=False):
+        super().optimizer_step(lr, momentum, wd, max_norm, clip)

@@ -157,6 +157,10 @@ SIGNATURES = {
     "cstp_pretext_ce": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _vp, _vp, _vp]),
     "cstp_ntxent_workspace_floats": (C.c_longlong, [_i, _i]),
     "cstp_ntxent": (_i, [_vp, _i, _i, _f, _i, _vp, _vp, _vp, C.c_longlong, _vp]),
+    "cstp_l2norm_fwd": (_i, [_vp, _i, _i, _i, _f, _vp, _i, _vp, _vp]),
+    "cstp_l2norm_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "cstp_ce_loss": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cstp_bn_eval_coeffs": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cstp_ema_update": (_i, [_vp, _vp, _i64, _f, _f, _vp]),
     "cstp_sgd_clip_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp]),
 }

@@ -151,24 +151,53 @@ class _LossComFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+class _FinetuneFn(torch.autograd.Function):
+    """One autograd node for the finetune forward (backbone + normalise + cls_bn + classify)."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        eng = model._engine
+        eng.eval_mode = False
+        eng.forward(x, repack=True)
+        ctx.model = model
+        return eng.logits[:, :model.num_classes].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.model
+        eng = model._engine
+        eng.dlogits.zero_()
+        eng.dlogits[:, :model.num_classes].copy_(g)
+        eng.backward()
+        grads = [eng.train.view(n, eng.grad).clone() for n in model._trainable_names]
+        return (None, None, *grads)
+
+
 class R21DBYOL(nn.Module):
-    """Drop-in for r21d_byol.py:260-401 (pretraining configuration)."""
+    """Drop-in for r21d_byol.py:260-401: pretrain=True is the `loss_com` pretraining model, pretrain=False the
+    finetune / test model (`ft_fc`, `ft_all`, `test`) with `num_classes` and `cls_bn` keyword arguments."""
 
     def __init__(self, pretrain=True, momentum=0.996, **kwargs):
         super().__init__()
-        if not pretrain:
-            raise NotImplementedError("cstp_b200 implements the pretraining hot path (pretrain=True); the finetune/test "
-                                      "configuration is the next scope row (SURVEY.md 8f-1)")
-        self.momentum = momentum
-        self.online_net = R2Plus1DNet(layer_sizes=(1, 1, 1, 1), proj_flag=True)
-        self.target_net = R2Plus1DNet(layer_sizes=(1, 1, 1, 1), proj_flag=True)
-        self.predictor = Predictor(dim=512, prediction_size=512, prediction_hidden_size=4096)
-        for p in self.target_net.parameters():
-            p.requires_grad = False
-        self.overlap_spa = _mlp(1024, 1024, 5)
-        self.overlap_tem = _mlp(1024, 1024, 5)
-        self.pb_cls = _mlp(512, 512, 5)
-        self.rotate_cls = _mlp(512, 512, 5)
+        self.pretrain = bool(pretrain)
+        if pretrain:
+            self.momentum = momentum
+            self.online_net = R2Plus1DNet(layer_sizes=(1, 1, 1, 1), proj_flag=True)
+            self.target_net = R2Plus1DNet(layer_sizes=(1, 1, 1, 1), proj_flag=True)
+            self.predictor = Predictor(dim=512, prediction_size=512, prediction_hidden_size=4096)
+            for p in self.target_net.parameters():
+                p.requires_grad = False
+            self.overlap_spa = _mlp(1024, 1024, 5)
+            self.overlap_tem = _mlp(1024, 1024, 5)
+            self.pb_cls = _mlp(512, 512, 5)
+            self.rotate_cls = _mlp(512, 512, 5)
+        else:
+            self.online_net = R2Plus1DNet(layer_sizes=(1, 1, 1, 1), proj_flag=False)
+            self.num_classes = kwargs["num_classes"]
+            self.classify = nn.Linear(512, self.num_classes)
+            self.cls_bn = kwargs["cls_bn"]
+            if self.cls_bn:
+                self.cls_bn = nn.BatchNorm1d(512)
         # r21d_byol.py:301-329: every Linear / Conv3d / BatchNorm weight (BN gamma included) is redrawn
         # U(+-sqrt(6/(fan_in+fan_out))); 1-D tensors use fan_in = fan_out = C/2.
         with torch.no_grad():
@@ -184,7 +213,11 @@ class R21DBYOL(nn.Module):
                     w.uniform_(-bound, bound)
         self._engine = None
         self._engine_key = None
-        self._trainable_names = [n for n, _ in _engine_mod.trainable_param_specs()]
+        if pretrain:
+            self._trainable_names = [n for n, _ in _engine_mod.trainable_param_specs()]
+        else:
+            from ... import engine_ft
+            self._trainable_names = [n for n, _ in engine_ft.finetune_param_specs(self.num_classes, bool(self.cls_bn))]
         self._dirty = True
 
     # ------------------------------------------------------------------------------------------ engine binding
@@ -229,6 +262,78 @@ class R21DBYOL(nn.Module):
             self._dirty = True
         return eng
 
+    def _bind_ft(self, x):
+        """Finetune / test flavour of _bind: a FinetuneEngine per (batch geometry, frozen-backbone) configuration."""
+        from ... import engine_ft
+        _engine_mod.ops.require_device(x)
+        if not isinstance(self.cls_bn, nn.Module):
+            raise TypeError("'bool' object is not callable")      # the reference calls self.cls_bn(feat) unconditionally
+        B, _, T, H, W = x.shape
+        bgrads = any(p.requires_grad for n, p in self.named_parameters() if n.startswith("online_net."))
+        key = (B, T, H, W, x.device, bgrads)
+        eng = self._engine
+        if eng is None or self._engine_key != key:
+            new = engine_ft.FinetuneEngine(B, T, H, W, device=x.device, num_classes=self.num_classes, cls_bn=True,
+                                           backbone_grads=bgrads, **getattr(self, "engine_options", {}))
+            if eng is not None:
+                new.mom.copy_(eng.mom)
+                new.first_step = eng.first_step
+            eng = self._engine = new
+            self._engine_key = key
+            self._alias_ptr = None
+        sentinel = self.online_net.conv1.spatial_conv.weight
+        if getattr(self, "_alias_ptr", None) != sentinel.data_ptr():
+            with torch.no_grad():
+                for name, p in self.named_parameters():
+                    v = eng.train.view(name)
+                    v.copy_(p.data)
+                    p.data = v
+                nbt = []
+                for mname, mod in self.named_modules():
+                    if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm3d)):
+                        for b in ("running_mean", "running_var"):
+                            v = eng.bufs.view(f"{mname}.{b}")
+                            v.copy_(mod._buffers[b])
+                            mod._buffers[b] = v
+                        nbt.append(mod)
+                flat = torch.stack([m._buffers["num_batches_tracked"].to(x.device) for m in nbt])
+                for i, m in enumerate(nbt):
+                    m._buffers["num_batches_tracked"] = flat[i]
+                self._nbt, self._nbt_inc = flat, torch.ones_like(flat)
+            self._alias_ptr = sentinel.data_ptr()
+            self._dirty = True
+        return eng
+
+    def _forward_ft(self, x1):
+        eng = self._bind_ft(x1)
+        x1 = x1.contiguous()
+        if self.training and torch.is_grad_enabled():
+            out = _FinetuneFn.apply(self, x1, *self._trainable())
+            self._nbt += self._nbt_inc
+            self._dirty = True
+            return out
+        eng.eval_mode = not self.training
+        eng.forward(x1, repack=True)
+        if self.training:
+            self._nbt += self._nbt_inc
+        return eng.logits[:, :self.num_classes].clone()
+
+    @torch.no_grad()
+    def finetune_step(self, x, labels, lr=0.025, momentum=0.9, weight_decay=1e-3, grad_sync=None):
+        """One fused finetune step (main_ft_mp.py:196-214: forward, CrossEntropyLoss, backward, SGD.step -- no gradient
+        clipping in the finetune driver).  Returns the device scalar loss without synchronising."""
+        eng = self._bind_ft(x)
+        eng.eval_mode = False
+        eng.forward(x.contiguous(), repack=self._dirty)
+        self._dirty = False
+        eng.cross_entropy(labels)
+        eng.backward()
+        if grad_sync is not None:
+            grad_sync(eng.grad)
+        eng.optimizer_step(lr, momentum, weight_decay)
+        self._nbt += self._nbt_inc
+        return eng.loss
+
     def mark_weights_dirty(self):
         """Call after changing parameters behind the engine's back (e.g. in-place edits) before a fused train_step."""
         self._dirty = True
@@ -240,15 +345,18 @@ class R21DBYOL(nn.Module):
 
     # ------------------------------------------------------------------------------------------ reference interface
     def forward(self, x1, x2=None, o_type=None):
-        if o_type == "loss_com":
+        if o_type in ("ft_fc", "ft_all", "test") and not self.pretrain:
+            return self._forward_ft(x1)
+        if o_type == "loss_com" and self.pretrain:
             self._bind(x1)
             outs = _LossComFn.apply(self, x1.contiguous(), x2.contiguous(), *self._trainable())
             self._nbt += self._nbt_inc
             self._dirty = True
             return outs[0], tuple(outs[1:])
-        if o_type in ("r_byol", "ft_fc", "ft_all", "test"):
-            raise NotImplementedError(f"o_type={o_type!r}: only the pretraining path 'loss_com' is implemented "
-                                      "(r_byol is broken in the reference itself, SURVEY.md 0.9)")
+        if o_type in ("r_byol", "ft_fc", "ft_all", "test", "loss_com"):
+            raise NotImplementedError(f"o_type={o_type!r} with pretrain={self.pretrain}: 'loss_com' needs the pretraining "
+                                      "model, 'ft_fc'/'ft_all'/'test' the finetune model (r_byol is broken in the reference "
+                                      "itself, SURVEY.md 0.9)")
         raise ValueError("Output cls is not exist!")
 
     def _trainable(self):

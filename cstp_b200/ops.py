@@ -731,6 +731,26 @@ def ntxent(z, temperature: float, use_cosine: bool, loss_out, dz, workspace) -> 
                                  _ptr(workspace), workspace.numel(), _stream()))
 
 
+def l2norm_fwd(x, y_bf16, norms, d: int, eps: float = 1e-12) -> None:
+    L.check(L.load().cstp_l2norm_fwd(_ptr(x), x.shape[0], d, x.shape[1], float(eps), _ptr(y_bf16), y_bf16.shape[1],
+                                     _ptr(norms), _stream()))
+
+
+def l2norm_bwd(x, norms, g_bf16, dx, d: int) -> None:
+    L.check(L.load().cstp_l2norm_bwd(_ptr(x), _ptr(norms), _ptr(g_bf16), x.shape[0], d, x.shape[1], g_bf16.shape[1],
+                                     _ptr(dx), _stream()))
+
+
+def ce_loss(logits, labels, n_cls: int, loss_out, dlogits, workspace) -> None:
+    L.check(L.load().cstp_ce_loss(_ptr(logits), _ptr(labels), logits.shape[0], n_cls, logits.shape[1], _ptr(loss_out),
+                                  _ptr(dlogits), _ptr(workspace), _stream()))
+
+
+def bn_eval_coeffs(st: BNState, gamma, beta, running_mean, running_var, eps: float = 1e-5) -> None:
+    L.check(L.load().cstp_bn_eval_coeffs(_ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), st.C, st.Cp,
+                                         st.groups, float(eps), _ptr(st.scale), _ptr(st.shift), _stream()))
+
+
 def ema_update(k, q, m: float) -> None:
     import numpy as np
     L.check(L.load().cstp_ema_update(_ptr(k), _ptr(q), k.numel(), float(np.float32(m)), float(np.float32(1.0 - m)),

@@ -268,6 +268,21 @@ long long cstp_ntxent_workspace_floats(int rows, int d);
 int cstp_ntxent(const float* z, int rows, int d, float temperature, int use_cosine, float* loss_out, float* dz,
                 float* workspace, long long workspace_floats, void* stream);
 
+/* ---- finetune / test branch (models/pace/r21d_byol.py:394-399, main_ft_mp.py:179-289, test.py:76-93) ----------
+ * F.normalize(x, p=2, dim=1): y = x / max(|x|_2, eps) for fp32 [rows][ld] -> bf16 [rows][ld_y] (zero padded); norms kept. */
+int cstp_l2norm_fwd(const float* x, int rows, int d, int ld, float eps, void* y_bf16, int ld_y, float* norms, void* stream);
+/* dx = (g - y (y.g)) / norm for the bf16 gradient g w.r.t. y. */
+int cstp_l2norm_bwd(const float* x, const float* norms, const void* g_bf16, int rows, int d, int ld, int ld_g, float* dx,
+                    void* stream);
+/* nn.CrossEntropyLoss() (mean) over fp32 [B][ld] logits with n_cls classes and int64 labels; dlogits optional;
+ * workspace: fp32 [B]. */
+int cstp_ce_loss(const float* logits, const int64_t* labels, int B, int n_cls, int ld, float* loss_out, float* dlogits,
+                 float* workspace, void* stream);
+/* Eval-mode BatchNorm as the affine map cstp_bn_apply consumes: scale = gamma/sqrt(running_var+eps),
+ * shift = beta - running_mean*scale, replicated for `groups` groups. */
+int cstp_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var, int C,
+                        int Cp, int groups, float eps, float* scale, float* shift, void* stream);
+
 /* ---- optimiser side -------------------------------------------------------------------------------------
  * EMA target update (r21d_byol.py:331-337): k = k*m + q*(1-m), bit-exact fp32 (two rounded products, one add). */
 int cstp_ema_update(float* k, const float* q, int64_t n, float m, float one_minus_m, void* stream);

@@ -237,6 +237,62 @@ def pretrain_step(state: dict, trainable: list[str], x1, x2, labels, loss_weight
                 logits=[l.detach() for l in logits], grads=grads)
 
 
+# ----------------------------------------------------------------------------------------------- finetune / test
+def _bn_eval(x, P, name):
+    return F.batch_norm(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"], P[name + ".bias"],
+                        False, BN_MOMENTUM, BN_EPS)
+
+
+def finetune_forward(state: dict, x, training: bool = True, tape: Tape | None = None):
+    """R21DBYOL(pretrain=False).forward(x, o_type in {'ft_fc','ft_all','test'}) -- r21d_byol.py:394-399:
+    classify(cls_bn(F.normalize(online_net(x), p=2, dim=1))).  training=False is model.eval() (running statistics,
+    main_ft_mp.py:281-289 / test.py:76-93).  Returns (logits, updated BN buffers)."""
+    tape = tape or Tape(False)
+    if training:
+        bufs: dict = {}
+        P = _ParamView(state, bufs)
+        feat = r2plus1d_net(x, P, "online_net", bufs, tape, "online.v1", proj=False)
+        feat = F.normalize(feat, p=2, dim=1)
+        feat = _bn(feat, P, "cls_bn", bufs, tape, "cls_bn")
+        return F.linear(feat, state["classify.weight"], state["classify.bias"]), bufs
+    # eval mode: the same graph with every BatchNorm replaced by its running-statistics affine map
+    P = state
+
+    def stc(x_, pre, kernel, stride, pad):
+        x_ = F.conv3d(x_, P[pre + ".spatial_conv.weight"], None, (1, stride[1], stride[2]), (0, pad[1], pad[2]))
+        x_ = F.relu(_bn_eval(x_, P, pre + ".bn"))
+        return F.conv3d(x_, P[pre + ".temporal_conv.weight"], None, (stride[0], 1, 1), (pad[0], 0, 0))
+    h = stc(x, "online_net.conv1", (3, 7, 7), (1, 2, 2), (1, 3, 3))
+    h = F.relu(_bn_eval(h, P, "online_net.bn1"))
+    for stage, down in (("conv2", False), ("conv3", True), ("conv4", True), ("conv5", True)):
+        pre = f"online_net.{stage}.block1"
+        s_ = (2, 2, 2) if down else (1, 1, 1)
+        r = stc(h, pre + ".conv1", (3, 3, 3), s_, (1, 1, 1))
+        r = F.relu(_bn_eval(r, P, pre + ".bn1"))
+        r = _bn_eval(stc(r, pre + ".conv2", (3, 3, 3), (1, 1, 1), (1, 1, 1)), P, pre + ".bn2")
+        if down:
+            h = _bn_eval(stc(h, pre + ".downsampleconv", (1, 1, 1), (2, 2, 2), (0, 0, 0)), P, pre + ".downsamplebn")
+        h = F.relu(h + r)
+    feat = F.adaptive_avg_pool3d(h, 1).view(-1, 512)
+    feat = _bn_eval(F.normalize(feat, p=2, dim=1), P, "cls_bn")
+    return F.linear(feat, state["classify.weight"], state["classify.bias"]), {}
+
+
+def finetune_step(state: dict, trainable: list[str], x, labels, lr, mom: dict, momentum=0.9, wd=1e-3, tape=None):
+    """One step of main_ft_mp.py:196-214 (CrossEntropyLoss, backward, SGD.step; no gradient clipping)."""
+    for k in trainable:
+        state[k] = state[k].detach().requires_grad_(True)
+    logits, bufs = finetune_forward(state, x, True, tape)
+    loss = F.cross_entropy(logits, labels)
+    grads = dict(zip(trainable, torch.autograd.grad(loss, [state[k] for k in trainable], allow_unused=True)))
+    params = {k: state[k].detach() for k in trainable}
+    clip_and_sgd(params, grads, mom, lr, momentum=momentum, wd=wd, clip=False)
+    for k in trainable:
+        state[k] = params[k]
+    state.update(bufs)
+    return dict(loss=float(loss), logits=logits.detach(), grads=grads)
+
+
 # ----------------------------------------------------------------------------------------------- NT-Xent
 def ntxent_reference_form(zis, zjs, temperature, use_cosine=True):
     """loss/NTXent.py:46-62 restated literally (materialises the 2N x 2N matrix; small N only)."""

@@ -144,11 +144,42 @@ def run_ntxent() -> dict:
     return res
 
 
+def run_finetune() -> dict:
+    """R21DBYOL(pretrain=False, num_classes=101, cls_bn=True): one training step of main_ft_mp.py:196-214 on B=4
+    video-like clips (SGD lr 0.025 momentum 0.9 wd 1e-3, README.md:68-78), then model.eval() logits of the first clip."""
+    sys.path.insert(0, REF)
+    from models.pace import r21d_byol as ref_mod  # the reference, unmodified
+    torch.manual_seed(1)
+    model = ref_mod.R21DBYOL(pretrain=False, num_classes=101, cls_bn=True)
+    model.train()
+    x = structured_batch(4, 0)[0]
+    labels = torch.randint(0, 101, (4,), generator=torch.Generator().manual_seed(11))
+    opt = torch.optim.SGD(model.parameters(), lr=0.025, momentum=0.9, weight_decay=1e-3)
+    out = dict(B=4, labels=labels.clone(), state_dict_keys=list(model.state_dict().keys()),
+               param_sum=sum(p.double().sum().item() for p in model.parameters()))
+    logits = model(x, o_type="ft_all")
+    loss = nn.CrossEntropyLoss()(logits, labels)
+    opt.zero_grad()
+    loss.backward()
+    out["train"] = dict(loss=loss.item(), logits=logits.detach().clone(),
+                        param_grads={n: summarize(p.grad, N_GRAD_SAMPLES) for n, p in model.named_parameters()})
+    opt.step()
+    out["params_after"] = {n: summarize(p, N_GRAD_SAMPLES) for n, p in model.named_parameters()}
+    out["buffers_after"] = {n: summarize(b, N_GRAD_SAMPLES) for n, b in model.named_buffers()
+                            if not n.endswith("num_batches_tracked")}
+    model.eval()
+    with torch.no_grad():
+        out["eval_logits_b1"] = model(x[:1], None, o_type="test").clone()
+        out["eval_logits_b4"] = model(x, None, o_type="test").clone()
+    print(f"[ref finetune] loss {loss.item():.6f} eval argmax {out['eval_logits_b4'].argmax(1).tolist()}", flush=True)
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
-    which = sys.argv[1:] or ["ntxent", "b2", "b4", "struct_b4"]
+    which = sys.argv[1:] or ["ntxent", "b2", "b4", "struct_b4", "finetune"]
     if "ntxent" in which:
         torch.save(run_ntxent(), os.path.join(gold, "ntxent_ref.pt"))
     if "b2" in which:
@@ -157,4 +188,6 @@ if __name__ == "__main__":
         torch.save(run_reference(4, 2, False), os.path.join(gold, "step_b4.pt"))
     if "struct_b4" in which:       # video-like clips (oracle.structured_batch): the bf16 per-layer parity fixture
         torch.save(run_reference(4, 2, True, structured_batch), os.path.join(gold, "step_struct_b4.pt"))
+    if "finetune" in which:
+        torch.save(run_finetune(), os.path.join(gold, "finetune_b4.pt"))
     print("golden fixtures written to", gold)

@@ -343,6 +343,45 @@ def ntxent(z, temperature, use_cosine, loss_out, dz, workspace):
     loss_out.copy_(loss.detach().reshape(loss_out.shape))
 
 
+def l2norm_fwd(x, y_bf16, norms, d, eps=1e-12):
+    _count()
+    n = x[:, :d].norm(dim=1).clamp_min(eps)
+    y_bf16.zero_()
+    y_bf16[:, :d] = (x[:, :d] / n[:, None]).to(y_bf16.dtype)
+    norms.copy_(n)
+
+
+def l2norm_bwd(x, norms, g_bf16, dx, d):
+    _count()
+    g = g_bf16[:, :d].float()
+    y = x[:, :d] / norms[:, None]
+    dx.zero_()
+    dx[:, :d] = (g - y * (y * g).sum(1, keepdim=True)) / norms[:, None]
+
+
+def ce_loss(logits, labels, n_cls, loss_out, dlogits, workspace):
+    _count()
+    lg = logits[:, :n_cls].detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        ce = F.cross_entropy(lg, labels)
+        (gr,) = torch.autograd.grad(ce, lg)
+    loss_out.copy_(ce.detach().reshape(loss_out.shape))
+    if dlogits is not None:
+        dlogits.zero_()
+        dlogits[:, :n_cls] = gr
+
+
+def bn_eval_coeffs(st, gamma, beta, running_mean, running_var, eps=1e-5):
+    _count()
+    sc = torch.zeros(st.groups, st.Cp)
+    sh = torch.zeros(st.groups, st.Cp)
+    s_ = gamma / torch.sqrt(running_var + eps)
+    sc[:, :st.C] = s_
+    sh[:, :st.C] = beta - running_mean * s_
+    st.scale.copy_(sc.reshape(-1))
+    st.shift.copy_(sh.reshape(-1))
+
+
 def ema_update(k, q, m):
     _count()
     import numpy as np

@@ -69,11 +69,13 @@ def check_conv_units(eng, params, which="online"):
         gamma = params[u["bnname"] + ".weight"].clone().requires_grad_(u["grads"])
         beta = params[u["bnname"] + ".bias"].clone().requires_grad_(u["grads"])
         leaf = raw_e5.clone().requires_grad_(u["grads"])
-        y = _bn_groups(leaf, gamma, beta)
+        views = getattr(eng, "VIEWS", 2)
+        y = _bn_groups(leaf, gamma, beta, views)
         if u["res"] is not None:
             if u["res_site"] is not None:
                 ds = by_raw[u["res"].data_ptr()]
-                r = _bn_groups(_ncdhw(u["res"], cout), params[ds["bnname"] + ".weight"], params[ds["bnname"] + ".bias"])
+                r = _bn_groups(_ncdhw(u["res"], cout), params[ds["bnname"] + ".weight"], params[ds["bnname"] + ".bias"],
+                               views)
             else:
                 r = _ncdhw(u["res"], cout)
             y = y + r

@@ -1,0 +1,136 @@
+"""Finetune / test branch on CPU: the oracle against the reference's golden vectors
+(tests/golden/finetune_b4.pt, produced by oracle/make_golden.py from the unmodified reference), and the finetune engine
+over tests/emulate_ops.py against the oracle (fp32 storage: wiring; train step, eval mode, frozen backbone)."""
+import os
+
+import pytest
+import torch
+
+from oracle import cstp_oracle as O
+from tests.parity import load_golden, rel, sample_idx
+
+LR, MOM, WD = 0.025, 0.9, 1e-3
+
+
+def _model():
+    from cstp_b200.models.pace.r21d_byol import R21DBYOL
+    torch.manual_seed(1)
+    return R21DBYOL(pretrain=False, num_classes=101, cls_bn=True)
+
+
+def _state(m):
+    return {k: v.clone() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+
+
+def test_oracle_matches_reference_golden():
+    g = load_golden("finetune_b4.pt")
+    m = _model()
+    assert list(m.state_dict().keys()) == g["state_dict_keys"]
+    assert abs(sum(p.double().sum().item() for p in m.parameters()) - g["param_sum"]) < 1e-9
+    state = _state(m)
+    trainable = [n for n, _ in m.named_parameters()]
+    x = O.structured_batch(4, 0)[0]
+    labels = torch.randint(0, 101, (4,), generator=torch.Generator().manual_seed(11))
+    assert torch.equal(labels, g["labels"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = O.finetune_step(state, trainable, x, labels, LR, {}, MOM, WD)
+    assert abs(r["loss"] - g["train"]["loss"]) < 1e-5 * g["train"]["loss"]
+    assert rel(r["logits"], g["train"]["logits"]) < 1e-4
+    errs = {}
+    for n, s in g["train"]["param_grads"].items():
+        gv = r["grads"][n].reshape(-1)
+        if s["l2"] > 1e-6:
+            errs[n] = rel(gv[sample_idx(gv.numel(), 256)], s["samples"])
+    assert sorted(errs.values())[len(errs) // 2] < 2e-3 and max(errs.values()) < 5e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    for n, s in g["params_after"].items():
+        v = state[n].detach().reshape(-1)
+        assert rel(v[sample_idx(v.numel(), 256)], s["samples"]) < 1e-4, n
+    for n, s in g["buffers_after"].items():
+        v = state[n].detach().reshape(-1)
+        assert rel(v[sample_idx(v.numel(), 256)], s["samples"]) < 1e-4, n
+    with torch.no_grad():
+        ev, _ = O.finetune_forward({k: v.detach() for k, v in state.items()}, x, training=False)
+        ev1, _ = O.finetune_forward({k: v.detach() for k, v in state.items()}, x[:1], training=False)
+    assert rel(ev, g["eval_logits_b4"]) < 1e-4 and rel(ev1, g["eval_logits_b1"]) < 1e-4
+    assert torch.equal(ev.argmax(1), g["eval_logits_b4"].argmax(1))
+
+
+@pytest.fixture()
+def emu():
+    from cstp_b200 import engine
+    from tests import emulate_ops
+    saved = engine.ops, engine.ACT_DTYPE
+    engine.ops, engine.ACT_DTYPE = emulate_ops, torch.float32
+    try:
+        yield engine
+    finally:
+        engine.ops, engine.ACT_DTYPE = saved
+
+
+def test_emulated_finetune_engine_matches_oracle(emu):
+    B, T, S = 4, 8, 64
+    x = O.structured_batch(B, 0, T, S)[0]
+    labels = torch.randint(0, 101, (B,), generator=torch.Generator().manual_seed(11))
+    m = _model()
+    state = _state(m)
+    trainable = [n for n, _ in m.named_parameters()]
+    # ---- drop-in training step: the unmodified loop body of main_ft_mp.py:196-214
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=LR, momentum=MOM, weight_decay=WD)
+    logits = m(x, o_type="ft_all")
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = O.finetune_step(state, trainable, x, labels, LR, {}, MOM, WD)
+    assert abs(loss.item() - r["loss"]) < 1e-5 * r["loss"]
+    assert rel(logits, r["logits"]) < 1e-4
+    sd = m.state_dict()
+    gerr = {n: rel(m._engine.train.view(n, m._engine.grad), r["grads"][n]) for n in trainable
+            if r["grads"][n].norm() > 1e-6}
+    assert sorted(gerr.values())[len(gerr) // 2] < 1e-2 and max(gerr.values()) < 5e-2, sorted(gerr.items(), key=lambda kv: -kv[1])[:4]
+    for k, v in state.items():
+        if "running" in k:
+            assert rel(sd[k], v) < 1e-4, k
+    assert sd["cls_bn.num_batches_tracked"].item() == 1 and sd["online_net.bn1.num_batches_tracked"].item() == 1
+    # ---- eval mode after the step (running statistics; different batch size -> a second engine)
+    m.eval()
+    with torch.no_grad():
+        ev = m(x[:1], None, o_type="test")
+        ref_ev, _ = O.finetune_forward({k: v.detach().clone() for k, v in m.state_dict().items()}, x[:1], training=False)
+    assert ev.shape == (1, 101) and rel(ev, ref_ev) < 1e-4
+    assert sd["cls_bn.num_batches_tracked"].item() == 1          # eval updates nothing
+
+
+def test_emulated_fused_step_and_frozen_backbone(emu):
+    from cstp_b200.models.pace.r21d_byol import get_fine_tuning_parameters
+    B, T, S = 2, 4, 32
+    x = O.structured_batch(B, 1, T, S)[0]
+    labels = torch.tensor([3, 77])
+    a, b = _model(), _model()
+    a.train()
+    b.train()
+    la = a.finetune_step(x, labels, lr=LR, momentum=MOM, weight_decay=WD).clone()
+    opt = torch.optim.SGD(b.parameters(), lr=LR, momentum=MOM, weight_decay=WD)
+    lb = torch.nn.CrossEntropyLoss()(b(x, o_type="ft_all"), labels)
+    opt.zero_grad()
+    lb.backward()
+    opt.step()
+    assert abs(la.item() - lb.item()) < 1e-6
+    sa, sb = a.state_dict(), b.state_dict()
+    assert max(rel(sa[k], sb[k]) for k in sa if sa[k].dtype.is_floating_point) < 1e-5
+    # ft_fc: get_fine_tuning_parameters(model, 5) freezes everything but `classify` (r21d_byol.py:10-35)
+    c = _model()
+    c.train()
+    groups = get_fine_tuning_parameters(c, 5)
+    assert sum(1 for g in groups if g.get("lr", 1) != 0.0) == 2
+    opt = torch.optim.SGD(groups, lr=LR, momentum=MOM, weight_decay=WD)
+    w0 = c.online_net.conv1.spatial_conv.weight.detach().clone()
+    lc = torch.nn.CrossEntropyLoss()(c(x, o_type="ft_fc"), labels)
+    opt.zero_grad()
+    lc.backward()
+    opt.step()
+    assert not c._engine.backbone_grads
+    assert torch.equal(c.online_net.conv1.spatial_conv.weight, w0) and c.online_net.conv1.spatial_conv.weight.grad is None
+    assert c.classify.weight.grad is not None and c.classify.weight.grad.abs().sum() > 0

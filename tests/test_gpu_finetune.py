@@ -1,0 +1,94 @@
+"""GPU parity of the finetune / test branch (R21DBYOL(pretrain=False) -> FinetuneEngine -> C ABI):
+per-layer parity of the single-view backbone, the training step against the oracle, and the reference's golden vectors
+(train loss / logits, eval-mode logits at batch 4 and batch 1)."""
+import os
+
+import pytest
+import torch
+
+from tests import local_parity as LP
+from tests.parity import load_golden, rel
+
+pytestmark = pytest.mark.gpu
+LR, MOM, WD = 0.025, 0.9, 1e-3
+
+
+def _model(record=False):
+    from cstp_b200.models.pace.r21d_byol import R21DBYOL
+    torch.manual_seed(1)
+    m = R21DBYOL(pretrain=False, num_classes=101, cls_bn=True)
+    m.engine_options = {"record": record}
+    return m
+
+
+def test_train_step_per_layer_and_oracle():
+    from oracle import cstp_oracle as O
+    B, T, S = 4, 8, 64
+    x = O.structured_batch(B, 0, T, S)[0]
+    labels = torch.randint(0, 101, (B,), generator=torch.Generator().manual_seed(11))
+    m = _model(record=True)
+    before = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    trainable = [n for n, _ in m.named_parameters()]
+    m.cuda().train()
+    opt = torch.optim.SGD(m.parameters(), lr=LR, momentum=MOM, weight_decay=WD)
+    logits = m(x.cuda(), o_type="ft_all")
+    loss = torch.nn.CrossEntropyLoss()(logits, labels.cuda())
+    opt.zero_grad()
+    loss.backward()
+    res = LP.check_conv_units(m._engine, before, "online")           # every backbone layer, forward and backward
+    w = LP.worst(res)
+    print("worst per-layer error (finetune, one view):", w)
+    assert len([t for t in res if t.startswith("online.")]) == 24 and w[0] < 1e-2, w
+    opt.step()
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = O.finetune_step({k: v.clone() for k, v in before.items()}, trainable, x, labels, LR, {}, MOM, WD)
+    assert abs(loss.item() - r["loss"]) < 1e-3 * r["loss"]
+    assert rel(logits, r["logits"]) < 3e-2                          # 101 logits behind a 4-sample BatchNorm1d
+    # head gradients (fp32 path after the bf16 GEMMs): classify / cls_bn against the oracle
+    eng = m._engine
+    assert rel(eng.train.view("classify.bias", eng.grad), r["grads"]["classify.bias"]) < 2e-2
+    assert rel(eng.train.view("classify.weight", eng.grad), r["grads"]["classify.weight"]) < 5e-2
+
+
+def test_reference_golden_train_and_eval():
+    from oracle import cstp_oracle as O
+    g = load_golden("finetune_b4.pt")
+    x = O.structured_batch(4, 0)[0]
+    m = _model().cuda().train()
+    opt = torch.optim.SGD(m.parameters(), lr=LR, momentum=MOM, weight_decay=WD)
+    logits = m(x.cuda(), o_type="ft_all")
+    loss = torch.nn.CrossEntropyLoss()(logits, g["labels"].cuda())
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    print("finetune loss", loss.item(), g["train"]["loss"])
+    assert abs(loss.item() - g["train"]["loss"]) < 1e-3 * g["train"]["loss"]
+    assert rel(logits, g["train"]["logits"]) < 3e-2
+    m.eval()
+    with torch.no_grad():
+        ev4 = m(x.cuda(), None, o_type="test")
+        ev1 = m(x[:1].cuda(), None, o_type="test")
+    print("eval logits rel err", rel(ev4, g["eval_logits_b4"]), rel(ev1, g["eval_logits_b1"]))
+    assert rel(ev4, g["eval_logits_b4"]) < 3e-2 and rel(ev1, g["eval_logits_b1"]) < 3e-2
+    assert torch.equal(ev4.argmax(1).cpu(), g["eval_logits_b4"].argmax(1))          # integer predictions
+    assert m.cls_bn.num_batches_tracked.item() == 1
+
+
+def test_fused_step_equals_dropin_and_is_reproducible():
+    from oracle import cstp_oracle as O
+    x = O.structured_batch(2, 1, 8, 64)[0].cuda()
+    labels = torch.tensor([3, 77], device="cuda")
+    a, b, c = _model().cuda().train(), _model().cuda().train(), _model().cuda().train()
+    la = a.finetune_step(x, labels, lr=LR, momentum=MOM, weight_decay=WD).clone()
+    lc = c.finetune_step(x, labels, lr=LR, momentum=MOM, weight_decay=WD).clone()
+    opt = torch.optim.SGD(b.parameters(), lr=LR, momentum=MOM, weight_decay=WD)
+    lb = torch.nn.CrossEntropyLoss()(b(x, o_type="ft_all"), labels)
+    opt.zero_grad()
+    lb.backward()
+    opt.step()
+    assert abs(la.item() - lb.item()) < 1e-5
+    sa, sb, sc = a.state_dict(), b.state_dict(), c.state_dict()
+    assert max(rel(sa[k], sb[k]) for k in sa if sa[k].dtype.is_floating_point) < 1e-5
+    assert torch.equal(la, lc) and all(torch.equal(sa[k], sc[k]) for k in sa)
+    with pytest.raises(NotImplementedError):
+        a(x, x, o_type="loss_com")
