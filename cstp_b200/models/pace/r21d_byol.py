@@ -304,6 +304,16 @@ class R21DBYOL(nn.Module):
             self._dirty = True
         return eng
 
+    def _repack_if_changed(self, eng):
+        """Re-packs the bf16 tensor-core weights when the fp32 parameters changed behind the engine's back.  The
+        parameters are views of the engine's flat buffer, so every in-place update (optimizer.step, load_state_dict)
+        bumps the version counter of that buffer."""
+        v = eng.train.data._version
+        if self._dirty or getattr(self, "_packed_version", None) != (id(eng), v):
+            eng.pack_online()
+            self._packed_version = (id(eng), v)
+            self._dirty = False
+
     def _forward_ft(self, x1):
         eng = self._bind_ft(x1)
         x1 = x1.contiguous()
@@ -312,10 +322,13 @@ class R21DBYOL(nn.Module):
             self._nbt += self._nbt_inc
             self._dirty = True
             return out
-        eng.eval_mode = not self.training
-        eng.forward(x1, repack=True)
+        self._repack_if_changed(eng)
         if self.training:
+            eng.eval_mode = False
+            eng.forward(x1)
             self._nbt += self._nbt_inc
+        else:
+            eng.forward_eval(x1)
         return eng.logits[:, :self.num_classes].clone()
 
     @torch.no_grad()
