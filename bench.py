@@ -80,12 +80,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def workload_config(B: int, world: int) -> dict:
+def workload_config(B: int, world: int, bn: str = "per-GPU (reference semantics)") -> dict:
     """`config` of the JSON line -- identical for the native and the reference arm."""
     return {"workload": f"r21d_byol UCF-101-shaped pretrain step (UcfRepreBYOLSpPre shape), batch {B}/GPU, "
                         "2 views x 3x16x112x112, loss_weight 0.1 1 1 1 1, SGD lr 0.03 m 0.9 wd 5e-4 clip 18",
             "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-            "bn": "per-GPU (reference semantics)"}
+            "bn": bn}
 
 
 def run_reference(args, rank: int):
@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bn-sync", default="local", choices=["local", "world"],
+                    help="local: per-GPU BatchNorm statistics (the reference's behaviour); world: SyncBN over all ranks")
     args = ap.parse_args()
     from cstp_b200 import parallel
     rank, world, local = parallel.env_world()
@@ -177,6 +179,8 @@ def main():
     B = args.batch
     torch.manual_seed(1)
     model = R21DBYOL(pretrain=True).cuda()
+    if args.bn_sync == "world" and world > 1:
+        model.engine_options = {"bn_sync": parallel.BnSync()}
     hx1, hx2, hlabels = synthetic_batch(B, seed=rank)
     hx1, hx2 = hx1.pin_memory(), hx2.pin_memory()
     hlabels = tuple(l.pin_memory() for l in hlabels)
@@ -283,7 +287,8 @@ def main():
         "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {**workload_config(B, world),
+        "config": {**workload_config(B, world, "per-GPU (reference semantics)" if args.bn_sync == "local" or world == 1
+                                     else "world-synchronised (SyncBN all-reduce per BatchNorm call)"),
                    "l2_policy": "inputs and activations far larger than the 126 MB L2 (clips alone 2x%.0f MB)" % (x1.numel() * 4 / 1e6),
                    "views_per_s": 2 * value, "schedule": "two streams (target fwd || online fwd, wgrad || BN backward)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,

@@ -214,6 +214,23 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   }
 }
 
+// Collapses the per-block partials to one row [groups][2][Cp] (fp32): the payload of the cross-rank statistics
+// all-reduce in world-synchronised BatchNorm (SyncBN); the finalize kernels then run with nblocks = 1.
+__global__ void __launch_bounds__(256) bn_partials_reduce_kernel(const float* __restrict__ partials, int nblocks, int groups,
+                                                                 int Cp, float* __restrict__ out) {
+  __shared__ double red[8][2][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < Cp;
+  for (int g = 0; g < groups; ++g) {
+    double s, ss;
+    reduce_partials(partials, nblocks, groups, g, Cp, c, c < Cp, red, s, ss);
+    if (lead) {
+      out[(g * 2 + 0) * Cp + c] = static_cast<float>(s);
+      out[(g * 2 + 1) * Cp + c] = static_cast<float>(ss);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
                                                           long long rows_per_group, int C, int Cp,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -548,6 +565,13 @@ extern "C" int cstp_bn_stats(const void* raw, int64_t rows, int Cp, int groups, 
   const dim3 grid(nblocks, groups, ceil_div(Cp / 8, kSegVecs));
   bn_reduce_kernel<false><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(raw), nullptr, nullptr,
                                                        rows / groups, Cp, nullptr, nullptr, nullptr, nullptr, partials);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_bn_partials_reduce(const float* partials, int nblocks, int groups, int Cp, float* out, void* stream) {
+  CSTP_REQUIRE(partials && out && nblocks > 0 && groups > 0 && Cp % 16 == 0);
+  bn_partials_reduce_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, Cp, out);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

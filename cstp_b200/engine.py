@@ -173,7 +173,7 @@ class StepEngine:
     VIEWS = 2          # clips per sample pushed through the backbone = BatchNorm statistics groups
 
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", momentum_ema: float = 0.996,
-                 record: bool = False, overlap: bool = True):
+                 record: bool = False, overlap: bool = True, bn_sync=None):
         if H % 2 or W % 2:
             raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
         self.B, self.T, self.H, self.W = B, T, H, W
@@ -182,6 +182,9 @@ class StepEngine:
         self.momentum_ema = momentum_ema
         self.record = record
         self.eval_mode = False       # True: BatchNorm uses its running statistics (finetune validation / test)
+        # None: per-GPU BatchNorm statistics (what the reference's --sync_bn actually does);
+        # a cstp_b200.parallel.BnSync: statistics over every rank of the data-parallel group (north-star SyncBN)
+        self.bn_sync = bn_sync
         # Two-stream schedule (CUDA only): the target network's forward runs beside the online network's, and every
         # weight-gradient GEMM runs beside the BatchNorm-backward streaming kernels of the next unit, so HBM-bound and
         # tensor-bound kernels share the machine.  Results are unchanged (same kernels, same reduction orders).
@@ -297,7 +300,7 @@ class StepEngine:
                 ops.bn_eval_coeffs(site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS)
             else:
                 ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
-                                     fused_blocks=fused)
+                                     fused_blocks=fused, sync=self.bn_sync)
             if apply:
                 ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_site.st if res_site else None)
         prog.append(fwd)
@@ -341,7 +344,7 @@ class StepEngine:
                 # the weight-gradient GEMM that last read this d(raw) buffer (two units ago) must have finished
                 torch.cuda.current_stream().wait_event(self._ev_wg[holder["gbuf"]])
             ops.bn_backward(d_out, act_for_mask, raw, site.st, site.gamma, site.dgamma, site.dbeta, g, dz=dz,
-                            mask_from_raw=from_raw)
+                            mask_from_raw=from_raw, sync=self.bn_sync)
             if self.record:      # parity tests: the shared d(raw) scratch is overwritten by a later unit
                 self.named[unit["tag"] + ".g"] = g.clone()
             if self.overlap and self._prof is None:
@@ -464,7 +467,8 @@ class StepEngine:
 
         def fwd():
             p0.run()
-            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM)
+            ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
+                                 sync=self.bn_sync)
             ops.bn_apply(raw, site.st, h, relu=True)
             p3.run()
         prog.append(fwd)
@@ -509,7 +513,8 @@ class StepEngine:
                 ops.colsum(g_out, cout, db3)
                 holder["wg3"].run(dW3)
                 pd_h.run()
-                ops.bn_backward(d_h, h, raw, site.st, site.gamma, site.dgamma, site.dbeta, g_h, mask_from_raw=True)
+                ops.bn_backward(d_h, h, raw, site.st, site.gamma, site.dgamma, site.dbeta, g_h, mask_from_raw=True,
+                                sync=self.bn_sync)
                 ops.colsum(g_h, hidden, db0)
                 holder["wg0"].run(dW0)
                 if pd_x is not None:

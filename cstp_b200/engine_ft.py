@@ -29,9 +29,10 @@ class FinetuneEngine(StepEngine):
     VIEWS = 1
 
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", num_classes: int = 101,
-                 cls_bn: bool = True, record: bool = False, overlap: bool = True, backbone_grads: bool = True):
+                 cls_bn: bool = True, record: bool = False, overlap: bool = True, backbone_grads: bool = True,
+                 bn_sync=None):
         self.num_classes, self.cls_bn, self.backbone_grads = num_classes, bool(cls_bn), backbone_grads
-        super().__init__(B, T, H, W, device=device, record=record, overlap=overlap)
+        super().__init__(B, T, H, W, device=device, record=record, overlap=overlap, bn_sync=bn_sync)
 
     def _make_stores(self):
         specs = finetune_param_specs(self.num_classes, self.cls_bn)
@@ -77,7 +78,7 @@ class FinetuneEngine(StepEngine):
                     ops.bn_eval_coeffs(site.st, site.gamma, site.beta, site.rm, site.rv, E.BN_EPS)
                 else:
                     ops.bn_forward_stats(self.nfeat, site.st, site.gamma, site.beta, site.rm, site.rv, E.BN_EPS,
-                                         E.BN_MOMENTUM)
+                                         E.BN_MOMENTUM, sync=self.bn_sync)
                 ops.bn_apply(self.nfeat, site.st, self.hfeat, relu=False)
             p_cls.run()
         self.fwd_online.append(head_fwd)
@@ -109,7 +110,8 @@ class FinetuneEngine(StepEngine):
                 return
             pd_h.run()
             if site is not None:
-                ops.bn_backward(d_h, None, self.nfeat, site.st, site.gamma, site.dgamma, site.dbeta, g_n)
+                ops.bn_backward(d_h, None, self.nfeat, site.st, site.gamma, site.dgamma, site.dbeta, g_n,
+                                sync=self.bn_sync)
             ops.l2norm_bwd(self.feat, self.norms, g_n, self.dfeat, 512)
             ops.avgpool_bwd(self.dfeat, d_x5)
         self.bwd.append(head_bwd)

@@ -144,6 +144,7 @@ SIGNATURES = {
     "cstp_pack_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "cstp_stem_im2col": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "cstp_bn_stats": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
+    "cstp_bn_partials_reduce": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "cstp_bn_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cstp_bn_apply": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cstp_bn_bwd_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

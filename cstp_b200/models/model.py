@@ -37,6 +37,10 @@ def generate_model(opts):
         model = r21d_byol.R21DBYOL(pretrain=False, num_classes=opts.n_classes, cls_bn=True)      # models/model.py:48-49
     else:
         raise NotImplementedError(f"task {opts.task!r} is outside the r21d_byol paths implemented by cstp_b200")
+    if getattr(opts, "bn_sync", "local") == "world":
+        # opt-in extension (not a reference flag): BatchNorm statistics over every rank of the default process group
+        from ..parallel import BnSync
+        model.engine_options = {"bn_sync": BnSync()}
     wrapped = False
     if getattr(opts, "distributed", False):
         # models/model.py:82-103.  The reference's --sync_bn builds a process group holding only the local rank, i.e.

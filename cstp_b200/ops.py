@@ -627,6 +627,7 @@ class BNState:
     mean: torch.Tensor
     invstd: torch.Tensor
     coef: torch.Tensor = field(default=None)
+    compact: torch.Tensor = field(default=None)      # [groups][2][Cp] row exchanged by world-synchronised BatchNorm
 
     @staticmethod
     def alloc(C_: int, Cp: int, groups: int, rows_per_group: int, device, backward: bool = True) -> "BNState":
@@ -635,19 +636,26 @@ class BNState:
         # room for the fused-statistics path too: one partial row per CTA of a persistent conv kernel (<= 148)
         return BNState(C_, Cp, groups, nb, torch.empty(max(nb, 160) * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f),
-                       torch.empty(groups * 3 * Cp, **f) if backward else None)
+                       torch.empty(groups * 3 * Cp, **f) if backward else None, torch.empty(groups * 2 * Cp, **f))
 
 
 def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1,
-                     fused_blocks: int = 0) -> None:
+                     fused_blocks: int = 0, sync=None) -> None:
     """Batch statistics of raw -> scale/shift/mean/invstd (+ running buffers).  fused_blocks > 0: the producing conv
-    kernel already wrote that many partial rows into st.partials (no statistics pass over raw)."""
+    kernel already wrote that many partial rows into st.partials (no statistics pass over raw).  `sync` (an object with
+    `.world` and `.all_reduce(tensor)`) makes the statistics span every rank (SyncBN over the data-parallel group): the
+    per-rank sums are collapsed to one row, summed across ranks and finalized with the global row count."""
     rows = raw.numel() // st.Cp
     lib = L.load()
     nblocks = fused_blocks or st.nblocks
     if not fused_blocks:
         L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
-    L.check(lib.cstp_bn_finalize(_ptr(st.partials), nblocks, st.groups, rows // st.groups, st.C, st.Cp, _ptr(gamma),
+    partials, rpg = st.partials, rows // st.groups
+    if sync is not None and sync.world > 1:
+        L.check(lib.cstp_bn_partials_reduce(_ptr(st.partials), nblocks, st.groups, st.Cp, _ptr(st.compact), _stream()))
+        sync.all_reduce(st.compact)
+        partials, nblocks, rpg = st.compact, 1, rpg * sync.world
+    L.check(lib.cstp_bn_finalize(_ptr(partials), nblocks, st.groups, rpg, st.C, st.Cp, _ptr(gamma),
                                  _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var), _ptr(st.scale),
                                  _ptr(st.shift), _ptr(st.mean), _ptr(st.invstd), _stream()))
 
@@ -661,7 +669,7 @@ def bn_apply(raw, st: BNState, out, *, relu: bool, res=None, res_state: BNState 
 
 
 def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False,
-                mask_from_raw: bool = False) -> None:
+                mask_from_raw: bool = False, sync=None) -> None:
     """g_out = dL/d(raw) given d = dL/d(act); fills dgamma/dbeta.  The ReLU mask is `act > 0` when act is given, or --
     with mask_from_raw -- recomputed as raw*scale + shift > 0 from the forward coefficients kept in `st` (the same fmaf
     the forward apply evaluated; saves reading act twice)."""
@@ -672,9 +680,21 @@ def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=Non
         act = None
     L.check(lib.cstp_bn_bwd_reduce(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean),
                                    _ptr(st.invstd), _ptr(ms), _ptr(mb), _ptr(st.partials), st.nblocks, _stream()))
-    L.check(lib.cstp_bn_bwd_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp,
-                                     _ptr(gamma), _ptr(st.mean), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta), int(accumulate),
-                                     _ptr(st.coef), _stream()))
+    if sync is not None and sync.world > 1:
+        # SyncBN backward: dgamma / dbeta stay this rank's local sums (the data-parallel gradient mean combines them),
+        # the dx coefficients use the sums over every rank and the global row count
+        L.check(lib.cstp_bn_partials_reduce(_ptr(st.partials), st.nblocks, st.groups, st.Cp, _ptr(st.compact), _stream()))
+        L.check(lib.cstp_bn_bwd_finalize(_ptr(st.compact), 1, st.groups, rows // st.groups, st.C, st.Cp, _ptr(gamma),
+                                         _ptr(st.mean), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta), int(accumulate),
+                                         _ptr(st.coef), _stream()))
+        sync.all_reduce(st.compact)
+        L.check(lib.cstp_bn_bwd_finalize(_ptr(st.compact), 1, st.groups, (rows // st.groups) * sync.world, st.C, st.Cp,
+                                         _ptr(gamma), _ptr(st.mean), _ptr(st.invstd), None, None, 0, _ptr(st.coef),
+                                         _stream()))
+    else:
+        L.check(lib.cstp_bn_bwd_finalize(_ptr(st.partials), st.nblocks, st.groups, rows // st.groups, st.C, st.Cp,
+                                         _ptr(gamma), _ptr(st.mean), _ptr(st.invstd), _ptr(dgamma), _ptr(dbeta),
+                                         int(accumulate), _ptr(st.coef), _stream()))
     L.check(lib.cstp_bn_bwd_apply(_ptr(d), _ptr(act), _ptr(raw), rows, st.Cp, st.groups, _ptr(st.mean), _ptr(st.invstd),
                                   _ptr(st.coef), _ptr(ms), _ptr(mb), _ptr(g_out), _ptr(dz), _stream()))
 

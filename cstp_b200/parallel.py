@@ -70,6 +70,21 @@ class GradSync:
                 piece.mul_(1.0 / self.world)
 
 
+class BnSync:
+    """World-synchronised BatchNorm statistics (the north star's SyncBN; the reference's own --sync_bn group holds one
+    rank).  Passed to the engine as `bn_sync`: every BatchNorm call exchanges ONE small row
+    ([groups][2][Cp] fp32 sums) per direction with an all-reduce(SUM) over the data-parallel group; with it a step over
+    world x B samples equals the single-GPU step over the global batch."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def all_reduce(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
 def broadcast_parameters(tensors, src: int = 0, group=None) -> None:
     """DDP's initial parameter broadcast (models/model.py:97-103) over the engine's flat buffers."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -212,6 +212,10 @@ int cstp_bn_stats(const void* raw, int64_t rows, int Cp, int groups, float* part
 int cstp_bn_finalize(const float* partials, int nblocks, int groups, int64_t rows_per_group, int C, int Cp,
                      const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                      float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* Sums the per-block partials of cstp_bn_stats / cstp_bn_bwd_reduce into one row fp32 [groups][2][Cp]: the payload of
+ * the cross-rank all-reduce of world-synchronised BatchNorm; finalize then runs with nblocks = 1 and the global row
+ * count. */
+int cstp_bn_partials_reduce(const float* partials, int nblocks, int groups, int Cp, float* out, void* stream);
 /* out = act(raw*scale+shift + residual); res_mode 0 none, 1 bf16 tensor, 2 raw2*scale2+shift2. */
 int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, const float* scale, const float* shift,
                   int relu, int res_mode, const void* res, const float* scale2, const float* shift2, void* out,

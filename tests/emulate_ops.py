@@ -180,13 +180,19 @@ def _group_view(t, groups):
     return t.reshape(groups, rows // groups, t.shape[-1])
 
 
-def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, fused_blocks=0):
+def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, fused_blocks=0,
+                     sync=None):
     _count(2)
     x = _group_view(raw, st.groups).float()
     n = x.shape[1]
     C, Cp = st.C, st.Cp
-    mean = x.double().mean(1)
-    var = (x.double() ** 2).mean(1) - mean ** 2
+    s1, s2 = x.double().sum(1), (x.double() ** 2).sum(1)
+    if sync is not None and sync.world > 1:          # SyncBN: one [groups][2][Cp] fp32 row summed over the ranks
+        row = torch.stack([s1, s2], 1).float()
+        sync.all_reduce(row)
+        s1, s2, n = row[:, 0].double(), row[:, 1].double(), n * sync.world
+    mean = s1 / n
+    var = s2 / n - mean ** 2
     var.clamp_(min=0)
     istd = (1.0 / torch.sqrt(var + eps)).float()
     mean_f = mean.float()
@@ -223,7 +229,7 @@ def bn_apply(raw, st: BNState, out, *, relu, res=None, res_state=None):
 
 
 def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=None, accumulate=False,
-                mask_from_raw=False):
+                mask_from_raw=False, sync=None):
     _count(3)
     G, C, Cp = st.groups, st.C, st.Cp
     dy = _group_view(d, G).float()
@@ -240,6 +246,11 @@ def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=Non
     xhat = (x - st.mean.view(G, 1, Cp)) * st.invstd.view(G, 1, Cp)
     s = dy.double().sum(1)
     sx = (dy * xhat).double().sum(1)
+    s_loc, sx_loc = s, sx                              # dgamma / dbeta stay local sums under SyncBN
+    if sync is not None and sync.world > 1:
+        row = torch.stack([s, sx], 1).float()
+        sync.all_reduce(row)
+        s, sx, n = row[:, 0].double(), row[:, 1].double(), n * sync.world
     c0 = torch.zeros(G, Cp)
     c0[:, :C] = gamma * st.invstd.view(G, Cp)[:, :C]
     c1 = (s / n).float()
@@ -249,7 +260,7 @@ def bn_backward(d, act, raw, st: BNState, gamma, dgamma, dbeta, g_out, *, dz=Non
     go = c0.view(G, 1, Cp) * (dy - c1.view(G, 1, Cp) - xhat * c2.view(G, 1, Cp))
     g_out.copy_(go.reshape(g_out.shape).to(g_out.dtype))
     if dgamma is not None:
-        dg, db = sx.sum(0)[:C].float(), s.sum(0)[:C].float()
+        dg, db = sx_loc.sum(0)[:C].float(), s_loc.sum(0)[:C].float()
         dgamma.copy_(dgamma + dg if accumulate else dg)
         dbeta.copy_(dbeta + db if accumulate else db)
 

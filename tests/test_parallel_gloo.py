@@ -42,7 +42,7 @@ def _worker_collectives(rank, world, path, out):
     dist.destroy_process_group()
 
 
-def _step(batch, rank_slice, grad_sync=None):
+def _step(batch, rank_slice, grad_sync=None, bn_sync=None):
     from cstp_b200 import engine
     from cstp_b200.models.pace.r21d_byol import R21DBYOL
     from tests import emulate_ops
@@ -50,6 +50,8 @@ def _step(batch, rank_slice, grad_sync=None):
     engine.ACT_DTYPE = torch.float32
     torch.manual_seed(1)
     m = R21DBYOL(pretrain=True)
+    if bn_sync is not None:
+        m.engine_options = {"bn_sync": bn_sync}
     lo, hi = rank_slice
     x1, x2, labels = batch
     m.train_step(x1[lo:hi].contiguous(), x2[lo:hi].contiguous(), tuple(l[lo:hi].contiguous() for l in labels), LW, lr=0.03,
@@ -65,6 +67,18 @@ def _worker_step(rank, world, path, out):
     batch = O.structured_batch(GLOBAL_B, 0, T, S)
     m = _step(batch, P.shard_bounds(GLOBAL_B, rank, world), P.GradSync())
     torch.save({"train": m._engine.train.data.clone(), "grad": m._engine.grad.clone()}, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def _worker_syncbn(rank, world, path, out):
+    from cstp_b200 import parallel as P
+    from oracle import cstp_oracle as O
+    torch.set_num_threads(2)
+    _init(rank, world, path)
+    batch = O.structured_batch(GLOBAL_B, 0, T, S)
+    m = _step(batch, P.shard_bounds(GLOBAL_B, rank, world), P.GradSync(), P.BnSync())
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.save({"grad": m._engine.grad.clone(), "losses": m._engine.losses.clone(), "state": sd}, f"{out}.{rank}")
     dist.destroy_process_group()
 
 
@@ -100,6 +114,31 @@ def test_data_parallel_step_world2():
     mean = (grads[0] + grads[1]) / 2
     # different thread counts -> different fp32 summation order (and the odd ReLU tie): norm-wise comparison
     assert ((r0["grad"] - mean).norm() / mean.norm()).item() < 5e-3
+
+
+def test_world_synchronised_batchnorm_equals_global_batch():
+    """bn_sync=BnSync(): two ranks x 2 samples with cross-rank BatchNorm statistics == one process x 4 samples
+    (gradients after the data-parallel mean, BatchNorm running statistics, updated weights)."""
+    from cstp_b200 import engine
+    from oracle import cstp_oracle as O
+    r0, r1 = _spawn(_worker_syncbn)
+    assert torch.equal(r0["grad"], r1["grad"])
+    saved = engine.ops, engine.ACT_DTYPE
+    try:
+        single = _step(O.structured_batch(GLOBAL_B, 0, T, S), (0, GLOBAL_B))
+        g1 = single._engine.grad.clone()
+        s1 = {k: v.clone() for k, v in single.state_dict().items()}
+        l1 = single._engine.losses.clone()
+    finally:
+        engine.ops, engine.ACT_DTYPE = saved
+    # global loss = mean of the per-rank losses (equal shard sizes)
+    assert torch.allclose((r0["losses"] + r1["losses"]) / 2, l1, rtol=1e-4, atol=1e-5)
+    assert ((r0["grad"] - g1).norm() / g1.norm()).item() < 1e-2          # fp32 ReLU ties / summation order only
+    for k, v in s1.items():
+        if "running" in k:
+            assert torch.allclose(r0["state"][k], v, rtol=1e-4, atol=1e-6), k
+    w = "online_net.conv3.block1.conv1.spatial_conv.weight"
+    assert ((r0["state"][w] - s1[w]).norm() / s1[w].norm()).item() < 1e-4
 
 
 @pytest.mark.parametrize("gb,world", [(128, 8), (60, 6), (60, 8), (4, 2)])
