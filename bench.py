@@ -248,9 +248,10 @@ def main():
     # ---------------- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv: fwd + dgrad launches)
     pk = peaks()
     roof = None
+    # the instrumented step runs on EVERY rank (with world-synchronised BatchNorm it contains collectives); rank 0 reports
+    model._engine.profile_tensor_launches(x1, x2)
     if rank == 0:
         eng = model._engine
-        eng.profile_tensor_launches(x1, x2)
         kern: dict = {}
         for kind, tag, t_ms, fl, n, name in eng.last_profile:
             k = kern.setdefault(name, {"ms_per_step": 0.0, "flops": 0.0, "launches_per_step": 0})
