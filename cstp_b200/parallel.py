@@ -8,6 +8,7 @@ BatchNorm statistics stay per GPU: the reference's --sync_bn builds a process gr
 """
 from __future__ import annotations
 
+import datetime
 import os
 
 import torch
@@ -25,7 +26,8 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-        kw = {}
+        # fail fast instead of holding the GPUs for NCCL's default 10 minutes when ranks disagree on a collective
+        kw = {"timeout": datetime.timedelta(seconds=int(os.environ.get("CSTP_DIST_TIMEOUT_S", "180")))}
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
