@@ -41,6 +41,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// All weight tensors of a network in ONE launch: job j packs w_j (fp32 reference layout) into packed_j exactly as
+// pack_weight_kernel does; `jobs` is a device table of 8 int64 per job {w, packed, cout, cin, taps, transpose, Rp, Kc},
+// `prefix[j]` the first global element index of job j (prefix[n_jobs] = total).  97 launches per step -> 2.
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs,
+                                                                   const long long* __restrict__ prefix, int n_jobs,
+                                                                   long long total) {
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {                       // last job whose prefix <= g
+      const int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const long long* jb = jobs + static_cast<long long>(lo) * 8;
+    const float* w = reinterpret_cast<const float*>(jb[0]);
+    __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(jb[1]);
+    const int cout = static_cast<int>(jb[2]), cin = static_cast<int>(jb[3]), taps = static_cast<int>(jb[4]);
+    const int transpose = static_cast<int>(jb[5]), Kc = static_cast<int>(jb[7]);
+    const long long i = g - prefix[lo];
+    const int c = static_cast<int>(i % Kc);
+    const int tap = static_cast<int>((i / Kc) % taps);
+    const int r = static_cast<int>(i / (static_cast<long long>(Kc) * taps));
+    float v = 0.f;
+    if (!transpose) {
+      if (r < cout && c < cin) v = w[(static_cast<long long>(r) * cin + c) * taps + tap];
+    } else {
+      if (r < cin && c < cout) v = w[(static_cast<long long>(c) * cin + r) * taps + tap];
+    }
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- stem im2col
 // One CTA per (n, t, ho): the 3 x 7 input rows this output row needs are staged in shared memory with coalesced
 // float4 loads (zero rows / columns for the padding), then every thread assembles 16-byte vectors of 8 consecutive
@@ -544,6 +576,16 @@ extern "C" int cstp_pack_weight(const float* w, int cout, int cin, int taps, int
   const long long total = static_cast<long long>(Rp) * taps * Kc;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, cout, cin, taps, transpose,
                                                                   reinterpret_cast<__nv_bfloat16*>(packed), Rp, Kc);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_pack_weights_batched(const int64_t* jobs_dev, const int64_t* prefix_dev, int n_jobs, int64_t total,
+                                         void* stream) {
+  CSTP_REQUIRE(jobs_dev && prefix_dev && n_jobs > 0 && total > 0);
+  static_assert(sizeof(long long) == sizeof(int64_t), "job table is int64");
+  pack_weights_batched_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const long long*>(jobs_dev), reinterpret_cast<const long long*>(prefix_dev), n_jobs, total);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -598,15 +598,24 @@ class StepEngine:
         self._deferred.clear()
 
     # ------------------------------------------------------------------------------------------ programs
-    def pack_online(self):
-        for w, wp, wt in self._pack_jobs_online:
-            ops.pack_weight(w, wp)
+    def _pack_list(self, jobs):
+        flat = []
+        for w, wp, wt in jobs:
+            flat.append((w, wp, False))
             if wt is not None:
-                ops.pack_weight(w, wt, transpose=True)
+                flat.append((w, wt, True))
+        return ops.PackList(flat, self.device)
+
+    def pack_online(self):
+        """fp32 master weights -> bf16 tensor-core copies (forward and dgrad-transposed), one launch for the network."""
+        if getattr(self, "_pl_online", None) is None:
+            self._pl_online = self._pack_list(self._pack_jobs_online)
+        self._pl_online.run()
 
     def pack_target(self):
-        for w, wp, _ in self._pack_jobs_target:
-            ops.pack_weight(w, wp)
+        if getattr(self, "_pl_target", None) is None:
+            self._pl_target = self._pack_list(self._pack_jobs_target)
+        self._pl_target.run()
 
     def load_clips(self, x1: torch.Tensor, x2: torch.Tensor):
         """fp32 NCDHW clips (B,3,T,H,W) -> bf16 im2col rows of the stem (shared by the online and target nets)."""

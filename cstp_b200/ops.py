@@ -602,6 +602,29 @@ def pack_weight(w: torch.Tensor, packed: torch.Tensor, *, transpose: bool = Fals
     L.check(L.load().cstp_pack_weight(_ptr(w), cout, cin, taps, int(transpose), _ptr(packed), Rp, Ktot // taps, _stream()))
 
 
+class PackList:
+    """A fixed list of (fp32 weight, bf16 packed, transpose) jobs executed as ONE launch (cstp_pack_weights_batched)."""
+
+    def __init__(self, jobs, device):
+        rows, prefix, total = [], [0], 0
+        for w, packed, transpose in jobs:
+            _require_cuda(w, packed)
+            cout, cin = w.shape[0], w.shape[1]
+            taps = w.numel() // (cout * cin)
+            Rp, Ktot = packed.shape
+            rows.append([w.data_ptr(), packed.data_ptr(), cout, cin, taps, int(transpose), Rp, Ktot // taps])
+            total += Rp * Ktot
+            prefix.append(total)
+        self.n, self.total = len(rows), total
+        self.jobs = torch.tensor(rows, dtype=torch.int64, device=device)
+        self.prefix = torch.tensor(prefix, dtype=torch.int64, device=device)
+        self._keep = jobs
+
+    def run(self) -> None:
+        if self.n:
+            L.check(L.load().cstp_pack_weights_batched(_ptr(self.jobs), _ptr(self.prefix), self.n, self.total, _stream()))
+
+
 def stem_im2col(x: torch.Tensor, col: torch.Tensor) -> None:
     _require_cuda(x, col)
     N, Cc, T, H, W = x.shape

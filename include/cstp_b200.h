@@ -200,6 +200,10 @@ void cstp_wgrad_halo_plan_destroy(cstp_wgrad_halo_plan* plan);
  * transpose=0: packed[r=co][tap*Kc + ci] (forward);  transpose=1: packed[r=ci][tap*Kc + co] (dgrad). */
 int cstp_pack_weight(const float* w, int cout, int cin, int taps, int transpose, void* packed, int Rp, int Kc,
                      void* stream);
+/* The same for a whole list of tensors in one launch.  jobs_dev: DEVICE int64 [n_jobs][8] = {w ptr, packed ptr, cout,
+ * cin, taps, transpose, Rp, Kc}; prefix_dev: DEVICE int64 [n_jobs + 1], prefix[j] = sum of Rp*taps*Kc of the jobs
+ * before j; total = prefix[n_jobs]. */
+int cstp_pack_weights_batched(const int64_t* jobs_dev, const int64_t* prefix_dev, int n_jobs, int64_t total, void* stream);
 /* Stem: fp32 NCDHW clip (N,3,T,H,W) -> bf16 im2col rows [N*T*Ho*Wo][ldk] for the 1x7x7 s(1,2,2) p(0,3,3) conv
  * (r21d_byol.py:198); column = ci*49 + kh*7 + kw, columns >= 147 are zero. */
 int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void* col, int ldk, void* stream);

@@ -164,6 +164,15 @@ def pack_weight(w, packed, *, transpose=False):
         p3[:cin, :, :cout] = w3.permute(1, 2, 0).to(packed.dtype)
 
 
+class PackList:
+    def __init__(self, jobs, device):
+        self.jobs = jobs
+
+    def run(self):
+        for w, packed, transpose in self.jobs:
+            pack_weight(w, packed, transpose=transpose)
+
+
 def stem_im2col(x, col):
     _count()
     N, C, T, H, W = x.shape
