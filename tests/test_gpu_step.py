@@ -206,6 +206,37 @@ def test_post_step_state(run):
     assert sd["overlap_spa.1.num_batches_tracked"].item() == 1
 
 
+@pytest.mark.parametrize("Bq,Tq,Hq,Wq", [(3, 6, 64, 48), (1, 4, 32, 32)])
+def test_ragged_geometries(Bq, Tq, Hq, Wq):
+    """Odd batch, non-square clips, frame counts that leave partial tiles in every tile-space axis (and, for 64x48, the
+    halo kernels with ragged boxes): per-layer parity on every layer + losses against the oracle."""
+    from cstp_b200.engine import trainable_param_specs
+    from oracle import cstp_oracle as O
+    g = torch.Generator().manual_seed(7)
+    base = torch.nn.functional.interpolate(torch.randn(Bq, 3, 2, 5, 5, generator=g), size=(Tq, Hq, Wq), mode="trilinear")
+    x1 = (torch.tanh(base) * 0.9 + 0.1 * (torch.rand(Bq, 3, Tq, Hq, Wq, generator=g) * 2 - 1)).clamp(-1, 1).contiguous()
+    x2 = (torch.tanh(base.flip(4)) * 0.7 + 0.1 * (torch.rand(Bq, 3, Tq, Hq, Wq, generator=g) * 2 - 1)).clamp(-1, 1).contiguous()
+    labels = tuple(torch.randint(0, k, (Bq,), generator=g) for k in (5, 5, 4, 4, 4))
+    m = _model(record=True)
+    before = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    m.cuda()
+    losses = m.train_step(x1.cuda(), x2.cuda(), tuple(l.cuda() for l in labels), LW, lr=0.03).cpu()
+    online = {k: v for k, v in before.items() if not k.startswith("target_net.")}
+    target = {k: v.detach().cpu().clone() for k, v in m.state_dict().items() if k.startswith("target_net.")}
+    res = LP.check_conv_units(m._engine, online, "online")
+    res.update(LP.check_conv_units(m._engine, target, "target"))
+    w = LP.worst(res)
+    print("ragged geometry worst per-layer error:", w)
+    assert w[0] < 1e-2, w
+    if Bq > 1:           # batch 1: every BatchNorm1d of the heads sees one sample (variance 0) -- no meaningful loss check
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = O.pretrain_step({k: v.clone() for k, v in before.items()}, [n for n, _ in trainable_param_specs()], x1, x2,
+                              labels, list(LW), 0.03, {})
+        total = LW[0] * losses[7].item() + losses[6].item()
+        assert abs(total - ref["loss_total"]) / ref["loss_total"] < 2e-3
+        assert abs(losses[7].item() - ref["loss_byol"]) / ref["loss_byol"] < 5e-3
+
+
 def test_dropin_autograd_path_equals_fused_path():
     """model(x1, x2, o_type='loss_com') + torch CE + backward + clip + torch SGD == train_step, same launches."""
     from oracle import cstp_oracle as O
