@@ -154,9 +154,18 @@ def dgrad_classes(shape_dx, geom: ConvGeom):
 
 
 def _fwd_taps(x: torch.Tensor, g: ConvGeom):
+    """TMA views + taps of a convolution over x.  A stride-parity class can be EMPTY (e.g. T = 1 under a stride-2
+    temporal conv has no odd frames): its taps only ever read padding, so they are redirected to view 0 at an offset far
+    outside the tensor, where TMA zero-fills -- the tap list (and the weight-gradient chunk layout) keeps its shape."""
     maps, taps = fwd_taps(g)
-    views = [_view5(x, r, g.stride) for r in maps]
-    return views, taps
+    geo = [view5_geometry(tuple(x.shape), r, g.stride) for r in maps]
+    alive = [i for i, (_, dims, _) in enumerate(geo) if min(dims) > 0]
+    if len(alive) == len(maps):
+        return [_view5(x, r, g.stride) for r in maps], taps
+    remap = {old: new for new, old in enumerate(alive)}
+    far = 1 << 20
+    taps = [(remap[m], dw, dh, dt, ti) if m in remap else (0, far, far, far, ti) for (m, dw, dh, dt, ti) in taps]
+    return [_view5(x, maps[i], g.stride) for i in alive], taps
 
 
 class _Plan:

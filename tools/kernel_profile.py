@@ -17,6 +17,8 @@ from oracle.cstp_oracle import synthetic_batch  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 torch.manual_seed(1)
 m = R21DBYOL(pretrain=True).cuda()
+if "--no-overlap" in sys.argv:          # one stream: kernel durations are not inflated by a concurrent kernel
+    m.engine_options = {"overlap": False}
 x1, x2, labels = synthetic_batch(B, 0)
 x1, x2 = x1.cuda(), x2.cuda()
 labels = tuple(l.cuda() for l in labels)
