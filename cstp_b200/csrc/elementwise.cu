@@ -99,22 +99,25 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     rows[r][c] = v;
   }
   __syncthreads();
+  // every thread keeps ONE vector column v (8 consecutive K columns): its 8 shared-memory offsets are computed once,
+  // the loop over the output positions of the row is 8 LDS + pack + one 16-byte store
   const int nvec = ldk / 8;
-  uint4* dst = reinterpret_cast<uint4*>(col) + ((static_cast<long long>(n) * T + t) * Ho + ho) * Wo * nvec;
-  for (int i = threadIdx.x; i < Wo * nvec; i += blockDim.x) {
-    const int v = i % nvec, wo = i / nvec;
-    float f[8];
+  const int v = threadIdx.x % nvec, wo0 = threadIdx.x / nvec, wstep = blockDim.x / nvec;
+  int offs[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int r = k / 7, kw = k % 7;          // r = ci*7 + kh
-        val = rows[r][2 * wo + kw];               // wi + 3 = 2*wo + kw - 3 + 3
-      }
-      f[j] = val;
+  for (int j = 0; j < 8; ++j) {
+    const int k = v * 8 + j;
+    offs[j] = k < 147 ? (k / 7) * (kStemMaxW + 8) + (k % 7) : -1;        // rows[k / 7][2 * wo + k % 7]
+  }
+  const float* flat = &rows[0][0];
+  uint4* dst = reinterpret_cast<uint4*>(col) + ((static_cast<long long>(n) * T + t) * Ho + ho) * Wo * nvec;
+  if (wo0 < wstep) {
+    for (int wo = wo0; wo < Wo; wo += wstep) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = offs[j] >= 0 ? flat[offs[j] + 2 * wo] : 0.f;
+      dst[wo * nvec + v] = pack8(f);
     }
-    dst[i] = pack8(f);
   }
 }
 
@@ -595,7 +598,9 @@ extern "C" int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void
   CSTP_REQUIRE(ldk >= 152 && ldk % 8 == 0 && W <= kStemMaxW);
   const long long blocks = static_cast<long long>(N) * T * (H / 2);
   CSTP_REQUIRE(blocks < (1LL << 31));
-  stem_im2col_kernel<<<static_cast<unsigned>(blocks), 256, 0, ST(stream)>>>(x, N, T, H, W,
+  const int nvec = ldk / 8;
+  const int threads = (256 / nvec) * nvec >= 64 ? (256 / nvec) * nvec : 256;   // a whole number of vector columns
+  stem_im2col_kernel<<<static_cast<unsigned>(blocks), threads, 0, ST(stream)>>>(x, N, T, H, W,
                                                                            reinterpret_cast<__nv_bfloat16*>(col), ldk);
   CSTP_LAUNCHED();
   return CSTP_OK;
