@@ -264,6 +264,31 @@ def test_dropin_autograd_path_equals_fused_path():
         b(batch[0], batch[1], o_type="nonsense")
 
 
+def test_several_steps_track_the_oracle():
+    """Five optimiser steps on the same batch: the loss trajectory of the CUDA path follows the fp32 oracle's (EMA,
+    momentum buffers, BatchNorm running statistics and the bf16 re-pack all feed back into the next step)."""
+    from cstp_b200.engine import trainable_param_specs
+    from oracle import cstp_oracle as O
+    batch = O.structured_batch(4, 2, 8, 64)
+    m = _model()
+    state = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    trainable = [n for n, _ in trainable_param_specs()]
+    m.cuda()
+    cb = _cuda(batch)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mom: dict = {}
+    got, want = [], []
+    for _ in range(5):
+        l = m.train_step(*cb, LW, lr=0.03).cpu()
+        got.append(LW[0] * l[7].item() + l[6].item())
+        want.append(O.pretrain_step(state, trainable, *batch[:2], batch[2], list(LW), 0.03, mom)["loss_total"])
+    print("total loss per step, CUDA:", [round(v, 4) for v in got], "oracle:", [round(v, 4) for v in want])
+    assert all(abs(a - b) / b < 1e-2 for a, b in zip(got, want)), (got, want)
+    assert got[-1] < got[0]
+    sd = m.state_dict()
+    assert all(torch.isfinite(v).all() for v in sd.values() if v.dtype.is_floating_point)
+
+
 def test_two_steps_are_bit_reproducible():
     """Fixed-order reductions everywhere: the same step twice from the same state gives identical bits."""
     from oracle import cstp_oracle as O
