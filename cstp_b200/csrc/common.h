@@ -43,8 +43,9 @@ inline int fail_inval(const char* what) {
 
 // Encodes a tiled bf16 tensor map (128B swizzle, zero OOB fill) through the driver entry point obtained from
 // the runtime, so the library never links libcuda directly (it must dlopen on a box without a driver).
+// swizzle_bytes: 128 (default), 64 or 32 -- the shared-memory row pitch of the box (its inner extent in bytes).
 int encode_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box);
+                     const uint32_t* box, int swizzle_bytes = 128);
 
 int num_sms();
 

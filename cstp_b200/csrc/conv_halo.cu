@@ -33,6 +33,10 @@ struct HcTap {
 struct ConvHaloKParams {
   CUtensorMap amap;
   CUtensorMap bmap;
+  CUtensorMap amap_tail;   // channel tail (16 or 32 channels beyond a multiple of 64): boxes with 32 / 64-byte rows
+  CUtensorMap bmap_tail;
+  int tail;                // 0, 16 or 32 channels in the last chunk (then staged with its own narrow boxes)
+  uint32_t a_bytes_tail, b_bytes_tail, tap_bytes;   // tap_bytes: resident weight bytes of one tap (all chunks)
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int bw, bh, bt, bn;
   int Wt, Ht, Tt, Nt;
@@ -101,12 +105,17 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
+    const int full_chunks = p.tail ? p.chunks - 1 : p.chunks;
     if (p.resident && leader) {
       mbar_expect_tx(bfull, p.res_bytes);
-      for (int t = 0; t < p.n_taps; ++t)
-        for (int c = 0; c < p.chunks; ++c)
-          tma_load_2d(smem + static_cast<size_t>(t * p.chunks + c) * p.b_bytes, &p.bmap, bfull, p.taps[t].k_off + c * 64,
-                      ntile * p.n_tile);
+      for (int t = 0; t < p.n_taps; ++t) {
+        uint8_t* tb = smem + static_cast<size_t>(t) * p.tap_bytes;
+        for (int c = 0; c < full_chunks; ++c)
+          tma_load_2d(tb + static_cast<size_t>(c) * p.b_bytes, &p.bmap, bfull, p.taps[t].k_off + c * 64, ntile * p.n_tile);
+        if (p.tail)
+          tma_load_2d(tb + static_cast<size_t>(full_chunks) * p.b_bytes, &p.bmap_tail, bfull,
+                      p.taps[t].k_off + full_chunks * 64, ntile * p.n_tile);
+      }
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -125,11 +134,13 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
           mbar_wait(&empty[stage], phase ^ 1u);
           if (leader) {
             uint8_t* st = stage0 + static_cast<size_t>(stage) * p.stage_bytes;
-            mbar_expect_tx(&full[stage], p.a_bytes + (p.resident ? 0u : static_cast<uint32_t>(gr.n_taps) * p.b_bytes));
-            tma_load_5d(st, &p.amap, &full[stage], c * 64, w0 + gr.dw, h0 + gr.dh, t0 + gr.dt, n0);
+            const bool tl = p.tail && c == p.chunks - 1;
+            const uint32_t ab = tl ? p.a_bytes_tail : p.a_bytes, bb = tl ? p.b_bytes_tail : p.b_bytes;
+            mbar_expect_tx(&full[stage], ab + (p.resident ? 0u : static_cast<uint32_t>(gr.n_taps) * bb));
+            tma_load_5d(st, tl ? &p.amap_tail : &p.amap, &full[stage], c * 64, w0 + gr.dw, h0 + gr.dh, t0 + gr.dt, n0);
             if (!p.resident) {
               for (int j = 0; j < gr.n_taps; ++j)
-                tma_load_2d(st + p.a_bytes + static_cast<size_t>(j) * p.b_bytes, &p.bmap, &full[stage],
+                tma_load_2d(st + p.a_bytes + static_cast<size_t>(j) * p.b_bytes, tl ? &p.bmap_tail : &p.bmap, &full[stage],
                             p.taps[gr.first_tap + j].k_off + c * 64, ntile * p.n_tile);
             }
           }
@@ -151,6 +162,9 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     const uint32_t res_addr = smem_u32(smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
     const uint64_t dhi = umma_desc_hi(16, 1024);
+    const uint64_t dhi_tail = umma_desc_hi_kmajor(static_cast<uint32_t>(p.tail) * 2u);
+    const int tail_shift = p.tail == 16 ? 2 : 1;        // a_shift is in 128-byte rows; tail rows are 32 / 64 bytes
+    const int full_chunks = p.tail ? p.chunks - 1 : p.chunks;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -168,13 +182,17 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
           tc_fence_after();
           if (leader) {
             const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
-            const bool full_chunk = (c != p.chunks - 1) || p.last_ksteps == 4;
+            const bool tl = p.tail && c == p.chunks - 1;
+            const bool full_chunk = !tl && ((c != p.chunks - 1) || p.last_ksteps == 4);
+            const uint64_t hi = tl ? dhi_tail : dhi;
             for (int j = 0; j < gr.n_taps; ++j) {
               const int t = gr.first_tap + j;
-              const uint64_t da = umma_desc_at(dhi, s_addr + p.taps[t].a_shift);
-              const uint64_t db =
-                  umma_desc_at(dhi, p.resident ? res_addr + static_cast<uint32_t>(t * p.chunks + c) * p.b_bytes
-                                               : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes);
+              const uint32_t a_sh = tl ? (p.taps[t].a_shift >> tail_shift) : p.taps[t].a_shift;
+              const uint64_t da = umma_desc_at(hi, s_addr + a_sh);
+              const uint64_t db = umma_desc_at(
+                  hi, p.resident ? res_addr + static_cast<uint32_t>(t) * p.tap_bytes +
+                                       static_cast<uint32_t>(tl ? full_chunks : c) * p.b_bytes
+                                 : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes);
               umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
               first = 0;
               if (full_chunk) {
@@ -393,6 +411,22 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
       const uint32_t bbox[2] = {64u, (uint32_t)d->n_tile};
       rc = encode_tmap_bf16(&k.bmap, d->w_packed, 2, bdims, bstr, bbox);
     }
+    // channel tail: exactly 16 or 32 channels beyond a multiple of 64 get their own narrow (32 / 64-byte row) boxes
+    const int tail = d->a_channels % 64;
+    k.tail = (d->use_tail_boxes && (tail == 16 || tail == 32) && d->a_channels > 64) ? tail : 0;
+    if (rc == CSTP_OK && k.tail) {
+      const uint32_t abox_t[5] = {(uint32_t)k.tail, abox[1], abox[2], abox[3], abox[4]};
+      rc = encode_tmap_bf16(&k.amap_tail, d->amap.ptr, 5, dims, strides, abox_t, k.tail * 2);
+      if (rc == CSTP_OK) {
+        const uint64_t bdims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
+        const uint64_t bstr[1] = {(uint64_t)d->Ktot * 2};
+        const uint32_t bbox_t[2] = {(uint32_t)k.tail, (uint32_t)d->n_tile};
+        rc = encode_tmap_bf16(&k.bmap_tail, d->w_packed, 2, bdims, bstr, bbox_t, k.tail * 2);
+      }
+    } else if (rc == CSTP_OK) {
+      k.amap_tail = k.amap;
+      k.bmap_tail = k.bmap;
+    }
     if (rc != CSTP_OK) {
       delete plan;
       return rc;
@@ -412,6 +446,10 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.Np = d->Np;
   k.a_bytes = static_cast<uint32_t>(xrows) * 128u;
   k.b_bytes = static_cast<uint32_t>(d->n_tile) * 128u;
+  k.a_bytes_tail = static_cast<uint32_t>(xrows) * static_cast<uint32_t>(k.tail) * 2u;
+  k.b_bytes_tail = static_cast<uint32_t>(d->n_tile) * static_cast<uint32_t>(k.tail) * 2u;
+  k.tap_bytes = k.tail ? static_cast<uint32_t>(k.chunks - 1) * k.b_bytes + k.b_bytes_tail
+                       : static_cast<uint32_t>(k.chunks) * k.b_bytes;
   k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 0, 0);
   k.accumulate = d->accumulate;
   k.out = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
@@ -450,7 +488,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   }
   // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
   const int bar_bytes = 256;
-  const long long res_all = 1LL * d->n_taps * k.chunks * k.b_bytes;
+  const long long res_all = 1LL * d->n_taps * k.tap_bytes;
   const long long budget = kHcSmemLimit - 1024 - bar_bytes - static_cast<long long>(k.stats_bytes);
   if (d->allow_resident && res_all + 3LL * k.a_bytes <= budget) {
     k.resident = 1;

@@ -183,6 +183,15 @@ __device__ __forceinline__ uint64_t umma_desc_hi(uint32_t lbo_bytes, uint32_t sb
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// K-major operand whose rows are `row_bytes` (128 / 64 / 32) wide: layout type 2 / 4 / 6, 8-row atoms of 8*row_bytes.
+__device__ __forceinline__ uint64_t umma_desc_hi_kmajor(uint32_t row_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>(1) << 16;                                           // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(((8u * row_bytes) >> 4) & 0x3FFF) << 32;             // SBO: next 8-row atom
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_at(uint64_t hi, uint32_t saddr) {
   return hi | static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
 }

@@ -93,6 +93,7 @@ class ConvHaloDesc(C.Structure):
         ("bias", C.c_void_p),
         ("accumulate", C.c_int32),
         ("allow_resident", C.c_int32),
+        ("use_tail_boxes", C.c_int32),
         ("stats_partials", C.c_void_p),
     ]
 

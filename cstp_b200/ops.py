@@ -292,18 +292,22 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int, stats: bool = F
                 out_taps.append(((dh - dhs[0]) * unit * 128, k_off))
     a_bytes = rows * 128
     chunks = pad64(a_channels) // 64
+    # a channel tail of exactly 16 / 32 beyond a multiple of 64 is staged with 32 / 64-byte rows (csrc/conv_halo.cu)
+    tail = a_channels % 64 if (USE_TAIL_BOXES and a_channels > 64 and a_channels % 64 in (16, 32)) else 0
+    k_bytes_per_row = ((chunks - 1) * 128 + tail * 2) if tail else chunks * 128      # resident weight bytes per (tap, n)
     # N tile: keep all weight K-blocks resident when they fit beside 3 activation stages, splitting N in two if needed
     n_tile, resident = (Np if Np <= 256 else _default_n_tile(Np)), False
     sb = 64 if stats else 0                  # fused-statistics accumulators: 64 bytes per output column of the N tile
     for cand in ([Np] if Np <= 256 else []) + ([pad16(math.ceil(Np / 2))] if Np > 64 else []):
-        if cand <= 256 and len(taps) * chunks * cand * 128 + 3 * a_bytes + sb * cand <= SMEM_BUDGET:
+        if cand <= 256 and len(taps) * k_bytes_per_row * cand + 3 * a_bytes + sb * cand <= SMEM_BUDGET:
             n_tile, resident = cand, True
             break
     if not resident:
         per_stage = a_bytes + max(g[4] for g in groups) * n_tile * 128
         if 2 * per_stage + sb * n_tile > SMEM_BUDGET:
             return None
-    return dict(box=box, halo=halo, groups=groups, taps=out_taps, n_tile=n_tile, a_bytes=a_bytes, resident=resident)
+    return dict(box=box, halo=halo, groups=groups, taps=out_taps, n_tile=n_tile, a_bytes=a_bytes, resident=resident,
+                tail=tail)
 
 
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
@@ -330,6 +334,7 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     d.bias = 0 if bias is None else bias.data_ptr()
     d.accumulate = int(accumulate)
     d.allow_resident = int(lay["resident"])
+    d.use_tail_boxes = int(bool(lay.get("tail", 0)))
     d.stats_partials = 0 if stats is None else stats.partials.data_ptr()
     h = C.c_void_p()
     L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
@@ -347,6 +352,7 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
 # of bn_reduce passes but costs more than that in the conv kernels (shuffle reduction in the epilogue, and the
 # accumulators push the 64->144 spatial conv out of its resident-weights configuration), so it is off by default.
 FUSE_BN_STATS = os.environ.get("CSTP_FUSE_BN_STATS", "0") == "1"
+USE_TAIL_BOXES = os.environ.get("CSTP_TAIL_BOXES", "1") == "1"
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
 
 

@@ -113,6 +113,9 @@ typedef struct {
   const float* bias;
   int32_t accumulate;
   int32_t allow_resident;
+  /* 1: when a_channels is 16 or 32 beyond a multiple of 64, stage that channel tail (activations and weights) as boxes
+   * with 32 / 64-byte rows (TMA + UMMA 32B / 64B swizzle) instead of zero-padded 128-byte rows. */
+  int32_t use_tail_boxes;
   /* Optional fused BatchNorm statistics of the stored (bf16-rounded) output, two groups = the two halves of the N axis:
    * fp32 [stat_blocks][2 groups][2: sum, sum of squares][Np], the partials layout cstp_bn_finalize consumes
    * (nblocks = cstp_conv_halo_plan_stat_blocks).  Replaces a cstp_bn_stats pass over the output. */
