@@ -166,7 +166,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if not torch.cuda.is_available():
+    if not parallel.wait_for_cuda() or not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the native path has no CPU fallback (use --impl reference for the CPU arm)")
     warm = max(args.warmup, 3)
     torch.cuda.set_device(local)

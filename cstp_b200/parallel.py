@@ -15,6 +15,24 @@ import torch
 import torch.distributed as dist
 
 
+def wait_for_cuda(max_wait_s: float = 45.0) -> bool:
+    """Probes CUDA in a SUBPROCESS until it initialises (a failed cuInit is sticky inside a process).  On the shared GPU
+    boxes the driver was once seen refusing to initialise for a moment right after another process had exited; callers
+    (bench.py, __graft_entry__.smoke) use this before they touch CUDA themselves."""
+    import subprocess
+    import sys
+    import time
+    t0 = time.time()
+    while True:
+        r = subprocess.run([sys.executable, "-c", "import torch,sys; sys.exit(0 if torch.cuda.is_available() else 1)"],
+                           capture_output=True)
+        if r.returncode == 0:
+            return True
+        if time.time() - t0 > max_wait_s:
+            return False
+        time.sleep(3.0)
+
+
 def env_world() -> tuple[int, int, int]:
     """(rank, world_size, local_rank) from the torchrun environment; (0, 1, 0) when launched as a plain process."""
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
