@@ -1,0 +1,105 @@
+"""Epoch-level pretraining driver on the fused step: the loop of main_byol.py:162-269 (`main_worker` / `train_BYOL`)
+without its per-step host synchronisation.
+
+What it keeps from the reference:
+  * SGD hyper-parameters from `opts` (learning_rate, momentum, weight_decay; main_byol.py:229-232), gradient clipping at 18
+    when `opts.clip_grad_norm` (main_byol.py:88-90), `--loss_weight` semantics (main_byol.py:70-73);
+  * `CosineAnnealingWarmupRestarts(first_cycle_steps=n_epochs, warmup_steps=0.5*n_epochs, min_lr=1e-5, gamma=0.5)` stepped
+    once per epoch (main_byol.py:252-258,269): the first epoch runs at 1e-5;
+  * the checkpoint format of main_byol.py:132-140 -- {'epoch': epoch + 1, 'arch', 'state_dict', 'optimizer'} in
+    `save_<epoch>.pth`, state-dict keys prefixed with `module.` when the reference would have saved a DDP-wrapped model --
+    and the resume rule of :214-215,243-244 (begin epoch parsed from the file name; scheduler state NOT restored, the
+    schedule is re-derived from the epoch index);
+  * the log columns of main_byol.py:216-225.
+What it changes: the six `.item()` host syncs per step (main_byol.py:77-84) become one read-back of the per-step loss
+vectors per epoch; the all-reduce of the logged loss (:75) is folded into that read-back.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from .scheduler.cosine_anneal import lr_at
+
+LOG_COLUMNS = ["epoch", "loss", "loss_byol", "loss_pred_spa", "loss_pred_tem", "loss_pred_pb", "loss_pred_rot", "acc", "lr"]
+
+
+def epoch_lr(epoch: int, n_epochs: int, max_lr: float, min_lr: float = 1e-5) -> float:
+    """Learning rate of 1-based `epoch` under main_byol.py:252-258 (scheduler.step() runs AFTER each epoch)."""
+    return lr_at(epoch - 1, n_epochs, max_lr, min_lr, 0.5 * n_epochs, 1.0, 0.5)
+
+
+def optimizer_state_dict(model) -> dict:
+    """torch.optim.SGD-compatible state dict of the engine's fused optimiser: momentum buffers addressed by the position
+    of each parameter in model.parameters() (frozen target_net entries keep their indices and have no state), so that
+    `optim.SGD(model.parameters()).load_state_dict(...)` of the reference accepts it (main_byol.py:138,243-244)."""
+    eng = model._engine
+    names = [n for n, _ in model.named_parameters()]
+    state = {}
+    if not eng.first_step:
+        for i, n in enumerate(names):
+            if n in eng.train.slots:
+                state[i] = {"momentum_buffer": eng.train.view(n, eng.mom).detach().clone().cpu()}
+    return {"state": state, "param_groups": [{"params": list(range(len(names)))}]}
+
+
+def load_optimizer_state_dict(model, sd: dict) -> None:
+    eng = model._engine
+    names = [n for n, _ in model.named_parameters()]
+    loaded = False
+    for i, st in sd.get("state", {}).items():
+        buf = st.get("momentum_buffer")
+        if buf is not None and names[int(i)] in eng.train.slots:
+            eng.train.view(names[int(i)], eng.mom).copy_(buf)
+            loaded = True
+    eng.first_step = not loaded
+
+
+def save_checkpoint(path: str, model, epoch: int, arch: str, ddp_prefix: bool = True) -> None:
+    """main_byol.py:132-140."""
+    sd = {("module." + k if ddp_prefix else k): v.detach().cpu() for k, v in model.state_dict().items()}
+    torch.save({"epoch": epoch + 1, "arch": arch, "state_dict": sd, "optimizer": optimizer_state_dict(model)}, path)
+
+
+def load_checkpoint(path: str, model, example_clip: torch.Tensor | None = None) -> int:
+    """Restores weights, BatchNorm buffers and SGD momentum; returns the epoch to continue with (the number in the file
+    name, main_byol.py:214-215).  `example_clip` (a device tensor of the training shape) binds the engine first so that
+    the momentum buffers have a home."""
+    md = torch.load(path, map_location="cpu", weights_only=False)
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in md["state_dict"].items()}
+    model.load_state_dict(sd)
+    if example_clip is not None:
+        model._bind(example_clip)
+        load_optimizer_state_dict(model, md["optimizer"])
+    return int(os.path.basename(path).split("_")[1].split(".")[0])
+
+
+def pretrain_epochs(model, batches, opts, begin_epoch: int = 1, result_path: str | None = None, arch: str = "r21d_byol-1",
+                    grad_sync=None, save_every: int = 100, log=None):
+    """Runs epochs begin_epoch..opts.n_epochs.  `batches(epoch)` yields (clip_1, clip_2, (spa, tem, pb, rot_1, rot_2)) on
+    the device.  Returns one dict of LOG_COLUMNS per epoch."""
+    rows = []
+    clip = 18.0 if getattr(opts, "clip_grad_norm", 1) else 0.0
+    for epoch in range(begin_epoch, opts.n_epochs + 1):
+        lr = epoch_lr(epoch, opts.n_epochs, opts.learning_rate)
+        per_step = []
+        for clip_1, clip_2, labels in batches(epoch):
+            losses = model.train_step(clip_1, clip_2, labels, opts.loss_weight, lr=lr, momentum=opts.momentum,
+                                      weight_decay=opts.weight_decay, clip_grad_norm=clip, grad_sync=grad_sync)
+            per_step.append(losses.clone())                       # device side; no host sync inside the epoch
+        L = torch.stack(per_step).mean(0)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(L)                       # reduce_mean of main_byol.py:22-26,75
+            L /= torch.distributed.get_world_size()
+        L = L.cpu()
+        w = opts.loss_weight
+        total = w[0] * L[7] + L[6]
+        row = dict(zip(LOG_COLUMNS, [epoch, total.item(), L[7].item(), L[0].item(), L[1].item(), (L[2] + L[3]).item(),
+                                     (L[4] + L[5]).item(), 0.0, lr]))
+        rows.append(row)
+        if log is not None:
+            log(row)
+        if result_path is not None and (epoch % save_every == 0 or epoch == opts.n_epochs):
+            save_checkpoint(os.path.join(result_path, f"save_{epoch}.pth"), model, epoch, arch)
+    return rows
