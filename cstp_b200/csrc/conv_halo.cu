@@ -49,8 +49,6 @@ struct ConvHaloKParams {
   float* out_f32;
   const float* bias;
   long long out_off, osw, osh, ost, osn;
-  float* stats;            // optional fused BatchNorm statistics: partials [gridDim.x][2 groups][2][Np]
-  uint32_t stats_bytes;    // shared-memory accumulators [4 warps][2 groups][2][n_tile] floats (0 = disabled)
   HcGroup groups[kHcMaxGroups];
   HcTap taps[kHcMaxTaps];
 };
@@ -59,8 +57,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage0 = smem + p.res_bytes;
-  float* sacc = reinterpret_cast<float*>(stage0 + static_cast<size_t>(p.stages) * p.stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + static_cast<size_t>(p.stages) * p.stage_bytes + p.stats_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + static_cast<size_t>(p.stages) * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kHcMaxStages;
   uint64_t* tfull = bars + 2 * kHcMaxStages;
@@ -225,12 +222,6 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     const int rn = row / (p.bw * p.bh * p.bt);
     const int col0 = ntile * p.n_tile;
     const int ncols = min(p.n_tile, p.Np - col0);
-    // fused BatchNorm statistics: this warp's accumulators [group][sum | sumsq][n_tile]; lane l owns column c0 + (l>>1)
-    float* wacc = sacc + static_cast<size_t>(q) * 4 * p.n_tile;
-    if (p.stats != nullptr) {
-      for (int i = lane; i < 4 * p.n_tile; i += 32) wacc[i] = 0.f;
-      __syncwarp();
-    }
     int it = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -245,8 +236,6 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       const int n = pt * p.bn + rn;
       const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
       const long long off = p.out_off + w * p.osw + h * p.osh + t * p.ost + n * p.osn + col0;
-      // statistics group of this tile: the two views are the two halves of the N axis (bn == 1: no tile straddles)
-      float* gacc = wacc + ((pt * p.bn) * 2 >= p.Nt ? 2 * p.n_tile : 0);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
@@ -254,34 +243,6 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
-        if (p.stats != nullptr) {
-          // per-column sum / sum of squares over this warp's 32 rows of the values AS STORED (bf16-rounded), by a
-          // reduce-scatter butterfly: 16 -> 8 -> 4 -> 2 -> 1 columns per lane, then the lane pair is combined
-          float a[16], b[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float r = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
-            a[i] = r;
-            b[i] = r * r;
-          }
-#pragma unroll
-          for (int half = 8, m = 16; half >= 1; half >>= 1, m >>= 1) {
-            const bool up = (lane & m) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float sa = up ? a[i] : a[i + half], ka = up ? a[i + half] : a[i];
-              const float sb = up ? b[i] : b[i + half], kb = up ? b[i + half] : b[i];
-              a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, m);
-              b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, m);
-            }
-          }
-          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-          b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
-          if ((lane & 1) == 0) {
-            gacc[c0 + (lane >> 1)] += a[0];
-            gacc[p.n_tile + c0 + (lane >> 1)] += b[0];
-          }
-        }
         if (valid) {
           float f[16];
 #pragma unroll
@@ -333,20 +294,6 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-    }
-    if (p.stats != nullptr) {
-      // combine the four warps in fixed order and publish this CTA's partial row (deterministic, no atomics)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = q * 32 + lane;
-      for (int c = e; c < ncols; c += 128) {
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {      // gq = group*2 + (0: sum, 1: sum of squares)
-          float sum = 0.f;
-#pragma unroll
-          for (int wq = 0; wq < 4; ++wq) sum += sacc[(static_cast<size_t>(wq) * 4 + gq) * p.n_tile + c];
-          p.stats[(static_cast<long long>(blockIdx.x) * 4 + gq) * p.Np + col0 + c] = sum;
-        }
-      }
     }
   }
 
@@ -456,12 +403,6 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.out_f32 = d->out_f32;
   k.bias = d->bias;
   k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
-  k.stats = d->stats_partials;
-  k.stats_bytes = d->stats_partials != nullptr ? 64u * static_cast<uint32_t>(d->n_tile) : 0u;
-  if (d->stats_partials != nullptr && (d->bn != 1 || d->Nt % 2 != 0)) {
-    delete plan;
-    return fail_inval("fused statistics need bn == 1 and an even N (two views)");
-  }
   int max_group_taps = 0, seen = 0;
   for (int g = 0; g < d->n_groups; ++g) {
     const cstp_halo_group& gr = d->groups[g];
@@ -489,7 +430,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
   const int bar_bytes = 256;
   const long long res_all = 1LL * d->n_taps * k.tap_bytes;
-  const long long budget = kHcSmemLimit - 1024 - bar_bytes - static_cast<long long>(k.stats_bytes);
+  const long long budget = kHcSmemLimit - 1024 - bar_bytes;
   if (d->allow_resident && res_all + 3LL * k.a_bytes <= budget) {
     k.resident = 1;
     k.res_bytes = static_cast<uint32_t>(res_all);
@@ -509,8 +450,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   int cols = 32;
   while (cols < 2 * d->n_tile) cols *= 2;
   k.tmem_cols = cols;
-  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) +
-                     static_cast<int>(k.stats_bytes) + bar_bytes;
+  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) + bar_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
   const int n_ntiles = ceil_div(d->Np, d->n_tile);
   const long long m_tiles = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
@@ -523,9 +463,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
 }
 
 extern "C" int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan) { return plan ? plan->kp.resident : CSTP_EINVAL; }
-extern "C" int cstp_conv_halo_plan_stat_blocks(const cstp_conv_halo_plan* plan) {
-  return plan ? static_cast<int>(plan->grid.x) : CSTP_EINVAL;
-}
+
 
 extern "C" int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream) {
   CSTP_REQUIRE(plan != nullptr);

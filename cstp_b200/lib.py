@@ -94,7 +94,6 @@ class ConvHaloDesc(C.Structure):
         ("accumulate", C.c_int32),
         ("allow_resident", C.c_int32),
         ("use_tail_boxes", C.c_int32),
-        ("stats_partials", C.c_void_p),
     ]
 
 
@@ -130,7 +129,6 @@ SIGNATURES = {
     "cstp_conv_plan_destroy": (None, [_vp]),
     "cstp_conv_halo_plan_create": (_i, [C.POINTER(ConvHaloDesc), C.POINTER(_vp)]),
     "cstp_conv_halo_plan_resident": (_i, [_vp]),
-    "cstp_conv_halo_plan_stat_blocks": (_i, [_vp]),
     "cstp_conv_halo_plan_run": (_i, [_vp, _vp]),
     "cstp_conv_halo_plan_destroy": (None, [_vp]),
     "cstp_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),

@@ -183,8 +183,6 @@ class _Plan:
 
 
 class ConvPlan(_Plan):
-    stat_blocks: int = 0         # > 0: the kernel also produced BatchNorm statistics partials (that many blocks)
-
     def run(self):
         L.check(L.load().cstp_conv_plan_run(self.handle, _stream()))
 
@@ -234,7 +232,6 @@ def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out,
 
 class ConvHaloPlan(_Plan):
     resident: bool = False
-    stat_blocks: int = 0
 
     def run(self):
         L.check(L.load().cstp_conv_halo_plan_run(self.handle, _stream()))
@@ -243,7 +240,7 @@ class ConvHaloPlan(_Plan):
 SMEM_BUDGET = 232448 - 1024 - 256
 
 
-def conv_halo_layout(tile_space, taps, a_channels: int, Np: int, stats: bool = False):
+def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
     """Geometry of csrc/conv_halo.cu for a single-view (stride-1) tap list [(dw, dh, dt, k_off)], or None when the
     layer does not qualify (then csrc/conv_gemm.cu is used).  Pure shape arithmetic.
 
@@ -297,21 +294,20 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int, stats: bool = F
     k_bytes_per_row = ((chunks - 1) * 128 + tail * 2) if tail else chunks * 128      # resident weight bytes per (tap, n)
     # N tile: keep all weight K-blocks resident when they fit beside 3 activation stages, splitting N in two if needed
     n_tile, resident = (Np if Np <= 256 else _default_n_tile(Np)), False
-    sb = 64 if stats else 0                  # fused-statistics accumulators: 64 bytes per output column of the N tile
     for cand in ([Np] if Np <= 256 else []) + ([pad16(math.ceil(Np / 2))] if Np > 64 else []):
-        if cand <= 256 and len(taps) * k_bytes_per_row * cand + 3 * a_bytes + sb * cand <= SMEM_BUDGET:
+        if cand <= 256 and len(taps) * k_bytes_per_row * cand + 3 * a_bytes <= SMEM_BUDGET:
             n_tile, resident = cand, True
             break
     if not resident:
         per_stage = a_bytes + max(g[4] for g in groups) * n_tile * 128
-        if 2 * per_stage + sb * n_tile > SMEM_BUDGET:
+        if 2 * per_stage > SMEM_BUDGET:
             return None
     return dict(box=box, halo=halo, groups=groups, taps=out_taps, n_tile=n_tile, a_bytes=a_bytes, resident=resident,
                 tail=tail)
 
 
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
-                         accumulate, keep, stats=None) -> ConvHaloPlan:
+                         accumulate, keep) -> ConvHaloPlan:
     lib = L.load()
     d = L.ConvHaloDesc()
     d.amap = view
@@ -335,32 +331,23 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     d.accumulate = int(accumulate)
     d.allow_resident = int(lay["resident"])
     d.use_tail_boxes = int(bool(lay.get("tail", 0)))
-    d.stats_partials = 0 if stats is None else stats.partials.data_ptr()
     h = C.c_void_p()
     L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
-    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep + ((stats.partials,) if stats is not None else ()))
+    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep)
     plan.resident = bool(lib.cstp_conv_halo_plan_resident(h))
-    if stats is not None:
-        plan.stat_blocks = lib.cstp_conv_halo_plan_stat_blocks(h)
-        if plan.stat_blocks * stats.groups * 2 * stats.Cp > stats.partials.numel():
-            raise L.CstpError("BatchNorm partials buffer too small for the fused statistics")
     return plan
 
 
-# Fused BatchNorm statistics in the halo-conv epilogue (csrc/conv_halo.cu), opt-in with CSTP_FUSE_BN_STATS=1.
-# Measured at B=60 (two variants: 4 epilogue warps / 16-column loads, and 8 warps / 32-column loads): it removes 2.3 ms
-# of bn_reduce passes but costs more than that in the conv kernels (shuffle reduction in the epilogue, and the
-# accumulators push the 64->144 spatial conv out of its resident-weights configuration), so it is off by default.
-FUSE_BN_STATS = os.environ.get("CSTP_FUSE_BN_STATS", "0") == "1"
+# Fusing the BatchNorm statistics into the halo-conv epilogue was built and measured this round (two epilogue variants):
+# it removes 2.3 ms of bn_reduce passes at batch 60 but costs 3-5 ms in the conv kernels, so it was taken out again
+# (profiles/README.md).
 USE_TAIL_BOXES = os.environ.get("CSTP_TAIL_BOXES", "1") == "1"
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
 
 
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None,
-                  box=None, allow_halo: bool = True, stats: "BNState | None" = None) -> ConvPlan:
-    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16.
-    With `stats` (two view groups) the kernel may also emit the BatchNorm statistics partials of `out`
-    (plan.stat_blocks > 0 tells the caller to skip the separate statistics pass)."""
+                  box=None, allow_halo: bool = True) -> ConvPlan:
+    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16."""
     _require_cuda(x, w_packed, out, out_f32, bias)
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
@@ -373,12 +360,10 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
     taps = [(m, dw, dh, dt, ti * Kc) for (m, dw, dh, dt, ti) in taps]
     ostr = (Np, Wo * Np, Ho * Wo * Np, To * Ho * Wo * Np)
     if allow_halo and box is None and n_tile is None and len(views) == 1 and Ho * Wo >= HALO_MIN_POSITIONS:
-        fuse = (FUSE_BN_STATS and stats is not None and stats.groups == 2 and N % 2 == 0 and out is not None
-                and not accumulate)
-        lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np, stats=fuse)
+        lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np)
         if lay is not None:
             return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, out_f32, 0, ostr, bias,
-                                        accumulate, (x, w_packed, out, out_f32, bias), stats=stats if fuse else None)
+                                        accumulate, (x, w_packed, out, out_f32, bias))
     box = box or pick_box(Wo, Ho, To, N, 128)
     return _make_conv_plan(views, taps, Ca, w_packed, Np, (Wo, Ho, To, N), box, out, out_f32, 0, ostr, bias, accumulate,
                            n_tile, (x, w_packed, out, out_f32, bias))
@@ -671,23 +656,20 @@ class BNState:
     def alloc(C_: int, Cp: int, groups: int, rows_per_group: int, device, backward: bool = True) -> "BNState":
         nb = bn_nblocks(rows_per_group, Cp)
         f = dict(dtype=torch.float32, device=device)
-        # room for the fused-statistics path too: one partial row per CTA of a persistent conv kernel (<= 148)
-        return BNState(C_, Cp, groups, nb, torch.empty(max(nb, 160) * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
+        return BNState(C_, Cp, groups, nb, torch.empty(nb * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * 3 * Cp, **f) if backward else None, torch.empty(groups * 2 * Cp, **f))
 
 
 def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1,
-                     fused_blocks: int = 0, sync=None) -> None:
-    """Batch statistics of raw -> scale/shift/mean/invstd (+ running buffers).  fused_blocks > 0: the producing conv
-    kernel already wrote that many partial rows into st.partials (no statistics pass over raw).  `sync` (an object with
+                     sync=None) -> None:
+    """Batch statistics of raw -> scale/shift/mean/invstd (+ running buffers).  `sync` (an object with
     `.world` and `.all_reduce(tensor)`) makes the statistics span every rank (SyncBN over the data-parallel group): the
     per-rank sums are collapsed to one row, summed across ranks and finalized with the global row count."""
     rows = raw.numel() // st.Cp
     lib = L.load()
-    nblocks = fused_blocks or st.nblocks
-    if not fused_blocks:
-        L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
+    nblocks = st.nblocks
+    L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
     partials, rpg = st.partials, rows // st.groups
     if sync is not None and sync.world > 1:
         L.check(lib.cstp_bn_partials_reduce(_ptr(st.partials), nblocks, st.groups, st.Cp, _ptr(st.compact), _stream()))

@@ -116,16 +116,11 @@ typedef struct {
   /* 1: when a_channels is 16 or 32 beyond a multiple of 64, stage that channel tail (activations and weights) as boxes
    * with 32 / 64-byte rows (TMA + UMMA 32B / 64B swizzle) instead of zero-padded 128-byte rows. */
   int32_t use_tail_boxes;
-  /* Optional fused BatchNorm statistics of the stored (bf16-rounded) output, two groups = the two halves of the N axis:
-   * fp32 [stat_blocks][2 groups][2: sum, sum of squares][Np], the partials layout cstp_bn_finalize consumes
-   * (nblocks = cstp_conv_halo_plan_stat_blocks).  Replaces a cstp_bn_stats pass over the output. */
-  float* stats_partials;
 } cstp_conv_halo_desc;
 
 typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;
 int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* desc, cstp_conv_halo_plan** plan);
 int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan);   /* 1 when the weights are kept in shared memory */
-int cstp_conv_halo_plan_stat_blocks(const cstp_conv_halo_plan* plan);
 int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream);
 void cstp_conv_halo_plan_destroy(cstp_conv_halo_plan* plan);
 

@@ -39,8 +39,6 @@ def kernel_name(plan):
 
 
 class _Plan:
-    stat_blocks = 0
-
     def __init__(self, fn):
         self.fn = fn
         self.splits = 1
@@ -63,7 +61,7 @@ def _store(out, out_f32, val, accumulate):
 
 
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None, box=None,
-                  stats=None, allow_halo=True):
+                  allow_halo=True):
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
     ref = out if out is not None else out_f32
@@ -189,8 +187,7 @@ def _group_view(t, groups):
     return t.reshape(groups, rows // groups, t.shape[-1])
 
 
-def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, fused_blocks=0,
-                     sync=None):
+def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, sync=None):
     _count(2)
     x = _group_view(raw, st.groups).float()
     n = x.shape[1]
