@@ -18,6 +18,8 @@ constexpr int kNtThreads = 256;
 constexpr int kNtMaxStages = 6;
 constexpr int kNtSmemLimit = 232448;
 constexpr uint32_t kNtBoxBytes = 128 * 64 * 2;   // 128 rows x 64 bf16 channels
+constexpr uint32_t kNtWPitch = 272;              // bytes per staged W row (256 + 16)
+constexpr uint32_t kNtWSlab = 32 * kNtWPitch;    // one warp's 32 rows (8704 B, a multiple of 16)
 
 struct NtxKParams {
   CUtensorMap zmap;          // bf16 [rows_pad][d], box 64 x 128
@@ -41,7 +43,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) ntxent_s_kernel(const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t tile_bytes = static_cast<uint32_t>(p.nkc) * kNtBoxBytes;      // one 128 x d operand tile
   uint8_t* stage0 = smem + tile_bytes;                                        // [0, tile_bytes): the resident row tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + static_cast<size_t>(p.stages) * tile_bytes);
+  // backward only: per-epilogue-warp staging of its 32 x 128 bf16 slab of W (row pitch 272 B against bank conflicts)
+  uint8_t* wstage = stage0 + static_cast<size_t>(p.stages) * tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wstage + (kBackward ? 4 * kNtWSlab : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + kNtMaxStages;
   uint64_t* tfull = bars + 2 * kNtMaxStages;
@@ -193,10 +197,26 @@ __global__ void __launch_bounds__(kNtThreads, 1) ntxent_s_kernel(const __grid_co
             }
             pk[c >> 1] = pack_bf16x2(w2[0], w2[1]);
           }
-          uint4* dst = reinterpret_cast<uint4*>(p.W + static_cast<long long>(i) * p.rows_pad + j0);
+          // stage this lane's 64 bytes (32 columns) in the warp's slab; written out coalesced once the tile is complete
+          uint4* srow = reinterpret_cast<uint4*>(wstage + static_cast<size_t>(q) * kNtWSlab + lane * kNtWPitch + c0 * 2);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          for (int u = 0; u < 4; ++u) srow[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         }
+      }
+      if (kBackward) {
+        // Each lane used to store its own row of W straight to global memory: 32 different 128-byte lines per store
+        // instruction, and the LSU serialised the whole backward (0.52 ms at rows = 8192).  Now the warp writes its
+        // 32 x 256-byte slab with 16 fully coalesced instructions (two rows of 256 contiguous bytes each).
+        __syncwarp();
+        const uint8_t* slab = wstage + static_cast<size_t>(q) * kNtWSlab;
+        const long long row0 = static_cast<long long>(rt) * 128 + q * 32;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+          const int r = 2 * k + (lane >> 4), piece = lane & 15;
+          const uint4 val = *reinterpret_cast<const uint4*>(slab + r * kNtWPitch + piece * 16);
+          *reinterpret_cast<uint4*>(p.W + (row0 + r) * p.rows_pad + jt * 128 + piece * 8) = val;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -324,7 +344,8 @@ int cstp::ntxent_tensor_path(const float* zn, int rows, int d, float temperature
   k.tiles_per_split = ceil_div(tiles, nsplit);
   const int nsplit_eff = ceil_div(tiles, k.tiles_per_split);
   const uint32_t tile_bytes = static_cast<uint32_t>(k.nkc) * kNtBoxBytes;
-  int stages = (kNtSmemLimit - 1024 - 256 - static_cast<int>(tile_bytes)) / static_cast<int>(tile_bytes);
+  int stages = (kNtSmemLimit - 1024 - 256 - 4 * static_cast<int>(kNtWSlab) - static_cast<int>(tile_bytes)) /
+               static_cast<int>(tile_bytes);
   if (stages > kNtMaxStages) stages = kNtMaxStages;
   if (stages < 2) return fail_inval("embedding dimension too large for the tensor-core NT-Xent path");
   k.stages = stages;
@@ -336,7 +357,7 @@ int cstp::ntxent_tensor_path(const float* zn, int rows, int d, float temperature
   k.ppos = ppos;
   k.lse2 = lse2;
   k.W = W;
-  const int smem = 1024 + static_cast<int>(tile_bytes) * (stages + 1) + 256;
+  const int smem = 1024 + static_cast<int>(tile_bytes) * (stages + 1) + 4 * static_cast<int>(kNtWSlab) + 256;
   static bool attr_set = false;
   if (!attr_set) {
     CSTP_CUDA(cudaFuncSetAttribute(ntxent_s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNtSmemLimit));
