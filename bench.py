@@ -149,6 +149,24 @@ def cpu_baseline(seconds_budget: float = 25.0) -> dict:
             "sample": f"oracle/cstp_oracle.pretrain_step on {Bs} full 16x112x112 clips, {len(times) - 1} timed steps after 1 warm-up"}
 
 
+def ncu_traffic(kernel: str, B: int):
+    """Average DRAM bytes (read + write) per launch of `kernel` from the committed ncu capture of this command at the same
+    per-GPU batch (profiles/r01_ncu_<kernel>_b<B>_dram.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch);
+    None when no capture exists for this batch size."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                        "r01_ncu_%s_b%d_dram.csv" % (kernel.replace("_kernel", ""), B))
+    if not os.path.exists(path):
+        return None
+    total, ids = 0.0, set()
+    with open(path) as f:
+        for r in csv.reader(f):
+            if len(r) > 10 and r[0].isdigit() and r[-3].startswith("dram__bytes_"):
+                total += float(r[-1].replace(",", ""))
+                ids.add(r[0])
+    return total / len(ids) if ids else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,7 +285,10 @@ def main():
         ach = kern[dom]["tflops"]
         tensor_ms = sum(k["ms_per_step"] for k in kern.values())
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": None,
+                "frac": ach / pk["tf_sustained"], "traffic": ncu_traffic(dom, B),
+                "traffic_how": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum averaged over the kernel's launches "
+                               "of one step in the committed ncu capture profiles/r01_ncu_<kernel>_b<batch>_dram.csv (null: no "
+                               "capture at this batch)",
                 "peak_source": pk["src"] + " sustained bf16 cuBLAS matmul (kernel timed inside a long step)",
                 "how": "CUDA events on the launching stream around every launch of the kernel in one extra instrumented "
                        "step; achieved = sum over its launches of 2*M*N*K (true channel counts) / sum of durations",

@@ -1,4 +1,5 @@
 #include "common.h"
+#include <cstdlib>
 
 #include <cudaTypedefs.h>
 
@@ -70,6 +71,23 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (v == nullptr || *v == 0) return dflt;
+  const int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+int smem_budget() {
+  static int b = env_int("CSTP_SMEM_KB", 227, 64, 227) * 1024;
+  return b;
+}
+
+int stream_ctas_per_sm() {
+  static int c = env_int("CSTP_STREAM_CTAS_PER_SM", 8, 1, 16);
+  return c;
 }
 
 }  // namespace cstp

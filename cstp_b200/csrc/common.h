@@ -49,6 +49,13 @@ int encode_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t
 
 int num_sms();
 
+// Shared-memory budget (bytes) of the one-CTA-per-SM tensor-core kernels and the CTAs-per-SM share of the streaming
+// kernels: together they decide whether an HBM-bound kernel on one stream can be co-resident with a tensor-bound
+// kernel on the other (every resident CTA also costs 1 KB of reserved shared memory).  Tunable for experiments through
+// CSTP_SMEM_KB / CSTP_STREAM_CTAS_PER_SM (read once).
+int smem_budget();
+int stream_ctas_per_sm();
+
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace cstp

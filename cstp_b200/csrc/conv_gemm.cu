@@ -348,7 +348,7 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   }
   const uint32_t stage_bytes = kABytes + k.b_bytes;
   const int bar_bytes = 256;
-  int stages = (kSmemLimit - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
+  int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     delete plan;

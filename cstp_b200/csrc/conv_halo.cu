@@ -430,7 +430,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
   const int bar_bytes = 256;
   const long long res_all = 1LL * d->n_taps * k.tap_bytes;
-  const long long budget = kHcSmemLimit - 1024 - bar_bytes;
+  const long long budget = smem_budget() - 1024 - bar_bytes;
   if (d->allow_resident && res_all + 3LL * k.a_bytes <= budget) {
     k.resident = 1;
     k.res_bytes = static_cast<uint32_t>(res_all);

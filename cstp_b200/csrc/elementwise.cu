@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256, 4) bn_reduce_kernel(const uint4* __restri
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ mscale, const float* __restrict__ mshift,
                                                         float* __restrict__ partials) {
-  __shared__ float red[2][256 * 8];
+  __shared__ float red[256 * 2];
   const int nvec = Cp / 8;
   const int g = blockIdx.y;
   const int seg0 = blockIdx.z * kSegVecs;
@@ -189,19 +189,24 @@ __global__ void __launch_bounds__(256, 4) bn_reduce_kernel(const uint4* __restri
       }
     }
   }
+  // Cross-row reduction through 2 KB of shared memory (a 16 KB staging buffer kept this kernel from sharing an SM with
+  // a one-CTA-per-SM tensor-core kernel on the other stream): 8 rounds, each over one channel pair (j, j+1) of one
+  // quantity; thread (rl, cv) writes at (rl*seg_vecs + cv)*2 + jo, the sum over rl runs in row order (deterministic).
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    red[0][threadIdx.x * 8 + j] = s0[j];
-    red[1][threadIdx.x * 8 + j] = s1[j];
-  }
-  __syncthreads();
-  // thread (rl, cv) data sits at ((rl*seg_vecs + cv)*8 + j); reduce over rl for each of seg_vecs*8 channels.
-  const int seg_ch = seg_vecs * 8;
-  for (int c = threadIdx.x; c < 2 * seg_ch; c += blockDim.x) {
-    const int q = c / seg_ch, ch = c % seg_ch;
-    float acc = 0.f;
-    for (int r = 0; r < rows_per_pass; ++r) acc += red[q][r * seg_ch + ch];
-    partials[((static_cast<long long>(blockIdx.x) * gridDim.y + g) * 2 + q) * Cp + seg0 * 8 + ch] = acc;
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      red[threadIdx.x * 2 + 0] = q == 0 ? s0[2 * jj] : s1[2 * jj];
+      red[threadIdx.x * 2 + 1] = q == 0 ? s0[2 * jj + 1] : s1[2 * jj + 1];
+      __syncthreads();
+      if (threadIdx.x < seg_vecs * 2) {
+        const int cvv = threadIdx.x >> 1, jo = threadIdx.x & 1;
+        float acc = 0.f;
+        for (int r = 0; r < rows_per_pass; ++r) acc += red[(r * seg_vecs + cvv) * 2 + jo];
+        partials[((static_cast<long long>(blockIdx.x) * gridDim.y + g) * 2 + q) * Cp + (seg0 + cvv) * 8 + 2 * jj + jo] = acc;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -552,7 +557,7 @@ static inline dim3 bn_grid(long long rows_per_group, int Cp, int groups) {
   const int segs = ceil_div(nvec, kSegVecs);
   const int seg_vecs = nvec < kSegVecs ? nvec : kSegVecs;
   const int rows_per_pass = 256 / seg_vecs;
-  long long want = (static_cast<long long>(num_sms()) * 8 + groups * segs - 1) / (groups * segs);
+  long long want = (static_cast<long long>(num_sms()) * stream_ctas_per_sm() + groups * segs - 1) / (groups * segs);
   long long have = (rows_per_group + rows_per_pass - 1) / rows_per_pass;
   if (want > have) want = have;
   if (want < 1) want = 1;

@@ -268,7 +268,7 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   }
   const uint32_t stage_bytes = (2u + static_cast<uint32_t>(k.n_gboxes)) * kBoxBytes;
   const int bar_bytes = 256;
-  int stages = (kWgSmemLimit - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
+  int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   k.stages = stages;
   int cols = 32;

@@ -283,7 +283,7 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
     k.mtiles[mt] = WhMtile{a, two ? b - a : 0u};
   }
   const int bar_bytes = 256;
-  int stages = (kWhSmemLimit - 1024 - bar_bytes) / static_cast<int>(k.stage_bytes);
+  int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(k.stage_bytes);
   if (stages > kWhMaxStages) stages = kWhMaxStages;
   if (stages < 2) {
     delete plan;

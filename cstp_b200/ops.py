@@ -237,7 +237,9 @@ class ConvHaloPlan(_Plan):
         L.check(L.load().cstp_conv_halo_plan_run(self.handle, _stream()))
 
 
-SMEM_BUDGET = 232448 - 1024 - 256
+# same knob as csrc/common.cu::smem_budget()
+SMEM_LIMIT = min(227, max(64, int(os.environ.get("CSTP_SMEM_KB") or 227))) * 1024
+SMEM_BUDGET = SMEM_LIMIT - 1024 - 256
 
 
 def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
@@ -496,7 +498,7 @@ def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
     chunks.sort()
     n_gboxes = math.ceil(n_tile / 64)
     stage = len(xboxes) * xbox_bytes + n_gboxes * 8192
-    if 2 * stage + 1280 > 232448:
+    if 2 * stage + 1280 > SMEM_LIMIT:
         return None
     splits = max(1, sms // n_ntiles)
     kblocks = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt) * N
@@ -632,9 +634,12 @@ def stem_im2col(x: torch.Tensor, col: torch.Tensor) -> None:
     L.check(L.load().cstp_stem_im2col(_ptr(x), N, T, H, W, _ptr(col), col.shape[-1], _stream()))
 
 
+BN_REDUCE_CTAS_PER_SM = max(1, int(os.environ.get("CSTP_BN_REDUCE_CTAS_PER_SM") or 2))   # per statistics group
+
+
 def bn_nblocks(rows_per_group: int, Cp: int, sms: int = 148) -> int:
     rows_per_pass = max(1, 256 // min(Cp // 8, 128))
-    return max(1, min(2 * sms, math.ceil(rows_per_group / (rows_per_pass * 8))))
+    return max(1, min(BN_REDUCE_CTAS_PER_SM * sms, math.ceil(rows_per_group / (rows_per_pass * 8))))
 
 
 @dataclass
