@@ -1,0 +1,124 @@
+"""the pretraining clip pipeline.  CPU part:
+  * cstp_b200.data_process.clip_plan.PretrainClipSampler against traces of the UNMODIFIED reference classes
+    (tests/golden/clips_trace.json, produced by oracle/make_golden_clips.py): labels, frame numbers, rotation codes, crop
+    boxes, flips and every base-transform parameter bit-exact, for 256 seeded (variant, video length, frame size) cases;
+  * oracle.clip_oracle.render_plan (the pixel oracle the GPU tests use) against the reference's output clips: bit-exact.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from cstp_b200.data_process.clip_plan import PretrainClipSampler
+from oracle.clip_oracle import ROT_METHOD, render_plan, synthetic_video
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+with open(os.path.join(GOLD, "clips_trace.json")) as f:
+    TRACES = json.load(f)
+
+
+def seeded_plan(case):
+    random.seed(case["seed"])
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    return PretrainClipSampler(16, 112, case["variant"]).plan(case["total_frames"], case["w"], case["h"])
+
+
+def dedupe(events):
+    out = []
+    for e in events:
+        e = tuple(e) if not isinstance(e[1], list) else (e[0], tuple(e[1]))
+        if out and out[-1] == e and e[0] not in ("open", "gray"):
+            continue
+        out.append(e)
+    return out
+
+
+def expected_events(plan):
+    """The Pillow / torchvision call sequence the reference makes for this plan (one entry per frame, as traced)."""
+    v1, v2 = plan.views
+    ev = []
+    m1, m2 = ROT_METHOD[v1.rot], ROT_METHOD[v2.rot]
+    short = plan.draws.get("short", None)
+    if short:
+        for n in v1.frames:                      # datasets.py:893-910: one open, both rotations
+            ev.append(("open", n))
+            if m1 is not None:
+                ev.append(("transpose", int(m1)))
+            if m2 is not None:
+                ev.append(("transpose", int(m2)))
+    else:
+        for v, m in ((v1, m1), (v2, m2)):
+            for n in v.frames:
+                ev.append(("open", n))
+                if m is not None:
+                    ev.append(("transpose", int(m)))
+    for v in (v1, v2):
+        T = len(v.frames)
+        ev += [("crop", tuple(v.box))] * T
+        if v.base:
+            ev += [("rotate", v.angle)] * T
+            if v.jitter is not None:
+                # transforms.Compose of the shuffled ops is applied frame by frame: op order cycles per frame
+                for _ in range(T):
+                    ev += [(name, factor) for name, factor in v.jitter]
+            if v.gray is not None:
+                ev += [("gray", c) for c in v.gray]
+            if v.blur_sigma is not None:
+                ev += [("blur", v.blur_sigma)] * T
+        if v.flip:
+            ev += [("transpose", 0)] * T
+    return ev
+
+
+@pytest.mark.parametrize("which", ["cases", "pixel_cases"])
+def test_sampler_matches_reference_traces(which):
+    n_base = n_short = n_retry = 0
+    for case in TRACES[which]:
+        plan = seeded_plan(case)
+        assert plan.labels() == case["labels"], case
+        got = dedupe(expected_events(plan))
+        want = dedupe(case["trace"])
+        assert got == want, (case["seed"], case["variant"], case["total_frames"], got[:40], want[:40])
+        n_base += plan.views[0].base + plan.views[1].base
+        n_short += bool(plan.draws.get("short"))
+        n_retry += plan.draws["temporal_retries"] > 0
+    if which == "cases":          # the fixture exercises every branch
+        assert n_base > 50 and n_short > 10 and n_retry > 20
+
+
+def test_label_and_index_ranges():
+    random.seed(7)
+    np.random.seed(7)
+    torch.manual_seed(7)
+    for variant in ("ucf", "kinetics"):
+        s = PretrainClipSampler(16, 112, variant)
+        for total in (15, 40, 200):
+            for _ in range(50):
+                p = s.plan(total, 320, 240)
+                assert 0 <= p.spa_label <= 4 and 0 <= p.tem_label <= 4 and 0 <= p.pb_label <= 3
+                assert all(0 <= r <= 3 for r in p.rot_labels)
+                lo, hi = (1, total) if variant == "ucf" else (0, total - 1)
+                for v in p.views:
+                    assert len(v.frames) == 16 and all(lo <= n <= hi for n in v.frames), (variant, total, v.frames)
+                    x0, y0, x1, y1 = v.box
+                    assert x1 - x0 == p.views[0].box[2] - p.views[0].box[0]      # the second crop keeps the first one's size
+                    assert y1 - y0 == p.views[0].box[3] - p.views[0].box[1]
+
+
+def test_pixel_oracle_matches_reference_clips():
+    ref = np.load(os.path.join(GOLD, "clips_ref.npz"))
+    for i, case in enumerate(TRACES["pixel_cases"]):
+        plan = seeded_plan(case)
+        n = case["total_frames"]
+        video = synthetic_video(n + 1, case["w"], case["h"], case["seed"])
+        if case["variant"] == "kinetics":
+            video = video[:n]
+        clips = render_plan(plan, video)
+        for v in range(2):
+            want = torch.from_numpy(ref["case%d_view%d" % (i, v)]).float() / 255 * 2.0 - 1.0
+            assert clips[v].shape == (3, 16, 112, 112)
+            assert torch.equal(clips[v], want), (i, v, (clips[v] - want).abs().max().item())
