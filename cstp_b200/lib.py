@@ -117,6 +117,32 @@ class WgradHaloDesc(C.Structure):
     ]
 
 
+CSTP_CLIP_T = 16
+CSTP_CLIP_KMAX = 24
+
+
+class ClipView(C.Structure):
+    """cstp_clip_view: one output clip of the pretraining clip pipeline (include/cstp_b200.h)."""
+    _fields_ = [
+        ("video", C.c_void_p), ("out", C.c_void_p), ("coef", C.c_void_p),
+        ("W", C.c_int32), ("H", C.c_int32),
+        ("frames", C.c_int32 * CSTP_CLIP_T),
+        ("rot", C.c_int32),
+        ("box", C.c_int32 * 4),
+        ("flip", C.c_int32),
+        ("rotate", C.c_int32),
+        ("rot_fix", C.c_int32 * 6),
+        ("n_jitter", C.c_int32),
+        ("jitter_op", C.c_int32 * 4),
+        ("jitter_f", C.c_float * 4),
+        ("hue_shift", C.c_int32),
+        ("gray", C.c_int32 * CSTP_CLIP_T),
+        ("blur", C.c_int32),
+        ("blur_radius", C.c_int32), ("blur_edge_a", C.c_int32), ("blur_edge_b", C.c_int32),
+        ("blur_ww", C.c_uint32), ("blur_fw", C.c_uint32),
+    ]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); the single source of truth for the symbols include/cstp_b200.h declares.
@@ -164,6 +190,7 @@ SIGNATURES = {
     "cstp_bn_eval_coeffs": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cstp_ema_update": (_i, [_vp, _vp, _i64, _f, _f, _vp]),
     "cstp_sgd_clip_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp]),
+    "cstp_clip_assemble": (_i, [_vp, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

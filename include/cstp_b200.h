@@ -298,6 +298,44 @@ int cstp_sgd_clip_step(float* p, const float* g, float* mom, int64_t n, float lr
                        float max_norm, int do_clip, int first_step, float* norm_out, float* workspace,
                        void* stream);
 
+/* ---- pretraining clip pipeline -----------------------------------------------------------
+ * Replaces the pixel work of the reference's CPU data pipeline for one batch of pretraining samples:
+ *   data_process/datasets.py:888-932 (Image.open + Image.transpose(ROTATE_*) per frame),
+ *   data_process/preprocess_data.py:514-515,537-562 (crop + resize((112,112), BICUBIC)),
+ *   data_process/preprocess_data.py:1112-1122 (RandomRotation -> ColorJitter -> ClipRandomGray -> GaussianBlur ->
+ *   horizontal flip -> ToTensor -> Normalize 'tf').
+ * Every random decision has been taken on the host (cstp_b200/data_process/clip_plan.py, bit-exact with the reference's
+ * draw order); a view descriptor carries them as integers / fixed-point tables, and one launch turns decoded uint8
+ * frames resident in HBM into the two fp32 NCDHW clips the model consumes.  The arithmetic is Pillow's, restated in
+ * integers (Q22 resampling taps, 16.16 affine walk, Q24 box blur, uint8 HSV), so the output equals the reference's
+ * clips bit for bit. */
+#define CSTP_CLIP_T 16     /* frames per clip (opts.sample_duration) upper bound */
+#define CSTP_CLIP_KMAX 24  /* resampling taps per output pixel upper bound (crop side <= 616 for a 112 output) */
+typedef struct {
+  const uint8_t* video;  /* device: frame 0 of this sample's decoded video, uint8 [F][H][W][3] */
+  float* out;            /* device: this view's clip, fp32 (3, T, S, S) */
+  const int32_t* coef;   /* device: [2][S][2 + CSTP_CLIP_KMAX]: x tables, then y tables; per output index: first source
+                            index, tap count, Q22 taps (Pillow's precompute_coeffs + normalize_coeffs_8bpc) */
+  int32_t W, H;          /* stored frame size */
+  int32_t frames[CSTP_CLIP_T];
+  int32_t rot;           /* rotation label: frame turned rot x 90 degrees counter-clockwise before cropping */
+  int32_t box[4];        /* crop (x0, y0, x1, y1) in the rotated frame; outside pixels read 0 */
+  int32_t flip;
+  int32_t rotate;        /* 1: Image.rotate(angle), NEAREST, as the 16.16 fixed-point affine walk rot_fix[a0..a5] */
+  int32_t rot_fix[6];
+  int32_t n_jitter;
+  int32_t jitter_op[4];  /* 0 brightness, 1 contrast, 2 saturation, 3 hue -- in application order */
+  float jitter_f[4];     /* blend factor of ops 0-2 */
+  int32_t hue_shift;     /* uint8 increment of the H channel (op 3) */
+  int32_t gray[CSTP_CLIP_T]; /* per frame: -1, or the channel copied into R, G and B */
+  int32_t blur;          /* 1: Pillow's 3-pass extended box blur with the parameters below (both axes) */
+  int32_t blur_radius, blur_edge_a, blur_edge_b;
+  uint32_t blur_ww, blur_fw;
+} cstp_clip_view;
+/* views: DEVICE array of n_views descriptors; max_crop_h: largest (box[3]-box[1]) among them (sizes the shared-memory
+ * staging of the horizontal pass; CSTP_EINVAL when it does not fit).  One CTA per (frame, view). */
+int cstp_clip_assemble(const cstp_clip_view* views, int n_views, int T, int S, int max_crop_h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,3 +122,81 @@ def test_pixel_oracle_matches_reference_clips():
             want = torch.from_numpy(ref["case%d_view%d" % (i, v)]).float() / 255 * 2.0 - 1.0
             assert clips[v].shape == (3, 16, 112, 112)
             assert torch.equal(clips[v], want), (i, v, (clips[v] - want).abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host side of the GPU path: descriptors + integer tables, executed by the numpy stand-in of csrc/clip_pipeline.cu
+def _emulate(plan, video, S=112):
+    from cstp_b200.data_process.gpu_clips import compile_view
+    from tests.emulate_clips import run_view
+    H, W = video.shape[1:3]
+    return [torch.from_numpy(run_view(*compile_view(v, plan.frame_base, W, H, S)[:2], video, len(v.frames), S))
+            for v in plan.views]
+
+
+def _force_base(plan, seed):
+    """Give both views a full base chain (the sampler only takes it 30 % of the time)."""
+    rng = random.Random(seed)
+    for v in plan.views:
+        v.base = True
+        v.angle = rng.uniform(-10, 10)
+        ops = [("brightness", rng.uniform(0.6, 1.4)), ("contrast", rng.uniform(0.6, 1.4)),
+               ("saturation", rng.uniform(0.6, 1.4)), ("hue", rng.uniform(-0.1, 0.1))]
+        rng.shuffle(ops)
+        v.jitter = ops
+        v.gray = [rng.randrange(3) for _ in v.frames] if rng.random() < 0.5 else None
+        v.blur_sigma = rng.uniform(0.1, 2.0)
+    return plan
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_descriptor_path_matches_pixel_oracle(idx):
+    """plan -> cstp_clip_view descriptors -> integer arithmetic == Pillow, bit-exact (null and base chains, all four
+    rotation labels, crops reaching outside the frame)."""
+    case = TRACES["pixel_cases"][idx]
+    plan = seeded_plan(case)
+    if idx % 2 == 1:
+        plan = _force_base(plan, idx)
+    plan.views[0].rot, plan.views[1].rot = idx % 4, (idx + 1) % 4       # pixel path only: any rotation pair is legal
+    w, h = case["w"], case["h"]
+    for v in plan.views:                                               # keep the boxes inside / around the rotated frame
+        wr, hr = (h, w) if v.rot & 1 else (w, h)
+        bw, bh = min(v.box[2] - v.box[0], wr), min(v.box[3] - v.box[1], hr)
+        v.box = (wr - bw + 3 * (idx % 2), 0 - 2 * (idx % 2), wr + 3 * (idx % 2), bh - 2 * (idx % 2))
+    n = case["total_frames"]
+    video = synthetic_video(n + 1, w, h, case["seed"])
+    # two frames per clip are enough for the CPU stand-in (every frame runs the same arithmetic)
+    for v in plan.views:
+        v.frames = v.frames[:2]
+        v.gray = v.gray[:2] if v.gray is not None else None
+    want = render_plan(plan, video)
+    got = _emulate(plan, video)
+    for v in range(2):
+        assert torch.equal(got[v], want[v]), (idx, v, (got[v] - want[v]).abs().max().item())
+
+
+def test_resample_tables_cover_every_crop_size():
+    from cstp_b200.data_process.gpu_clips import KMAX, resample_tables
+    for n in (1, 2, 37, 111, 112, 113, 240, 320, 616):
+        t = resample_tables(n, 112)
+        assert t.shape == (112, 2 + KMAX) and (t[:, 1] > 0).all() and (t[:, 0] + t[:, 1] <= n).all()
+        s = t[:, 2:].astype(np.int64).sum(1)
+        assert np.abs(s - (1 << 22)).max() <= KMAX            # taps sum to 1.0 in Q22 up to rounding
+    with pytest.raises(ValueError):
+        resample_tables(700, 112)
+
+
+def test_collate_labels_layout():
+    from cstp_b200.data_process.gpu_clips import collate_labels
+    plans = [seeded_plan(c) for c in TRACES["cases"][:5]]
+    spa, tem, pb, (r1, r2) = collate_labels(plans)
+    for i, c in enumerate(TRACES["cases"][:5]):
+        assert [int(spa[i]), int(tem[i]), int(pb[i]), [int(r1[i]), int(r2[i])]] == c["labels"]
+    assert spa.dtype == torch.int64 and spa.shape == (5,)
+
+
+def test_pipeline_has_no_cpu_fallback():
+    from cstp_b200.data_process.gpu_clips import GpuClipPipeline
+    from cstp_b200.lib import CstpError
+    with pytest.raises(CstpError):
+        GpuClipPipeline(device="cpu").assemble([], [])
