@@ -17,7 +17,7 @@
 
 namespace cstp {
 
-constexpr int kClipThreads = 256;
+constexpr int kClipThreads = 1024;   // one CTA per SM (the staging buffers fill shared memory): all 32 warps hide the gather latency
 constexpr int kPrecisionBits = 22;                       // Pillow: 32 - 8 - 2
 constexpr int kCoefStride = 2 + CSTP_CLIP_KMAX;
 

@@ -200,3 +200,15 @@ def test_pipeline_has_no_cpu_fallback():
     from cstp_b200.lib import CstpError
     with pytest.raises(CstpError):
         GpuClipPipeline(device="cpu").assemble([], [])
+
+
+def test_index_order_is_the_distributed_samplers():
+    from torch.utils.data import DistributedSampler
+    from cstp_b200.data_process.datasets import distributed_indices
+    data = list(range(103))
+    for world in (1, 2, 4):
+        for rank in range(world):
+            s = DistributedSampler(data, num_replicas=world, rank=rank, shuffle=True, seed=0)
+            for epoch in (0, 3):
+                s.set_epoch(epoch)
+                assert list(iter(s)) == distributed_indices(len(data), epoch, rank, world, 0, True)

@@ -87,3 +87,29 @@ def test_assembled_clips_drive_a_training_step():
     losses = model.train_step(x1, x2, (spa, tem, pb, r1, r2), (0.1, 1, 1, 1, 1), lr=0.03)
     torch.cuda.synchronize()
     assert torch.isfinite(losses).all()
+
+
+def test_batch_source_feeds_the_epoch_driver():
+    from types import SimpleNamespace
+    from cstp_b200.data_process.datasets import GpuVideoStore, PretrainBatches
+    from cstp_b200.models.pace.r21d_byol import R21DBYOL
+    from cstp_b200.train import pretrain_epochs
+    random.seed(3)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    store = GpuVideoStore()
+    totals = [40, 90, 20, 64, 33]
+    for i, n in enumerate(totals):
+        store.put(i, synthetic_video(n, 160, 120, i))
+    batches = PretrainBatches(store, totals, batch_size=2, variant="ucf")
+    got = list(batches(1))
+    assert len(got) == 2 and got[0][0].shape == (2, 3, 16, 112, 112) and got[0][2][0].dtype == torch.int64
+    ref = PretrainBatches(store, totals, batch_size=2, reference_format=True)
+    clips, targets = next(iter(ref(1)))
+    assert len(clips) == 2 and len(targets) == 4 and len(targets[3]) == 2
+    torch.manual_seed(1)
+    model = R21DBYOL(pretrain=True).cuda()
+    opts = SimpleNamespace(n_epochs=1, learning_rate=0.03, momentum=0.9, weight_decay=5e-4, loss_weight=[0.1, 1, 1, 1, 1],
+                           clip_grad_norm=1)
+    rows = pretrain_epochs(model, batches, opts)
+    assert len(rows) == 1 and np.isfinite(rows[0]["loss"])

@@ -42,12 +42,19 @@ for it in range(8):
     if it >= 3:
         t_plan.append(t1 - t0)
         t_gpu.append((a.elapsed_time(b_), t2 - t1))
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    out = pipe.assemble(plans, vids, out)
+    torch.cuda.synchronize()
+kern_us = sum(e.device_time for e in prof.events() if "clip_assemble" in e.name)
 # Pillow oracle on the host: 4 samples
 t0 = time.perf_counter()
 for i in range(4):
     render_plan(plans[i], host_vids[i % 4])
 cpu_per_sample = (time.perf_counter() - t0) / 4
 res = {"B": B, "frame": [W, H], "plan_ms_per_batch": 1e3 * float(np.mean(t_plan)),
+       "kernel_ms_per_batch": kern_us / 1e3, "in_bytes_touched_per_batch": int(sum(
+           (v.box[2] - v.box[0]) * (v.box[3] - v.box[1]) * 3 * 16 for p in plans for v in p.views)),
        "gpu_ms_per_batch_events": float(np.mean([g[0] for g in t_gpu])),
        "host_wall_ms_per_batch": 1e3 * float(np.mean([g[1] for g in t_gpu])),
        "samples_per_s_gpu": B / (float(np.mean([g[1] for g in t_gpu])) + float(np.mean(t_plan))),
