@@ -44,6 +44,8 @@ struct ConvHaloKParams {
   int n_tile, Np;
   int stages, tmem_cols, resident;
   uint32_t a_bytes, b_bytes, stage_bytes, res_bytes, idesc;
+  uint32_t a_stride;       // a_bytes rounded up to 1024: where the per-stage weight tiles start (non-resident mode)
+  uint32_t a_sbo;          // bytes between consecutive 8-row atoms of a tap's rows inside the staged box (128-byte rows)
   int accumulate;
   __nv_bfloat16* out;
   float* out_f32;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
             tma_load_5d(st, tl ? &p.amap_tail : &p.amap, &full[stage], c * 64, w0 + gr.dw, h0 + gr.dh, t0 + gr.dt, n0);
             if (!p.resident) {
               for (int j = 0; j < gr.n_taps; ++j)
-                tma_load_2d(st + p.a_bytes + static_cast<size_t>(j) * p.b_bytes, tl ? &p.bmap_tail : &p.bmap, &full[stage],
+                tma_load_2d(st + p.a_stride + static_cast<size_t>(j) * p.b_bytes, tl ? &p.bmap_tail : &p.bmap, &full[stage],
                             p.taps[gr.first_tap + j].k_off + c * 64, ntile * p.n_tile);
             }
           }
@@ -158,8 +160,11 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     }
     const uint32_t res_addr = smem_u32(smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
-    const uint64_t dhi = umma_desc_hi(16, 1024);
-    const uint64_t dhi_tail = umma_desc_hi_kmajor(static_cast<uint32_t>(p.tail) * 2u);
+    const uint64_t dhi_b = umma_desc_hi(16, 1024);
+    const uint64_t dhi_a = umma_desc_hi(16, p.a_sbo);
+    const uint64_t dhi_tail_b = umma_desc_hi_kmajor(static_cast<uint32_t>(p.tail) * 2u);
+    // tail rows are 32 / 64 bytes wide: the atom pitch shrinks with the row width
+    const uint64_t dhi_tail_a = umma_desc_hi_kmajor_sbo(static_cast<uint32_t>(p.tail) * 2u, p.a_sbo / 128u * static_cast<uint32_t>(p.tail) * 2u);
     const int tail_shift = p.tail == 16 ? 2 : 1;        // a_shift is in 128-byte rows; tail rows are 32 / 64 bytes
     const int full_chunks = p.tail ? p.chunks - 1 : p.chunks;
     int stage = 0;
@@ -181,15 +186,18 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
             const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
             const bool tl = p.tail && c == p.chunks - 1;
             const bool full_chunk = !tl && ((c != p.chunks - 1) || p.last_ksteps == 4);
-            const uint64_t hi = tl ? dhi_tail : dhi;
+            const uint64_t hi_a = tl ? dhi_tail_a : dhi_a, hi_b = tl ? dhi_tail_b : dhi_b;
             for (int j = 0; j < gr.n_taps; ++j) {
               const int t = gr.first_tap + j;
               const uint32_t a_sh = tl ? (p.taps[t].a_shift >> tail_shift) : p.taps[t].a_shift;
-              const uint64_t da = umma_desc_at(hi, s_addr + a_sh);
+              // a_sh is a whole number of rows: the 128B-swizzle XOR follows the absolute shared-memory address, so a
+              // start address that is not 1024-aligned needs no descriptor base offset (measured: setting it breaks the
+              // result, leaving it 0 reproduces the one-axis layout bit for bit)
+              const uint64_t da = umma_desc_at(hi_a, s_addr + a_sh);
               const uint64_t db = umma_desc_at(
-                  hi, p.resident ? res_addr + static_cast<uint32_t>(t) * p.tap_bytes +
-                                       static_cast<uint32_t>(tl ? full_chunks : c) * p.b_bytes
-                                 : s_addr + p.a_bytes + static_cast<uint32_t>(j) * p.b_bytes);
+                  hi_b, p.resident ? res_addr + static_cast<uint32_t>(t) * p.tap_bytes +
+                                         static_cast<uint32_t>(tl ? full_chunks : c) * p.b_bytes
+                                   : s_addr + p.a_stride + static_cast<uint32_t>(j) * p.b_bytes);
               umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
               first = 0;
               if (full_chunk) {
@@ -329,7 +337,12 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   CSTP_REQUIRE(d->w_packed != nullptr && (d->out_bf16 != nullptr || d->out_f32 != nullptr));
   CSTP_REQUIRE(d->osw % 8 == 0 && d->osh % 8 == 0 && d->ost % 8 == 0 && d->osn % 8 == 0 && d->out_off % 8 == 0);
   const int xrows = (d->bw + d->halo_w) * (d->bh + d->halo_h) * (d->bt + d->halo_t) * d->bn;
-  CSTP_REQUIRE(xrows % 8 == 0 && d->bw + d->halo_w <= 256 && d->bh + d->halo_h <= 256 && d->bt + d->halo_t <= 256);
+  CSTP_REQUIRE(d->bw + d->halo_w <= 256 && d->bh + d->halo_h <= 256 && d->bt + d->halo_t <= 256);
+  // atom pitch: 8 rows when a tap's 128 rows are contiguous in the staged box (halo along the slowest tile axes only);
+  // a halo along w breaks the rows into runs of bw, which must then be exactly one 8-row atom each
+  const int pitch = d->atom_pitch_rows > 0 ? d->atom_pitch_rows : 8;
+  CSTP_REQUIRE(pitch >= 8 && pitch <= 64);
+  CSTP_REQUIRE(d->halo_w == 0 ? (pitch == 8 && xrows % 8 == 0) : (d->bw == 8 && pitch == d->bw + d->halo_w));
 
   cstp_conv_halo_plan* plan = new (std::nothrow) cstp_conv_halo_plan();
   if (!plan) {
@@ -392,6 +405,8 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.n_tile = d->n_tile;
   k.Np = d->Np;
   k.a_bytes = static_cast<uint32_t>(xrows) * 128u;
+  k.a_stride = (k.a_bytes + 1023u) & ~1023u;
+  k.a_sbo = static_cast<uint32_t>(pitch) * 128u;
   k.b_bytes = static_cast<uint32_t>(d->n_tile) * 128u;
   k.a_bytes_tail = static_cast<uint32_t>(xrows) * static_cast<uint32_t>(k.tail) * 2u;
   k.b_bytes_tail = static_cast<uint32_t>(d->n_tile) * static_cast<uint32_t>(k.tail) * 2u;
@@ -420,10 +435,11 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   }
   for (int t = 0; t < d->n_taps; ++t) {
     const cstp_halo_tap& tp = d->taps[t];
-    if (tp.a_shift % 1024 != 0 || tp.a_shift + 128u * 128u > k.a_bytes || tp.k_off < 0 || tp.k_off % 64 != 0 ||
+    if (tp.a_shift % (pitch == 8 ? 1024u : 128u) != 0 || tp.a_shift + 15u * k.a_sbo + 1024u > k.a_bytes || tp.k_off < 0 ||
+        tp.k_off % 64 != 0 ||
         tp.k_off + k.chunks * 64 > d->Ktot) {
       delete plan;
-      return fail_inval("tap a_shift (1024-aligned, 128 rows inside the staged box) / k_off out of range");
+      return fail_inval("tap a_shift (whole atoms, or whole rows with a w halo; 128 rows inside the staged box) / k_off out of range");
     }
     k.taps[t] = HcTap{tp.a_shift, tp.k_off};
   }
@@ -431,14 +447,14 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   const int bar_bytes = 256;
   const long long res_all = 1LL * d->n_taps * k.tap_bytes;
   const long long budget = smem_budget() - 1024 - bar_bytes;
-  if (d->allow_resident && res_all + 3LL * k.a_bytes <= budget) {
+  if (d->allow_resident && res_all + (pitch == 8 ? 3LL : 2LL) * k.a_stride <= budget) {
     k.resident = 1;
     k.res_bytes = static_cast<uint32_t>(res_all);
-    k.stage_bytes = k.a_bytes;
+    k.stage_bytes = k.a_stride;
   } else {
     k.resident = 0;
     k.res_bytes = 0;
-    k.stage_bytes = k.a_bytes + static_cast<uint32_t>(max_group_taps) * k.b_bytes;
+    k.stage_bytes = k.a_stride + static_cast<uint32_t>(max_group_taps) * k.b_bytes;
   }
   int stages = static_cast<int>((budget - k.res_bytes) / k.stage_bytes);
   if (stages > kHcMaxStages) stages = kHcMaxStages;

@@ -192,6 +192,15 @@ __device__ __forceinline__ uint64_t umma_desc_hi_kmajor(uint32_t row_bytes) {
   d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
   return d;
 }
+// Same, with an explicit stride between 8-row atoms (rows of a tap inside a staged box with a halo along w).
+__device__ __forceinline__ uint64_t umma_desc_hi_kmajor_sbo(uint32_t row_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_at(uint64_t hi, uint32_t saddr) {
   return hi | static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
 }

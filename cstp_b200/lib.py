@@ -94,6 +94,7 @@ class ConvHaloDesc(C.Structure):
         ("accumulate", C.c_int32),
         ("allow_resident", C.c_int32),
         ("use_tail_boxes", C.c_int32),
+        ("atom_pitch_rows", C.c_int32),
     ]
 
 

@@ -243,6 +243,15 @@ SMEM_BUDGET = SMEM_LIMIT - 1024 - 256
 
 
 def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
+    """The 2-D halo layout when it applies and keeps the full-width weights resident, else the one-axis halo layout."""
+    if USE_HALO_2D:
+        lay = _conv_halo_layout(tile_space, taps, a_channels, Np, True)
+        if lay is not None and lay["pitch"] != 8 and lay["resident"] and lay["n_tile"] == min(Np, 256):
+            return lay
+    return _conv_halo_layout(tile_space, taps, a_channels, Np, False)
+
+
+def _conv_halo_layout(tile_space, taps, a_channels: int, Np: int, halo_2d: bool):
     """Geometry of csrc/conv_halo.cu for a single-view (stride-1) tap list [(dw, dh, dt, k_off)], or None when the
     layer does not qualify (then csrc/conv_gemm.cu is used).  Pure shape arithmetic.
 
@@ -279,7 +288,20 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
     _, box, rows, unit = best
     halo = (0, 0, span) if temporal else (0, span, 0)
     groups, out_taps = [], []
-    if temporal:
+    pitch = 8
+    # 1 x k x k filters, 2-D halo: ONE staged box (8 + wspan) x (16 + span) serves every tap.  A tap's 128 rows are then
+    # 16 runs of 8 consecutive box rows (one swizzle atom each) spaced by the box width: atom pitch 8 + wspan rows,
+    # a_shift in whole rows.  Taken when it does not need more tiles than the best one-axis layout (56 x 56 planes: 28
+    # tiles either way, 180 staged rows per 64-channel chunk instead of 3 x 160).
+    wspan = dws[-1] - dws[0]
+    if (halo_2d and spatial and len(dws) > 1 and dws == list(range(dws[0], dws[-1] + 1))
+            and math.ceil(Wt / 8) * math.ceil(Ht / 16) * Tt <= best[0][0]):
+        box, halo, pitch = (8, 16, 1, 1), (wspan, span, 0), 8 + wspan
+        rows = (8 + wspan) * (16 + span)
+        groups.append((dws[0], dhs[0], dts[0], 0, len(taps)))
+        for (dw, dh, dt, k_off) in sorted(taps, key=lambda t: (t[1], t[0])):
+            out_taps.append((((dh - dhs[0]) * pitch + (dw - dws[0])) * 128, k_off))
+    elif temporal:
         groups.append((0, 0, dts[0], 0, len(taps)))
         for (dw, dh, dt, k_off) in sorted(taps, key=lambda t: t[2]):
             out_taps.append(((dt - dts[0]) * unit * 128, k_off))
@@ -289,7 +311,7 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
             groups.append((dw, dhs[0], dts[0], len(out_taps), len(mine)))
             for (_, dh, _, k_off) in mine:
                 out_taps.append(((dh - dhs[0]) * unit * 128, k_off))
-    a_bytes = rows * 128
+    a_bytes = (rows * 128 + 1023) // 1024 * 1024          # stage pitch (csrc/conv_halo.cu a_stride)
     chunks = pad64(a_channels) // 64
     # a channel tail of exactly 16 / 32 beyond a multiple of 64 is staged with 32 / 64-byte rows (csrc/conv_halo.cu)
     tail = a_channels % 64 if (USE_TAIL_BOXES and a_channels > 64 and a_channels % 64 in (16, 32)) else 0
@@ -297,7 +319,8 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
     # N tile: keep all weight K-blocks resident when they fit beside 3 activation stages, splitting N in two if needed
     n_tile, resident = (Np if Np <= 256 else _default_n_tile(Np)), False
     for cand in ([Np] if Np <= 256 else []) + ([pad16(math.ceil(Np / 2))] if Np > 64 else []):
-        if cand <= 256 and len(taps) * k_bytes_per_row * cand + 3 * a_bytes <= SMEM_BUDGET:
+        # (a 2-D halo stage feeds every tap of the filter: two of them already double-buffer whole K-blocks)
+        if cand <= 256 and len(taps) * k_bytes_per_row * cand + (3 if pitch == 8 else 2) * a_bytes <= SMEM_BUDGET:
             n_tile, resident = cand, True
             break
     if not resident:
@@ -305,7 +328,7 @@ def conv_halo_layout(tile_space, taps, a_channels: int, Np: int):
         if 2 * per_stage > SMEM_BUDGET:
             return None
     return dict(box=box, halo=halo, groups=groups, taps=out_taps, n_tile=n_tile, a_bytes=a_bytes, resident=resident,
-                tail=tail)
+                tail=tail, pitch=pitch)
 
 
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
@@ -333,6 +356,7 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     d.accumulate = int(accumulate)
     d.allow_resident = int(lay["resident"])
     d.use_tail_boxes = int(bool(lay.get("tail", 0)))
+    d.atom_pitch_rows = lay.get("pitch", 8)
     h = C.c_void_p()
     L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
     plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep)
@@ -344,6 +368,7 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
 # it removes 2.3 ms of bn_reduce passes at batch 60 but costs 3-5 ms in the conv kernels, so it was taken out again
 # (profiles/README.md).
 USE_TAIL_BOXES = os.environ.get("CSTP_TAIL_BOXES", "1") == "1"
+USE_HALO_2D = os.environ.get("CSTP_HALO_2D", "1") == "1"
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
 
 

@@ -116,6 +116,10 @@ typedef struct {
   /* 1: when a_channels is 16 or 32 beyond a multiple of 64, stage that channel tail (activations and weights) as boxes
    * with 32 / 64-byte rows (TMA + UMMA 32B / 64B swizzle) instead of zero-padded 128-byte rows. */
   int32_t use_tail_boxes;
+  /* Rows between consecutive 8-row atoms of one tap's 128 rows inside the staged box.  0 / 8: the rows are contiguous
+   * (halo only along the slower tile axes, a_shift in whole 1024-byte atoms).  bw + halo_w with bw == 8: the box also
+   * carries a halo along w (all k x k taps of a 1 x k x k filter read ONE staged box; a_shift in whole 128-byte rows). */
+  int32_t atom_pitch_rows;
 } cstp_conv_halo_desc;
 
 typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;

@@ -1,11 +1,4 @@
-set -x
-python -m pytest tests/test_gpu_kernels.py tests/test_gpu_step.py -m gpu -x -q 2>&1 | tail -3
-run() { env "$@" python tools/step_time.py 60 2>&1 | tail -1; }
-python tools/step_time.py 60 --no-overlap 2>&1 | tail -1
-run CSTP_SMEM_KB=227 CSTP_STREAM_CTAS_PER_SM=8 CSTP_BN_REDUCE_CTAS_PER_SM=2
-run CSTP_SMEM_KB=212 CSTP_STREAM_CTAS_PER_SM=4 CSTP_BN_REDUCE_CTAS_PER_SM=2
-run CSTP_SMEM_KB=212 CSTP_STREAM_CTAS_PER_SM=3 CSTP_BN_REDUCE_CTAS_PER_SM=1
-run CSTP_SMEM_KB=216 CSTP_STREAM_CTAS_PER_SM=2 CSTP_BN_REDUCE_CTAS_PER_SM=1
-run CSTP_SMEM_KB=212 CSTP_STREAM_CTAS_PER_SM=6 CSTP_BN_REDUCE_CTAS_PER_SM=2
-run CSTP_SMEM_KB=227 CSTP_STREAM_CTAS_PER_SM=4 CSTP_BN_REDUCE_CTAS_PER_SM=2
-run CSTP_SMEM_KB=200 CSTP_STREAM_CTAS_PER_SM=4 CSTP_BN_REDUCE_CTAS_PER_SM=2
+python tools/step_time.py 60 2>&1 | tail -1
+CSTP_HALO_2D=0 python tools/step_time.py 60 2>&1 | tail -1
+python tools/layer_profile.py 60 > gpurun_out/layer_profile_2d.log 2>&1
+grep -E "conv2|conv3.block1.conv2|TOTAL" gpurun_out/layer_profile_2d.log | grep -v wgrad
