@@ -45,8 +45,11 @@ struct ConvHaloKParams {
   int stages, tmem_cols, resident;
   uint32_t a_bytes, b_bytes, stage_bytes, res_bytes, idesc;
   uint32_t a_stride;       // a_bytes rounded up to 1024: where the per-stage weight tiles start (non-resident mode)
+  int tap_nw;              // regular tap walk of a load group: tap j sits (j % tap_nw) * tap_sw + (j / tap_nw) * tap_sh
+  uint32_t tap_sw, tap_sh; // bytes into the staged box (validated against taps[].a_shift when the plan is built)
   uint32_t a_sbo;          // bytes between consecutive 8-row atoms of a tap's rows inside the staged box (128-byte rows)
   int accumulate;
+  int fast_store;          // bf16 output only, no bias / accumulate, 32-byte aligned rows: pipelined epilogue with STG.256
   __nv_bfloat16* out;
   float* out_f32;
   const float* bias;
@@ -153,8 +156,22 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    // Every loop-invariant parameter is copied out of the constant bank once, the tap walk is pure uniform arithmetic
+    // (tap j of a group sits (j % nw) * sw + (j / nw) * sh bytes into the staged box; its weights follow the previous
+    // tap's), and the MMAs are issued without a compiler memory clobber: with the taps[] table and the clobbering
+    // wrappers the issuing warp spent ~85 cycles per UTCHMMA on LDCU round trips (ncu source page, profiles/README.md)
+    // while a 128x64x16 MMA occupies the tensor pipe for 32.
     const bool leader = elect_one();
-    if (p.resident) {
+    const uint32_t stage_bytes = p.stage_bytes, a_stride = p.a_stride, b_bytes = p.b_bytes, tap_bytes = p.tap_bytes;
+    uint32_t idesc;             // pinned in a register: the compiler otherwise re-loads it in front of every tap
+    asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
+    const int n_groups = p.n_groups, chunks = p.chunks, last_ksteps = p.last_ksteps, stages = p.stages, n_tile = p.n_tile;
+    const int nw = p.tap_nw;
+    const bool resident = p.resident != 0, has_tail = p.tail != 0;
+    const int tail_shift = p.tail == 16 ? 2 : 1;        // shifts are in 128-byte rows; tail rows are 32 / 64 bytes
+    const uint32_t sw_full = p.tap_sw, sh_full = p.tap_sh;
+    const int full_chunks = has_tail ? chunks - 1 : chunks;
+    if (resident) {
       mbar_wait(bfull, 0);
       tc_fence_after();
     }
@@ -165,8 +182,6 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     const uint64_t dhi_tail_b = umma_desc_hi_kmajor(static_cast<uint32_t>(p.tail) * 2u);
     // tail rows are 32 / 64 bytes wide: the atom pitch shrinks with the row width
     const uint64_t dhi_tail_a = umma_desc_hi_kmajor_sbo(static_cast<uint32_t>(p.tail) * 2u, p.a_sbo / 128u * static_cast<uint32_t>(p.tail) * 2u);
-    const int tail_shift = p.tail == 16 ? 2 : 1;        // a_shift is in 128-byte rows; tail rows are 32 / 64 bytes
-    const int full_chunks = p.tail ? p.chunks - 1 : p.chunks;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -175,45 +190,54 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * n_tile);
       uint32_t first = 1;
-      for (int g = 0; g < p.n_groups; ++g) {
-        const HcGroup gr = p.groups[g];
-        for (int c = 0; c < p.chunks; ++c) {
+      for (int g = 0; g < n_groups; ++g) {
+        const int g_first = p.groups[g].first_tap, g_taps = p.groups[g].n_taps;
+        for (int c = 0; c < chunks; ++c) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (leader) {
-            const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
-            const bool tl = p.tail && c == p.chunks - 1;
-            const bool full_chunk = !tl && ((c != p.chunks - 1) || p.last_ksteps == 4);
+            const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+            const bool tl = has_tail && c == chunks - 1;
+            const int ks = (c == chunks - 1) ? last_ksteps : 4;
             const uint64_t hi_a = tl ? dhi_tail_a : dhi_a, hi_b = tl ? dhi_tail_b : dhi_b;
-            for (int j = 0; j < gr.n_taps; ++j) {
-              const int t = gr.first_tap + j;
-              const uint32_t a_sh = tl ? (p.taps[t].a_shift >> tail_shift) : p.taps[t].a_shift;
-              // a_sh is a whole number of rows: the 128B-swizzle XOR follows the absolute shared-memory address, so a
-              // start address that is not 1024-aligned needs no descriptor base offset (measured: setting it breaks the
-              // result, leaving it 0 reproduces the one-axis layout bit for bit)
-              const uint64_t da = umma_desc_at(hi_a, s_addr + a_sh);
-              const uint64_t db = umma_desc_at(
-                  hi_b, p.resident ? res_addr + static_cast<uint32_t>(t) * p.tap_bytes +
-                                         static_cast<uint32_t>(tl ? full_chunks : c) * p.b_bytes
-                                   : s_addr + p.a_stride + static_cast<uint32_t>(j) * p.b_bytes);
-              umma_bf16(d_tmem, da, db, p.idesc, first ? 0u : 1u);
+            const uint32_t sw = tl ? sw_full >> tail_shift : sw_full, sh = tl ? sh_full >> tail_shift : sh_full;
+            uint32_t b_addr = resident ? res_addr + static_cast<uint32_t>(g_first) * tap_bytes +
+                                             static_cast<uint32_t>(tl ? full_chunks : c) * b_bytes
+                                       : s_addr + a_stride;
+            const uint32_t b_step = resident ? tap_bytes : b_bytes;
+            uint32_t a_addr = s_addr, a_row0 = s_addr;       // a_addr walks along w, a_row0 is the start of its h row
+            int jw = 0;
+            for (int j = 0; j < g_taps; ++j) {
+              // the swizzle XOR follows the absolute shared-memory address: a start that is a whole number of rows but
+              // not 1024-aligned needs no descriptor base offset (measured: setting it breaks the result)
+              const uint64_t da = umma_desc_at(hi_a, a_addr);
+              const uint64_t db = umma_desc_at(hi_b, b_addr);
+              umma_bf16_nc(d_tmem, da, db, idesc, first ? 0u : 1u);
               first = 0;
-              if (full_chunk) {
-                umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
-                umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
-                umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
+              if (ks == 4) {
+                umma_bf16_acc_nc(d_tmem, da + 2, db + 2, idesc);
+                umma_bf16_acc_nc(d_tmem, da + 4, db + 4, idesc);
+                umma_bf16_acc_nc(d_tmem, da + 6, db + 6, idesc);
               } else {
-                for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
+                for (int k = 1; k < ks; ++k) umma_bf16_acc_nc(d_tmem, da + 2 * k, db + 2 * k, idesc);
+              }
+              b_addr += b_step;
+              if (++jw == nw) {
+                jw = 0;
+                a_row0 += sh;
+                a_addr = a_row0;
+              } else {
+                a_addr += sw;
               }
             }
             umma_commit(&empty[stage]);
-            if (g == p.n_groups - 1 && c == p.chunks - 1) umma_commit(&tfull[as]);
+            if (g == n_groups - 1 && c == chunks - 1) umma_commit(&tfull[as]);
           }
           first = 0;
           __syncwarp();
-          if (++stage == p.stages) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -247,6 +271,26 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      if (p.fast_store) {
+        // plain bf16 output: the TMEM load of the next 16 columns is in flight while this chunk is packed and written
+        // with ONE 32-byte store per row (the row-per-thread layout makes every 16-byte store a half-written sector;
+        // with nine serial load -> wait -> 2 x STG.128 rounds the epilogue warps were busy 93 % of a 64->144 tile and
+        // the issuer waited on the accumulator 21 % of the time: ncu source page, profiles/README.md)
+        __nv_bfloat16* dst = p.out + off;
+        uint32_t va[16], vb[16];
+        tmem_ld16(taddr, va);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          tmem_ld_wait();
+          const bool more = c0 + 16 < ncols;
+          if (more) tmem_ld16(taddr + c0 + 16, vb);
+          if (valid) store_bf16x16(dst + c0, va);
+          if (more) {
+            tmem_ld_wait();
+            if (c0 + 32 < ncols) tmem_ld16(taddr + c0 + 32, va);
+            if (valid) store_bf16x16(dst + c0 + 16, vb);
+          }
+        }
+      } else
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
@@ -418,6 +462,9 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.out_f32 = d->out_f32;
   k.bias = d->bias;
   k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
+  k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr && !d->accumulate &&
+                 reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && d->out_off % 16 == 0 && d->osw % 16 == 0 &&
+                 d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
   int max_group_taps = 0, seen = 0;
   for (int g = 0; g < d->n_groups; ++g) {
     const cstp_halo_group& gr = d->groups[g];
@@ -442,6 +489,31 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
       return fail_inval("tap a_shift (whole atoms, or whole rows with a w halo; 128 rows inside the staged box) / k_off out of range");
     }
     k.taps[t] = HcTap{tp.a_shift, tp.k_off};
+  }
+  // the issuer walks the taps of a group arithmetically: derive (nw, sw, sh) from the first group and hold every group to it
+  {
+    const cstp_halo_group& g0 = d->groups[0];
+    const uint32_t base0 = d->taps[g0.first_tap].a_shift;
+    uint32_t sw = g0.n_taps > 1 ? d->taps[g0.first_tap + 1].a_shift - base0 : 0u;
+    int nw = g0.n_taps;
+    for (int j = 1; j < g0.n_taps; ++j)
+      if (d->taps[g0.first_tap + j].a_shift - base0 != static_cast<uint32_t>(j) * sw) {
+        nw = j;
+        break;
+      }
+    const uint32_t sh = nw < g0.n_taps ? d->taps[g0.first_tap + nw].a_shift - base0 : 0u;
+    bool regular = base0 == 0;
+    for (int g = 0; g < d->n_groups && regular; ++g)
+      for (int j = 0; j < d->groups[g].n_taps; ++j)
+        regular = regular && d->taps[d->groups[g].first_tap + j].a_shift ==
+                                 static_cast<uint32_t>(j % nw) * sw + static_cast<uint32_t>(j / nw) * sh;
+    if (!regular) {
+      delete plan;
+      return fail_inval("tap shifts of a load group must form a regular (w, h) walk starting at 0");
+    }
+    k.tap_nw = nw;
+    k.tap_sw = sw;
+    k.tap_sh = sh;
   }
   // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
   const int bar_bytes = 256;

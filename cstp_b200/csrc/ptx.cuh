@@ -124,6 +124,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same two instructions without the "memory" clobber, for tight issue loops: nothing the issuing warp reads or writes
+// through ordinary memory operations is touched by the MMA (operands are written by TMA, read by the tensor core), and
+// volatile asm statements keep their order among themselves -- but a clobber makes the compiler re-load every kernel
+// parameter from the constant bank (LDCU + scoreboard wait) in front of each instruction.
+__device__ __forceinline__ void umma_bf16_nc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_bf16_acc_nc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc));
+}
 // Make all previously issued MMAs arrive on an mbarrier when they retire. Issued by ONE thread.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -235,6 +258,19 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// One 32-byte global store (STG.256, sm_100): a full sector per thread.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+// 16 fp32 accumulator columns -> 16 bf16 -> one 32-byte store.
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const uint32_t (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+  st_global_256(dst, w);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
