@@ -29,6 +29,7 @@ struct ConvKParams {
   int stages, tmem_cols;
   uint32_t b_bytes, idesc;
   int accumulate;
+  int fast_store;          // bf16 output only, no bias, 32-byte aligned rows: pipelined epilogue with STG.256
   __nv_bfloat16* out;
   float* out_f32;
   const float* bias;
@@ -127,7 +128,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    const int kblocks = p.n_taps * p.chunks_per_tap;
+    // loop-invariant parameters live in registers and the MMAs are issued without a compiler memory clobber (see
+    // conv_halo.cu: otherwise every UTCHMMA waits for a fresh LDCU of the kernel parameters)
+    const int n_taps = p.n_taps, chunks_per_tap = p.chunks_per_tap, last_ksteps = p.last_ksteps, stages = p.stages;
+    const int n_tile = p.n_tile;
+    const int kblocks = n_taps * chunks_per_tap;
+    uint32_t idesc;
+    asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     const uint32_t smem_addr0 = smem_u32(smem);
     const uint64_t dhi = umma_desc_hi(16, 1024);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -135,29 +142,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * n_tile);
       int kb = 0;
-      for (int t = 0; t < p.n_taps; ++t) {
-        for (int c = 0; c < p.chunks_per_tap; ++c, ++kb) {
+      for (int t = 0; t < n_taps; ++t) {
+        for (int c = 0; c < chunks_per_tap; ++c, ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (leader) {
             const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
             const uint64_t da = umma_desc_at(dhi, a_addr);
             const uint64_t db = umma_desc_at(dhi, a_addr + kABytes);
-            umma_bf16(d_tmem, da, db, p.idesc, kb != 0 ? 1u : 0u);
-            if (c != p.chunks_per_tap - 1 || p.last_ksteps == 4) {
-              umma_bf16_acc(d_tmem, da + 2, db + 2, p.idesc);
-              umma_bf16_acc(d_tmem, da + 4, db + 4, p.idesc);
-              umma_bf16_acc(d_tmem, da + 6, db + 6, p.idesc);
+            umma_bf16_nc(d_tmem, da, db, idesc, kb != 0 ? 1u : 0u);
+            if (c != chunks_per_tap - 1 || last_ksteps == 4) {
+              umma_bf16_acc_nc(d_tmem, da + 2, db + 2, idesc);
+              umma_bf16_acc_nc(d_tmem, da + 4, db + 4, idesc);
+              umma_bf16_acc_nc(d_tmem, da + 6, db + 6, idesc);
             } else {
-              for (int k = 1; k < p.last_ksteps; ++k) umma_bf16_acc(d_tmem, da + 2 * k, db + 2 * k, p.idesc);
+              for (int k = 1; k < last_ksteps; ++k) umma_bf16_acc_nc(d_tmem, da + 2 * k, db + 2 * k, idesc);
             }
             umma_commit(&empty[stage]);
             if (kb == kblocks - 1) umma_commit(&tfull[as]);
           }
           __syncwarp();
-          if (++stage == p.stages) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -185,6 +192,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      if (p.fast_store) {        // plain bf16 output: pipelined TMEM loads, one 32-byte store per 16 columns (ptx.cuh)
+        if (p.accumulate) epilogue_row_bf16<true>(taddr, ncols, p.out + off, valid);
+        else epilogue_row_bf16<false>(taddr, ncols, p.out + off, valid);
+      } else
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
@@ -337,6 +348,9 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   k.out_f32 = d->out_f32;
   k.bias = d->bias;
   k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
+  k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr &&
+                 reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && d->out_off % 16 == 0 && d->osw % 16 == 0 &&
+                 d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
   for (int t = 0; t < d->n_taps; ++t) {
     const cstp_tap& tp = d->taps[t];
     if (tp.map_id < 0 || tp.map_id >= d->n_amaps || tp.k_off < 0 || tp.k_off % 64 != 0 ||

@@ -49,7 +49,7 @@ struct ConvHaloKParams {
   uint32_t tap_sw, tap_sh; // bytes into the staged box (validated against taps[].a_shift when the plan is built)
   uint32_t a_sbo;          // bytes between consecutive 8-row atoms of a tap's rows inside the staged box (128-byte rows)
   int accumulate;
-  int fast_store;          // bf16 output only, no bias / accumulate, 32-byte aligned rows: pipelined epilogue with STG.256
+  int fast_store;          // bf16 output only, no bias, 32-byte aligned rows: pipelined epilogue with STG.256
   __nv_bfloat16* out;
   float* out_f32;
   const float* bias;
@@ -272,24 +272,12 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
       if (p.fast_store) {
-        // plain bf16 output: the TMEM load of the next 16 columns is in flight while this chunk is packed and written
-        // with ONE 32-byte store per row (the row-per-thread layout makes every 16-byte store a half-written sector;
-        // with nine serial load -> wait -> 2 x STG.128 rounds the epilogue warps were busy 93 % of a 64->144 tile and
-        // the issuer waited on the accumulator 21 % of the time: ncu source page, profiles/README.md)
-        __nv_bfloat16* dst = p.out + off;
-        uint32_t va[16], vb[16];
-        tmem_ld16(taddr, va);
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          tmem_ld_wait();
-          const bool more = c0 + 16 < ncols;
-          if (more) tmem_ld16(taddr + c0 + 16, vb);
-          if (valid) store_bf16x16(dst + c0, va);
-          if (more) {
-            tmem_ld_wait();
-            if (c0 + 32 < ncols) tmem_ld16(taddr + c0 + 32, va);
-            if (valid) store_bf16x16(dst + c0 + 16, vb);
-          }
-        }
+        // plain bf16 output (optionally accumulated into what is there): pipelined, one 32-byte store per 16 columns.
+        // (The row-per-thread layout makes every 16-byte store a half-written sector; with nine serial
+        // load -> wait -> 2 x STG.128 rounds the epilogue warps were busy 93 % of a 64->144 tile and the issuer waited
+        // on the accumulator 21 % of the time: ncu source page, profiles/README.md.)
+        if (p.accumulate) epilogue_row_bf16<true>(taddr, ncols, p.out + off, valid);
+        else epilogue_row_bf16<false>(taddr, ncols, p.out + off, valid);
       } else
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
@@ -462,7 +450,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.out_f32 = d->out_f32;
   k.bias = d->bias;
   k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
-  k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr && !d->accumulate &&
+  k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr &&
                  reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && d->out_off % 16 == 0 && d->osw % 16 == 0 &&
                  d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
   int max_group_taps = 0, seen = 0;

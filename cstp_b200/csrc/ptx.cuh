@@ -272,7 +272,84 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const uint32_t
   for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
   st_global_256(dst, w);
 }
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p)
+               : "memory");
+}
+// 16 fp32 accumulator columns + 16 bf16 already in memory -> 16 bf16 -> one 32-byte store.
+__device__ __forceinline__ void store_bf16x16_acc(__nv_bfloat16* dst, const uint32_t (&v)[16], const uint32_t (&o)[8]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    w[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + __uint_as_float(o[i] << 16),
+                       __uint_as_float(v[2 * i + 1]) + __uint_as_float(o[i] & 0xFFFF0000u));
+  st_global_256(dst, w);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// Epilogue of one accumulator row (thread = TMEM lane) for a plain bf16 output: `ncols` (a multiple of 16) fp32 columns
+// at `taddr` -> dst[0..ncols), optionally added to what dst holds.  Software-pipelined: the TMEM load (and, when
+// accumulating, the 32-byte global load) of the next 16 columns is in flight while the current 16 are packed and written
+// with ONE 32-byte store.  dst must be 32-byte aligned.  Every lane of the warp must call it (tcgen05.ld is .aligned);
+// `valid` only gates the global accesses.
+template <bool kAcc>
+__device__ __forceinline__ void epilogue_row_bf16(uint32_t taddr, int ncols, __nv_bfloat16* dst, bool valid) {
+  uint32_t va[16], vb[16], oa[8], ob[8];
+  tmem_ld16(taddr, va);
+  if (kAcc && valid) ld_global_256(dst, oa);
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    tmem_ld_wait();
+    const bool more = c0 + 16 < ncols;
+    if (more) {
+      tmem_ld16(taddr + c0 + 16, vb);
+      if (kAcc && valid) ld_global_256(dst + c0 + 16, ob);
+    }
+    if (valid) {
+      if (kAcc) store_bf16x16_acc(dst + c0, va, oa);
+      else store_bf16x16(dst + c0, va);
+    }
+    if (more) {
+      tmem_ld_wait();
+      if (c0 + 32 < ncols) {
+        tmem_ld16(taddr + c0 + 32, va);
+        if (kAcc && valid) ld_global_256(dst + c0 + 32, oa);
+      }
+      if (valid) {
+        if (kAcc) store_bf16x16_acc(dst + c0 + 16, vb, ob);
+        else store_bf16x16(dst + c0 + 16, vb);
+      }
+    }
+  }
+}
+
+// The fp32 flavour (split-K partials of the weight-gradient kernels): 16 columns = two 32-byte stores.
+__device__ __forceinline__ void epilogue_row_f32(uint32_t taddr, int ncols, float* dst, bool valid) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(taddr, va);
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    tmem_ld_wait();
+    const bool more = c0 + 16 < ncols;
+    if (more) tmem_ld16(taddr + c0 + 16, vb);
+    if (valid) {
+      const uint32_t lo[8] = {va[0], va[1], va[2], va[3], va[4], va[5], va[6], va[7]};
+      const uint32_t hi[8] = {va[8], va[9], va[10], va[11], va[12], va[13], va[14], va[15]};
+      st_global_256(dst + c0, lo);
+      st_global_256(dst + c0 + 8, hi);
+    }
+    if (more) {
+      tmem_ld_wait();
+      if (c0 + 32 < ncols) tmem_ld16(taddr + c0 + 32, va);
+      if (valid) {
+        const uint32_t lo[8] = {vb[0], vb[1], vb[2], vb[3], vb[4], vb[5], vb[6], vb[7]};
+        const uint32_t hi[8] = {vb[8], vb[9], vb[10], vb[11], vb[12], vb[13], vb[14], vb[15]};
+        st_global_256(dst + c0 + 16, lo);
+        st_global_256(dst + c0 + 24, hi);
+      }
+    }
+  }
+}
 
 }  // namespace cstp

@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     uint32_t phase = 0;
     const uint32_t smem_addr0 = smem_u32(smem);
     const uint64_t dhi = umma_desc_hi(kBoxBytes, 1024);
+    const int stages = p.stages;        // loop invariants in registers, clobber-free MMA issue (see conv_halo.cu)
+    uint32_t idesc;
+    asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
@@ -117,15 +120,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         // chunk, SBO = next 8 K-rows.
         const uint64_t da = umma_desc_at(dhi, a_addr);
         const uint64_t db = umma_desc_at(dhi, a_addr + a_bytes);
-        umma_bf16(tmem_base, da, db, p.idesc, kb > kb_begin ? 1u : 0u);
-        umma_bf16_acc(tmem_base, da + 128, db + 128, p.idesc);
-        umma_bf16_acc(tmem_base, da + 256, db + 256, p.idesc);
-        umma_bf16_acc(tmem_base, da + 384, db + 384, p.idesc);
+        umma_bf16_nc(tmem_base, da, db, idesc, kb > kb_begin ? 1u : 0u);
+        umma_bf16_acc_nc(tmem_base, da + 128, db + 128, idesc);
+        umma_bf16_acc_nc(tmem_base, da + 256, db + 256, idesc);
+        umma_bf16_acc_nc(tmem_base, da + 384, db + 384, idesc);
         umma_commit(&empty[stage]);
         if (kb == kb_end - 1) umma_commit(tfull);
       }
       __syncwarp();
-      if (++stage == p.stages) {
+      if (++stage == stages) {
         stage = 0;
         phase ^= 1u;
       }
@@ -141,18 +144,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     mbar_wait(tfull, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c0, v);
-      tmem_ld_wait();
-      if (valid) {
-        float4* d4 = reinterpret_cast<float4*>(dst + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                              __uint_as_float(v[4 * i + 3]));
-      }
-    }
+    epilogue_row_f32(taddr, ncols, dst, valid);     // pipelined TMEM loads, 32-byte stores (ptx.cuh)
   }
 
   tc_fence_before();
@@ -218,7 +210,7 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   CSTP_REQUIRE(d->bw >= 1 && d->bh >= 1 && d->bt >= 1 && d->bn >= 1);
   CSTP_REQUIRE(d->bw * d->bh * d->bt * d->bn == 64);
   CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
-  CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr);
+  CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr && reinterpret_cast<uintptr_t>(d->partials) % 32 == 0);   // 32-byte stores
 
   cstp_wgrad_plan* plan = new (std::nothrow) cstp_wgrad_plan();
   if (!plan) {

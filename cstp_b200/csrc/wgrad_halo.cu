@@ -120,31 +120,36 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
     const bool leader = elect_one();
     const uint32_t smem_addr0 = smem_u32(smem);
     const uint64_t dhi_b = umma_desc_hi(kGBoxBytes, 1024);
+    // loop invariants in registers, clobber-free MMA issue (see conv_halo.cu)
+    const int stages = p.stages, n_mtiles = p.n_mtiles, n_tile = p.n_tile;
+    const uint32_t stage_bytes = p.stage_bytes;
+    uint32_t idesc;
+    asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       if (leader) {
-        const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
+        const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
         const uint64_t db = umma_desc_at(dhi_b, s_addr + x_bytes);
         // MN-major, 128B swizzle: 16 K-rows (positions) per step = 2048 B (+128 in the address field); LBO = next
         // 64-channel block of the M (resp. N) axis, SBO = next 8 K-rows.
         const uint32_t acc = kb > kb_begin ? 1u : 0u;
-        for (int mt = 0; mt < p.n_mtiles; ++mt) {
+        for (int mt = 0; mt < n_mtiles; ++mt) {
           const WhMtile m = p.mtiles[mt];
           const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, 1024), s_addr + m.a_off);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * p.n_tile);
-          umma_bf16(d_tmem, da, db, p.idesc, acc);
-          umma_bf16_acc(d_tmem, da + 128, db + 128, p.idesc);
-          umma_bf16_acc(d_tmem, da + 256, db + 256, p.idesc);
-          umma_bf16_acc(d_tmem, da + 384, db + 384, p.idesc);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * n_tile);
+          umma_bf16_nc(d_tmem, da, db, idesc, acc);
+          umma_bf16_acc_nc(d_tmem, da + 128, db + 128, idesc);
+          umma_bf16_acc_nc(d_tmem, da + 256, db + 256, idesc);
+          umma_bf16_acc_nc(d_tmem, da + 384, db + 384, idesc);
         }
         umma_commit(&empty[stage]);
         if (kb == kb_end - 1) umma_commit(tfull);
       }
       __syncwarp();
-      if (++stage == p.stages) {
+      if (++stage == stages) {
         stage = 0;
         phase ^= 1u;
       }
@@ -162,18 +167,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
       const bool valid = (mt * 2 + (row >> 6)) < p.n_chunks;
       float* dst = p.partials + (static_cast<long long>(split) * mtot + static_cast<long long>(mt) * 128 + row) * p.Np + col0;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * p.n_tile);
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                __uint_as_float(v[4 * i + 3]));
-        }
-      }
+      epilogue_row_f32(taddr, ncols, dst, valid);     // pipelined TMEM loads, 32-byte stores (ptx.cuh)
     }
   }
 
@@ -219,7 +213,7 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   CSTP_REQUIRE(d->bw >= 1 && d->bh >= 1 && d->bt >= 1 && d->bn >= 1 && d->bw * d->bh * d->bt * d->bn == 64);
   CSTP_REQUIRE(d->halo_w >= 0 && d->halo_h >= 0 && d->halo_t >= 0);
   CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
-  CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr);
+  CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr && reinterpret_cast<uintptr_t>(d->partials) % 32 == 0);   // 32-byte stores
   const int n_mtiles = (d->n_chunks + 1) / 2;
   CSTP_REQUIRE(n_mtiles * d->n_tile <= 512);
   const int xrows = (d->bw + d->halo_w) * (d->bh + d->halo_h) * (d->bt + d->halo_t) * d->bn;

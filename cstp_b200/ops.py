@@ -299,7 +299,8 @@ def _conv_halo_layout(tile_space, taps, a_channels: int, Np: int, halo_2d: bool)
         box, halo, pitch = (8, 16, 1, 1), (wspan, span, 0), 8 + wspan
         rows = (8 + wspan) * (16 + span)
         groups.append((dws[0], dhs[0], dts[0], 0, len(taps)))
-        for (dw, dh, dt, k_off) in sorted(taps, key=lambda t: (t[1], t[0])):
+        # same accumulation order as the one-axis layout (dw outermost): single-chunk layers keep their bits
+        for (dw, dh, dt, k_off) in sorted(taps, key=lambda t: (t[0], t[1])):
             out_taps.append((((dh - dhs[0]) * pitch + (dw - dws[0])) * 128, k_off))
     elif temporal:
         groups.append((0, 0, dts[0], 0, len(taps)))
