@@ -188,6 +188,8 @@ def main():
         raise SystemExit("bench.py needs a B200: the native path has no CPU fallback (use --impl reference for the CPU arm)")
     warm = max(args.warmup, 3)
     torch.cuda.set_device(local)
+    # NCCL's own banner / debug lines (NCCL_DEBUG may be set by the environment) must not land on stdout: one JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     parallel.init_from_env("nccl")
     import torch.distributed as dist
     from cstp_b200 import ops
