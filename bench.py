@@ -114,14 +114,14 @@ def run_reference(args, rank: int):
     sec = sum(times) / len(times)
     v = Bs / sec
     sample = f"{Bs} of the {args.batch} clips of one step per timed step (full 16x112x112 clips, full network)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": v, "unit": "clips/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.batch, args.gpus),
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def cpu_baseline(seconds_budget: float = 25.0) -> dict:
@@ -147,6 +147,26 @@ def cpu_baseline(seconds_budget: float = 25.0) -> dict:
     sec = sum(times[1:]) / len(times[1:])
     return {"value": Bs / sec, "unit": "clips/s", "cores": cores, "kind": "port",
             "sample": f"oracle/cstp_oracle.pretrain_step on {Bs} full 16x112x112 clips, {len(times) - 1} timed steps after 1 warm-up"}
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL's version banner under NCCL_DEBUG), so
+    file descriptor 1 is pointed at stderr for the rest of the process and the JSON line goes to a private duplicate of the
+    original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def ncu_traffic(kernel: str, B: int):
@@ -176,9 +196,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bn-sync", default="local", choices=["local", "world"],
+    ap.add_argument("--bn-sync", default="local", choices=["local", "world", "world-p2p"],
                     help="local: per-GPU BatchNorm statistics (the reference's behaviour); world: SyncBN over all ranks")
     args = ap.parse_args()
+    claim_stdout()
     from cstp_b200 import parallel
     rank, world, local = parallel.env_world()
     if args.impl == "reference":
@@ -201,6 +222,8 @@ def main():
     model = R21DBYOL(pretrain=True).cuda()
     if args.bn_sync == "world" and world > 1:
         model.engine_options = {"bn_sync": parallel.BnSync()}
+    elif args.bn_sync == "world-p2p" and world > 1:
+        model.engine_options = {"bn_sync": parallel.BnSyncP2P()}
     hx1, hx2, hlabels = synthetic_batch(B, seed=rank)
     hx1, hx2 = hx1.pin_memory(), hx2.pin_memory()
     hlabels = tuple(l.pin_memory() for l in hlabels)
@@ -312,7 +335,8 @@ def main():
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {**workload_config(B, world, "per-GPU (reference semantics)" if args.bn_sync == "local" or world == 1
-                                     else "world-synchronised (SyncBN all-reduce per BatchNorm call)"),
+                                     else ("world-synchronised (SyncBN all-reduce per BatchNorm call)" if args.bn_sync == "world" else
+                                           "world-synchronised (SyncBN rows exchanged over NVLink peer memory, one kernel per call)")),
                    "l2_policy": "inputs and activations far larger than the 126 MB L2 (clips alone 2x%.0f MB)" % (x1.numel() * 4 / 1e6),
                    "views_per_s": 2 * value, "schedule": "two streams (target fwd || online fwd, wgrad || BN backward)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
@@ -320,7 +344,7 @@ def main():
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         "losses_last_step": {"byol": final[7], "ce": final[:6]},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -340,6 +340,18 @@ typedef struct {
  * staging of the horizontal pass; CSTP_EINVAL when it does not fit).  One CTA per (frame, view). */
 int cstp_clip_assemble(const cstp_clip_view* views, int n_views, int T, int S, int max_crop_h, void* stream);
 
+/* ---- SyncBN statistics exchange over NVLink peer memory ----------------------------------------------------
+ * The all-reduce(SUM) of the [groups][2][Cp] row a world-synchronised BatchNorm call exchanges (the north star's SyncBN;
+ * no counterpart in the reference, whose --sync_bn group holds one rank: models/model.py:95-96), as ONE kernel that
+ * stores the local row into every peer's receive buffer, publishes a flag, waits for every peer's flag and sums the rows
+ * in rank order (csrc/p2p_sync.cu).  peer_buffers: DEVICE array of `world` pointers to the per-rank buffers
+ * (peer-mapped, e.g. torch symmetric memory), each cstp_bn_sync_buffer_bytes(world, slots, row_max) bytes, zeroed before
+ * the first call; seq = 1, 2, ... per buffer set, identical on every rank; out may alias row; *err_flag becomes
+ * 1 + peer when a peer's flag did not arrive within the spin limit. */
+long long cstp_bn_sync_buffer_bytes(int world, int slots, int row_max);
+int cstp_bn_sync_exchange(const float* row, int n, const uint64_t* peer_buffers, int world, int rank, int slots,
+                          int row_max, uint32_t seq, float* out, int* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,7 +33,11 @@ def run(xa, xb, lab, bn_sync, sync):
     return m, losses
 
 
-m, losses = run(x1[lo:hi], x2[lo:hi], tuple(l[lo:hi] for l in labels), parallel.BnSync(), parallel.GradSync())
+P2P = "--p2p" in sys.argv
+bsync = parallel.BnSyncP2P() if P2P else parallel.BnSync()
+m, losses = run(x1[lo:hi], x2[lo:hi], tuple(l[lo:hi] for l in labels), bsync, parallel.GradSync())
+if P2P:
+    bsync.check()
 mean_losses = losses.clone()
 dist.all_reduce(mean_losses)
 mean_losses /= world
@@ -42,12 +46,23 @@ if rank == 0:
     ref, ref_losses = run(x1, x2, labels, None, None)
     sd, rd = m.state_dict(), ref.state_dict()
     rs = max(((sd[k] - rd[k]).norm() / rd[k].norm().clamp_min(1e-12)).item() for k in sd if "running" in k)
-    out = {"world": world, "byol": [mean_losses[7].item(), ref_losses[7].item()],
+    out = {"world": world, "p2p": P2P, "byol": [mean_losses[7].item(), ref_losses[7].item()],
            "total_ce": [mean_losses[6].item(), ref_losses[6].item()], "grad_norm": [gn, ref._engine.norm_out[0].item()],
            "worst_running_stat_rel": rs}
     print("SYNCBN " + json.dumps(out), flush=True)
     assert abs(out["byol"][0] - out["byol"][1]) < 2e-3 * out["byol"][1]
     assert abs(out["total_ce"][0] - out["total_ce"][1]) < 2e-3 * out["total_ce"][1]
     assert rs < 2e-2
+dist.barrier()
+if P2P:
+    # a few more steps on the same model: slot reuse on both streams, sequence numbers far beyond the slot count
+    for _ in range(3):
+        more = m.train_step(x1[lo:hi].cuda().contiguous(), x2[lo:hi].cuda().contiguous(),
+                            tuple(l[lo:hi].cuda().contiguous() for l in labels), LW, lr=0.03, grad_sync=parallel.GradSync())
+    torch.cuda.synchronize()
+    bsync.check()
+    assert torch.isfinite(more).all()
+    if rank == 0:
+        print("SYNCBN_P2P_MORE_STEPS ok", more.tolist(), flush=True)
 dist.barrier()
 dist.destroy_process_group()
