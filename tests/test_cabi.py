@@ -59,3 +59,11 @@ def test_product_path_rejects_cpu_tensors():
                           torch.zeros(1, 1, 1, 128, 16, dtype=torch.bfloat16), ops.ConvGeom((1, 1, 1)))
     with pytest.raises(L.CstpError):
         NTXentLoss("cpu", 4, 0.1, True)(torch.randn(4, 8), torch.randn(4, 8))
+
+
+def test_bn_sync_exchange_argument_checks():
+    lib = L.load()
+    assert lib.cstp_bn_sync_buffer_bytes(8, 4, 16384) == 4 * 8 * 16384 * 4 + 4 * 8 * 4
+    assert lib.cstp_bn_sync_buffer_bytes(0, 4, 16) == -1
+    assert lib.cstp_bn_sync_exchange(None, 16, None, 2, 0, 4, 64, 1, None, None, None) == -1
+    assert b"invalid argument" in lib.cstp_last_error()

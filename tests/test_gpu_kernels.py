@@ -73,3 +73,41 @@ def test_ragged_and_tiny_geometries():
         assert r["fwd_nan"] == 0 and r["fwd_pad_zero"] and r["fwd_rel"] < 4e-3, (kw, r)
         assert r["dgrad_nan"] == 0 and r["dgrad_rel"] < 4e-3, (kw, r)
         assert r["wgrad_nan"] == 0 and r["wgrad_rel"] < 2e-4, (kw, r)
+
+
+def test_bn_sync_exchange_protocol_on_one_gpu():
+    """csrc/p2p_sync.cu without a second GPU: (a) world 1 is the identity through the slot / flag machinery for many calls;
+    (b) two "ranks" with their own buffers on the same device, launched on two streams, exchange rows through the flag
+    protocol exactly as two GPUs would (each kernel spins until the other has published)."""
+    from cstp_b200 import lib as L
+    lib = L.load()
+    slots, row_max, n = 4, 64, 48
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def buffers(world):
+        nbytes = lib.cstp_bn_sync_buffer_bytes(world, slots, row_max)
+        bufs = [torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device="cuda") for _ in range(world)]
+        return bufs, torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+
+    bufs, peers = buffers(1)
+    for seq in range(1, 11):
+        row = torch.randn(n, device="cuda")
+        out = torch.empty_like(row)
+        L.check(lib.cstp_bn_sync_exchange(row.data_ptr(), n, peers.data_ptr(), 1, 0, slots, row_max, seq, out.data_ptr(),
+                                          err.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        assert torch.equal(out, row)
+    bufs, peers = buffers(2)
+    s = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for seq in range(1, 13):
+        rows = [torch.randn(n, device="cuda"), torch.randn(n, device="cuda")]
+        want = rows[0] + rows[1]
+        torch.cuda.synchronize()
+        for r in (seq % 2, 1 - seq % 2):                     # alternate which "rank" is launched first
+            with torch.cuda.stream(s[r]):
+                L.check(lib.cstp_bn_sync_exchange(rows[r].data_ptr(), n, peers.data_ptr(), 2, r, slots, row_max, seq,
+                                                  rows[r].data_ptr(), err.data_ptr(), s[r].cuda_stream))     # in place
+        torch.cuda.synchronize()
+        assert torch.equal(rows[0], rows[1])                 # same order of summation on both ranks: identical bits
+        assert torch.equal(rows[0], want)
+    assert int(err.item()) == 0
