@@ -40,6 +40,9 @@ struct WgradHaloKParams {
   int total_kblocks, kblocks_per_split;
   int stages, tmem_cols;
   uint32_t xbox_bytes, stage_bytes, idesc;
+  uint32_t x_tx_bytes;     // bytes the X boxes of one stage really carry (xbox_bytes is their 1024-aligned pitch)
+  uint32_t a_sbo;          // bytes between consecutive 8-position atoms of a chunk inside its staged box
+  uint32_t a_kstep;        // descriptor start-address advance (>> 4) per 16-position K step: two atoms
   float* partials;
   WhXBox xboxes[kWhMaxBoxes];
   WhMtile mtiles[kWhMaxMtiles];
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
       mbar_wait(&empty[stage], phase ^ 1u);
       if (leader) {
         uint8_t* st = smem + static_cast<size_t>(stage) * p.stage_bytes;
-        mbar_expect_tx(&full[stage], x_bytes + static_cast<uint32_t>(p.n_gboxes) * kGBoxBytes);
+        mbar_expect_tx(&full[stage], p.x_tx_bytes + static_cast<uint32_t>(p.n_gboxes) * kGBoxBytes);
         for (int b = 0; b < p.n_xboxes; ++b) {
           const WhXBox xb = p.xboxes[b];
           tma_load_5d(st + static_cast<size_t>(b) * p.xbox_bytes, &p.xmap, &full[stage], xb.c_off, w0 + xb.dw, h0 + xb.dh,
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
     const uint64_t dhi_b = umma_desc_hi(kGBoxBytes, 1024);
     // loop invariants in registers, clobber-free MMA issue (see conv_halo.cu)
     const int stages = p.stages, n_mtiles = p.n_mtiles, n_tile = p.n_tile;
-    const uint32_t stage_bytes = p.stage_bytes;
+    const uint32_t stage_bytes = p.stage_bytes, a_sbo = p.a_sbo;
+    const uint64_t k1 = p.a_kstep, k2 = 2ull * p.a_kstep, k3 = 3ull * p.a_kstep;
     uint32_t idesc;
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     int stage = 0;
@@ -138,12 +142,12 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
         const uint32_t acc = kb > kb_begin ? 1u : 0u;
         for (int mt = 0; mt < n_mtiles; ++mt) {
           const WhMtile m = p.mtiles[mt];
-          const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, 1024), s_addr + m.a_off);
+          const uint64_t da = umma_desc_at(umma_desc_hi(m.lbo != 0 ? m.lbo : 1024u, a_sbo), s_addr + m.a_off);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt * n_tile);
           umma_bf16_nc(d_tmem, da, db, idesc, acc);
-          umma_bf16_acc_nc(d_tmem, da + 128, db + 128, idesc);
-          umma_bf16_acc_nc(d_tmem, da + 256, db + 256, idesc);
-          umma_bf16_acc_nc(d_tmem, da + 384, db + 384, idesc);
+          umma_bf16_acc_nc(d_tmem, da + k1, db + 128, idesc);
+          umma_bf16_acc_nc(d_tmem, da + k2, db + 256, idesc);
+          umma_bf16_acc_nc(d_tmem, da + k3, db + 384, idesc);
         }
         umma_commit(&empty[stage]);
         if (kb == kb_end - 1) umma_commit(tfull);
@@ -217,7 +221,11 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   const int n_mtiles = (d->n_chunks + 1) / 2;
   CSTP_REQUIRE(n_mtiles * d->n_tile <= 512);
   const int xrows = (d->bw + d->halo_w) * (d->bh + d->halo_h) * (d->bt + d->halo_t) * d->bn;
-  CSTP_REQUIRE(xrows % 8 == 0 && d->bw + d->halo_w <= 256 && d->bh + d->halo_h <= 256 && d->bt + d->halo_t <= 256);
+  CSTP_REQUIRE(d->bw + d->halo_w <= 256 && d->bh + d->halo_h <= 256 && d->bt + d->halo_t <= 256);
+  // atom pitch: 8 rows when the 64 positions of a chunk are contiguous rows of the staged box; with a halo along w (bw == 8)
+  // every run of 8 positions is one atom and consecutive atoms are one box row (bw + halo_w positions) apart
+  const int pitch = d->atom_pitch_rows > 0 ? d->atom_pitch_rows : 8;
+  CSTP_REQUIRE(d->halo_w == 0 ? (pitch == 8 && xrows % 8 == 0) : (d->bw == 8 && pitch == d->bw + d->halo_w));
 
   cstp_wgrad_halo_plan* plan = new (std::nothrow) cstp_wgrad_halo_plan();
   if (!plan) {
@@ -246,7 +254,10 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   k.Np = d->Np;
   k.n_tile = d->n_tile;
   k.n_gboxes = ceil_div(d->n_tile, 64);
-  k.xbox_bytes = static_cast<uint32_t>(xrows) * 128u;
+  k.xbox_bytes = (static_cast<uint32_t>(xrows) * 128u + 1023u) & ~1023u;
+  k.x_tx_bytes = static_cast<uint32_t>(d->n_xboxes) * static_cast<uint32_t>(xrows) * 128u;
+  k.a_sbo = static_cast<uint32_t>(pitch) * 128u;
+  k.a_kstep = (2u * k.a_sbo) >> 4;
   k.stage_bytes = static_cast<uint32_t>(d->n_xboxes) * k.xbox_bytes + static_cast<uint32_t>(k.n_gboxes) * kGBoxBytes;
   k.total_kblocks = k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
   int splits = d->splits < k.total_kblocks ? d->splits : k.total_kblocks;
@@ -270,9 +281,11 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
     const uint32_t a = d->chunk_off[2 * mt];
     const bool two = 2 * mt + 1 < d->n_chunks;
     const uint32_t b = two ? d->chunk_off[2 * mt + 1] : a;
-    if (a % 1024 != 0 || b % 1024 != 0 || (two && b <= a) || b + kGBoxBytes > x_bytes || (b - a) / 16 >= (1u << 14)) {
+    const uint32_t align = pitch == 8 ? 1024u : 128u;
+    if (a % align != 0 || b % align != 0 || (two && b <= a) || b + 7u * k.a_sbo + 1024u > x_bytes ||
+        (b - a) / 16 >= (1u << 14)) {
       delete plan;
-      return fail_inval("chunk_off must be 1024-aligned, ascending within a pair and inside the staged X boxes");
+      return fail_inval("chunk_off must be atom- (row- with a w halo) aligned, ascending within a pair and inside the staged X boxes");
     }
     k.mtiles[mt] = WhMtile{a, two ? b - a : 0u};
   }

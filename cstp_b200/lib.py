@@ -115,6 +115,7 @@ class WgradHaloDesc(C.Structure):
         ("halo_w", C.c_int32), ("halo_h", C.c_int32), ("halo_t", C.c_int32),
         ("splits", C.c_int32),
         ("partials", C.c_void_p),
+        ("atom_pitch_rows", C.c_int32),
     ]
 
 

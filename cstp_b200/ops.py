@@ -485,40 +485,55 @@ def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
     if n_tile < 16:
         return None
     n_ntiles = math.ceil(Np / n_tile)
-    if n_ntiles > 2:                      # X is re-staged once per N tile
-        return None
     temporal = kt > 1
-    best = None
-    for bw in (8, 16, 32, 64):
-        for bh in (1, 2, 4, 8):
-            for bt in ((1, 2, 4, 8) if temporal else (1,)):
-                if bw * bh * bt != 64:
-                    continue
-                halo = (0, 0, kt - 1) if temporal else (0, kh - 1, 0)
-                tiles = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt)
-                staged = tiles * (bw + halo[0]) * (bh + halo[1]) * (bt + halo[2]) * (1 if temporal else kw)
-                key = (staged, -bw)
-                if best is None or key < best[0]:
-                    best = (key, (bw, bh, bt, 1), halo)
-    _, box, halo = best
-    bw, bh, bt, _ = box
-    xrows = (bw + halo[0]) * (bh + halo[1]) * (bt + halo[2])
-    xbox_bytes = xrows * 128
-    xboxes, chunks = [], []
-    if temporal:
-        for cc in range(n_cc):
-            xboxes.append((cc * 64, 0, 0, -pt))
-        for a in range(kt):
-            for cc in range(n_cc):
-                chunks.append((cc * xbox_bytes + a * (bw * bh) * 128, a, cc * 64))
+    # 1 x k x k filters, 2-D halo: ONE staged (8 + kw - 1) x (8 + kh - 1) box per 64-channel chunk serves every tap (a tap
+    # is a whole-row shift of it; the 8 positions of a w run are one swizzle atom, atoms one box row apart).  X is then
+    # cheap enough to be re-staged for up to 6 N tiles, which admits layers whose taps x channels need many accumulators.
+    halo_2d = (USE_HALO_2D and not temporal and kw > 1 and kh > 1 and n_ntiles <= 6
+               and math.ceil(Wo / 8) * math.ceil(Ho / 8) * 64 <= 1.35 * Wo * Ho)
+    if n_ntiles > 2 and not halo_2d:          # X is re-staged once per N tile
+        return None
+    pitch = 8
+    if halo_2d:
+        box, halo, pitch = (8, 8, 1, 1), (kw - 1, kh - 1, 0), 8 + kw - 1
+        bw, bh, bt, _ = box
+        xrows = (bw + halo[0]) * (bh + halo[1])
+        xbox_bytes = (xrows * 128 + 1023) // 1024 * 1024
+        xboxes = [(cc * 64, -pw, -ph, 0) for cc in range(n_cc)]
+        chunks = [(cc * xbox_bytes + (b_ * pitch + c) * 128, b_ * kw + c, cc * 64)
+                  for b_ in range(kh) for c in range(kw) for cc in range(n_cc)]
     else:
-        for c in range(kw):
+        best = None
+        for bw in (8, 16, 32, 64):
+            for bh in (1, 2, 4, 8):
+                for bt in ((1, 2, 4, 8) if temporal else (1,)):
+                    if bw * bh * bt != 64:
+                        continue
+                    halo = (0, 0, kt - 1) if temporal else (0, kh - 1, 0)
+                    tiles = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt)
+                    staged = tiles * (bw + halo[0]) * (bh + halo[1]) * (bt + halo[2]) * (1 if temporal else kw)
+                    key = (staged, -bw)
+                    if best is None or key < best[0]:
+                        best = (key, (bw, bh, bt, 1), halo)
+        _, box, halo = best
+        bw, bh, bt, _ = box
+        xrows = (bw + halo[0]) * (bh + halo[1]) * (bt + halo[2])
+        xbox_bytes = xrows * 128
+        xboxes, chunks = [], []
+        if temporal:
             for cc in range(n_cc):
-                xboxes.append((cc * 64, c - pw, -ph, 0))
-        for b_ in range(kh):
+                xboxes.append((cc * 64, 0, 0, -pt))
+            for a in range(kt):
+                for cc in range(n_cc):
+                    chunks.append((cc * xbox_bytes + a * (bw * bh) * 128, a, cc * 64))
+        else:
             for c in range(kw):
                 for cc in range(n_cc):
-                    chunks.append(((c * n_cc + cc) * xbox_bytes + b_ * bw * 128, b_ * kw + c, cc * 64))
+                    xboxes.append((cc * 64, c - pw, -ph, 0))
+            for b_ in range(kh):
+                for c in range(kw):
+                    for cc in range(n_cc):
+                        chunks.append(((c * n_cc + cc) * xbox_bytes + b_ * bw * 128, b_ * kw + c, cc * 64))
     if len(xboxes) > 16:
         return None
     chunks.sort()
@@ -530,7 +545,7 @@ def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
     kblocks = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt) * N
     splits = min(splits, kblocks)
     return dict(box=box, halo=halo, xboxes=xboxes, chunks=chunks, xbox_bytes=xbox_bytes, n_tile=n_tile,
-                n_ntiles=n_ntiles, splits=splits, need=splits * n_chunks * 64 * Np)
+                n_ntiles=n_ntiles, splits=splits, need=splits * n_chunks * 64 * Np, pitch=pitch)
 
 
 def wgrad_partials_need(x_shape, g_shape, geom: ConvGeom, sms: int = 148) -> int:
@@ -569,6 +584,7 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
         d.bw, d.bh, d.bt, d.bn = lay["box"]
         d.halo_w, d.halo_h, d.halo_t = lay["halo"]
         d.splits = lay["splits"]
+        d.atom_pitch_rows = lay.get("pitch", 8)
         if partials.numel() < lay["need"]:
             raise L.CstpError(f"wgrad partials scratch too small: {partials.numel()} < {lay['need']}")
         d.partials = partials.data_ptr()

@@ -189,6 +189,10 @@ typedef struct {
   int32_t halo_w, halo_h, halo_t;
   int32_t splits;
   float* partials;                      /* fp32 [splits_eff][n_chunks*64][Np] */
+  /* 0 / 8: the 64 positions of a chunk are contiguous box rows (chunk_off in whole 1024-byte atoms).  bw + halo_w with
+   * bw == 8: the box carries a halo along w as well (all k x k taps of a 1 x k x k filter read ONE staged box per channel
+   * chunk; chunk_off in whole 128-byte rows). */
+  int32_t atom_pitch_rows;
 } cstp_wgrad_halo_desc;
 
 typedef struct cstp_wgrad_halo_plan cstp_wgrad_halo_plan;

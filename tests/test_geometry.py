@@ -85,6 +85,7 @@ def test_intermediate_channels_table():
     ((3, 1, 1), (1, 0, 0), (1, 8, 8, 16), 144, 64),       # conv2 temporal (3 channel chunks, last one 16 wide)
     ((3, 1, 1), (1, 0, 0), (2, 4, 6, 8), 83, 64),         # stem temporal, ragged tiles
     ((1, 3, 3), (0, 1, 1), (1, 2, 10, 12), 128, 32),
+    ((1, 3, 3), (0, 1, 1), (1, 1, 16, 24), 128, 240),     # 2-D halo, two channel chunks, 5 N tiles (conv3.conv2.spatial)
 ])
 def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
     """Interprets ops.wgrad_halo_layout exactly as csrc/wgrad_halo.cu does (staged X boxes with halo, chunks as row
@@ -103,7 +104,9 @@ def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
     assert lay is not None
     bw, bh, bt, bn = lay["box"]
     hw, hh, ht = lay["halo"]
-    assert all(off % 1024 == 0 for off, _, _ in lay["chunks"])
+    pitch = lay["pitch"]                    # box rows between the 8-position atoms of a chunk (8: contiguous rows)
+    assert all(off % (1024 if pitch == 8 else 128) == 0 for off, _, _ in lay["chunks"])
+    box_rows = lay["xbox_bytes"] // 128      # staged boxes start on 1024-byte boundaries
     offs = [c[0] for c in lay["chunks"]]
     assert all(offs[i] < offs[i + 1] for i in range(len(offs) - 1))
 
@@ -126,11 +129,13 @@ def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
         for t0 in range(0, T, bt):
             for h0 in range(0, H, bh):
                 for w0 in range(0, W, bw):
-                    staged = torch.cat([fetch(x, c0, w0 + dw, h0 + dh, t0 + dt, n0, bw + hw, bh + hh, bt + ht)
-                                        for (c0, dw, dh, dt) in lay["xboxes"]], 0)          # rows of 128 bytes
+                    boxes = [fetch(x, c0, w0 + dw, h0 + dh, t0 + dt, n0, bw + hw, bh + hh, bt + ht)
+                             for (c0, dw, dh, dt) in lay["xboxes"]]
+                    staged = torch.cat([torch.cat([b_, torch.zeros(box_rows - b_.shape[0], 64)], 0) for b_ in boxes], 0)
                     G = torch.cat([fetch(gr, c0, w0, h0, t0, n0, bw, bh, bt) for c0 in range(0, Np, 64)], 1)[:, :Np]
                     for i, (off, _, _) in enumerate(lay["chunks"]):
-                        rows = staged[off // 128: off // 128 + 64]
+                        idx = [off // 128 + a_ * pitch + j for a_ in range(8) for j in range(8)]
+                        rows = staged[idx]
                         P[i * 64:(i + 1) * 64] += rows.t() @ G
     dw_ = torch.zeros(cout, cin, geom.taps)
     for i, (_, tap, c0) in enumerate(lay["chunks"]):
@@ -147,6 +152,8 @@ def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
     ((3, 1, 1), (1, 0, 0), (1, 20, 8, 8), 144, 64, False),
     ((1, 3, 3), (0, 1, 1), (1, 1, 18, 40), 144, 64, True),
     ((3, 1, 1), (1, 0, 0), (2, 5, 4, 12), 64, 144, True),
+    ((1, 3, 3), (0, 1, 1), (1, 2, 32, 16), 64, 144, False),     # 2-D halo (8 x 16 tiles, one box for nine taps)
+    ((1, 3, 3), (0, 1, 1), (1, 1, 16, 24), 144, 64, True),      # 2-D halo dgrad with a 16-channel tail
 ])
 def test_conv_halo_layout_semantics(k, p, shape, cin, cout, dgrad):
     """Interprets ops.conv_halo_layout exactly as csrc/conv_halo.cu does (one staged halo box per load group and
@@ -174,7 +181,8 @@ def test_conv_halo_layout_semantics(k, p, shape, cin, cout, dgrad):
     assert lay is not None
     bw, bh, bt, bn = lay["box"]
     hw, hh, ht = lay["halo"]
-    assert bw * bh * bt * bn == 128 and all(s_ % 1024 == 0 for s_, _ in lay["taps"])
+    pitch = lay["pitch"]                    # box rows between the 8-row atoms of a tap (8: its 128 rows are contiguous)
+    assert bw * bh * bt * bn == 128 and all(s_ % (1024 if pitch == 8 else 128) == 0 for s_, _ in lay["taps"])
     out = torch.zeros(N, T, H, W, n_c)
     tap_of_koff = {ti * pad64(Ca): ti for (_, _, _, ti) in taps}
 
@@ -198,7 +206,7 @@ def test_conv_halo_layout_semantics(k, p, shape, cin, cout, dgrad):
                         for c0 in range(0, Ca, 64):
                             staged = fetch(c0, w0 + gdw, h0 + gdh, t0 + gdt, n0)
                             for (shift, k_off) in lay["taps"][first:first + cnt]:
-                                rows = staged[shift // 128: shift // 128 + 128]
+                                rows = staged[[shift // 128 + a_ * pitch + j for a_ in range(16) for j in range(8)]]
                                 wm = wmat(tap_of_koff[k_off])[:, c0:c0 + 64]
                                 acc += rows[:, :wm.shape[1]] @ wm.t()
                     for r in range(128):
