@@ -47,29 +47,47 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long long* __restrict__ jobs,
                                                                    const long long* __restrict__ prefix, int n_jobs,
                                                                    long long total) {
-  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
-       g += static_cast<long long>(gridDim.x) * blockDim.x) {
-    int lo = 0, hi = n_jobs - 1;
-    while (lo < hi) {                       // last job whose prefix <= g
-      const int mid = (lo + hi + 1) >> 1;
-      if (prefix[mid] <= g) lo = mid; else hi = mid - 1;
+  // Each CTA owns a contiguous span of kPackSpan elements: ONE binary search per CTA (first element of the span), then
+  // every thread walks forward from there (a span rarely crosses more than one job boundary); 32-bit index arithmetic
+  // inside a job.  The per-element search + 64-bit div/mod version took 0.28 ms per launch for 0.2 GB of traffic.
+  constexpr int kPackSpan = 256 * 16;
+  __shared__ int job0;
+  for (long long base = static_cast<long long>(blockIdx.x) * kPackSpan; base < total;
+       base += static_cast<long long>(gridDim.x) * kPackSpan) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = n_jobs - 1;
+      while (lo < hi) {                       // last job whose prefix <= base
+        const int mid = (lo + hi + 1) >> 1;
+        if (prefix[mid] <= base) lo = mid; else hi = mid - 1;
+      }
+      job0 = lo;
     }
-    const long long* jb = jobs + static_cast<long long>(lo) * 8;
-    const float* w = reinterpret_cast<const float*>(jb[0]);
-    __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(jb[1]);
-    const int cout = static_cast<int>(jb[2]), cin = static_cast<int>(jb[3]), taps = static_cast<int>(jb[4]);
-    const int transpose = static_cast<int>(jb[5]), Kc = static_cast<int>(jb[7]);
-    const long long i = g - prefix[lo];
-    const int c = static_cast<int>(i % Kc);
-    const int tap = static_cast<int>((i / Kc) % taps);
-    const int r = static_cast<int>(i / (static_cast<long long>(Kc) * taps));
-    float v = 0.f;
-    if (!transpose) {
-      if (r < cout && c < cin) v = w[(static_cast<long long>(r) * cin + c) * taps + tap];
-    } else {
-      if (r < cin && c < cout) v = w[(static_cast<long long>(c) * cin + r) * taps + tap];
+    __syncthreads();
+    int lo = job0;
+    for (int e = threadIdx.x; e < kPackSpan; e += 256) {
+      const long long g = base + e;
+      if (g >= total) break;
+      while (lo + 1 < n_jobs && prefix[lo + 1] <= g) ++lo;
+      const long long* jb = jobs + static_cast<long long>(lo) * 8;
+      const float* w = reinterpret_cast<const float*>(jb[0]);
+      __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(jb[1]);
+      const unsigned cout = static_cast<unsigned>(jb[2]), cin = static_cast<unsigned>(jb[3]), taps = static_cast<unsigned>(jb[4]);
+      const int transpose = static_cast<int>(jb[5]);
+      const unsigned Kc = static_cast<unsigned>(jb[7]);
+      const unsigned i = static_cast<unsigned>(g - prefix[lo]);          // a job holds < 2^32 elements
+      const unsigned c = i % Kc;
+      const unsigned q = i / Kc;
+      const unsigned tap = q % taps;
+      const unsigned r = q / taps;
+      float v = 0.f;
+      if (!transpose) {
+        if (r < cout && c < cin) v = w[(static_cast<size_t>(r) * cin + c) * taps + tap];
+      } else {
+        if (r < cin && c < cout) v = w[(static_cast<size_t>(c) * cin + r) * taps + tap];
+      }
+      packed[i] = __float2bfloat16_rn(v);
     }
-    packed[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -614,7 +632,7 @@ extern "C" int cstp_pack_weights_batched(const int64_t* jobs_dev, const int64_t*
                                          void* stream) {
   CSTP_REQUIRE(jobs_dev && prefix_dev && n_jobs > 0 && total > 0);
   static_assert(sizeof(long long) == sizeof(int64_t), "job table is int64");
-  pack_weights_batched_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
+  pack_weights_batched_kernel<<<grid_for((total + 15) / 16, 256), 256, 0, ST(stream)>>>(
       reinterpret_cast<const long long*>(jobs_dev), reinterpret_cast<const long long*>(prefix_dev), n_jobs, total);
   CSTP_LAUNCHED();
   return CSTP_OK;
