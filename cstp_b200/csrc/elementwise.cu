@@ -196,9 +196,28 @@ __global__ void __launch_bounds__(256, 4) bn_reduce_kernel(const uint4* __restri
       }
     }
     const long long base = static_cast<long long>(g) * rows_per_group;
+    long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + rl;
+    const long long rstep = static_cast<long long>(gridDim.x) * rows_per_pass;
+    if (!kBackward) {
+      // one stream only: four independent 16-byte loads in flight per thread before the (order-preserving) accumulation
+      for (; r + 3 * rstep < rows_per_group; r += 4 * rstep) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = a[(base + r + u * rstep) * nvec + seg0 + cv];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float x[8];
+          unpack8(v[u], x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s0[j] += x[j];
+            s1[j] += x[j] * x[j];
+          }
+        }
+      }
+    }
 #pragma unroll 2
-    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + rl; r < rows_per_group;
-         r += static_cast<long long>(gridDim.x) * rows_per_pass) {
+    for (; r < rows_per_group; r += rstep) {
       const long long idx = (base + r) * nvec + seg0 + cv;
       float x[8];
       if (!kBackward) {
