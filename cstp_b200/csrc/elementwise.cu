@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 //   act != NULL            mask = act > 0            (block outputs: the pre-activation includes the residual)
 //   mscale != NULL         mask = raw*mscale + mshift > 0, the same fmaf the forward apply evaluated (saves the act read)
 //   neither                no ReLU behind this BatchNorm
-__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
                                                            const uint4* __restrict__ raw, int Cp, long long rows_per_group,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ coef, const float* __restrict__ mscale,
@@ -517,15 +517,14 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const uint4* __res
   }
   const long long base = static_cast<long long>(t.g) * rows_per_group;
   const long long rstep = static_cast<long long>(gridDim.x) * t.rows_per_pass;
-#pragma unroll 2
-  for (long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl; r < rows_per_group; r += rstep) {
-    const long long i = (base + r) * nvec + t.cvec;
+  // one row: d (and act) and raw are already loaded as 16-byte vectors
+  auto row = [&](long long i, const uint4& vd, const uint4& vx, const uint4& vy) {
     float dy[8], x[8];
-    unpack8(d[i], dy);
-    unpack8(raw[i], x);
+    unpack8(vd, dy);
+    unpack8(vx, x);
     if (act != nullptr) {
       float y[8];
-      unpack8(act[i], y);
+      unpack8(vy, y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dy[j] = y[j] > 0.f ? dy[j] : 0.f;
     } else if (mscale != nullptr) {
@@ -537,6 +536,23 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const uint4* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dy[j], fmaf(Bc[j], x[j], Cc[j]));
     gout[i] = pack8(o);
+  };
+  long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl;
+  // two rows per trip with every load issued before the first use: 4 (6 with act) independent 16-byte loads in flight
+  for (; r + rstep < rows_per_group; r += 2 * rstep) {
+    const long long i0 = (base + r) * nvec + t.cvec, i1 = (base + r + rstep) * nvec + t.cvec;
+    const uint4 d0 = d[i0], x0 = raw[i0], d1 = d[i1], x1 = raw[i1];
+    uint4 y0 = make_uint4(0, 0, 0, 0), y1 = y0;
+    if (act != nullptr) {
+      y0 = act[i0];
+      y1 = act[i1];
+    }
+    row(i0, d0, x0, y0);
+    row(i1, d1, x1, y1);
+  }
+  if (r < rows_per_group) {
+    const long long i = (base + r) * nvec + t.cvec;
+    row(i, d[i], raw[i], act != nullptr ? act[i] : make_uint4(0, 0, 0, 0));
   }
 }
 
