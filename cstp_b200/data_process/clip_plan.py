@@ -44,6 +44,9 @@ class ViewPlan:
     jitter: Optional[List[Tuple[str, float]]] = None       # colour-jitter ops in the order they are applied
     gray: Optional[List[int]] = None                       # per frame: the channel replicated into R, G and B
     blur_sigma: Optional[float] = None
+    # finetune / test chains: the whole frame is first resized to (ow, oh) -- ClipScale -- and `box` then crops the RESIZED
+    # frame (ClipCenterCrop); None: `box` crops the (rotated) source frame and the crop is resized to size x size
+    resize: Optional[Tuple[int, int]] = None
 
 
 @dataclass
@@ -206,3 +209,104 @@ class PretrainClipSampler:
         self._chain(v2)
         return SamplePlan((v1, v2), spa, tem, pb, (rot1, rot2), base,
                           dict(temporal_retries=retries, crop1_attempts=a1, crop2_attempts=a2, short=short))
+
+
+@dataclass
+class ClipPlan:
+    """One finetune / validation / test clip: a single view plus what the loader returns next to it."""
+    view: ViewPlan
+    frame_base: int = 1
+
+
+class FinetuneClipSampler:
+    """The clip decisions of `UcfFineTune` (data_process/datasets.py:951-1097) under get_transforms('img' | 'img_val' |
+    'img_test') (data_process/preprocess_data.py:1131-1155), in the reference's draw order on Python `random`:
+
+      train : start = randint(1, total - clip_range) (:1007-1017), then ClipRandomSizedCrop(size, bottom_area=0.2)
+              (preprocess_data.py:440-476: random() < 1.0, up to ten (area, aspect, swap, x1, y1) attempts, else
+              ClipScale(size) + ClipCenterCrop(size)) and ClipColorJitter(0.4, 0.4, 0.4, 0.1, p=0.3) (:659-663)
+      val   : the same temporal draw (:1033-1047), ClipScale(short side 128 for size 112 / 256 for 224) + ClipCenterCrop
+      test  : every window of (T - 1) * pb_rate frames plus the last one (:1062-1080), no random draw; same spatial chain
+    """
+
+    def __init__(self, sample_duration: int = 16, sample_size: int = 112, pb_rate: int = 4):
+        self.T, self.size, self.rate = int(sample_duration), int(sample_size), int(pb_rate)
+        self.short = {112: 128, 224: 256}.get(self.size)
+
+    def _frames(self, total_frames: int) -> List[int]:
+        clip_range = (self.T - 1) * self.rate
+        if total_frames - clip_range <= 0:
+            idx, f = [], 0
+            while len(idx) < self.T:
+                idx.append(f)
+                f += self.rate
+                if f >= total_frames:
+                    f = 0
+            return [1 + i for i in idx]
+        start = random.randint(1, total_frames - clip_range)
+        return [start + i for i in range(0, clip_range + 1, self.rate)]
+
+    @staticmethod
+    def _scale_center(w: int, h: int, short: int, size: int):
+        """ClipScale(short) + ClipCenterCrop(size) (preprocess_data.py:843-866, 815-840) -> (resize or None, box)."""
+        if (w <= h and w == short) or (h <= w and h == short):
+            ow, oh = w, h
+        elif w < h:
+            ow, oh = short, int(short * h / w)
+        else:
+            ow, oh = int(short * w / h), short
+        x1 = int(round((ow - size) / 2.))
+        y1 = int(round((oh - size) / 2.))
+        return (ow, oh), (x1, y1, x1 + size, y1 + size)
+
+    def plan_train(self, total_frames: int, frame_w: int, frame_h: int) -> ClipPlan:
+        frames = self._frames(total_frames)
+        view = None
+        random.random()                                        # ClipRandomSizedCrop p = 1.0: drawn, always true
+        for _ in range(10):
+            area = frame_w * frame_h
+            target_area = random.uniform(0.2, 1) * area
+            aspect = random.uniform(3. / 4, 4. / 3)
+            w = int(round(math.sqrt(target_area * aspect)))
+            h = int(round(math.sqrt(target_area / aspect)))
+            if random.random() < 0.5:
+                w, h = h, w
+            if w <= frame_w and h <= frame_h:
+                x1 = random.randint(0, frame_w - w)
+                y1 = random.randint(0, frame_h - h)
+                view = ViewPlan(frames, 0, (x1, y1, x1 + w, y1 + h), False, False)
+                break
+        if view is None:                                       # fallback: scale to `size`, centre crop
+            resize, box = self._scale_center(frame_w, frame_h, self.size, self.size)
+            view = ViewPlan(frames, 0, box, False, False, resize=resize)
+        if random.random() < 0.3:                              # ClipColorJitter(p=0.3)
+            ops = [("brightness", random.uniform(1 - 0.4, 1 + 0.4)), ("contrast", random.uniform(1 - 0.4, 1 + 0.4)),
+                   ("saturation", random.uniform(1 - 0.4, 1 + 0.4)), ("hue", random.uniform(0 - 0.1, 0 + 0.1))]
+            random.shuffle(ops)
+            view.base, view.angle, view.jitter = True, 0.0, ops
+        return ClipPlan(view)
+
+    def plan_val(self, total_frames: int, frame_w: int, frame_h: int) -> ClipPlan:
+        if self.short is None:
+            raise ValueError("img_val is defined for sample_size 112 or 224 (preprocess_data.py:1140-1143)")
+        frames = self._frames(total_frames)
+        resize, box = self._scale_center(frame_w, frame_h, self.short, self.size)
+        return ClipPlan(ViewPlan(frames, 0, box, False, False, resize=resize))
+
+    def plan_test(self, total_frames: int, frame_w: int, frame_h: int) -> List[ClipPlan]:
+        if self.short is None:
+            raise ValueError("img_test is defined for sample_size 112 or 224")
+        clip_range = (self.T - 1) * self.rate
+        if total_frames - clip_range <= 0:
+            seq, f = [], 1
+            while len(seq) < self.T:
+                seq.append(f)
+                f += self.rate
+                if f >= total_frames:
+                    f = 1
+            windows = [seq]
+        else:
+            windows = [[s_ + i * self.rate for i in range(self.T)] for s_ in range(1, total_frames - clip_range + 1, clip_range)]
+            windows.append(list(range(total_frames - clip_range, total_frames + 1, self.rate)))
+        resize, box = self._scale_center(frame_w, frame_h, self.short, self.size)
+        return [ClipPlan(ViewPlan(list(w_), 0, box, False, False, resize=resize)) for w_ in windows]

@@ -147,6 +147,16 @@ def compile_view(view: ViewPlan, frame_base: int, W: int, H: int, S: int, video_
             if bp is not None:
                 d.blur = 1
                 d.blur_radius, d.blur_edge_a, d.blur_edge_b, d.blur_ww, d.blur_fw = bp
+    if view.resize is not None:
+        # ClipScale + ClipCenterCrop: the WHOLE (unrotated) frame is resized to (ow, oh) and the S x S crop of the result is
+        # rows x0.. / y0.. of Pillow's tap tables for that resize -- the kernel reads the full frame through them
+        ow, oh = view.resize
+        if view.rot != 0 or x1 - x0 != S or y1 - y0 != S or x0 < 0 or y0 < 0 or x1 > ow or y1 > oh:
+            raise ValueError("resize views crop an S x S window inside the resized, unrotated frame")
+        coef = np.stack([resample_tables(W, ow)[x0:x1], resample_tables(H, oh)[y0:y1]])
+        for i, b in enumerate((0, 0, W, H)):
+            d.box[i] = b
+        return d, coef, H
     coef = np.stack([resample_tables(x1 - x0, S), resample_tables(y1 - y0, S)])
     return d, coef, y1 - y0
 
@@ -183,34 +193,52 @@ class GpuClipPipeline:
                 event=None)
         return self._stage[n_views]
 
+    def assemble_clips(self, plans, videos: List[torch.Tensor], out=None):
+        """Finetune / validation / test clips (clip_plan.ClipPlan, one view each) -> (B, 3, T, S, S) fp32."""
+        class _One:                      # a ClipPlan as a one-view SamplePlan for the shared descriptor path
+            def __init__(self, p):
+                self.views, self.frame_base = (p.view,), p.frame_base
+        B = len(plans)
+        if out is None:
+            out = torch.empty((B, 3, self.T, self.S, self.S), dtype=torch.float32, device=self.device)
+        self._assemble([_One(p) for p in plans], videos, (out,))
+        return out
+
     def assemble(self, plans: List[SamplePlan], videos: List[torch.Tensor], out=None):
+        B = len(plans)
+        if out is None and self.device.type == "cuda":
+            out = (torch.empty((B, 3, self.T, self.S, self.S), dtype=torch.float32, device=self.device),
+                   torch.empty((B, 3, self.T, self.S, self.S), dtype=torch.float32, device=self.device))
+        self._assemble(plans, videos, out)
+        return out
+
+    def _assemble(self, plans, videos: List[torch.Tensor], outs):
         if self.device.type != "cuda":
             raise L.CstpError("GpuClipPipeline needs a CUDA device: the clip pipeline has no CPU fallback")
         B = len(plans)
         if len(videos) != B:
             raise ValueError("one video tensor per plan")
-        if out is None:
-            out = (torch.empty((B, 3, self.T, self.S, self.S), dtype=torch.float32, device=self.device),
-                   torch.empty((B, 3, self.T, self.S, self.S), dtype=torch.float32, device=self.device))
-        x1, x2 = out
-        buf = self._buffers(2 * B)
+        nv = len(outs)
+        buf = self._buffers(nv * B)
         if buf["event"] is not None:
             buf["event"].synchronize()          # the previous batch's descriptor upload has left the pinned staging
-        descs = (L.ClipView * (2 * B))()
+        descs = (L.ClipView * (nv * B))()
         clip_bytes = 3 * self.T * self.S * self.S * 4
         coef_bytes = 2 * self.S * (2 + KMAX) * 4
         max_h = 0
         for b, (plan, vid) in enumerate(zip(plans, videos)):
-            if vid.dtype != torch.uint8 or vid.device != x1.device or vid.dim() != 4 or vid.shape[3] != 3 or not vid.is_contiguous():
+            if vid.dtype != torch.uint8 or vid.device != outs[0].device or vid.dim() != 4 or vid.shape[3] != 3 or not vid.is_contiguous():
                 raise ValueError("videos must be contiguous CUDA uint8 tensors [F][H][W][3]")
             F_, H, W, _ = vid.shape
-            for v, (view, dst) in enumerate(zip(plan.views, (x1, x2))):
+            if len(plan.views) != nv:
+                raise ValueError("plan and output disagree on the number of views")
+            for v, (view, dst) in enumerate(zip(plan.views, outs)):
                 if len(view.frames) != self.T:
                     raise ValueError("plan and pipeline disagree on sample_duration")
                 lo, hi = min(view.frames) - plan.frame_base, max(view.frames) - plan.frame_base
                 if lo < 0 or hi >= F_:
                     raise ValueError(f"plan reads frame {hi + plan.frame_base} of a {F_}-frame video")
-                i = 2 * b + v
+                i = nv * b + v
                 d, coef, ch = compile_view(view, plan.frame_base, W, H, self.S, vid.data_ptr(), dst.data_ptr() + b * clip_bytes,
                                            buf["dcoef"].data_ptr() + i * coef_bytes)
                 descs[i] = d
@@ -222,6 +250,5 @@ class GpuClipPipeline:
         ev = torch.cuda.Event()
         ev.record()
         buf["event"] = ev
-        L.check(L.load().cstp_clip_assemble(buf["ddesc"].data_ptr(), 2 * B, self.T, self.S, max_h,
+        L.check(L.load().cstp_clip_assemble(buf["ddesc"].data_ptr(), nv * B, self.T, self.S, max_h,
                                             torch.cuda.current_stream().cuda_stream))
-        return x1, x2

@@ -9,11 +9,13 @@ What it restates (reference file:line):
                                                                                frames: `raw[start_frame + i]` at :1397)
   * data_process/preprocess_data.py:479-565  ClipRandomSizedCropOverlap      -- crop boxes, bicubic resize to 112
   * data_process/preprocess_data.py:1103-1130 get_transforms('pre_train')    -- null / base transform chains
+  * data_process/datasets.py:951-1097 UcfFineTune + preprocess_data.py:1131-1155 get_transforms('img' | 'img_val' |
+    'img_test'), :440-476 ClipRandomSizedCrop, :843-866 ClipScale, :815-840 ClipCenterCrop -- finetune / val / test clips
 The pixel arithmetic of the reference lives in third-party Pillow / torchvision (unpinned by the reference; this image:
 Pillow 12.2.0, torchvision 0.26.0).  `render_plan` therefore replays a *plan* (every random decision already taken,
 see cstp_b200/data_process/clip_plan.py) through the same Pillow / torchvision calls in the same order; it is pinned by
 tests/test_clip_pipeline.py against clips produced by the unmodified reference classes (oracle/make_golden_clips.py ->
-tests/golden/clips_ref.npz): bit-exact.
+tests/golden/clips_ref.npz; oracle/make_golden_clips_ft.py -> clips_ft_ref.npz): bit-exact.
 """
 from __future__ import annotations
 
@@ -55,9 +57,14 @@ def render_view(view, video: np.ndarray, frame_base: int, size: int = 112) -> to
             img = img.transpose(ROT_METHOD[view.rot])                                # datasets.py:896-903, 931-932
         imgs.append(img)
     x0, y0, x1, y1 = view.box
-    imgs = [i.crop((x0, y0, x1, y1)).resize((size, size), Image.BICUBIC) for i in imgs]   # preprocess_data.py:514-515
+    if getattr(view, "resize", None) is not None:       # ClipScale + ClipCenterCrop (preprocess_data.py:843-866, 829-840)
+        ow, oh = view.resize
+        imgs = [(i if i.size == (ow, oh) else i.resize((ow, oh), Image.BICUBIC)).crop((x0, y0, x1, y1)) for i in imgs]
+    else:
+        imgs = [i.crop((x0, y0, x1, y1)).resize((size, size), Image.BICUBIC) for i in imgs]   # preprocess_data.py:514-515
     if view.base:                                                                   # preprocess_data.py:1112-1122
-        imgs = [i.rotate(view.angle) for i in imgs]                                  # RandomRotation :1095
+        if view.angle:                               # RandomRotation :1095 (the finetune chain has none: angle 0.0)
+            imgs = [i.rotate(view.angle) for i in imgs]
         if view.jitter is not None:                                                  # ClipColorJitter :659-663
             fn = dict(brightness=F.adjust_brightness, contrast=F.adjust_contrast, saturation=F.adjust_saturation,
                       hue=F.adjust_hue)

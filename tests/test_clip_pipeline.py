@@ -212,3 +212,77 @@ def test_index_order_is_the_distributed_samplers():
             for epoch in (0, 3):
                 s.set_epoch(epoch)
                 assert list(iter(s)) == distributed_indices(len(data), epoch, rank, world, 0, True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# finetune / validation / test clips (UcfFineTune + get_transforms('img' | 'img_val' | 'img_test'))
+with open(os.path.join(GOLD, "clips_ft_trace.json")) as f:
+    FT_TRACES = json.load(f)
+
+
+def seeded_ft_plans(case):
+    from cstp_b200.data_process.clip_plan import FinetuneClipSampler
+    random.seed(case["seed"])
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    s = FinetuneClipSampler(16, 112, 4)
+    if case["mode"] == "train":
+        return [s.plan_train(case["total_frames"], case["w"], case["h"])]
+    if case["mode"] == "val":
+        return [s.plan_val(case["total_frames"], case["w"], case["h"])]
+    return s.plan_test(case["total_frames"], case["w"], case["h"])
+
+
+def expected_ft_events(plans, w, h):
+    ev = []
+    for p in plans:
+        v, T = p.view, len(p.view.frames)
+        ev += [("open", n) for n in v.frames]
+        if v.resize is None:
+            ev += [("crop", tuple(v.box))] * T + [("resize", (112, 112))] * T
+        else:
+            if tuple(v.resize) != (w, h):
+                ev += [("resize", tuple(v.resize))] * T
+            ev += [("crop", tuple(v.box))] * T
+        if v.jitter is not None:
+            for _ in range(T):
+                ev += [(name, factor) for name, factor in v.jitter]
+    return ev
+
+
+@pytest.mark.parametrize("which", ["cases", "pixel_cases"])
+def test_finetune_sampler_matches_reference_traces(which):
+    n_jit = n_multi = n_fallback = 0
+    for case in FT_TRACES[which]:
+        plans = seeded_ft_plans(case)
+        assert len(plans) == case["n_clips"], case
+        assert dedupe(expected_ft_events(plans, case["w"], case["h"])) == dedupe(case["trace"]), \
+            (case["seed"], case["mode"], case["total_frames"], case["w"], case["h"])
+        n_jit += plans[0].view.jitter is not None
+        n_multi += len(plans) > 1
+        n_fallback += case["mode"] == "train" and plans[0].view.resize is not None
+    if which == "cases":
+        assert n_jit >= 5 and n_multi >= 8
+
+
+def test_finetune_pixel_oracle_and_descriptor_path_match_reference_clips():
+    """Pillow oracle == the reference's finetune / val / test clips, and the integer descriptor path == both (resize views:
+    the whole frame through slices of the tap tables)."""
+    from oracle.clip_oracle import render_view
+    ref = np.load(os.path.join(GOLD, "clips_ft_ref.npz"))
+    for i, case in enumerate(FT_TRACES["pixel_cases"]):
+        plans = seeded_ft_plans(case)
+        video = synthetic_video(case["total_frames"] + 1, case["w"], case["h"], case["seed"])
+        for j in case["kept"]:
+            want = torch.from_numpy(ref["case%d_clip%d" % (i, j)]).float() / 255 * 2.0 - 1.0
+            got = render_view(plans[j].view, video, plans[j].frame_base)
+            assert torch.equal(got, want), (i, j, (got - want).abs().max().item())
+            from cstp_b200.data_process.gpu_clips import compile_view
+            from tests.emulate_clips import run_view
+            v = plans[j].view
+            keep = v.frames
+            v.frames = v.frames[:2]                              # two frames are enough for the numpy stand-in
+            d, coef, _ = compile_view(v, plans[j].frame_base, case["w"], case["h"], 112)
+            emu = torch.from_numpy(run_view(d, coef, video, 2, 112))
+            v.frames = keep
+            assert torch.equal(emu, want[:, :2]), (i, j, (emu - want[:, :2]).abs().max().item())

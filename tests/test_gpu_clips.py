@@ -113,3 +113,24 @@ def test_batch_source_feeds_the_epoch_driver():
                            clip_grad_norm=1)
     rows = pretrain_epochs(model, batches, opts)
     assert len(rows) == 1 and np.isfinite(rows[0]["loss"])
+
+
+def test_finetune_val_test_clips_bit_exact():
+    """`assemble_clips` on UcfFineTune-style plans (random-sized crop + colour jitter, scale + centre crop, the multi-clip
+    test windows) against the reference's own clips and the Pillow oracle."""
+    from oracle.clip_oracle import render_view
+    from tests.test_clip_pipeline import FT_TRACES, seeded_ft_plans
+    ref = np.load(os.path.join(GOLD, "clips_ft_ref.npz"))
+    pipe = GpuClipPipeline()
+    for i, case in enumerate(FT_TRACES["pixel_cases"]):
+        plans = seeded_ft_plans(case)
+        video = synthetic_video(case["total_frames"] + 1, case["w"], case["h"], case["seed"])
+        dvid = torch.from_numpy(video).cuda()
+        out = pipe.assemble_clips(plans, [dvid] * len(plans))
+        torch.cuda.synchronize()
+        assert out.shape == (len(plans), 3, 16, 112, 112)
+        for j in case["kept"]:
+            want = torch.from_numpy(ref["case%d_clip%d" % (i, j)]).float() / 255 * 2.0 - 1.0
+            assert torch.equal(out[j].cpu(), want), (i, j)
+        for j, p in enumerate(plans):                          # every clip of the case against the oracle
+            assert torch.equal(out[j].cpu(), render_view(p.view, video, p.frame_base)), (i, j)
