@@ -68,7 +68,10 @@ def test_ragged_and_tiny_geometries():
     for kw in (dict(N=1, T=3, H=10, W=6, cin=42, cout=85, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1)),
                dict(N=1, T=5, H=6, W=10, cin=85, cout=42, kernel=(3, 1, 1), stride=(2, 1, 1), pad=(1, 0, 0)),
                dict(N=3, T=2, H=14, W=14, cin=170, cout=21, kernel=(1, 3, 3), stride=(1, 2, 2), pad=(0, 1, 1)),
-               dict(N=1, T=1, H=2, W=2, cin=16, cout=16, kernel=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0))):
+               dict(N=1, T=1, H=2, W=2, cin=16, cout=16, kernel=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0)),
+               # 2-D halo layouts (conv fwd / dgrad with a 16-channel tail / wgrad) with partial tiles along h and w
+               dict(N=1, T=2, H=40, W=36, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1)),
+               dict(N=2, T=1, H=36, W=28, cin=128, cout=240, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))):
         r = case_conv(**kw)
         assert r["fwd_nan"] == 0 and r["fwd_pad_zero"] and r["fwd_rel"] < 4e-3, (kw, r)
         assert r["dgrad_nan"] == 0 and r["dgrad_rel"] < 4e-3, (kw, r)
