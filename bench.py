@@ -215,7 +215,7 @@ def main():
     import torch.distributed as dist
     from cstp_b200 import ops
     from cstp_b200.models.pace.r21d_byol import R21DBYOL
-    from oracle.cstp_oracle import synthetic_batch   # seeded input protocol only; no compute
+    from cstp_b200.synthetic import synthetic_batch   # seeded input protocol
 
     B = args.batch
     torch.manual_seed(1)

@@ -26,19 +26,7 @@ from PIL import Image, ImageFilter
 ROT_METHOD = (None, Image.ROTATE_90, Image.ROTATE_180, Image.ROTATE_270)      # datasets.py:19  ROTATE = [0, 2, 3, 4]
 
 
-def synthetic_video(n_frames: int, w: int, h: int, seed: int) -> np.ndarray:
-    """Deterministic uint8 video [n_frames][h][w][3] (integer arithmetic only: identical on every machine)."""
-    f = np.arange(n_frames, dtype=np.int64)[:, None, None]
-    y = np.arange(h, dtype=np.int64)[None, :, None]
-    x = np.arange(w, dtype=np.int64)[None, None, :]
-    chans = []
-    for c in range(3):
-        smooth = (x * (2 + c) + y * (3 - c) + f * (5 + 2 * c) + seed * 17) % 512
-        smooth = np.where(smooth > 255, 511 - smooth, smooth)              # triangle wave: no hard wrap edges
-        checker = ((x // 8 + y // 8 + f) % 2) * 24
-        texture = ((x * y + f * 3 + c) % 7) * 3
-        chans.append(np.clip(smooth // 2 + 40 + checker + texture, 0, 255))
-    return np.stack(chans, -1).astype(np.uint8)
+from cstp_b200.synthetic import synthetic_video  # noqa: E402,F401  (seeded test video; no algorithm in it)
 
 
 def _to_tensor_tf(img: Image.Image) -> torch.Tensor:

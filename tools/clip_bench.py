@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cstp_b200.data_process.clip_plan import PretrainClipSampler  # noqa: E402
 from cstp_b200.data_process.gpu_clips import GpuClipPipeline, collate_labels  # noqa: E402
-from oracle.clip_oracle import render_plan, synthetic_video  # noqa: E402
+from cstp_b200.synthetic import synthetic_video  # noqa: E402
+from oracle.clip_oracle import render_plan  # noqa: E402  (only for the Pillow CPU timing leg below)
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 W, H, F = 320, 240, 150

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cstp_b200.models.pace.r21d_byol import R21DBYOL  # noqa: E402
 from cstp_b200 import ops  # noqa: E402
-from oracle.cstp_oracle import synthetic_batch  # noqa: E402
+from cstp_b200.synthetic import synthetic_batch  # noqa: E402
 
 
 def golden_check(B):

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cstp_b200 import parallel  # noqa: E402
 from cstp_b200.models.pace.r21d_byol import R21DBYOL  # noqa: E402
-from oracle.cstp_oracle import structured_batch  # noqa: E402
+from cstp_b200.synthetic import structured_batch  # noqa: E402
 
 rank, world, local = parallel.init_from_env("nccl")
 torch.cuda.set_device(local)

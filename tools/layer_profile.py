@@ -5,7 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cstp_b200.models.pace.r21d_byol import R21DBYOL  # noqa: E402
-from oracle.cstp_oracle import synthetic_batch  # noqa: E402
+from cstp_b200.synthetic import synthetic_batch  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 torch.manual_seed(1)
