@@ -67,3 +67,16 @@ def test_bn_sync_exchange_argument_checks():
     assert lib.cstp_bn_sync_buffer_bytes(0, 4, 16) == -1
     assert lib.cstp_bn_sync_exchange(None, 16, None, 2, 0, 4, 64, 1, None, None, None) == -1
     assert b"invalid argument" in lib.cstp_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under cstp_b200/ (nor the native arm of bench.py) may import it."""
+    pkg = os.path.join(ROOT, "cstp_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
