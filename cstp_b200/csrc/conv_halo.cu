@@ -49,6 +49,8 @@ struct ConvHaloKParams {
   uint32_t tap_sw, tap_sh; // bytes into the staged box (validated against taps[].a_shift when the plan is built)
   uint32_t a_sbo;          // bytes between consecutive 8-row atoms of a tap's rows inside the staged box (128-byte rows)
   int accumulate;
+  float* stats;            // optional fused BatchNorm statistics: partials [gridDim.x][stats_groups][2][Np] (Np == 64)
+  int stats_groups;
   int fast_store;          // bf16 output only, no bias, 32-byte aligned rows: pipelined epilogue with STG.256
   __nv_bfloat16* out;
   float* out_f32;
@@ -58,6 +60,50 @@ struct ConvHaloKParams {
   HcTap taps[kHcMaxTaps];
 };
 
+// Fused BatchNorm statistics (kStats): one 16-column chunk of a 64-column tile -- pack, store, and add the values AS
+// STORED (bf16-rounded) to this thread's running sum / sum of squares of its row (acc[c], acc[64 + c]; static indices).
+template <int kC0>
+__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[16], __nv_bfloat16* dst, bool valid, float (&acc)[128]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+  if (valid) {
+    st_global_256(dst + kC0, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float lo = bf16_lo(w[i]), hi = bf16_hi(w[i]);
+      acc[kC0 + 2 * i] += lo;
+      acc[kC0 + 2 * i + 1] += hi;
+      acc[64 + kC0 + 2 * i] = fmaf(lo, lo, acc[64 + kC0 + 2 * i]);
+      acc[64 + kC0 + 2 * i + 1] = fmaf(hi, hi, acc[64 + kC0 + 2 * i + 1]);
+    }
+  }
+}
+
+// Adds the 128 per-thread accumulators of the four epilogue warps (= 128 rows) into tot[e] (e = quantity * 64 + column),
+// in a fixed order, and clears them.  Reduce-scatter butterfly: after the five steps lane L holds entries 4L .. 4L+3.
+__device__ __forceinline__ void stats_flush(float (&acc)[128], float* wsum, float* tot, int q, int lane) {
+#pragma unroll
+  for (int half = 64, m = 16; half >= 4; half >>= 1, m >>= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? acc[i] : acc[i + half];
+      const float keep = up ? acc[i + half] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wsum[q * 128 + 4 * lane + j] = acc[j];
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int e = q * 32 + lane;
+  tot[e] += ((wsum[e] + wsum[128 + e]) + wsum[256 + e]) + wsum[384 + e];
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+}
+
+template <bool kStats>
 __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_constant__ ConvHaloKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -254,6 +300,17 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     const int rn = row / (p.bw * p.bh * p.bt);
     const int col0 = ntile * p.n_tile;
     const int ncols = min(p.n_tile, p.Np - col0);
+    // fused statistics: [4 warps][128] cross-warp staging + [2 groups][128] CTA totals behind the mbarriers
+    float* wsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* tot = wsum + 512;
+    float acc[128];            // only touched (and only allocated) in the kStats instantiation
+    int cur_group = -1;
+    if constexpr (kStats) {
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      tot[row] = 0.f;
+      tot[128 + row] = 0.f;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -271,7 +328,30 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
-      if (p.fast_store) {
+      if constexpr (kStats) {
+        // 64-column tile, plain bf16 output, bn == 1: the whole tile belongs to ONE statistics group (the halves of the N
+        // axis are the two views); the accumulators are flushed when the group changes (at most once per CTA) and at
+        // the end -- no shuffle and no shared memory per tile, two FMAs per element
+        const int g = (p.stats_groups == 2 && 2 * n >= p.Nt) ? 1 : 0;       // n: this tile's sample (rn == 0)
+        if (g != cur_group) {
+          if (cur_group >= 0) stats_flush(acc, wsum, tot + cur_group * 128, q, lane);
+          cur_group = g;
+        }
+        __nv_bfloat16* dst = p.out + off;
+        uint32_t va[16], vb[16];
+        tmem_ld16(taddr, va);
+        tmem_ld_wait();
+        tmem_ld16(taddr + 16, vb);
+        stats_chunk<0>(va, dst, valid, acc);
+        tmem_ld_wait();
+        tmem_ld16(taddr + 32, va);
+        stats_chunk<16>(vb, dst, valid, acc);
+        tmem_ld_wait();
+        tmem_ld16(taddr + 48, vb);
+        stats_chunk<32>(va, dst, valid, acc);
+        tmem_ld_wait();
+        stats_chunk<48>(vb, dst, valid, acc);
+      } else if (p.fast_store) {
         // plain bf16 output (optionally accumulated into what is there): pipelined, one 32-byte store per 16 columns.
         // (The row-per-thread layout makes every 16-byte store a half-written sector; with nine serial
         // load -> wait -> 2 x STG.128 rounds the epilogue warps were busy 93 % of a 64->144 tile and the issuer waited
@@ -334,6 +414,13 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+    if constexpr (kStats) {
+      if (cur_group >= 0) stats_flush(acc, wsum, tot + cur_group * 128, q, lane);
+      // every CTA publishes a row for every group (zeros for a group it never saw): cstp_bn_finalize sums all blocks
+      for (int g = 0; g < p.stats_groups; ++g)
+        p.stats[((static_cast<long long>(blockIdx.x) * p.stats_groups + g) * 2 + (row >> 6)) * p.Np + (row & 63)] =
+            tot[g * 128 + row];
     }
   }
 
@@ -453,6 +540,15 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr &&
                  reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && d->out_off % 16 == 0 && d->osw % 16 == 0 &&
                  d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
+  k.stats = d->stats_partials;
+  k.stats_groups = d->stats_groups;
+  if (d->stats_partials != nullptr &&
+      !(k.fast_store && !d->accumulate && d->Np == 64 && d->n_tile == 64 && d->bn == 1 &&
+        (d->stats_groups == 1 || d->stats_groups == 2) && d->Nt % d->stats_groups == 0)) {
+    delete plan;
+    return fail_inval("fused statistics need Np == n_tile == 64, bn == 1, a plain aligned bf16 output and 1 or 2 groups dividing N");
+  }
+  const int stats_bytes = d->stats_partials != nullptr ? 3072 : 0;
   int max_group_taps = 0, seen = 0;
   for (int g = 0; g < d->n_groups; ++g) {
     const cstp_halo_group& gr = d->groups[g];
@@ -506,7 +602,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
   const int bar_bytes = 256;
   const long long res_all = 1LL * d->n_taps * k.tap_bytes;
-  const long long budget = smem_budget() - 1024 - bar_bytes;
+  const long long budget = smem_budget() - 1024 - bar_bytes - stats_bytes;
   if (d->allow_resident && res_all + (pitch == 8 ? 3LL : 2LL) * k.a_stride <= budget) {
     k.resident = 1;
     k.res_bytes = static_cast<uint32_t>(res_all);
@@ -526,7 +622,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   int cols = 32;
   while (cols < 2 * d->n_tile) cols *= 2;
   k.tmem_cols = cols;
-  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) + bar_bytes;
+  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) + bar_bytes + stats_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
   const int n_ntiles = ceil_div(d->Np, d->n_tile);
   const long long m_tiles = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
@@ -539,16 +635,23 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
 }
 
 extern "C" int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan) { return plan ? plan->kp.resident : CSTP_EINVAL; }
+extern "C" int cstp_conv_halo_plan_stat_blocks(const cstp_conv_halo_plan* plan) {
+  return plan ? (plan->kp.stats != nullptr ? static_cast<int>(plan->grid.x) : 0) : CSTP_EINVAL;
+}
 
 
 extern "C" int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream) {
   CSTP_REQUIRE(plan != nullptr);
   static bool attr_set = false;
   if (!attr_set) {
-    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
     attr_set = true;
   }
-  conv_halo_kernel<<<plan->grid, kHcThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  if (plan->kp.stats != nullptr)
+    conv_halo_kernel<true><<<plan->grid, kHcThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  else
+    conv_halo_kernel<false><<<plan->grid, kHcThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

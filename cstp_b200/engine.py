@@ -290,7 +290,9 @@ class StepEngine:
         rows = N * To * Ho * Wo
         flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
         site = self._site(store, grads, bnname, cout, self.VIEWS, rows // self.VIEWS)
-        plan = _Timed(self, "conv_fwd", flops, [ops.conv_fwd_plan(x, wp, raw, geom)], tag)
+        cplan = ops.conv_fwd_plan(x, wp, raw, geom, stats=site.st)
+        plan = _Timed(self, "conv_fwd", flops, [cplan], tag)
+        fused = getattr(cplan, "stat_blocks", 0)   # > 0: the conv epilogue already wrote the BatchNorm statistics partials
 
         def fwd():
             plan.run()
@@ -298,7 +300,7 @@ class StepEngine:
                 ops.bn_eval_coeffs(site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS)
             else:
                 ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
-                                     sync=self.bn_sync)
+                                     fused_blocks=fused, sync=self.bn_sync)
             if apply:
                 ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_site.st if res_site else None)
         prog.append(fwd)

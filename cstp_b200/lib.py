@@ -95,6 +95,8 @@ class ConvHaloDesc(C.Structure):
         ("allow_resident", C.c_int32),
         ("use_tail_boxes", C.c_int32),
         ("atom_pitch_rows", C.c_int32),
+        ("stats_groups", C.c_int32),
+        ("stats_partials", C.c_void_p),
     ]
 
 
@@ -157,6 +159,7 @@ SIGNATURES = {
     "cstp_conv_plan_destroy": (None, [_vp]),
     "cstp_conv_halo_plan_create": (_i, [C.POINTER(ConvHaloDesc), C.POINTER(_vp)]),
     "cstp_conv_halo_plan_resident": (_i, [_vp]),
+    "cstp_conv_halo_plan_stat_blocks": (_i, [_vp]),
     "cstp_conv_halo_plan_run": (_i, [_vp, _vp]),
     "cstp_conv_halo_plan_destroy": (None, [_vp]),
     "cstp_wgrad_plan_create": (_i, [C.POINTER(WgradDesc), C.POINTER(_vp)]),

@@ -232,6 +232,7 @@ def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out,
 
 class ConvHaloPlan(_Plan):
     resident: bool = False
+    stat_blocks: int = 0         # > 0: the kernel also writes BatchNorm statistics partials (that many blocks)
 
     def run(self):
         L.check(L.load().cstp_conv_halo_plan_run(self.handle, _stream()))
@@ -333,7 +334,7 @@ def _conv_halo_layout(tile_space, taps, a_channels: int, Np: int, halo_2d: bool)
 
 
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
-                         accumulate, keep) -> ConvHaloPlan:
+                         accumulate, keep, stats=None) -> ConvHaloPlan:
     lib = L.load()
     d = L.ConvHaloDesc()
     d.amap = view
@@ -358,24 +359,34 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     d.allow_resident = int(lay["resident"])
     d.use_tail_boxes = int(bool(lay.get("tail", 0)))
     d.atom_pitch_rows = lay.get("pitch", 8)
+    d.stats_partials = 0 if stats is None else stats.partials.data_ptr()
+    d.stats_groups = 0 if stats is None else stats.groups
     h = C.c_void_p()
     L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
-    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep)
+    plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep + ((stats.partials,) if stats is not None else ()))
     plan.resident = bool(lib.cstp_conv_halo_plan_resident(h))
+    if stats is not None:
+        plan.stat_blocks = lib.cstp_conv_halo_plan_stat_blocks(h)
+        if plan.stat_blocks * stats.groups * 2 * stats.Cp > stats.partials.numel():
+            raise L.CstpError("BatchNorm partials buffer too small for the fused statistics")
     return plan
 
 
-# Fusing the BatchNorm statistics into the halo-conv epilogue was built and measured this round (two epilogue variants):
-# it removes 2.3 ms of bn_reduce passes at batch 60 but costs 3-5 ms in the conv kernels, so it was taken out again
-# (profiles/README.md).
+# BatchNorm statistics fused into the halo-conv epilogue (csrc/conv_halo.cu): only for single 64-column N tiles, where every
+# epilogue thread can keep the running sum / sum of squares of its row's 64 columns in registers (no shuffles per tile).
+# The first attempt (shuffle butterfly per 16-column chunk, all tile widths) removed 2.3 ms of bn_reduce passes at batch 60
+# but cost 3-5 ms in the conv kernels and was taken out (profiles/README.md).
+FUSE_BN_STATS = os.environ.get("CSTP_FUSE_BN_STATS", "1") == "1"
 USE_TAIL_BOXES = os.environ.get("CSTP_TAIL_BOXES", "1") == "1"
 USE_HALO_2D = os.environ.get("CSTP_HALO_2D", "1") == "1"
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
 
 
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None,
-                  box=None, allow_halo: bool = True) -> ConvPlan:
-    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16."""
+                  box=None, allow_halo: bool = True, stats: "BNState | None" = None) -> ConvPlan:
+    """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16.
+    With `stats` the kernel may also emit the BatchNorm statistics partials of `out` (plan.stat_blocks > 0 tells the caller
+    to skip the separate statistics pass)."""
     _require_cuda(x, w_packed, out, out_f32, bias)
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
@@ -390,8 +401,11 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
     if allow_halo and box is None and n_tile is None and len(views) == 1 and Ho * Wo >= HALO_MIN_POSITIONS:
         lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np)
         if lay is not None:
+            fuse = (FUSE_BN_STATS and stats is not None and stats.groups in (1, 2) and N % stats.groups == 0
+                    and out is not None and out_f32 is None and bias is None and not accumulate
+                    and Np == 64 and lay["n_tile"] == 64 and lay["box"][3] == 1)
             return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, out_f32, 0, ostr, bias,
-                                        accumulate, (x, w_packed, out, out_f32, bias))
+                                        accumulate, (x, w_packed, out, out_f32, bias), stats=stats if fuse else None)
     box = box or pick_box(Wo, Ho, To, N, 128)
     return _make_conv_plan(views, taps, Ca, w_packed, Np, (Wo, Ho, To, N), box, out, out_f32, 0, ostr, bias, accumulate,
                            n_tile, (x, w_packed, out, out_f32, bias))
@@ -703,20 +717,23 @@ class BNState:
     def alloc(C_: int, Cp: int, groups: int, rows_per_group: int, device, backward: bool = True) -> "BNState":
         nb = bn_nblocks(rows_per_group, Cp)
         f = dict(dtype=torch.float32, device=device)
-        return BNState(C_, Cp, groups, nb, torch.empty(nb * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
+        # (room for the fused-statistics path too: one partial row per CTA of a persistent conv kernel, <= 148 + slack)
+        return BNState(C_, Cp, groups, nb, torch.empty(max(nb, 160) * groups * 2 * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f), torch.empty(groups * Cp, **f),
                        torch.empty(groups * 3 * Cp, **f) if backward else None, torch.empty(groups * 2 * Cp, **f))
 
 
 def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1,
-                     sync=None) -> None:
-    """Batch statistics of raw -> scale/shift/mean/invstd (+ running buffers).  `sync` (an object with
+                     fused_blocks: int = 0, sync=None) -> None:
+    """Batch statistics of raw -> scale/shift/mean/invstd (+ running buffers).  fused_blocks > 0: the producing conv
+    kernel already wrote that many partial rows into st.partials (no statistics pass over raw).  `sync` (an object with
     `.world` and `.all_reduce(tensor)`) makes the statistics span every rank (SyncBN over the data-parallel group): the
     per-rank sums are collapsed to one row, summed across ranks and finalized with the global row count."""
     rows = raw.numel() // st.Cp
     lib = L.load()
-    nblocks = st.nblocks
-    L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
+    nblocks = fused_blocks or st.nblocks
+    if not fused_blocks:
+        L.check(lib.cstp_bn_stats(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.partials), st.nblocks, _stream()))
     partials, rpg = st.partials, rows // st.groups
     if sync is not None and sync.world > 1:
         L.check(lib.cstp_bn_partials_reduce(_ptr(st.partials), nblocks, st.groups, st.Cp, _ptr(st.compact), _stream()))

@@ -120,10 +120,18 @@ typedef struct {
    * (halo only along the slower tile axes, a_shift in whole 1024-byte atoms).  bw + halo_w with bw == 8: the box also
    * carries a halo along w (all k x k taps of a 1 x k x k filter read ONE staged box; a_shift in whole 128-byte rows). */
   int32_t atom_pitch_rows;
+  /* Optional fused BatchNorm statistics of the stored (bf16-rounded) output (replaces a cstp_bn_stats pass over it):
+   * stats_groups (1 or 2) equal parts of the N axis are separate statistics groups; fp32
+   * [stat_blocks][stats_groups][2: sum, sum of squares][Np], the partials layout cstp_bn_finalize consumes with
+   * nblocks = cstp_conv_halo_plan_stat_blocks.  Needs a single 64-column N tile (Np == n_tile == 64), bn == 1, a plain
+   * bf16 output: every epilogue thread keeps the sums of its row's 64 columns in registers. */
+  int32_t stats_groups;
+  float* stats_partials;
 } cstp_conv_halo_desc;
 
 typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;
 int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* desc, cstp_conv_halo_plan** plan);
+int cstp_conv_halo_plan_stat_blocks(const cstp_conv_halo_plan* plan);   /* 0: no fused statistics */
 int cstp_conv_halo_plan_resident(const cstp_conv_halo_plan* plan);   /* 1 when the weights are kept in shared memory */
 int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* stream);
 void cstp_conv_halo_plan_destroy(cstp_conv_halo_plan* plan);

@@ -61,7 +61,7 @@ def _store(out, out_f32, val, accumulate):
 
 
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None, box=None,
-                  allow_halo=True):
+                  allow_halo=True, stats=None):       # stats: never fused here (plan.stat_blocks stays 0)
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
     ref = out if out is not None else out_f32
@@ -187,7 +187,8 @@ def _group_view(t, groups):
     return t.reshape(groups, rows // groups, t.shape[-1])
 
 
-def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, sync=None):
+def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, fused_blocks=0,
+                     sync=None):
     _count(2)
     x = _group_view(raw, st.groups).float()
     n = x.shape[1]
