@@ -286,3 +286,16 @@ def test_finetune_pixel_oracle_and_descriptor_path_match_reference_clips():
             emu = torch.from_numpy(run_view(d, coef, video, 2, 112))
             v.frames = keep
             assert torch.equal(emu, want[:, :2]), (i, j, (emu - want[:, :2]).abs().max().item())
+
+
+def test_video_store_bookkeeping_on_cpu():
+    """GpuVideoStore's residency logic does not need a GPU: capacity-bounded, oldest entries dropped first."""
+    from cstp_b200.data_process.datasets import GpuVideoStore
+    store = GpuVideoStore(device="cpu", capacity_bytes=3 * 4 * 6 * 5 * 3 + 10)
+    for i in range(4):
+        store.put(i, synthetic_video(4, 5, 6, i))
+    assert len(store) == 3 and 0 not in store and 3 in store and store[3].shape == (4, 6, 5, 3)
+    store.put(1, synthetic_video(4, 5, 6, 9))              # replacing an entry keeps the byte count right
+    assert store.bytes == 3 * 4 * 6 * 5 * 3
+    with pytest.raises(ValueError):
+        store.put(7, np.zeros((2, 3, 4), np.uint8))
