@@ -44,8 +44,10 @@ inline int fail_inval(const char* what) {
 // Encodes a tiled bf16 tensor map (128B swizzle, zero OOB fill) through the driver entry point obtained from
 // the runtime, so the library never links libcuda directly (it must dlopen on a box without a driver).
 // swizzle_bytes: 128 (default), 64 or 32 -- the shared-memory row pitch of the box (its inner extent in bytes).
+// oob_nan: out-of-range elements are filled with NaN instead of zero (operands that pass through the BatchNorm + ReLU
+// prologue of ptx.cuh, where fmaxf(NaN, 0) restores the exact zero of the convolution padding).
 int encode_tmap_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle_bytes = 128);
+                     const uint32_t* box, int swizzle_bytes = 128, bool oob_nan = false);
 
 int num_sms();
 

@@ -14,6 +14,7 @@
 namespace cstp {
 
 constexpr int kConvThreads = 256;
+constexpr int kConvXformThreads = 128;      // warps 8..11: operand prologue (BatchNorm affine + ReLU on the staged A box)
 constexpr uint32_t kABytes = 128 * 64 * 2;  // one A stage: 128 positions x 64 bf16 channels
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;  // 227 KB
@@ -30,6 +31,9 @@ struct ConvKParams {
   uint32_t b_bytes, idesc;
   int accumulate;
   int fast_store;          // bf16 output only, no bias, 32-byte aligned rows: pipelined epilogue with STG.256
+  const float* pro_scale;  // operand prologue (kXform): fp32 [pro_groups][pro_cp] BatchNorm affine of the producer of A
+  const float* pro_shift;
+  int pro_groups, pro_cp;
   __nv_bfloat16* out;
   float* out_f32;
   const float* bias;
@@ -55,7 +59,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   return c;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+template <bool kXform>
+__global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kConvThreads, 1)
+    conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = kABytes + p.b_bytes;
@@ -65,6 +71,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* xfull = bars + 2 * kMaxStages + 5;          // [kMaxStages]: staged A box transformed (kXform)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,6 +85,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      if constexpr (kXform) mbar_init(&xfull[s], kConvXformThreads / 32);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int kb = 0;
       for (int t = 0; t < n_taps; ++t) {
         for (int c = 0; c < chunks_per_tap; ++c, ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(kXform ? &xfull[stage] : &full[stage], phase);
           tc_fence_after();
           if (leader) {
             const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
@@ -171,7 +179,46 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (kXform && warp >= 8) {
+    // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU in place
+    // Thread t owns the 16-byte units t, t + 128, ... of every staged A box (one swizzle phase = one 8-channel vector of
+    // the chunk).  Box rows run (w, h, t, n): the rows of samples below Nt / 2 take the coefficients of statistics group 0,
+    // the others those of group 1.
+    const uint32_t tid = threadIdx.x - kConvThreads;
+    const uint32_t smem_addr0 = smem_u32(smem);
+    const int n_taps = p.n_taps, chunks_per_tap = p.chunks_per_tap, stages = p.stages, Cp = p.pro_cp;
+    const int rows_per_n = p.bw * p.bh * p.bt;
+    constexpr uint32_t kUnits = kABytes / 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      uint32_t split = kUnits;                     // units below `split` belong to group 0
+      if (p.pro_groups == 2) {
+        const int rb = (p.Nt / 2 - tc.n0) * rows_per_n;
+        split = rb <= 0 ? 0u : (rb >= 128 ? kUnits : static_cast<uint32_t>(rb) * 8u);
+      }
+      for (int t = 0; t < n_taps; ++t) {
+        for (int c = 0; c < chunks_per_tap; ++c) {
+          const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+          const int ch = c * 64 + xform_unit_channel(s_addr + tid * 16u, 7u);
+          XformCoef k0, k1;
+          if (split > 0) xform_load(k0, p.pro_scale, p.pro_shift, ch, Cp);
+          if (split < kUnits) xform_load(k1, p.pro_scale + Cp, p.pro_shift + Cp, ch, Cp);
+          mbar_wait(&full[stage], phase);
+          if (split > 0) xform_span<kConvXformThreads>(s_addr, tid, split, k0);
+          if (split < kUnits) xform_span<kConvXformThreads>(s_addr, xform_first<kConvXformThreads>(split, tid), kUnits, k1);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xfull[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------ epilogue (warp w owns TMEM lanes 32*(w%4)..)
     const int q = warp - 4;
     const int row = q * 32 + lane;
@@ -272,7 +319,7 @@ struct cstp_conv_plan {
 
 using namespace cstp;
 
-static int encode_tensor5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5]) {
+static int encode_tensor5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5], bool oob_nan = false) {
   uint64_t dims[5], strides[4];
   for (int i = 0; i < 5; ++i) {
     if (t.dims[i] <= 0) return fail_inval("tensor5 dim <= 0");
@@ -283,7 +330,7 @@ static int encode_tensor5(CUtensorMap* map, const cstp_tensor5& t, const uint32_
     strides[i] = static_cast<uint64_t>(t.strides[i]);
   }
   if ((reinterpret_cast<uintptr_t>(t.ptr) % 16) != 0 || t.ptr == nullptr) return fail_inval("tensor5 ptr must be 16B aligned");
-  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box);
+  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box, 128, oob_nan);
 }
 
 extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** out_plan) {
@@ -301,6 +348,12 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   CSTP_REQUIRE(d->w_packed != nullptr);
   CSTP_REQUIRE(d->out_bf16 != nullptr || d->out_f32 != nullptr);
   CSTP_REQUIRE(d->osw % 8 == 0 && d->osh % 8 == 0 && d->ost % 8 == 0 && d->osn % 8 == 0 && d->out_off % 8 == 0);
+  const bool xform = d->pro.scale != nullptr;
+  if (xform) {
+    CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
+    CSTP_REQUIRE(d->pro.Cp == d->a_channels);
+    CSTP_REQUIRE(reinterpret_cast<uintptr_t>(d->pro.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(d->pro.shift) % 16 == 0);
+  }
 
   cstp_conv_plan* plan = new (std::nothrow) cstp_conv_plan();
   if (!plan) {
@@ -313,7 +366,7 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   for (int i = 0; i < CSTP_MAX_AMAPS; ++i) {
     // Unused slots alias map 0 so the descriptor prefetch in the kernel always sees a valid descriptor.
     const cstp_tensor5& t = d->amap[i < d->n_amaps ? i : 0];
-    int rc = encode_tensor5(&k.amap[i], t, abox);
+    int rc = encode_tensor5(&k.amap[i], t, abox, xform);
     if (rc != CSTP_OK) {
       delete plan;
       return rc;
@@ -351,6 +404,10 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr &&
                  reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && d->out_off % 16 == 0 && d->osw % 16 == 0 &&
                  d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
+  k.pro_scale = d->pro.scale;
+  k.pro_shift = d->pro.shift;
+  k.pro_groups = d->pro.groups;
+  k.pro_cp = d->pro.Cp;
   for (int t = 0; t < d->n_taps; ++t) {
     const cstp_tap& tp = d->taps[t];
     if (tp.map_id < 0 || tp.map_id >= d->n_amaps || tp.k_off < 0 || tp.k_off % 64 != 0 ||
@@ -361,7 +418,7 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
     k.taps[t] = tp;
   }
   const uint32_t stage_bytes = kABytes + k.b_bytes;
-  const int bar_bytes = 256;
+  const int bar_bytes = 256;       // 5 + 3 * kMaxStages mbarriers + the TMEM slot
   int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
@@ -385,10 +442,14 @@ extern "C" int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream) {
   CSTP_REQUIRE(plan != nullptr);
   static bool attr_set = false;
   if (!attr_set) {
-    CSTP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  conv_gemm_kernel<<<plan->grid, kConvThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  if (plan->kp.pro_scale != nullptr)
+    conv_gemm_kernel<true><<<plan->grid, kConvThreads + kConvXformThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  else
+    conv_gemm_kernel<false><<<plan->grid, kConvThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -16,6 +16,7 @@
 namespace cstp {
 
 constexpr int kHcThreads = 256;
+constexpr int kHcXformThreads = 128;
 constexpr int kHcMaxStages = 8;
 constexpr int kHcSmemLimit = 232448;
 constexpr int kHcMaxGroups = 4;
@@ -52,6 +53,10 @@ struct ConvHaloKParams {
   float* stats;            // optional fused BatchNorm statistics: partials [gridDim.x][stats_groups][2][Np] (Np == 64)
   int stats_groups;
   int fast_store;          // bf16 output only, no bias, 32-byte aligned rows: pipelined epilogue with STG.256
+  // operand prologue (kXform): A is the producer's raw output; BatchNorm affine + ReLU applied to every staged box
+  const float* pro_scale;  // fp32 [pro_groups][pro_cp]
+  const float* pro_shift;
+  int pro_groups, pro_cp;
   __nv_bfloat16* out;
   float* out_f32;
   const float* bias;
@@ -103,8 +108,11 @@ __device__ __forceinline__ void stats_flush(float (&acc)[128], float* wsum, floa
   for (int i = 0; i < 128; ++i) acc[i] = 0.f;
 }
 
-template <bool kStats>
-__global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_constant__ ConvHaloKParams p) {
+// kXform: four more warps (8..11) rewrite every staged activation box in place -- BatchNorm affine + ReLU of the producing
+// unit (ptx.cuh) -- between the TMA arrival (full[]) and the MMA issue (xfull[]).
+template <bool kStats, bool kXform>
+__global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThreads, 1)
+    conv_halo_kernel(const __grid_constant__ ConvHaloKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage0 = smem + p.res_bytes;
@@ -115,6 +123,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
   uint64_t* tempty = bars + 2 * kHcMaxStages + 2;
   uint64_t* bfull = bars + 2 * kHcMaxStages + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHcMaxStages + 5);
+  uint64_t* xfull = bars + 2 * kHcMaxStages + 6;        // [kHcMaxStages]: staged box transformed (kXform)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      if constexpr (kXform) mbar_init(&xfull[s], kHcXformThreads / 32);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -145,12 +155,18 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // kStats && kXform: 384 threads leave 168 registers each, but the statistics epilogue keeps 128 accumulators per thread:
+  // the producer / issuer warpgroup and the transform warpgroup hand registers to the epilogue warpgroup (setmaxnreg at
+  // the head of each warpgroup's branch, where ptxas can see which code runs under which budget).
+  constexpr bool kRealloc = kStats && kXform;
 
   // Roles run WARP-CONVERGED: all 32 lanes walk the loops and poll the mbarriers, one elected lane issues the TMA /
   // tcgen05 instructions.  (With a single-lane branch the compiler cannot keep descriptors and addresses in uniform
   // registers and wraps every UTCHMMA in an ELECT / R2UR loop: the issuer then ran at ~25 cycles per instruction and
   // the N=64 layers sat at 19% tensor-pipe activity, ncu r01_conv_halo.)
-  if (warp == 0) {
+  if (warp < 4) {
+   if constexpr (kRealloc) warpgroup_reg_dec<112>();
+   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
     const int full_chunks = p.tail ? p.chunks - 1 : p.chunks;
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
       for (int g = 0; g < n_groups; ++g) {
         const int g_first = p.groups[g].first_tap, g_taps = p.groups[g].n_taps;
         for (int c = 0; c < chunks; ++c) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(kXform ? &xfull[stage] : &full[stage], phase);
           tc_fence_after();
           if (leader) {
             const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
@@ -290,7 +306,47 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv_halo_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= 4) {
+   }
+  } else if (kXform && warp >= 8) {
+    if constexpr (kRealloc) warpgroup_reg_dec<112>();
+    // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU in place
+    // Thread t owns the 16-byte units t, t + 128, ... of every staged box: a fixed swizzle phase, i.e. one 8-channel
+    // vector of the chunk, whose coefficients are fetched (L1 / L2) while the TMA load is still in flight.
+    const uint32_t tid = threadIdx.x - kHcThreads;
+    const uint32_t stage_addr0 = smem_u32(stage0);
+    const uint32_t stage_bytes = p.stage_bytes;
+    const int n_groups = p.n_groups, chunks = p.chunks, stages = p.stages, Cp = p.pro_cp;
+    const bool has_tail = p.tail != 0;
+    const uint32_t units_full = p.a_bytes >> 4, units_tail = p.a_bytes_tail >> 4;
+    const uint32_t mask_tail = p.tail == 16 ? 1u : 3u;
+    const int slab = p.tiles_w * p.tiles_h * p.tiles_t;        // tiles per sample (bn == 1)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      const int n0 = tile / slab;
+      const int grp = (p.pro_groups == 2 && 2 * n0 >= p.Nt) ? 1 : 0;
+      const float* sc = p.pro_scale + grp * Cp;
+      const float* sh = p.pro_shift + grp * Cp;
+      for (int g = 0; g < n_groups; ++g) {
+        for (int c = 0; c < chunks; ++c) {
+          const bool tl = has_tail && c == chunks - 1;
+          const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+          XformCoef k;
+          xform_load(k, sc, sh, c * 64 + xform_unit_channel(s_addr + tid * 16u, tl ? mask_tail : 7u), Cp);
+          mbar_wait(&full[stage], phase);
+          xform_span<kHcXformThreads>(s_addr, tid, tl ? units_tail : units_full, k);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xfull[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    if constexpr (kRealloc) warpgroup_reg_inc<216>();
     // ------------------------------------------------------------ epilogue (warp w owns TMEM lanes 32*(w%4)..)
     const int q = warp - 4;
     const int row = q * 32 + lane;
@@ -462,6 +518,13 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   const int pitch = d->atom_pitch_rows > 0 ? d->atom_pitch_rows : 8;
   CSTP_REQUIRE(pitch >= 8 && pitch <= 64);
   CSTP_REQUIRE(d->halo_w == 0 ? (pitch == 8 && xrows % 8 == 0) : (d->bw == 8 && pitch == d->bw + d->halo_w));
+  const bool xform = d->pro.scale != nullptr;
+  if (xform) {
+    // the prologue picks its coefficient row per tile: one sample per tile, the statistics groups split the N axis evenly
+    CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
+    CSTP_REQUIRE(d->pro.Cp == d->a_channels && d->bn == 1);
+    CSTP_REQUIRE(reinterpret_cast<uintptr_t>(d->pro.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(d->pro.shift) % 16 == 0);
+  }
 
   cstp_conv_halo_plan* plan = new (std::nothrow) cstp_conv_halo_plan();
   if (!plan) {
@@ -483,7 +546,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
     }
     const uint32_t abox[5] = {64u, (uint32_t)(d->bw + d->halo_w), (uint32_t)(d->bh + d->halo_h),
                               (uint32_t)(d->bt + d->halo_t), (uint32_t)d->bn};
-    int rc = encode_tmap_bf16(&k.amap, d->amap.ptr, 5, dims, strides, abox);
+    int rc = encode_tmap_bf16(&k.amap, d->amap.ptr, 5, dims, strides, abox, 128, xform);
     if (rc == CSTP_OK) {
       const uint64_t bdims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
       const uint64_t bstr[1] = {(uint64_t)d->Ktot * 2};
@@ -495,7 +558,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
     k.tail = (d->use_tail_boxes && (tail == 16 || tail == 32) && d->a_channels > 64) ? tail : 0;
     if (rc == CSTP_OK && k.tail) {
       const uint32_t abox_t[5] = {(uint32_t)k.tail, abox[1], abox[2], abox[3], abox[4]};
-      rc = encode_tmap_bf16(&k.amap_tail, d->amap.ptr, 5, dims, strides, abox_t, k.tail * 2);
+      rc = encode_tmap_bf16(&k.amap_tail, d->amap.ptr, 5, dims, strides, abox_t, k.tail * 2, xform);
       if (rc == CSTP_OK) {
         const uint64_t bdims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
         const uint64_t bstr[1] = {(uint64_t)d->Ktot * 2};
@@ -542,6 +605,10 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
                  d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
   k.stats = d->stats_partials;
   k.stats_groups = d->stats_groups;
+  k.pro_scale = d->pro.scale;
+  k.pro_shift = d->pro.shift;
+  k.pro_groups = d->pro.groups;
+  k.pro_cp = d->pro.Cp;
   if (d->stats_partials != nullptr &&
       !(k.fast_store && !d->accumulate && d->Np == 64 && d->n_tile == 64 && d->bn == 1 &&
         (d->stats_groups == 1 || d->stats_groups == 2) && d->Nt % d->stats_groups == 0)) {
@@ -644,14 +711,19 @@ extern "C" int cstp_conv_halo_plan_run(const cstp_conv_halo_plan* plan, void* st
   CSTP_REQUIRE(plan != nullptr);
   static bool attr_set = false;
   if (!attr_set) {
-    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
-    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHcSmemLimit));
     attr_set = true;
   }
-  if (plan->kp.stats != nullptr)
-    conv_halo_kernel<true><<<plan->grid, kHcThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
-  else
-    conv_halo_kernel<false><<<plan->grid, kHcThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool stats = plan->kp.stats != nullptr, xform = plan->kp.pro_scale != nullptr;
+  const int threads = xform ? kHcThreads + kHcXformThreads : kHcThreads;
+  if (stats && xform) conv_halo_kernel<true, true><<<plan->grid, threads, plan->smem_bytes, st>>>(plan->kp);
+  else if (stats) conv_halo_kernel<true, false><<<plan->grid, threads, plan->smem_bytes, st>>>(plan->kp);
+  else if (xform) conv_halo_kernel<false, true><<<plan->grid, threads, plan->smem_bytes, st>>>(plan->kp);
+  else conv_halo_kernel<false, false><<<plan->grid, threads, plan->smem_bytes, st>>>(plan->kp);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

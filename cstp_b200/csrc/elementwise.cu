@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
   float s[8], b[8], s2[8], b2[8];
   load8(scale + t.g * Cp + t.cvec * 8, s);
   load8(shift + t.g * Cp + t.cvec * 8, b);
-  if (res_mode == 2) {
+  if (res_mode >= 2) {
     load8(scale2 + t.g * Cp + t.cvec * 8, s2);
     load8(shift2 + t.g * Cp + t.cvec * 8, b2);
   }
@@ -436,6 +436,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
       unpack8(res[i], y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] += fmaf(y[j], s2[j], b2[j]);
+    } else if (res_mode == 3) {
+      // the shortcut is an activation that was never materialised: rebuild the bf16 value its consumers see
+      float y[8];
+      unpack8(res[i], y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(y[j], s2[j], b2[j]), 0.f)));
     }
     if (relu) {
 #pragma unroll
@@ -719,8 +725,8 @@ extern "C" int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, 
                              int relu, int res_mode, const void* res, const float* scale2, const float* shift2,
                              void* out, void* stream) {
   CSTP_REQUIRE(raw && out && scale && shift && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
-  CSTP_REQUIRE(res_mode == 0 || res != nullptr);
-  CSTP_REQUIRE(res_mode != 2 || (scale2 && shift2));
+  CSTP_REQUIRE(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || res != nullptr));
+  CSTP_REQUIRE(res_mode < 2 || (scale2 && shift2));
   bn_apply_kernel<<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
       reinterpret_cast<const uint4*>(raw), Cp, rows / groups, scale, shift, relu, res_mode,
       reinterpret_cast<const uint4*>(res), scale2, shift2, reinterpret_cast<uint4*>(out));

@@ -352,4 +352,92 @@ __device__ __forceinline__ void epilogue_row_f32(uint32_t taddr, int ncols, floa
   }
 }
 
+
+// ---------------------------------------------------------------- warpgroup register re-allocation
+// All four warps of a warpgroup must execute these (setmaxnreg is .sync.aligned over the warpgroup).
+template <uint32_t kRegs>
+__device__ __forceinline__ void warpgroup_reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <uint32_t kRegs>
+__device__ __forceinline__ void warpgroup_reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
+// ---------------------------------------------------------------- operand prologue: BatchNorm affine + ReLU in place
+// The consumer of a conv+BN unit reads the producer's RAW output and applies y = max(x*scale[c] + shift[c], 0) to the
+// TMA-staged operand box in shared memory (then bf16 again: the very value cstp_bn_apply would have written to HBM and
+// the consumer would have loaded), so the normalised activation never exists in HBM (models/pace/r21d_byol.py:94-97:
+// conv -> bn -> relu -> conv).  Convolution zero padding must stay exactly 0 behind the affine map: the tensor map of a
+// transformed operand fills out-of-range elements with NaN (CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) and
+// fmaxf(NaN, 0) == 0 -- no coordinate predicates.  Padded channels carry scale == shift == 0.
+//
+// Swizzled boxes (128 / 64 / 32-byte rows): the 16-byte unit at shared address a holds the channels
+// 8 * (((a >> 4) ^ (a >> 7)) & (units_per_row - 1)) .. + 8 of its row's chunk.  A thread that walks units with a stride
+// that is a multiple of 1024 bytes therefore keeps ONE channel vector: its 16 coefficients stay in registers.
+struct XformCoef {
+  float s[8], b[8];
+};
+
+// Coefficients of the 8 channels starting at `ch` (a multiple of 8) of a [Cp] fp32 row; zeros beyond Cp.
+__device__ __forceinline__ void xform_load(XformCoef& k, const float* __restrict__ scale, const float* __restrict__ shift,
+                                           int ch, int Cp) {
+  if (ch < Cp) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(scale + ch) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + ch)), b1 = __ldg(reinterpret_cast<const float4*>(shift + ch) + 1);
+    k.s[0] = s0.x; k.s[1] = s0.y; k.s[2] = s0.z; k.s[3] = s0.w; k.s[4] = s1.x; k.s[5] = s1.y; k.s[6] = s1.z; k.s[7] = s1.w;
+    k.b[0] = b0.x; k.b[1] = b0.y; k.b[2] = b0.z; k.b[3] = b0.w; k.b[4] = b1.x; k.b[5] = b1.y; k.b[6] = b1.z; k.b[7] = b1.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k.s[i] = k.b[i] = 0.f;
+  }
+}
+// First channel (within its 64-channel chunk) of the 16-byte unit at shared address `a`; units_mask = units per row - 1.
+__device__ __forceinline__ int xform_unit_channel(uint32_t a, uint32_t units_mask) {
+  return static_cast<int>((((a >> 4) ^ (a >> 7)) & units_mask) * 8u);
+}
+__device__ __forceinline__ uint32_t xform_pair(uint32_t v, float s0, float b0, float s1, float b1) {
+  return pack_bf16x2(fmaxf(fmaf(bf16_lo(v), s0, b0), 0.f), fmaxf(fmaf(bf16_hi(v), s1, b1), 0.f));
+}
+__device__ __forceinline__ uint4 xform_unit(const uint4& v, const XformCoef& k) {
+  uint4 o;
+  o.x = xform_pair(v.x, k.s[0], k.b[0], k.s[1], k.b[1]);
+  o.y = xform_pair(v.y, k.s[2], k.b[2], k.s[3], k.b[3]);
+  o.z = xform_pair(v.z, k.s[4], k.b[4], k.s[5], k.b[5]);
+  o.w = xform_pair(v.w, k.s[6], k.b[6], k.s[7], k.b[7]);
+  return o;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// Transforms the units [first, end) of the box at shared address `base` that belong to this thread: first, first + kStep,
+// ...  (kStep = participating threads; kStep * 16 must be a multiple of 1024).  Four independent units in flight.
+template <int kStep>
+__device__ __forceinline__ void xform_span(uint32_t base, uint32_t first, uint32_t end, const XformCoef& k) {
+  static_assert((kStep * 16) % 1024 == 0, "thread stride must keep the swizzle phase");
+  uint32_t u = first;
+  for (; u + 3 * kStep < end; u += 4 * kStep) {
+    const uint32_t a = base + u * 16u;
+    const uint4 v0 = lds128(a), v1 = lds128(a + kStep * 16u), v2 = lds128(a + 2u * kStep * 16u), v3 = lds128(a + 3u * kStep * 16u);
+    sts128(a, xform_unit(v0, k));
+    sts128(a + kStep * 16u, xform_unit(v1, k));
+    sts128(a + 2u * kStep * 16u, xform_unit(v2, k));
+    sts128(a + 3u * kStep * 16u, xform_unit(v3, k));
+  }
+  for (; u < end; u += kStep) {
+    const uint32_t a = base + u * 16u;
+    sts128(a, xform_unit(lds128(a), k));
+  }
+}
+// Smallest u >= lo with u == tid (mod kStep).
+template <int kStep>
+__device__ __forceinline__ uint32_t xform_first(uint32_t lo, uint32_t tid) {
+  return lo + (tid + kStep - lo % kStep) % kStep;
+}
+
 }  // namespace cstp

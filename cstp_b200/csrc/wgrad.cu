@@ -12,6 +12,7 @@
 namespace cstp {
 
 constexpr int kWgThreads = 256;
+constexpr int kWgXformThreads = 192;   // warps 2..7 run the operand prologue during the main loop
 constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // 64 positions x 64 channels
 constexpr int kWgMaxStages = 8;
 constexpr int kWgSmemLimit = 232448;
@@ -26,9 +27,13 @@ struct WgradKParams {
   int stages, tmem_cols;
   uint32_t idesc;
   float* partials;
+  const float* pro_scale;  // operand prologue (kXform): fp32 [pro_groups][pro_cp] BatchNorm affine of the producer of X
+  const float* pro_shift;
+  int pro_groups, pro_cp, Nt;
   cstp_mchunk mchunks[CSTP_MAX_MCHUNKS];
 };
 
+template <bool kXform>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -39,6 +44,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   uint64_t* empty = bars + kWgMaxStages;
   uint64_t* tfull = bars + 2 * kWgMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
+  uint64_t* xfull = bars + 2 * kWgMaxStages + 2;        // [kWgMaxStages]: staged X boxes transformed (kXform)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      if constexpr (kXform) mbar_init(&xfull[s], kWgXformThreads / 32);
     }
     mbar_init(tfull, 1);
     fence_mbar_init();
@@ -68,6 +75,49 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  if (kXform && warp >= 2) {
+    // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU on X in place
+    // Thread t owns the 16-byte units t, t + 192, ... of the (up to) two staged X boxes; box rows run (w, h, t, n): rows of
+    // samples below Nt / 2 take the coefficients of statistics group 0, the others those of group 1.
+    const uint32_t tid = threadIdx.x - 64;
+    const uint32_t smem_addr0 = smem_u32(smem);
+    const int Cp = p.pro_cp, stages = p.stages;
+    const int rows_per_n = p.bw * p.bh * p.bt;
+    const int kb_per_n = p.tiles_w * p.tiles_h * p.tiles_t;
+    constexpr uint32_t kUnits = kBoxBytes / 16;
+    const int c_off[2] = {p.mchunks[chunk0].c_off, p.mchunks[nchunks > 1 ? chunk0 + 1 : chunk0].c_off};
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int n0 = (kb / kb_per_n) * p.bn;
+      uint32_t split = kUnits;                     // units below `split` belong to group 0
+      if (p.pro_groups == 2) {
+        const int rb = (p.Nt / 2 - n0) * rows_per_n;
+        split = rb <= 0 ? 0u : (rb >= 64 ? kUnits : static_cast<uint32_t>(rb) * 8u);
+      }
+      const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
+      const int cj = xform_unit_channel(s_addr + tid * 16u, 7u);
+      XformCoef k0[2], k1[2];
+      for (int b = 0; b < nchunks; ++b) {
+        if (split > 0) xform_load(k0[b], p.pro_scale, p.pro_shift, c_off[b] + cj, Cp);
+        if (split < kUnits) xform_load(k1[b], p.pro_scale + Cp, p.pro_shift + Cp, c_off[b] + cj, Cp);
+      }
+      mbar_wait(&full[stage], phase);
+      for (int b = 0; b < nchunks; ++b) {
+        const uint32_t box = s_addr + static_cast<uint32_t>(b) * kBoxBytes;
+        if (split > 0) xform_span<kWgXformThreads>(box, tid, split, k0[b]);
+        if (split < kUnits) xform_span<kWgXformThreads>(box, xform_first<kWgXformThreads>(split, tid), kUnits, k1[b]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfull[stage]);
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
 
   // Roles run warp-converged with one elected issuing lane (see conv_halo.cu).
   if (warp == 0) {
@@ -112,7 +162,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
     uint32_t idesc;
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&full[stage], phase);
+      mbar_wait(kXform ? &xfull[stage] : &full[stage], phase);
       tc_fence_after();
       if (leader) {
         const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
@@ -186,7 +236,7 @@ struct cstp_wgrad_plan {
 
 using namespace cstp;
 
-static int encode_tensor5_w(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5]) {
+static int encode_tensor5_w(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5], bool oob_nan = false) {
   uint64_t dims[5], strides[4];
   for (int i = 0; i < 5; ++i) {
     if (t.dims[i] <= 0) return fail_inval("tensor5 dim <= 0");
@@ -197,7 +247,7 @@ static int encode_tensor5_w(CUtensorMap* map, const cstp_tensor5& t, const uint3
     strides[i] = static_cast<uint64_t>(t.strides[i]);
   }
   if ((reinterpret_cast<uintptr_t>(t.ptr) % 16) != 0 || t.ptr == nullptr) return fail_inval("tensor5 ptr must be 16B aligned");
-  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box);
+  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box, 128, oob_nan);
 }
 
 extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan** out_plan) {
@@ -211,6 +261,12 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   CSTP_REQUIRE(d->bw * d->bh * d->bt * d->bn == 64);
   CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
   CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr && reinterpret_cast<uintptr_t>(d->partials) % 32 == 0);   // 32-byte stores
+  const bool xform = d->pro.scale != nullptr;
+  if (xform) {
+    CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
+    CSTP_REQUIRE(d->pro.Cp == d->amap[0].dims[0]);
+    CSTP_REQUIRE(reinterpret_cast<uintptr_t>(d->pro.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(d->pro.shift) % 16 == 0);
+  }
 
   cstp_wgrad_plan* plan = new (std::nothrow) cstp_wgrad_plan();
   if (!plan) {
@@ -221,7 +277,7 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   memset(&k, 0, sizeof(k));
   const uint32_t box[5] = {64u, (uint32_t)d->bw, (uint32_t)d->bh, (uint32_t)d->bt, (uint32_t)d->bn};
   for (int i = 0; i < CSTP_MAX_AMAPS; ++i) {
-    int rc = encode_tensor5_w(&k.amap[i], d->amap[i < d->n_amaps ? i : 0], box);
+    int rc = encode_tensor5_w(&k.amap[i], d->amap[i < d->n_amaps ? i : 0], box, xform);
     if (rc != CSTP_OK) {
       delete plan;
       return rc;
@@ -250,6 +306,11 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   plan->splits = splits;
   k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 1, 1);
   k.partials = d->partials;
+  k.pro_scale = d->pro.scale;
+  k.pro_shift = d->pro.shift;
+  k.pro_groups = d->pro.groups;
+  k.pro_cp = d->pro.Cp;
+  k.Nt = d->Nt;
   for (int i = 0; i < d->n_mchunks; ++i) {
     const cstp_mchunk& mc = d->mchunks[i];
     if (mc.map_id < 0 || mc.map_id >= d->n_amaps || mc.c_off < 0 || mc.c_off % 8 != 0) {
@@ -280,10 +341,14 @@ extern "C" int cstp_wgrad_plan_run(const cstp_wgrad_plan* plan, void* stream) {
   CSTP_REQUIRE(plan != nullptr);
   static bool attr_set = false;
   if (!attr_set) {
-    CSTP_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemLimit));
     attr_set = true;
   }
-  wgrad_gemm_kernel<<<plan->grid, kWgThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  if (plan->kp.pro_scale != nullptr)
+    wgrad_gemm_kernel<true><<<plan->grid, kWgThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  else
+    wgrad_gemm_kernel<false><<<plan->grid, kWgThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -17,6 +17,7 @@
 namespace cstp {
 
 constexpr int kWhThreads = 256;
+constexpr int kWhXformThreads = 192;   // warps 2..7 run the operand prologue during the main loop (the epilogue warps idle there)
 constexpr int kWhMaxStages = 8;
 constexpr int kWhSmemLimit = 232448;
 constexpr int kWhMaxMtiles = 16;
@@ -44,10 +45,15 @@ struct WgradHaloKParams {
   uint32_t a_sbo;          // bytes between consecutive 8-position atoms of a chunk inside its staged box
   uint32_t a_kstep;        // descriptor start-address advance (>> 4) per 16-position K step: two atoms
   float* partials;
+  const float* pro_scale;  // operand prologue (kXform): fp32 [pro_groups][pro_cp] BatchNorm affine of the producer of X
+  const float* pro_shift;
+  int pro_groups, pro_cp, Nt;
+  uint32_t xbox_units;     // 16-byte units one staged X box really carries
   WhXBox xboxes[kWhMaxBoxes];
   WhMtile mtiles[kWhMaxMtiles];
 };
 
+template <bool kXform>
 __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
   uint64_t* empty = bars + kWhMaxStages;
   uint64_t* tfull = bars + 2 * kWhMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWhMaxStages + 1);
+  uint64_t* xfull = bars + 2 * kWhMaxStages + 2;        // [kWhMaxStages]: staged X boxes transformed (kXform)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,6 +79,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      if constexpr (kXform) mbar_init(&xfull[s], kWhXformThreads / 32);
     }
     mbar_init(tfull, 1);
     fence_mbar_init();
@@ -84,6 +92,39 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  if (kXform && warp >= 2) {
+    // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU on X in place
+    // Thread t owns the 16-byte units t, t + 192, ... of every staged X box (one swizzle phase = one 8-channel vector of
+    // the box's chunk); one K-block is one sample (bn == 1), hence one statistics group.
+    const uint32_t tid = threadIdx.x - 64;
+    const uint32_t smem_addr0 = smem_u32(smem);
+    const int slab = p.tiles_w * p.tiles_h * p.tiles_t, Cp = p.pro_cp, n_xboxes = p.n_xboxes, stages = p.stages;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int n0 = kb / slab;
+      const int grp = (p.pro_groups == 2 && 2 * n0 >= p.Nt) ? 1 : 0;
+      const float* sc = p.pro_scale + grp * Cp;
+      const float* sh = p.pro_shift + grp * Cp;
+      const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
+      const int cj = xform_unit_channel(s_addr + tid * 16u, 7u);       // boxes are 1024-byte aligned: the same for all
+      XformCoef k;
+      xform_load(k, sc, sh, p.xboxes[0].c_off + cj, Cp);
+      mbar_wait(&full[stage], phase);
+      for (int b = 0; b < n_xboxes; ++b) {
+        xform_span<kWhXformThreads>(s_addr + static_cast<uint32_t>(b) * p.xbox_bytes, tid, p.xbox_units, k);
+        if (b + 1 < n_xboxes) xform_load(k, sc, sh, p.xboxes[b + 1].c_off + cj, Cp);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfull[stage]);
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
 
   // Roles run warp-converged with one elected issuing lane (see conv_halo.cu).
   if (warp == 0) {
@@ -132,7 +173,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&full[stage], phase);
+      mbar_wait(kXform ? &xfull[stage] : &full[stage], phase);
       tc_fence_after();
       if (leader) {
         const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
@@ -194,7 +235,7 @@ struct cstp_wgrad_halo_plan {
 
 using namespace cstp;
 
-static int encode5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5]) {
+static int encode5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5], bool oob_nan = false) {
   uint64_t dims[5], strides[4];
   for (int i = 0; i < 5; ++i) {
     if (t.dims[i] <= 0) return fail_inval("tensor5 dim <= 0");
@@ -205,7 +246,7 @@ static int encode5(CUtensorMap* map, const cstp_tensor5& t, const uint32_t box[5
     strides[i] = static_cast<uint64_t>(t.strides[i]);
   }
   if ((reinterpret_cast<uintptr_t>(t.ptr) % 16) != 0 || t.ptr == nullptr) return fail_inval("tensor5 ptr must be 16B aligned");
-  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box);
+  return encode_tmap_bf16(map, t.ptr, 5, dims, strides, box, 128, oob_nan);
 }
 
 extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_wgrad_halo_plan** out_plan) {
@@ -226,6 +267,12 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   // every run of 8 positions is one atom and consecutive atoms are one box row (bw + halo_w positions) apart
   const int pitch = d->atom_pitch_rows > 0 ? d->atom_pitch_rows : 8;
   CSTP_REQUIRE(d->halo_w == 0 ? (pitch == 8 && xrows % 8 == 0) : (d->bw == 8 && pitch == d->bw + d->halo_w));
+  const bool xform = d->pro.scale != nullptr;
+  if (xform) {
+    CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
+    CSTP_REQUIRE(d->pro.Cp == d->xmap.dims[0] && d->bn == 1);
+    CSTP_REQUIRE(reinterpret_cast<uintptr_t>(d->pro.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(d->pro.shift) % 16 == 0);
+  }
 
   cstp_wgrad_halo_plan* plan = new (std::nothrow) cstp_wgrad_halo_plan();
   if (!plan) {
@@ -237,7 +284,7 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   const uint32_t xbox[5] = {64u, (uint32_t)(d->bw + d->halo_w), (uint32_t)(d->bh + d->halo_h),
                             (uint32_t)(d->bt + d->halo_t), (uint32_t)d->bn};
   const uint32_t gbox[5] = {64u, (uint32_t)d->bw, (uint32_t)d->bh, (uint32_t)d->bt, (uint32_t)d->bn};
-  int rc = encode5(&k.xmap, d->xmap, xbox);
+  int rc = encode5(&k.xmap, d->xmap, xbox, xform);
   if (rc == CSTP_OK) rc = encode5(&k.gmap, d->gmap, gbox);
   if (rc != CSTP_OK) {
     delete plan;
@@ -266,6 +313,12 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   plan->splits = splits;
   k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 1, 1);
   k.partials = d->partials;
+  k.pro_scale = d->pro.scale;
+  k.pro_shift = d->pro.shift;
+  k.pro_groups = d->pro.groups;
+  k.pro_cp = d->pro.Cp;
+  k.Nt = d->Nt;
+  k.xbox_units = static_cast<uint32_t>(xrows) * 8u;
   for (int i = 0; i < d->n_xboxes; ++i) {
     const cstp_xbox& b = d->xboxes[i];
     if (b.c_off < 0 || b.c_off % 8 != 0) {
@@ -313,10 +366,14 @@ extern "C" int cstp_wgrad_halo_plan_run(const cstp_wgrad_halo_plan* plan, void* 
   CSTP_REQUIRE(plan != nullptr);
   static bool attr_set = false;
   if (!attr_set) {
-    CSTP_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmemLimit));
+    CSTP_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmemLimit));
     attr_set = true;
   }
-  wgrad_halo_kernel<<<plan->grid, kWhThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  if (plan->kp.pro_scale != nullptr)
+    wgrad_halo_kernel<true><<<plan->grid, kWhThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+  else
+    wgrad_halo_kernel<false><<<plan->grid, kWhThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -30,8 +30,15 @@ import torch
 from . import ops
 from .ops import ConvGeom, pad16, pad64
 
+import os
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+# conv -> BatchNorm -> ReLU -> conv edges (r21d_byol.py:94-97): the consumer's forward and weight-gradient kernels read the
+# producer's RAW output and apply the BatchNorm affine map + ReLU to their staged operand tiles (ops.conv_fwd_plan /
+# ops.wgrad_plan `prologue`), so the normalised activation is neither written nor re-read.  "0" restores the standalone
+# cstp_bn_apply pass on every edge (same bits either way: tests/test_gpu_step.py).
+FUSE_BN_APPLY = os.environ.get("CSTP_FUSE_BN_APPLY", "1") == "1"
 # Storage type of activations, activation gradients and packed weights.  The CUDA kernels only implement bf16; the
 # CPU emulator in tests/ also runs the orchestration in fp32 to separate wiring errors from rounding.
 ACT_DTYPE = torch.bfloat16
@@ -194,6 +201,9 @@ class StepEngine:
             self._ev_fwd, self._ev_tgt = torch.cuda.Event(), torch.cuda.Event()
             self._ev_g = [torch.cuda.Event(), torch.cuda.Event()]
             self._ev_wg = [torch.cuda.Event(), torch.cuda.Event()]
+        self.fuse_apply = FUSE_BN_APPLY
+        self._pending: dict[int, "ops.BNState"] = {}   # raw tensor address -> BatchNorm state its consumers must apply
+        self._pending_act: dict[int, torch.Tensor] = {}   # record mode: the same activations, materialised for the tests
         self.named: dict[str, torch.Tensor] = {}      # name -> activation / gradient tensors (parity tests)
         self.units: list[dict] = []                   # every conv+BN unit in build order (parity tests, profiling)
         self._prof = None                             # list of (kind, flops, launches, ev0, ev1) while profiling
@@ -279,20 +289,30 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------ conv + BN unit
     def _conv_bn(self, prog, store, grads, x, wname, bnname, geom: ConvGeom, cin, cout, *, relu=True, res=None,
                  res_site=None, apply=True, tag="", skip_dgrad=False, x_is_col=False):
-        """raw = conv(x); BN statistics; act = [relu](bn(raw) [+ res]).  Returns (raw, act, site) and, when `grads`,
-        appends this unit's backward closure to self._units (run in reverse by _finish_backward)."""
+        """raw = conv(x); BN statistics; act = [relu](bn(raw) [+ res]).  Returns (raw, act, site, unit); the backward
+        closure of the unit is built by _unit_backward.
+
+        Plain BatchNorm -> ReLU outputs (no shortcut) are NOT materialised when self.fuse_apply: the returned `act` is then
+        the raw tensor itself, registered in self._pending with the BatchNorm state its consumers have to apply -- the next
+        convolution's forward and weight-gradient kernels through their operand prologue, a residual add through
+        bn_apply's res_relu mode, the ReLU mask of the backward pass from raw (it always was)."""
         N, T, H, W, _ = x.shape
         To, Ho, Wo = geom.out_dims(T, H, W)
         Cop = pad16(cout)
         raw = self._act(N, To, Ho, Wo, Cop)
-        act = self._act(N, To, Ho, Wo, Cop) if apply else None
+        pro = self._pending.get(x.data_ptr())         # x is a raw tensor whose BatchNorm + ReLU we apply on the way in
+        defer = apply and relu and res is None and self.fuse_apply
+        keep_act = apply and (not defer or self.record)          # parity tests still look at every activation
+        act = self._act(N, To, Ho, Wo, Cop) if keep_act else None
         wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
         rows = N * To * Ho * Wo
         flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
         site = self._site(store, grads, bnname, cout, self.VIEWS, rows // self.VIEWS)
-        cplan = ops.conv_fwd_plan(x, wp, raw, geom, stats=site.st)
+        cplan = ops.conv_fwd_plan(x, wp, raw, geom, stats=site.st, prologue=pro)
         plan = _Timed(self, "conv_fwd", flops, [cplan], tag)
         fused = getattr(cplan, "stat_blocks", 0)   # > 0: the conv epilogue already wrote the BatchNorm statistics partials
+        res_pro = self._pending.get(res.data_ptr()) if res is not None else None
+        res_state = res_site.st if res_site else res_pro
 
         def fwd():
             plan.run()
@@ -301,18 +321,27 @@ class StepEngine:
             else:
                 ops.bn_forward_stats(raw, site.st, site.gamma, site.beta, site.rm, site.rv, BN_EPS, BN_MOMENTUM,
                                      fused_blocks=fused, sync=self.bn_sync)
-            if apply:
-                ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_site.st if res_site else None)
+            if keep_act:
+                ops.bn_apply(raw, site.st, act, relu=relu, res=res, res_state=res_state, res_relu=res_pro is not None)
         prog.append(fwd)
         self._rec(tag + ".raw", raw)
         if act is not None:
             self._rec(tag + ".act", act)
         unit = dict(x=x, raw=raw, act=act, site=site, relu=relu, geom=geom, wname=wname, cin=cin, cout=cout, wt=wt,
                     skip_dgrad=skip_dgrad, tag=tag, flops=flops, bnname=bnname, res=res, res_site=res_site,
-                    x_is_col=x_is_col, grads=grads)
+                    x_is_col=x_is_col, grads=grads, pro=pro, deferred=defer,
+                    # what the tensor cores really consume, as materialised tensors (record mode; parity tests)
+                    x_act=self._pending_act.get(x.data_ptr(), x).view(x.shape),
+                    res_act=self._pending_act.get(res.data_ptr(), res).view(res.shape) if res is not None else None)
         self.units.append(unit)
         self._g_numel = max(self._g_numel, raw.numel())
-        return raw, act, site, unit
+        out = act
+        if defer:
+            self._pending[raw.data_ptr()] = site.st
+            if act is not None:
+                self._pending_act[raw.data_ptr()] = act
+            out = raw
+        return raw, out, site, unit
 
     def _unit_backward(self, unit, d_out, *, act_for_mask, dz=None, dx_accumulate=False):
         """Backward closure of one conv+BN unit: BN backward -> wgrad -> dgrad (see _conv_bn)."""
@@ -324,7 +353,8 @@ class StepEngine:
             g = self._gbufs[holder["gbuf"]][:raw.numel()].view(raw.shape)
             holder["g"] = g
             holder["wg"] = _Timed(self, "wgrad", unit["flops"],
-                                  [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg)], unit["tag"])
+                                  [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg, prologue=unit["pro"])],
+                                  unit["tag"])
             if not unit["skip_dgrad"]:
                 dx = self._dbuf(x)
                 plans, covers = ops.conv_dgrad_plans(g, unit["wt"], dx, geom, accumulate=dx_accumulate)

@@ -156,5 +156,33 @@ class FinetuneEngine(StepEngine):
         """nn.CrossEntropyLoss() of main_ft_mp.py:188,203 on the current logits; fills self.loss and self.dlogits."""
         E.ops.ce_loss(self.logits, labels, self.num_classes, self.loss, self.dlogits, self.ce_ws)
 
-    def optimizer_step(self, lr, momentum=0.9, wd=1e-3, max_norm=0.0, clip=False):
-        super().optimizer_step(lr, momentum, wd, max_norm, clip)
+    def trainable_ranges(self, frozen_names) -> list[tuple[int, int]]:
+        """(offset, length) runs of the flat buffer that hold the parameters NOT in `frozen_names`, merged where the
+        slots are adjacent.  optim.SGD skips parameters without a gradient entirely -- no weight decay, no momentum
+        (r21d_byol.py:10-35 sets requires_grad = False on everything but `classify` for ft_fc)."""
+        runs: list[list[int]] = []
+        for name, (off, shape) in self.train.slots.items():
+            if name in frozen_names:
+                continue
+            n = 1
+            for d in shape:
+                n *= d
+            n = (n + 15) // 16 * 16
+            if runs and runs[-1][0] + runs[-1][1] == off:
+                runs[-1][1] += n
+            else:
+                runs.append([off, n])
+        return [(o, n) for o, n in runs]
+
+    def optimizer_step(self, lr, momentum=0.9, wd=1e-3, max_norm=0.0, clip=False, ranges=None):
+        """SGD.step of main_ft_mp.py:117-121,212 (no gradient clipping in the finetune driver).  `ranges` restricts the
+        update to the trainable runs of the flat buffer (see trainable_ranges); None updates every parameter."""
+        if ranges is None:
+            return super().optimizer_step(lr, momentum, wd, max_norm, clip)
+        if clip:
+            raise E.ops.L.CstpError("gradient clipping over a partial parameter set is not part of the finetune path")
+        for off, n in ranges:
+            E.ops.sgd_clip_step(self.train.data[off:off + n], self.grad[off:off + n], self.mom[off:off + n], lr, momentum, wd,
+                                0.0, False, self.first_step, self.norm_out, self.sgd_ws)
+        self.first_step = False
+        self.pack_online()

@@ -23,6 +23,11 @@ class Tap(C.Structure):
     _fields_ = [("map_id", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32), ("dt", C.c_int32), ("k_off", C.c_int32)]
 
 
+class Prologue(C.Structure):
+    """cstp_prologue: BatchNorm affine + ReLU applied to the activation operand inside the kernel."""
+    _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("groups", C.c_int32), ("Cp", C.c_int32)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
         ("n_amaps", C.c_int32),
@@ -42,6 +47,7 @@ class ConvDesc(C.Structure):
         ("osw", C.c_int64), ("osh", C.c_int64), ("ost", C.c_int64), ("osn", C.c_int64),
         ("bias", C.c_void_p),
         ("accumulate", C.c_int32),
+        ("pro", Prologue),
     ]
 
 
@@ -62,6 +68,7 @@ class WgradDesc(C.Structure):
         ("bw", C.c_int32), ("bh", C.c_int32), ("bt", C.c_int32), ("bn", C.c_int32),
         ("splits", C.c_int32),
         ("partials", C.c_void_p),
+        ("pro", Prologue),
     ]
 
 
@@ -97,6 +104,7 @@ class ConvHaloDesc(C.Structure):
         ("atom_pitch_rows", C.c_int32),
         ("stats_groups", C.c_int32),
         ("stats_partials", C.c_void_p),
+        ("pro", Prologue),
     ]
 
 
@@ -118,6 +126,7 @@ class WgradHaloDesc(C.Structure):
         ("splits", C.c_int32),
         ("partials", C.c_void_p),
         ("atom_pitch_rows", C.c_int32),
+        ("pro", Prologue),
     ]
 
 

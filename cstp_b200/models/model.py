@@ -17,12 +17,12 @@ def neq_load_customized(model, pretrained_dict, verbose=True):
     model_dict = model.state_dict()
     tmp = {k: v for k, v in pretrained_dict.items() if k in model_dict}
     if verbose:
-        print("\\n=======Check Weights Loading======")
+        print("\n=======Check Weights Loading======")
         print("Weights not loaded into new model:")
         for k in model_dict:
             if k not in pretrained_dict:
                 print(k)
-        print("===================================\\n")
+        print("===================================\n")
     model_dict.update(tmp)
     model.load_state_dict(model_dict)
     return model

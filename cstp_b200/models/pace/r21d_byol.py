@@ -343,7 +343,12 @@ class R21DBYOL(nn.Module):
         eng.backward()
         if grad_sync is not None:
             grad_sync(eng.grad)
-        eng.optimizer_step(lr, momentum, weight_decay)
+        # parameters frozen by get_fine_tuning_parameters (requires_grad = False) are skipped like optim.SGD skips them
+        frozen = frozenset(n for n, p in self.named_parameters() if not p.requires_grad)
+        if frozen != getattr(self, "_ft_frozen", None) or getattr(self, "_ft_ranges_eng", None) is not eng:
+            self._ft_frozen, self._ft_ranges_eng = frozen, eng
+            self._ft_ranges = eng.trainable_ranges(frozen) if frozen else None
+        eng.optimizer_step(lr, momentum, weight_decay, ranges=self._ft_ranges)
         self._nbt += self._nbt_inc
         return eng.loss
 

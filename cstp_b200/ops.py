@@ -202,10 +202,23 @@ def _default_n_tile(Np: int) -> int:
     return pad16(math.ceil(Np / nt))
 
 
+def _set_prologue(d, prologue: "BNState | None", a_channels: int) -> tuple:
+    """Fills desc.pro from the BatchNorm state of the unit that PRODUCED the operand (its raw output is what the kernel
+    reads); returns the tensors the plan must keep alive."""
+    if prologue is None:
+        return ()
+    if prologue.Cp != a_channels:
+        raise L.CstpError(f"prologue BatchNorm has {prologue.Cp} padded channels, the operand {a_channels}")
+    d.pro.scale, d.pro.shift = prologue.scale.data_ptr(), prologue.shift.data_ptr()
+    d.pro.groups, d.pro.Cp = prologue.groups, prologue.Cp
+    return (prologue.scale, prologue.shift)
+
+
 def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out, out_f32, out_off, ostrides, bias,
-                    accumulate, n_tile, keep) -> ConvPlan:
+                    accumulate, n_tile, keep, prologue=None) -> ConvPlan:
     lib = L.load()
     d = L.ConvDesc()
+    keep = keep + _set_prologue(d, prologue, a_channels)
     d.n_amaps = len(views)
     for i, v in enumerate(views):
         d.amap[i] = v
@@ -334,9 +347,10 @@ def _conv_halo_layout(tile_space, taps, a_channels: int, Np: int, halo_2d: bool)
 
 
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
-                         accumulate, keep, stats=None) -> ConvHaloPlan:
+                         accumulate, keep, stats=None, prologue=None) -> ConvHaloPlan:
     lib = L.load()
     d = L.ConvHaloDesc()
+    keep = keep + _set_prologue(d, prologue, a_channels)
     d.amap = view
     d.a_channels = a_channels
     d.n_groups = len(lay["groups"])
@@ -383,10 +397,13 @@ HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill
 
 
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None,
-                  box=None, allow_halo: bool = True, stats: "BNState | None" = None) -> ConvPlan:
+                  box=None, allow_halo: bool = True, stats: "BNState | None" = None,
+                  prologue: "BNState | None" = None) -> ConvPlan:
     """out[n,to,ho,wo,:] = conv3d(x, w) with x (N,T,H,W,Cp_in) bf16, w_packed [Np][taps*pad64(Cp_in)] bf16.
     With `stats` the kernel may also emit the BatchNorm statistics partials of `out` (plan.stat_blocks > 0 tells the caller
-    to skip the separate statistics pass)."""
+    to skip the separate statistics pass).  With `prologue` x is the RAW output of the producing convolution and the kernel
+    convolves bf16(relu(x * prologue.scale + prologue.shift)) (include/cstp_b200.h cstp_prologue; the coefficients are
+    read at run time, i.e. after the producer's cstp_bn_finalize of the same step)."""
     _require_cuda(x, w_packed, out, out_f32, bias)
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
@@ -405,10 +422,11 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
                     and out is not None and out_f32 is None and bias is None and not accumulate
                     and Np == 64 and lay["n_tile"] == 64 and lay["box"][3] == 1)
             return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, out_f32, 0, ostr, bias,
-                                        accumulate, (x, w_packed, out, out_f32, bias), stats=stats if fuse else None)
+                                        accumulate, (x, w_packed, out, out_f32, bias), stats=stats if fuse else None,
+                                        prologue=prologue)
     box = box or pick_box(Wo, Ho, To, N, 128)
     return _make_conv_plan(views, taps, Ca, w_packed, Np, (Wo, Ho, To, N), box, out, out_f32, 0, ostr, bias, accumulate,
-                           n_tile, (x, w_packed, out, out_f32, bias))
+                           n_tile, (x, w_packed, out, out_f32, bias), prologue=prologue)
 
 
 def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False, allow_halo: bool = True) -> tuple[list[ConvPlan], bool]:
@@ -575,8 +593,9 @@ def wgrad_partials_need(x_shape, g_shape, geom: ConvGeom, sms: int = 148) -> int
 
 
 def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor, *, splits: int | None = None,
-               box=None, sms: int = 148, allow_halo: bool = True) -> WgradSpec:
-    """dW (cout, cin, kt, kh, kw) from x (N,T,H,W,Cp_in) and g (N,To,Ho,Wo,Cp_out); `partials` is fp32 scratch."""
+               box=None, sms: int = 148, allow_halo: bool = True, prologue: "BNState | None" = None) -> WgradSpec:
+    """dW (cout, cin, kt, kh, kw) from x (N,T,H,W,Cp_in) and g (N,To,Ho,Wo,Cp_out); `partials` is fp32 scratch.
+    With `prologue` x is the raw output of the producing convolution (see conv_fwd_plan)."""
     _require_cuda(x, g, partials)
     lib = L.load()
     N, T, H, W, Ca = x.shape
@@ -602,9 +621,10 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
         if partials.numel() < lay["need"]:
             raise L.CstpError(f"wgrad partials scratch too small: {partials.numel()} < {lay['need']}")
         d.partials = partials.data_ptr()
+        keep = _set_prologue(d, prologue, Ca)
         h = C.c_void_p()
         L.check(lib.cstp_wgrad_halo_plan_create(C.byref(d), C.byref(h)))
-        plan = WgradHaloPlan(h, lib.cstp_wgrad_halo_plan_destroy, (x, g, partials))
+        plan = WgradHaloPlan(h, lib.cstp_wgrad_halo_plan_destroy, (x, g, partials) + keep)
         plan.splits = lib.cstp_wgrad_halo_plan_splits(h)
         return WgradSpec(plan, len(lay["chunks"]), Np,
                          torch.tensor([c[1] for c in lay["chunks"]], dtype=torch.int32, device=dev),
@@ -642,9 +662,10 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
     if partials.numel() < need:
         raise L.CstpError(f"wgrad partials scratch too small: {partials.numel()} < {need}")
     d.partials = partials.data_ptr()
+    keep = _set_prologue(d, prologue, Ca)
     h = C.c_void_p()
     L.check(lib.cstp_wgrad_plan_create(C.byref(d), C.byref(h)))
-    plan = WgradPlan(h, lib.cstp_wgrad_plan_destroy, (x, g, partials))
+    plan = WgradPlan(h, lib.cstp_wgrad_plan_destroy, (x, g, partials) + keep)
     plan.splits = lib.cstp_wgrad_plan_splits(h)
     return WgradSpec(plan, len(mch), Np, torch.tensor(ctap, dtype=torch.int32, device=dev),
                      torch.tensor(ccoff, dtype=torch.int32, device=dev), cout, cin, geom.taps, partials)
@@ -744,9 +765,13 @@ def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, e
                                  _ptr(st.shift), _ptr(st.mean), _ptr(st.invstd), _stream()))
 
 
-def bn_apply(raw, st: BNState, out, *, relu: bool, res=None, res_state: BNState | None = None) -> None:
+def bn_apply(raw, st: BNState, out, *, relu: bool, res=None, res_state: BNState | None = None,
+             res_relu: bool = False) -> None:
+    """out = [relu](raw*scale + shift [+ shortcut]).  The shortcut is `res` itself, or -- with res_state -- the BatchNorm
+    output res*scale2 + shift2 of a raw conv output (downsample branch), or -- with res_relu as well -- the BatchNorm + ReLU
+    activation bf16(relu(res*scale2 + shift2)) that was never written out (fused-prologue edges)."""
     rows = raw.numel() // st.Cp
-    mode = 0 if res is None else (2 if res_state is not None else 1)
+    mode = 0 if res is None else ((3 if res_relu else 2) if res_state is not None else 1)
     L.check(L.load().cstp_bn_apply(_ptr(raw), rows, st.Cp, st.groups, _ptr(st.scale), _ptr(st.shift), int(relu), mode,
                                    _ptr(res), _ptr(res_state.scale if res_state else None),
                                    _ptr(res_state.shift if res_state else None), _ptr(out), _stream()))

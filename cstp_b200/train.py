@@ -30,10 +30,19 @@ def epoch_lr(epoch: int, n_epochs: int, max_lr: float, min_lr: float = 1e-5) -> 
     return lr_at(epoch - 1, n_epochs, max_lr, min_lr, 0.5 * n_epochs, 1.0, 0.5)
 
 
-def optimizer_state_dict(model) -> dict:
-    """torch.optim.SGD-compatible state dict of the engine's fused optimiser: momentum buffers addressed by the position
-    of each parameter in model.parameters() (frozen target_net entries keep their indices and have no state), so that
-    `optim.SGD(model.parameters()).load_state_dict(...)` of the reference accepts it (main_byol.py:138,243-244)."""
+def unwrap(model):
+    """The bare R21DBYOL behind the DistributedDataParallel / DataParallel wrapper generate_model may return."""
+    return getattr(model, "module", model)
+
+
+def optimizer_state_dict(model, lr: float = 0.03, momentum: float = 0.9, weight_decay: float = 5e-4,
+                         initial_lr: float | None = None) -> dict:
+    """torch.optim.SGD state dict of the engine's fused optimiser: momentum buffers addressed by the position of each
+    parameter in model.parameters() (frozen target_net entries keep their indices and have no state) and ONE complete
+    parameter group -- SGD.load_state_dict replaces the live groups by the saved ones, so every hyper-parameter key of
+    torch's SGD has to be there for the reference's `optimizer.load_state_dict(...)` + `optimizer.step()` +
+    `CosineAnnealingWarmupRestarts(optimizer, ...)` to work on it (main_byol.py:138,243-258)."""
+    model = unwrap(model)
     eng = model._engine
     names = [n for n, _ in model.named_parameters()]
     state = {}
@@ -41,10 +50,17 @@ def optimizer_state_dict(model) -> dict:
         for i, n in enumerate(names):
             if n in eng.train.slots:
                 state[i] = {"momentum_buffer": eng.train.view(n, eng.mom).detach().clone().cpu()}
-    return {"state": state, "param_groups": [{"params": list(range(len(names)))}]}
+    group = {"lr": float(lr), "momentum": float(momentum), "dampening": 0, "weight_decay": float(weight_decay),
+             "nesterov": False, "maximize": False, "foreach": None, "differentiable": False, "fused": None,
+             "initial_lr": float(lr if initial_lr is None else initial_lr), "params": list(range(len(names)))}
+    return {"state": state, "param_groups": [group]}
 
 
 def load_optimizer_state_dict(model, sd: dict) -> None:
+    """Momentum buffers of an `optim.SGD.state_dict()` (ours or one the reference wrote, main_byol.py:138) -> the
+    engine's flat momentum buffer.  Hyper-parameters are not taken from the file: the reference re-creates them from
+    `opts` on resume as well (main_byol.py:229-232 builds the optimizer before :243-244 loads the state)."""
+    model = unwrap(model)
     eng = model._engine
     names = [n for n, _ in model.named_parameters()]
     loaded = False
@@ -56,10 +72,16 @@ def load_optimizer_state_dict(model, sd: dict) -> None:
     eng.first_step = not loaded
 
 
-def save_checkpoint(path: str, model, epoch: int, arch: str, ddp_prefix: bool = True) -> None:
-    """main_byol.py:132-140."""
-    sd = {("module." + k if ddp_prefix else k): v.detach().cpu() for k, v in model.state_dict().items()}
-    torch.save({"epoch": epoch + 1, "arch": arch, "state_dict": sd, "optimizer": optimizer_state_dict(model)}, path)
+def save_checkpoint(path: str, model, epoch: int, arch: str, ddp_prefix: bool = True, lr: float = 0.03,
+                    momentum: float = 0.9, weight_decay: float = 5e-4, initial_lr: float | None = None) -> None:
+    """main_byol.py:132-140.  Keys carry the `module.` prefix of the DDP-wrapped model the reference saves (once: a model
+    that is already wrapped contributes it itself)."""
+    sd = {}
+    for k, v in model.state_dict().items():
+        k = k if (k.startswith("module.") or not ddp_prefix) else "module." + k
+        sd[k] = v.detach().cpu()
+    torch.save({"epoch": epoch + 1, "arch": arch, "state_dict": sd,
+                "optimizer": optimizer_state_dict(model, lr, momentum, weight_decay, initial_lr)}, path)
 
 
 def load_checkpoint(path: str, model, example_clip: torch.Tensor | None = None) -> int:
@@ -68,6 +90,7 @@ def load_checkpoint(path: str, model, example_clip: torch.Tensor | None = None) 
     the momentum buffers have a home."""
     md = torch.load(path, map_location="cpu", weights_only=False)
     sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in md["state_dict"].items()}
+    model = unwrap(model)
     model.load_state_dict(sd)
     if example_clip is not None:
         model._bind(example_clip)
@@ -80,6 +103,7 @@ def pretrain_epochs(model, batches, opts, begin_epoch: int = 1, result_path: str
     """Runs epochs begin_epoch..opts.n_epochs.  `batches(epoch)` yields (clip_1, clip_2, (spa, tem, pb, rot_1, rot_2)) on
     the device.  Returns one dict of LOG_COLUMNS per epoch."""
     rows = []
+    wrapped, model = model, unwrap(model)        # the fused step lives on the bare module; checkpoints keep the wrapper's keys
     clip = 18.0 if getattr(opts, "clip_grad_norm", 1) else 0.0
     for epoch in range(begin_epoch, opts.n_epochs + 1):
         lr = epoch_lr(epoch, opts.n_epochs, opts.learning_rate)
@@ -95,11 +119,13 @@ def pretrain_epochs(model, batches, opts, begin_epoch: int = 1, result_path: str
         L = L.cpu()
         w = opts.loss_weight
         total = w[0] * L[7] + L[6]
-        row = dict(zip(LOG_COLUMNS, [epoch, total.item(), L[7].item(), L[0].item(), L[1].item(), (L[2] + L[3]).item(),
-                                     (L[4] + L[5]).item(), 0.0, lr]))
+        # main_byol.py:81-84,119-129: pb / rot columns are the MEAN of the two views' terms, acc is None, lr has 5 decimals
+        row = dict(zip(LOG_COLUMNS, [epoch, total.item(), L[7].item(), L[0].item(), L[1].item(), ((L[2] + L[3]) / 2).item(),
+                                     ((L[4] + L[5]) / 2).item(), None, float("{:.5f}".format(lr))]))
         rows.append(row)
         if log is not None:
             log(row)
         if result_path is not None and (epoch % save_every == 0 or epoch == opts.n_epochs):
-            save_checkpoint(os.path.join(result_path, f"save_{epoch}.pth"), model, epoch, arch)
+            save_checkpoint(os.path.join(result_path, f"save_{epoch}.pth"), wrapped, epoch, arch, lr=lr,
+                            momentum=opts.momentum, weight_decay=opts.weight_decay, initial_lr=opts.learning_rate)
     return rows

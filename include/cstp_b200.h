@@ -50,6 +50,21 @@ typedef struct {
   int32_t k_off;
 } cstp_tap;
 
+/* Optional operand prologue of the conv-forward and weight-gradient kernels: the activation operand is the RAW output
+ * of the producing convolution and the kernel applies the producer's BatchNorm affine map and ReLU,
+ *   a = bf16(max(raw * scale[g][c] + shift[g][c], 0)),
+ * to the TMA-staged tiles in shared memory before the tensor cores read them -- bit for bit the tensor cstp_bn_apply
+ * (relu = 1, no residual) would have written, which then never exists in HBM (conv -> bn -> relu -> conv,
+ * models/pace/r21d_byol.py:94-97).  scale / shift: fp32 [groups][Cp] as cstp_bn_finalize / cstp_bn_eval_coeffs write
+ * them (zero for padded channels); `groups` (1 or 2) equal parts of the operand's N axis use their own rows.  The
+ * convolution's zero padding stays exactly zero.  scale == NULL: the operand is used as it is. */
+typedef struct {
+  const float* scale;
+  const float* shift;
+  int32_t groups;
+  int32_t Cp;
+} cstp_prologue;
+
 /* ---- implicit-GEMM convolution / linear: forward and dgrad ---------------------------------------------
  * Replaces nn.Conv3d forward (models/pace/r21d_byol.py:81-82,91-92,94-97) and its autograd dgrad
  * (main_byol.py:87), and nn.Linear forward/dgrad (r21d_byol.py:236-239,250-253,276-291).
@@ -73,6 +88,7 @@ typedef struct {
   int64_t osw, osh, ost, osn;   /* element strides of the tile-space axes in `out` */
   const float* bias;            /* fp32 [Np] or NULL */
   int32_t accumulate;           /* 1: out += D (read-modify-write) */
+  cstp_prologue pro;            /* BatchNorm + ReLU applied to A on the way in (scale NULL: none) */
 } cstp_conv_desc;
 
 typedef struct cstp_conv_plan cstp_conv_plan;
@@ -127,6 +143,7 @@ typedef struct {
    * bf16 output: every epilogue thread keeps the sums of its row's 64 columns in registers. */
   int32_t stats_groups;
   float* stats_partials;
+  cstp_prologue pro;            /* BatchNorm + ReLU applied to A on the way in (scale NULL: none) */
 } cstp_conv_halo_desc;
 
 typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;
@@ -160,6 +177,7 @@ typedef struct {
   int32_t bw, bh, bt, bn;               /* box: product == 64 */
   int32_t splits;                       /* requested split-K factor (>=1) */
   float* partials;                      /* fp32 [splits_eff][n_mchunks*64][Np] */
+  cstp_prologue pro;                    /* BatchNorm + ReLU applied to X on the way in (scale NULL: none) */
 } cstp_wgrad_desc;
 
 typedef struct cstp_wgrad_plan cstp_wgrad_plan;
@@ -201,6 +219,7 @@ typedef struct {
    * bw == 8: the box carries a halo along w as well (all k x k taps of a 1 x k x k filter read ONE staged box per channel
    * chunk; chunk_off in whole 128-byte rows). */
   int32_t atom_pitch_rows;
+  cstp_prologue pro;                    /* BatchNorm + ReLU applied to X on the way in (scale NULL: none) */
 } cstp_wgrad_halo_desc;
 
 typedef struct cstp_wgrad_halo_plan cstp_wgrad_halo_plan;
@@ -234,7 +253,9 @@ int cstp_bn_finalize(const float* partials, int nblocks, int groups, int64_t row
  * the cross-rank all-reduce of world-synchronised BatchNorm; finalize then runs with nblocks = 1 and the global row
  * count. */
 int cstp_bn_partials_reduce(const float* partials, int nblocks, int groups, int Cp, float* out, void* stream);
-/* out = act(raw*scale+shift + residual); res_mode 0 none, 1 bf16 tensor, 2 raw2*scale2+shift2. */
+/* out = act(raw*scale+shift + residual); res_mode 0 none, 1 bf16 tensor, 2 raw2*scale2+shift2 (the shortcut is a
+ * BatchNorm output, r21d_byol.py:144-145), 3 bf16(relu(raw2*scale2+shift2)) (the shortcut is a BatchNorm + ReLU
+ * activation that only exists as its producer's raw output, see cstp_prologue). */
 int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, const float* scale, const float* shift,
                   int relu, int res_mode, const void* res, const float* scale2, const float* shift2, void* out,
                   void* stream);

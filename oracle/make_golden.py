@@ -42,7 +42,35 @@ def summarize(t: torch.Tensor, k: int) -> dict:
                 l2=f.norm().item(), samples=f[sample_idx(f.numel(), k)].clone())
 
 
-def run_reference(B: int, steps: int, with_layers: bool, batch_fn=synthetic_batch) -> dict:
+class disk_offload(torch.autograd.graph.saved_tensors_hooks):
+    """Parks every large tensor autograd saves for backward in a scratch file, so the UNMODIFIED reference can run its
+    batch-60 step (BASELINE config 3: ~55 GB of saved fp32 activations) on a 62 GB host.  Values are untouched."""
+
+    def __init__(self, root: str, min_numel: int = 1 << 20):
+        import numpy as np
+        os.makedirs(root, exist_ok=True)
+        count = [0]
+
+        def pack(t):
+            if t.numel() < min_numel or t.dtype != torch.float32 or not t.is_contiguous():
+                return t
+            count[0] += 1
+            path = os.path.join(root, f"t{count[0]}.bin")
+            t.detach().numpy().tofile(path)
+            return (path, tuple(t.shape))
+
+        def unpack(h):
+            if isinstance(h, torch.Tensor):
+                return h
+            path, shape = h
+            t = torch.from_numpy(np.fromfile(path, dtype=np.float32)).view(shape)
+            os.remove(path)
+            return t
+        super().__init__(pack, unpack)
+
+
+def run_reference(B: int, steps: int, with_layers: bool, batch_fn=synthetic_batch, offload: str | None = None) -> dict:
+    import contextlib
     sys.path.insert(0, REF)
     from models.pace import r21d_byol as ref_mod  # the reference, unmodified
 
@@ -77,12 +105,14 @@ def run_reference(B: int, steps: int, with_layers: bool, batch_fn=synthetic_batc
                     handles.append(m.register_forward_hook(mk(name)))
         t0 = time.time()
         # ---- the step body of main_byol.py:60-91 ----
-        loss_byol, preds = model(x1, x2, o_type="loss_com")
-        loss_byol = loss_byol.mean()
-        spa, tem, pb, r1, r2 = labels
-        ce = [crit(preds[0], spa), crit(preds[1], tem), crit(preds[2], pb), crit(preds[3], pb), crit(preds[4], r1),
-              crit(preds[5], r2)]
-        total = w[0] * loss_byol + w[1] * ce[0] + w[2] * ce[1] + w[3] * ce[2] + w[3] * ce[3] + w[4] * ce[4] + w[4] * ce[5]
+        with (disk_offload(offload) if offload else contextlib.nullcontext()):
+            loss_byol, preds = model(x1, x2, o_type="loss_com")
+            loss_byol = loss_byol.mean()
+            spa, tem, pb, r1, r2 = labels
+            ce = [crit(preds[0], spa), crit(preds[1], tem), crit(preds[2], pb), crit(preds[3], pb), crit(preds[4], r1),
+                  crit(preds[5], r2)]
+            total = (w[0] * loss_byol + w[1] * ce[0] + w[2] * ce[1] + w[3] * ce[2] + w[3] * ce[3] + w[4] * ce[4]
+                     + w[4] * ce[5])
         opt.zero_grad()
         total.backward()
         gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), 18)
@@ -144,21 +174,23 @@ def run_ntxent() -> dict:
     return res
 
 
-def run_finetune() -> dict:
-    """R21DBYOL(pretrain=False, num_classes=101, cls_bn=True): one training step of main_ft_mp.py:196-214 on B=4
-    video-like clips (SGD lr 0.025 momentum 0.9 wd 1e-3, README.md:68-78), then model.eval() logits of the first clip."""
+def run_finetune(B: int = 4, offload: str | None = None) -> dict:
+    """R21DBYOL(pretrain=False, num_classes=101, cls_bn=True): one training step of main_ft_mp.py:196-214 on B
+    video-like clips (SGD lr 0.025 momentum 0.9 wd 1e-3, README.md:68-78), then model.eval() logits of the first clips."""
+    import contextlib
     sys.path.insert(0, REF)
     from models.pace import r21d_byol as ref_mod  # the reference, unmodified
     torch.manual_seed(1)
     model = ref_mod.R21DBYOL(pretrain=False, num_classes=101, cls_bn=True)
     model.train()
-    x = structured_batch(4, 0)[0]
-    labels = torch.randint(0, 101, (4,), generator=torch.Generator().manual_seed(11))
+    x = structured_batch(B, 0)[0]
+    labels = torch.randint(0, 101, (B,), generator=torch.Generator().manual_seed(11))
     opt = torch.optim.SGD(model.parameters(), lr=0.025, momentum=0.9, weight_decay=1e-3)
-    out = dict(B=4, labels=labels.clone(), state_dict_keys=list(model.state_dict().keys()),
+    out = dict(B=B, labels=labels.clone(), state_dict_keys=list(model.state_dict().keys()),
                param_sum=sum(p.double().sum().item() for p in model.parameters()))
-    logits = model(x, o_type="ft_all")
-    loss = nn.CrossEntropyLoss()(logits, labels)
+    with (disk_offload(offload) if offload else contextlib.nullcontext()):
+        logits = model(x, o_type="ft_all")
+        loss = nn.CrossEntropyLoss()(logits, labels)
     opt.zero_grad()
     loss.backward()
     out["train"] = dict(loss=loss.item(), logits=logits.detach().clone(),
@@ -170,7 +202,7 @@ def run_finetune() -> dict:
     model.eval()
     with torch.no_grad():
         out["eval_logits_b1"] = model(x[:1], None, o_type="test").clone()
-        out["eval_logits_b4"] = model(x, None, o_type="test").clone()
+        out["eval_logits_b4"] = model(x[:4], None, o_type="test").clone()
     print(f"[ref finetune] loss {loss.item():.6f} eval argmax {out['eval_logits_b4'].argmax(1).tolist()}", flush=True)
     return out
 
@@ -190,4 +222,10 @@ if __name__ == "__main__":
         torch.save(run_reference(4, 2, True, structured_batch), os.path.join(gold, "step_struct_b4.pt"))
     if "finetune" in which:
         torch.save(run_finetune(), os.path.join(gold, "finetune_b4.pt"))
+    # BASELINE configs 3 / 4 at their full batch (opt-in: minutes of CPU and ~60 GB of scratch disk; one step, with layers)
+    scratch = os.environ.get("CSTP_GOLDEN_SCRATCH", "/tmp/cstp_golden_scratch")
+    if "b60" in which:
+        torch.save(run_reference(60, 1, True, structured_batch, offload=scratch), os.path.join(gold, "step_struct_b60.pt"))
+    if "finetune_b60" in which:
+        torch.save(run_finetune(60, offload=scratch), os.path.join(gold, "finetune_b60.pt"))
     print("golden fixtures written to", gold)

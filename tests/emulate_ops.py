@@ -60,8 +60,19 @@ def _store(out, out_f32, val, accumulate):
         out_f32.copy_(val)
 
 
+def _prologue(x, st):
+    """What the kernels' operand prologue feeds the tensor cores: relu(bn(x)) of the producer, rounded to the storage
+    type, per statistics group (equal parts of the N axis)."""
+    if st is None:
+        return x.float()
+    G, N = st.groups, x.shape[0]
+    xf = x.float().reshape(G, N // G, -1, x.shape[-1])
+    y = (xf * st.scale.view(G, 1, 1, -1) + st.shift.view(G, 1, 1, -1)).clamp_min(0)
+    return y.reshape(x.shape).to(x.dtype).float()
+
+
 def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, accumulate=False, n_tile=None, box=None,
-                  allow_halo=True, stats=None):       # stats: never fused here (plan.stat_blocks stays 0)
+                  allow_halo=True, stats=None, prologue=None):       # stats: never fused here (plan.stat_blocks stays 0)
     N, T, H, W, Ca = x.shape
     To, Ho, Wo = geom.out_dims(T, H, W)
     ref = out if out is not None else out_f32
@@ -73,7 +84,7 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
 
     def run():
         acc = torch.zeros(N, To, Ho, Wo, Np)
-        xf = x.float()
+        xf = _prologue(x, prologue)
         for (m, dw, dh, dt, ti) in taps:
             a = _gather(xf, maps[m], geom.stride, (dw, dh, dt), (Wo, Ho, To, N))
             acc += a @ w_packed[:Np, ti * Kc: ti * Kc + Ca].float().t()
@@ -122,13 +133,13 @@ def linear_plan(x, w_packed, out, *, out_f32=None, bias=None, accumulate=False):
 
 
 class _WgradSpec:
-    def __init__(self, x, g, geom, cout, cin):
-        self.x, self.g, self.geom, self.cout, self.cin = x, g, geom, cout, cin
+    def __init__(self, x, g, geom, cout, cin, prologue=None):
+        self.x, self.g, self.geom, self.cout, self.cin, self.prologue = x, g, geom, cout, cin, prologue
         self.plan = _Plan(lambda: None)
 
     def run(self, dw, accumulate=False):
         _count(2)
-        x, g, geom = self.x.float(), self.g.float(), self.geom
+        x, g, geom = _prologue(self.x, self.prologue), self.g.float(), self.geom
         N, T, H, W, Ci = x.shape
         _, To, Ho, Wo, Co = g.shape
         maps, taps = fwd_taps(geom)
@@ -140,11 +151,11 @@ class _WgradSpec:
         dw.copy_(dw + res if accumulate else res)
 
 
-def wgrad_plan(x, g, geom, cout, cin, partials, *, splits=None, box=None, sms=148):
+def wgrad_plan(x, g, geom, cout, cin, partials, *, splits=None, box=None, sms=148, prologue=None):
     need_chunks = geom.taps * (pad64(x.shape[-1]) // 64)
     if need_chunks > L.CSTP_MAX_MCHUNKS:
         raise L.CstpError("too many M chunks")
-    return _WgradSpec(x, g, geom, cout, cin)
+    return _WgradSpec(x, g, geom, cout, cin, prologue)
 
 
 def pack_weight(w, packed, *, transpose=False):
@@ -221,7 +232,7 @@ def bn_forward_stats(raw, st: BNState, gamma, beta, running_mean, running_var, e
             running_var.copy_((1 - momentum) * running_var + momentum * unb.float())
 
 
-def bn_apply(raw, st: BNState, out, *, relu, res=None, res_state=None):
+def bn_apply(raw, st: BNState, out, *, relu, res=None, res_state=None, res_relu=False):
     _count()
     x = _group_view(raw, st.groups).float()
     y = x * st.scale.view(st.groups, 1, -1) + st.shift.view(st.groups, 1, -1)
@@ -229,6 +240,8 @@ def bn_apply(raw, st: BNState, out, *, relu, res=None, res_state=None):
         r = _group_view(res, st.groups).float()
         if res_state is not None:
             r = r * res_state.scale.view(st.groups, 1, -1) + res_state.shift.view(st.groups, 1, -1)
+            if res_relu:
+                r = r.clamp_min(0).to(res.dtype).float()
         y = y + r
     if relu:
         y = y.clamp_min(0)

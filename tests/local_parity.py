@@ -51,7 +51,7 @@ def check_conv_units(eng, params, which="online"):
         # ---------------------------------------------------------------- convolution
         if u["x_is_col"]:
             rows = u["x"].shape[-2]
-            xin = _f(u["x"]).reshape(rows, -1)[:, :cin]
+            xin = _f(u["x_act"]).reshape(rows, -1)[:, :cin]
             raw_r = xin @ W.reshape(cout, -1).t()
             raw_e = _f(u["raw"]).reshape(rows, -1)[:, :cout]
             e["conv"] = rel(raw_e, raw_r)
@@ -60,7 +60,9 @@ def check_conv_units(eng, params, which="online"):
             raw_e5 = raw_e.reshape(N, rows // N, cout).permute(0, 2, 1).contiguous()
             to_eng = lambda t: t.permute(0, 2, 1).reshape(rows, cout)              # noqa: E731
         else:
-            xin = _ncdhw(u["x"], cin).requires_grad_(u["grads"] and not u["skip_dgrad"])
+            # (x_act: with the BatchNorm apply fused into this conv's operand path, u["x"] is the producer's raw output and
+            # x_act the activation the engine materialised for the tests -- the values the tensor cores consumed)
+            xin = _ncdhw(u["x_act"], cin).requires_grad_(u["grads"] and not u["skip_dgrad"])
             raw_r = F.conv3d(xin, W, None, geom.stride, geom.pad)
             raw_e5 = _ncdhw(u["raw"], cout)
             e["conv"] = rel(raw_e5, raw_r)
@@ -77,7 +79,7 @@ def check_conv_units(eng, params, which="online"):
                 r = _bn_groups(_ncdhw(u["res"], cout), params[ds["bnname"] + ".weight"], params[ds["bnname"] + ".bias"],
                                views)
             else:
-                r = _ncdhw(u["res"], cout)
+                r = _ncdhw(u["res_act"], cout)
             y = y + r
         act_e = None
         if u["act"] is not None:
@@ -130,7 +132,7 @@ def check_conv_units(eng, params, which="online"):
     for k, ref in dx_ref.items():
         t, C = dx_shape[k]
         name = next(n for n, v in eng.named.items() if torch.is_tensor(v) and v.data_ptr() == k and
-                    n.endswith((".act", ".out")))
+                    n.endswith((".act", ".out", ".raw")))
         out["dx:" + name] = {"dgrad": rel(_ncdhw(eng._dbuf(t), C), ref)}
     return out
 

@@ -134,3 +134,33 @@ def test_emulated_fused_step_and_frozen_backbone(emu):
     assert not c._engine.backbone_grads
     assert torch.equal(c.online_net.conv1.spatial_conv.weight, w0) and c.online_net.conv1.spatial_conv.weight.grad is None
     assert c.classify.weight.grad is not None and c.classify.weight.grad.abs().sum() > 0
+
+
+def test_emulated_fused_step_leaves_frozen_parameters_untouched(emu):
+    """ft_fc through the FUSED step: everything but `classify` is frozen (cls_bn included, r21d_byol.py:10-35); optim.SGD
+    never touches a parameter without a gradient, so neither weight decay nor momentum may move it."""
+    from cstp_b200.models.pace.r21d_byol import get_fine_tuning_parameters
+    B, T, S = 2, 4, 32
+    x = O.structured_batch(B, 1, T, S)[0]
+    labels = torch.tensor([3, 77])
+    a, b = _model(), _model()
+    a.train()
+    b.train()
+    get_fine_tuning_parameters(a, 5)
+    groups = get_fine_tuning_parameters(b, 5)
+    before = {n: p.detach().clone() for n, p in a.named_parameters()}
+    for _ in range(2):
+        a.finetune_step(x, labels, lr=LR, momentum=MOM, weight_decay=WD)
+    opt = torch.optim.SGD(groups, lr=LR, momentum=MOM, weight_decay=WD)
+    for _ in range(2):
+        lb = torch.nn.CrossEntropyLoss()(b(x, o_type="ft_fc"), labels)
+        opt.zero_grad()
+        lb.backward()
+        opt.step()
+    for n, p in a.named_parameters():
+        if n.startswith("classify."):
+            assert not torch.equal(p, before[n]), n
+        else:
+            assert torch.equal(p, before[n]), n               # backbone AND cls_bn: bit-identical
+    sa, sb = a.state_dict(), b.state_dict()
+    assert max(rel(sa[k], sb[k]) for k in sa if sa[k].dtype.is_floating_point) < 1e-5

@@ -40,6 +40,52 @@ def _opts(n_epochs):
                                  loss_weight=[0.1, 1.0, 1.0, 1.0, 1.0])
 
 
+def test_checkpoint_optimizer_entry_drives_a_real_torch_sgd(emulated_engine, tmp_path):
+    """main_byol.py:243-258 on a checkpoint written by save_checkpoint: the reference builds optim.SGD + the cosine
+    scheduler from opts, loads ck['optimizer'] (which REPLACES the parameter groups) and steps.  Every SGD hyper-parameter
+    therefore has to be in the saved group; the momentum buffers must land on the right parameters."""
+    from cstp_b200 import train as TR
+    from cstp_b200.models.pace.r21d_byol import R21DBYOL
+    from cstp_b200.scheduler.cosine_anneal import CosineAnnealingWarmupRestarts
+    from oracle.cstp_oracle import structured_batch
+    torch.manual_seed(1)
+    m = R21DBYOL(pretrain=True)
+    x1, x2, lab = structured_batch(2, 0, 4, 32)
+    m.train_step(x1, x2, lab, (0.1, 1, 1, 1, 1), lr=0.02)
+    path = tmp_path / "save_7.pth"
+    TR.save_checkpoint(str(path), torch.nn.DataParallel(m), 7, "r21d_byol-1", lr=0.02, initial_lr=0.03)   # wrapped: one prefix
+    ck = torch.load(path, weights_only=False)
+    assert all(k.startswith("module.") and not k.startswith("module.module.") for k in ck["state_dict"])
+    probe = R21DBYOL(pretrain=True)
+    probe.load_state_dict({k[len("module."):]: v for k, v in ck["state_dict"].items()})
+    opt = torch.optim.SGD(probe.parameters(), lr=0.03, momentum=0.9, weight_decay=5e-4)
+    opt.load_state_dict(ck["optimizer"])
+    g = opt.param_groups[0]
+    assert (g["lr"], g["momentum"], g["dampening"], g["weight_decay"], g["nesterov"]) == (0.02, 0.9, 0, 5e-4, False)
+    sched = CosineAnnealingWarmupRestarts(opt, first_cycle_steps=300, max_lr=0.03, min_lr=1e-5, warmup_steps=150, gamma=0.5)
+    names = [n for n, _ in probe.named_parameters()]
+    i = names.index("online_net.conv2.block1.conv1.spatial_conv.weight")
+    p = list(probe.parameters())[i]
+    buf = opt.state[p]["momentum_buffer"].clone()                # (SGD updates the buffer in place)
+    assert torch.equal(buf, m._engine.train.view(names[i], m._engine.mom).cpu())
+    assert all(list(probe.parameters())[j] not in opt.state for j, n in enumerate(names) if n.startswith("target_net."))
+    for q in probe.parameters():
+        if q.requires_grad:
+            q.grad = torch.zeros_like(q)
+    before = p.detach().clone()
+    opt.step()                                                  # KeyError here before the group carried its hyper-parameters
+    sched.step()
+    lr_used = 1e-5                                               # the scheduler's __init__ put the group at min_lr
+    want = before - lr_used * (0.9 * buf + 5e-4 * before)
+    assert torch.allclose(p.detach(), want, rtol=0, atol=1e-8)
+    # and back: the engine takes the momentum buffers of an optimizer state the reference wrote
+    m2 = R21DBYOL(pretrain=True)
+    m2._bind(x1)
+    TR.load_optimizer_state_dict(m2, opt.state_dict())
+    assert not m2._engine.first_step
+    assert torch.equal(m2._engine.train.view(names[i], m2._engine.mom), opt.state[p]["momentum_buffer"])
+
+
 @pytest.mark.gpu
 def test_checkpoint_save_resume_continues_bit_identically(tmp_path):
     from cstp_b200 import train as TR

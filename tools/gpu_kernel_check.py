@@ -111,6 +111,91 @@ def case_conv(N, T, H, W, cin, cout, kernel, stride, pad, check_dgrad=True, chec
     return res
 
 
+def case_prologue(N, T, H, W, cin, cout, kernel, stride, pad, with_stats=False, iters=10):
+    """Operand prologue (cstp_prologue): conv forward and weight gradient reading the producer's RAW output and applying
+    its BatchNorm affine + ReLU in shared memory, against the two-pass path (cstp_bn_apply, then the plain kernels).
+    Both feed the tensor cores the same bf16 values in the same order, so outputs must be bit-identical."""
+    import torch
+    from cstp_b200 import ops
+
+    geom = ops.ConvGeom(tuple(kernel), tuple(stride), tuple(pad))
+    Cip, Cop = ops.pad16(cin), ops.pad16(cout)
+    raw = _mk_act(N, T, H, W, cin, Cip, 1)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    rows = N * T * H * W
+    st = ops.BNState.alloc(cin, Cip, 2, rows // 2, "cuda")
+    sc = torch.zeros(2, Cip, device="cuda")
+    sh = torch.zeros(2, Cip, device="cuda")
+    sc[:, :cin] = torch.randn(2, cin, device="cuda", generator=gen)          # negative scales too (glorot'ed gamma)
+    sh[:, :cin] = torch.randn(2, cin, device="cuda", generator=gen) * 0.5
+    st.scale.copy_(sc.view(-1))
+    st.shift.copy_(sh.view(-1))
+    act = torch.empty_like(raw)
+    ops.bn_apply(raw, st, act, relu=True)
+    w = torch.randn(cout, cin, *kernel, device="cuda", generator=gen) / (cin * geom.taps) ** 0.5
+    wp = torch.empty(Cop, geom.taps * ops.pad64(Cip), device="cuda", dtype=torch.bfloat16)
+    ops.pack_weight(w, wp)
+    To, Ho, Wo = geom.out_dims(T, H, W)
+    res = {}
+    outs, sts, plans = [], [], []
+    for x, pro in ((act, None), (raw, st)):
+        out = torch.full((N, To, Ho, Wo, Cop), float("nan"), device="cuda", dtype=torch.bfloat16)
+        so = ops.BNState.alloc(cout, Cop, 2, N * To * Ho * Wo // 2, "cuda") if with_stats else None
+        plan = ops.conv_fwd_plan(x, wp, out, geom, stats=so, prologue=pro)
+        plan.run()
+        if so is not None:
+            res["stat_blocks"] = getattr(plan, "stat_blocks", 0)
+            gam, bet = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+            ops.bn_forward_stats(out, so, gam, bet, None, None, fused_blocks=getattr(plan, "stat_blocks", 0))
+        outs.append(out)
+        sts.append(so)
+        plans.append(plan)
+    torch.cuda.synchronize()
+    res["kernel"] = ops.kernel_name(plans[1])
+    res["fwd_nan"] = int(torch.isnan(outs[1].float()).sum().item())
+    res["fwd_equal"] = bool(torch.equal(outs[0], outs[1]))
+    res["fwd_rel"] = _rel(outs[1], outs[0])
+    if with_stats:
+        res["stats_equal"] = bool(torch.equal(sts[0].mean, sts[1].mean) and torch.equal(sts[0].invstd, sts[1].invstd))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for tag, plan in (("fwd_ms_plain", plans[0]), ("fwd_ms_fused", plans[1])):
+        for _ in range(2):
+            plan.run()
+        e0.record()
+        for _ in range(iters):
+            plan.run()
+        e1.record()
+        torch.cuda.synchronize()
+        res[tag] = e0.elapsed_time(e1) / iters
+    e0.record()
+    for _ in range(iters):
+        ops.bn_apply(raw, st, act, relu=True)
+    e1.record()
+    torch.cuda.synchronize()
+    res["bn_apply_ms"] = e0.elapsed_time(e1) / iters
+    # weight gradient
+    g = _mk_act(N, To, Ho, Wo, cout, Cop, 3)
+    part = torch.empty(64 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    dws = []
+    for tag, x, pro in (("wgrad_ms_plain", act, None), ("wgrad_ms_fused", raw, st)):
+        spec = ops.wgrad_plan(x, g, geom, cout, cin, part, prologue=pro)
+        dw = torch.full_like(w, float("nan"))
+        spec.run(dw)
+        torch.cuda.synchronize()
+        dws.append(dw)
+        e0.record()
+        for _ in range(iters):
+            spec.run(dw)
+        e1.record()
+        torch.cuda.synchronize()
+        res[tag] = e0.elapsed_time(e1) / iters
+        res["wgrad_kernel"] = ops.kernel_name(spec)
+    res["wgrad_nan"] = int(torch.isnan(dws[1]).sum().item())
+    res["wgrad_equal"] = bool(torch.equal(dws[0], dws[1]))
+    res["wgrad_rel"] = _rel(dws[1], dws[0])
+    return res
+
+
 def case_linear(B, cin, cout):
     import torch
     from cstp_b200 import ops
@@ -283,6 +368,18 @@ CASES = {
     "conv2_spatial_big": ("conv", dict(N=8, T=16, H=56, W=56, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
     "conv2_temporal_big": ("conv", dict(N=8, T=16, H=56, W=56, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0))),
     "conv3_spatial_big": ("conv", dict(N=8, T=8, H=28, W=28, cin=128, cout=288, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    # operand prologue (BatchNorm + ReLU applied to the staged operand): every kernel / layout that carries it
+    "pro_conv2_spatial": ("prologue", dict(N=2, T=4, H=56, W=56, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    "pro_conv2_temporal": ("prologue", dict(N=2, T=8, H=56, W=56, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True)),
+    "pro_stem_temporal": ("prologue", dict(N=2, T=8, H=56, W=56, cin=83, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True)),
+    "pro_conv3_temporal_s2": ("prologue", dict(N=2, T=8, H=28, W=28, cin=230, cout=128, kernel=(3, 1, 1), stride=(2, 1, 1), pad=(1, 0, 0))),
+    "pro_conv3_spatial": ("prologue", dict(N=2, T=4, H=28, W=28, cin=128, cout=288, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    "pro_conv3_temporal": ("prologue", dict(N=2, T=4, H=28, W=28, cin=288, cout=128, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0))),
+    "pro_conv4_spatial": ("prologue", dict(N=4, T=2, H=14, W=14, cin=256, cout=576, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    "pro_conv5_spatial": ("prologue", dict(N=6, T=2, H=7, W=7, cin=512, cout=1152, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    "pro_conv5_temporal": ("prologue", dict(N=6, T=2, H=7, W=7, cin=1152, cout=512, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0))),
+    "pro_ds_temporal": ("prologue", dict(N=2, T=8, H=28, W=28, cin=42, cout=128, kernel=(1, 1, 1), stride=(2, 1, 1), pad=(0, 0, 0))),
+    "pro_ragged": ("prologue", dict(N=2, T=3, H=10, W=6, cin=42, cout=85, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
     "linear_proj1": ("linear", dict(B=60, cin=512, cout=4096)),
     "linear_proj2": ("linear", dict(B=60, cin=4096, cout=512)),
     "linear_head": ("linear", dict(B=4, cin=1024, cout=5)),
@@ -293,7 +390,8 @@ CASES = {
 
 def run_case(name):
     kind, kw = CASES[name]
-    fn = {"conv": case_conv, "linear": case_linear, "elementwise": case_elementwise, "losses": case_losses}[kind]
+    fn = {"conv": case_conv, "linear": case_linear, "elementwise": case_elementwise, "losses": case_losses,
+          "prologue": case_prologue}[kind]
     return fn(**kw)
 
 
