@@ -113,12 +113,18 @@ def run_reference(args, rank: int):
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     v = Bs / sec
-    sample = f"{Bs} of the {args.batch} clips of one step per timed step (full 16x112x112 clips, full network)"
+    sample = (f"{Bs} full 16x112x112 clips per timed step through the full network -- a bounded sample of the native arm's "
+              f"{args.batch}-clip step (BatchNorm over {Bs} instead of {args.batch} samples; the cost per clip is the same)")
+    cfg = workload_config(args.batch, args.gpus)
+    # the config names the workload both arms are quoted on; what this arm actually ran per step is stated beside it
+    cfg.update({"sampled_batch": Bs, "same_config": Bs == args.batch,
+                "note": "one CPU process (rank 0) whatever --gpus says: the CPU arm does not scale with the GPU count, so "
+                        "ratios against it at N > 1 are not comparable"})
     emit({
         "impl": "reference", "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": v, "unit": "clips/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch, args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -149,6 +155,108 @@ def cpu_baseline(seconds_budget: float = 25.0) -> dict:
             "sample": f"oracle/cstp_oracle.pretrain_step on {Bs} full 16x112x112 clips, {len(times) - 1} timed steps after 1 warm-up"}
 
 
+def config5_record(args, rank: int, world: int) -> dict | None:
+    """BASELINE config 5 (Kinetics-400 recipe, README.md:41-49): GLOBAL batch 128 split contiguous-by-rank (utils.py:111),
+    BatchNorm statistics over every rank (north-star SyncBN; row exchange over NVLink peer memory), NT-Xent over the
+    all-gathered projector outputs of both views (global negatives, loss/NTXent.py with batch_size = the global batch,
+    main_byol.py:191-196), gradient all-reduce.  Timed like the main arm; beside it (a) the same build's one-GPU step at
+    the same per-GPU batch without any cross-rank exchange -- the denominator of a scaling efficiency -- and (b) the first
+    step from the seeded init compared with ONE GPU stepping the whole global batch (N x 128/N == 1 x 128)."""
+    import gc
+    import torch.distributed as dist
+    from cstp_b200 import parallel
+    from cstp_b200.models.pace.r21d_byol import R21DBYOL
+    from cstp_b200.synthetic import synthetic_batch
+    GB = 128
+    b = parallel.per_rank_batch(GB, world)
+    lo, hi = parallel.shard_bounds(GB, rank, world)
+    gx1, gx2, glab = synthetic_batch(GB, seed=0)
+    x1, x2 = gx1[lo:hi].contiguous().cuda(), gx2[lo:hi].contiguous().cuda()
+    lab = tuple(l[lo:hi].contiguous().cuda() for l in glab)
+    nx = {"weight": 1.0, "temperature": 0.1}
+    sync = parallel.GradSync()
+    try:
+        bn, bn_name = parallel.BnSyncP2P(), "world-p2p (one peer-memory exchange kernel per BatchNorm call)"
+    except Exception as e:  # noqa: BLE001   symmetric memory unavailable: the NCCL all-reduce path
+        bn, bn_name = parallel.BnSync(), f"world-nccl (all-reduce per BatchNorm call; peer-memory path unavailable: {e})"
+
+    def make(opts):
+        torch.manual_seed(1)
+        m = R21DBYOL(pretrain=True).cuda()
+        m.engine_options = opts
+        return m
+
+    def step(m, a, c, lb, gs):
+        return m.train_step(a, c, lb, LOSS_WEIGHT, lr=0.09, momentum=0.9, weight_decay=5e-4, clip_grad_norm=18.0, grad_sync=gs)
+
+    def timed(m, gs):
+        for _ in range(max(args.warmup, 3)):
+            step(m, x1, x2, lab, gs)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(m, x1, x2, lab, gs)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / args.steps
+
+    # ---- data parallel, world statistics, gathered NT-Xent
+    dp = make({"bn_sync": bn, "ntxent": {**nx, "gather": True}})
+    first = step(dp, x1, x2, lab, sync).clone()
+    first_nx = dp._engine.ntxent_loss.clone()
+    mean_first = first.clone()
+    dist.all_reduce(mean_first)
+    mean_first /= world
+    ms_dp = timed(dp, sync)
+    if hasattr(bn, "check"):
+        bn.check()                        # a timed-out peer exchange must not produce a number
+    del dp
+    gc.collect()
+    torch.cuda.empty_cache()
+    # ---- denominator: the same per-GPU batch on one GPU, nothing exchanged
+    local = make({"ntxent": dict(nx)})
+    ms_local = timed(local, None)
+    del local
+    gc.collect()
+    torch.cuda.empty_cache()
+    # ---- parity: one GPU steps the whole global batch once
+    parity = None
+    if rank == 0:
+        whole = make({"ntxent": dict(nx)})
+        w = step(whole, gx1.cuda(), gx2.cuda(), tuple(l.cuda() for l in glab), None).cpu()
+        wnx = whole._engine.ntxent_loss.item()
+        mf = mean_first.cpu()
+        tot = lambda v, n: LOSS_WEIGHT[0] * v[7].item() + v[6].item() + nx["weight"] * n     # noqa: E731
+        parity = {"what": f"first step from the seeded init: {world} ranks x {b} samples vs ONE GPU x {GB} samples "
+                          "(same clips, labels and weights)",
+                  "loss_total_dp": tot(mf, first_nx.item()), "loss_total_one_gpu": tot(w, wnx),
+                  "loss_total_rel": abs(tot(mf, first_nx.item()) - tot(w, wnx)) / abs(tot(w, wnx)),
+                  "loss_byol_dp": mf[7].item(), "loss_byol_one_gpu": w[7].item(),
+                  "ntxent_dp": first_nx.item(), "ntxent_one_gpu": wnx,
+                  "ce_rel_max": max(abs(mf[i].item() - w[i].item()) / abs(w[i].item()) for i in range(6))}
+        del whole
+        gc.collect()
+        torch.cuda.empty_cache()
+    dist.barrier()
+    if rank != 0:
+        return None
+    return {"workload": "r21d_byol Kinetics-400-shaped pretrain step (Kin400RepreLMDB shape), GLOBAL batch 128, 2 views x "
+                        "3x16x112x112, SyncBN over all ranks + NT-Xent (tau 0.1, weight 1) on the all-gathered projector "
+                        "outputs, SGD lr 0.09 m 0.9 wd 5e-4 clip 18",
+            "global_batch": GB, "per_gpu_batch": b, "parallelism": f"dp{world}", "scaling": "strong", "bn_sync": bn_name,
+            "ntxent": {"rows": 2 * GB, "d": 512, "gather": "all_gather of 2 x (per_gpu_batch, 512) per step"},
+            "ms_per_step": ms_dp, "value": GB / (ms_dp * 1e-3), "unit": "clips/s",
+            "denominator": {"what": "same build, ONE GPU, the same per-GPU batch, per-GPU BatchNorm, local NT-Xent, no collective "
+                                    "(max over ranks); N x its rate is the ceiling of this configuration",
+                            "ms_per_step": ms_local, "clips_per_s_times_n": world * b / (ms_local * 1e-3)},
+            "parity": parity}
+
+
 _JSON_OUT = None
 
 
@@ -170,21 +278,24 @@ def emit(line: dict) -> None:
 
 
 def ncu_traffic(kernel: str, B: int):
-    """Average DRAM bytes (read + write) per launch of `kernel` from the committed ncu capture of this command at the same
-    per-GPU batch (profiles/r01_ncu_<kernel>_b<B>_dram.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch);
-    None when no capture exists for this batch size."""
+    """(bytes, source): average DRAM bytes (read + write) per launch of `kernel` from the newest committed ncu capture of
+    this command at the same per-GPU batch (profiles/rNN_ncu_<kernel>_b<B>_dram.csv: dram__bytes_read.sum +
+    dram__bytes_write.sum per launch), or (None, None).  The number is NOT measured in this run: `source` names the file
+    so that a reader can check it against the kernel revision."""
     import csv
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
-                        "r01_ncu_%s_b%d_dram.csv" % (kernel.replace("_kernel", ""), B))
-    if not os.path.exists(path):
-        return None
+    import glob
+    pat = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                       "r[0-9][0-9]_ncu_%s_b%d_dram.csv" % (kernel.replace("_kernel", ""), B))
+    paths = sorted(glob.glob(pat))
+    if not paths:
+        return None, None
     total, ids = 0.0, set()
-    with open(path) as f:
+    with open(paths[-1]) as f:
         for r in csv.reader(f):
             if len(r) > 10 and r[0].isdigit() and r[-3].startswith("dram__bytes_"):
                 total += float(r[-1].replace(",", ""))
                 ids.add(r[0])
-    return total / len(ids) if ids else None
+    return (total / len(ids) if ids else None), os.path.relpath(paths[-1], os.path.dirname(os.path.abspath(__file__)))
 
 
 def main():
@@ -196,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the BASELINE config 5 sub-record")
     ap.add_argument("--bn-sync", default="local", choices=["local", "world", "world-p2p"],
                     help="local: per-GPU BatchNorm statistics (the reference's behaviour); world: SyncBN over all ranks")
     args = ap.parse_args()
@@ -261,6 +373,9 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item() / args.steps
+    bs = getattr(model, "engine_options", {}).get("bn_sync")
+    if hasattr(bs, "check"):
+        bs.check()                        # a timed-out peer exchange must not produce a number
     clk = clocks.stop() if rank == 0 else None
     final = losses.tolist()
 
@@ -309,17 +424,26 @@ def main():
         dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
         ach = kern[dom]["tflops"]
         tensor_ms = sum(k["ms_per_step"] for k in kern.values())
+        traffic, traffic_src = ncu_traffic(dom, B)
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": ncu_traffic(dom, B),
+                "frac": ach / pk["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_how": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum averaged over the kernel's launches "
-                               "of one step in the committed ncu capture profiles/r01_ncu_<kernel>_b<batch>_dram.csv (null: no "
-                               "capture at this batch)",
+                               "of one step in a COMMITTED ncu capture of this command (traffic_source; not measured in this "
+                               "run; null: no capture at this batch)",
                 "peak_source": pk["src"] + " sustained bf16 cuBLAS matmul (kernel timed inside a long step)",
                 "how": "CUDA events on the launching stream around every launch of the kernel in one extra instrumented "
                        "step; achieved = sum over its launches of 2*M*N*K (true channel counts) / sum of durations",
                 "kernels": kern,
                 "all_tensor_kernels_tflops": B * FLOPS_PER_SAMPLE / (tensor_ms * 1e-3) / 1e12,
                 "step_tflops": B * FLOPS_PER_SAMPLE / (ms_step * 1e-3) / 1e12}
+    c5 = None
+    if world > 1 and not args.no_config5:
+        eng = None                        # (rank 0's handle from the roofline block) the batch-60 engine must go first
+        del model
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        c5 = config5_record(args, rank, world)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -344,6 +468,8 @@ def main():
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         "losses_last_step": {"byol": final[7], "ce": final[:6]},
     }
+    if c5 is not None:
+        line["config5"] = c5
     emit(line)
     if world > 1:
         dist.destroy_process_group()

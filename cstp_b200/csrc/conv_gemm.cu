@@ -14,7 +14,7 @@
 namespace cstp {
 
 constexpr int kConvThreads = 256;
-constexpr int kConvXformThreads = 128;      // warps 8..11: operand prologue (BatchNorm affine + ReLU on the staged A box)
+constexpr int kConvXformThreads = 256;      // warps 8..15: operand prologue (BatchNorm affine + ReLU on the staged A box)
 constexpr uint32_t kABytes = 128 * 64 * 2;  // one A stage: 128 positions x 64 bf16 channels
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;  // 227 KB
@@ -181,12 +181,16 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     }
   } else if (kXform && warp >= 8) {
     // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU in place
-    // Thread t owns the 16-byte units t, t + 128, ... of every staged A box (one swizzle phase = one 8-channel vector of
-    // the chunk).  Box rows run (w, h, t, n): the rows of samples below Nt / 2 take the coefficients of statistics group 0,
-    // the others those of group 1.
+    // Thread t owns the 16-byte units t, t + 256, ... of every staged A box (one swizzle phase = one 8-channel vector of
+    // the chunk; coefficients from a table built once in shared memory).  Box rows run (w, h, t, n): the rows of samples
+    // below Nt / 2 take the coefficients of statistics group 0, the others those of group 1.
     const uint32_t tid = threadIdx.x - kConvThreads;
     const uint32_t smem_addr0 = smem_u32(smem);
-    const int n_taps = p.n_taps, chunks_per_tap = p.chunks_per_tap, stages = p.stages, Cp = p.pro_cp;
+    const int n_taps = p.n_taps, chunks_per_tap = p.chunks_per_tap, stages = p.stages;
+    float* xtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    xform_table_fill<kConvXformThreads>(xtab, p.pro_scale, p.pro_shift, p.pro_groups, p.pro_cp, tid);
+    xform_bar_sync<kConvXformThreads>();
+    const uint32_t xtab_addr = smem_u32(xtab);
     const int rows_per_n = p.bw * p.bh * p.bt;
     constexpr uint32_t kUnits = kABytes / 16;
     int stage = 0;
@@ -201,10 +205,10 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
       for (int t = 0; t < n_taps; ++t) {
         for (int c = 0; c < chunks_per_tap; ++c) {
           const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
-          const int ch = c * 64 + xform_unit_channel(s_addr + tid * 16u, 7u);
+          const int cj = xform_unit_channel(s_addr + tid * 16u, 7u);
           XformCoef k0, k1;
-          if (split > 0) xform_load(k0, p.pro_scale, p.pro_shift, ch, Cp);
-          if (split < kUnits) xform_load(k1, p.pro_scale + Cp, p.pro_shift + Cp, ch, Cp);
+          if (split > 0) xform_load_smem(k0, xtab_addr, chunks_per_tap, 0, c, cj);
+          if (split < kUnits) xform_load_smem(k1, xtab_addr, chunks_per_tap, 1, c, cj);
           mbar_wait(&full[stage], phase);
           if (split > 0) xform_span<kConvXformThreads>(s_addr, tid, split, k0);
           if (split < kUnits) xform_span<kConvXformThreads>(s_addr, xform_first<kConvXformThreads>(split, tid), kUnits, k1);
@@ -419,7 +423,8 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   }
   const uint32_t stage_bytes = kABytes + k.b_bytes;
   const int bar_bytes = 256;       // 5 + 3 * kMaxStages mbarriers + the TMEM slot
-  int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
+  const int xtab_bytes = xform ? static_cast<int>(xform_table_bytes(d->pro.groups, d->pro.Cp)) : 0;      // prologue coefficient table
+  int stages = (smem_budget() - 1024 - bar_bytes - xtab_bytes) / static_cast<int>(stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     delete plan;
@@ -429,7 +434,7 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   int cols = 32;
   while (cols < 2 * d->n_tile) cols *= 2;
   k.tmem_cols = cols;
-  plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes;
+  plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes + xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
   const long long total = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n * k.n_ntiles;
   const int sms = num_sms();

@@ -16,7 +16,7 @@
 namespace cstp {
 
 constexpr int kHcThreads = 256;
-constexpr int kHcXformThreads = 128;
+constexpr int kHcXformThreads = 256;     // warps 8..15: operand prologue
 constexpr int kHcMaxStages = 8;
 constexpr int kHcSmemLimit = 232448;
 constexpr int kHcMaxGroups = 4;
@@ -57,6 +57,7 @@ struct ConvHaloKParams {
   const float* pro_scale;  // fp32 [pro_groups][pro_cp]
   const float* pro_shift;
   int pro_groups, pro_cp;
+  uint32_t xtab_off;       // byte offset (from the mbarrier block) of the prologue's coefficient table in shared memory
   __nv_bfloat16* out;
   float* out_f32;
   const float* bias;
@@ -108,7 +109,7 @@ __device__ __forceinline__ void stats_flush(float (&acc)[128], float* wsum, floa
   for (int i = 0; i < 128; ++i) acc[i] = 0.f;
 }
 
-// kXform: four more warps (8..11) rewrite every staged activation box in place -- BatchNorm affine + ReLU of the producing
+// kXform: eight more warps (8..15) rewrite every staged activation box in place -- BatchNorm affine + ReLU of the producing
 // unit (ptx.cuh) -- between the TMA arrival (full[]) and the MMA issue (xfull[]).
 template <bool kStats, bool kXform>
 __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThreads, 1)
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
   // registers and wraps every UTCHMMA in an ELECT / R2UR loop: the issuer then ran at ~25 cycles per instruction and
   // the N=64 layers sat at 19% tensor-pipe activity, ncu r01_conv_halo.)
   if (warp < 4) {
-   if constexpr (kRealloc) warpgroup_reg_dec<112>();
+   if constexpr (kRealloc) warpgroup_reg_dec<120>();
    if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
@@ -308,14 +309,18 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     }
    }
   } else if (kXform && warp >= 8) {
-    if constexpr (kRealloc) warpgroup_reg_dec<112>();
+    if constexpr (kRealloc) warpgroup_reg_dec<88>();
     // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU in place
-    // Thread t owns the 16-byte units t, t + 128, ... of every staged box: a fixed swizzle phase, i.e. one 8-channel
-    // vector of the chunk, whose coefficients are fetched (L1 / L2) while the TMA load is still in flight.
+    // Thread t owns the 16-byte units t, t + 256, ... of every staged box: a fixed swizzle phase, i.e. one 8-channel
+    // vector of the chunk, whose coefficients come from a table the transform warps build once in shared memory.
     const uint32_t tid = threadIdx.x - kHcThreads;
+    float* xtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + p.xtab_off);
+    xform_table_fill<kHcXformThreads>(xtab, p.pro_scale, p.pro_shift, p.pro_groups, p.pro_cp, tid);
+    xform_bar_sync<kHcXformThreads>();
+    const uint32_t xtab_addr = smem_u32(xtab);
     const uint32_t stage_addr0 = smem_u32(stage0);
     const uint32_t stage_bytes = p.stage_bytes;
-    const int n_groups = p.n_groups, chunks = p.chunks, stages = p.stages, Cp = p.pro_cp;
+    const int n_groups = p.n_groups, chunks = p.chunks, stages = p.stages;
     const bool has_tail = p.tail != 0;
     const uint32_t units_full = p.a_bytes >> 4, units_tail = p.a_bytes_tail >> 4;
     const uint32_t mask_tail = p.tail == 16 ? 1u : 3u;
@@ -325,14 +330,12 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       const int n0 = tile / slab;
       const int grp = (p.pro_groups == 2 && 2 * n0 >= p.Nt) ? 1 : 0;
-      const float* sc = p.pro_scale + grp * Cp;
-      const float* sh = p.pro_shift + grp * Cp;
       for (int g = 0; g < n_groups; ++g) {
         for (int c = 0; c < chunks; ++c) {
           const bool tl = has_tail && c == chunks - 1;
           const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
           XformCoef k;
-          xform_load(k, sc, sh, c * 64 + xform_unit_channel(s_addr + tid * 16u, tl ? mask_tail : 7u), Cp);
+          xform_load_smem(k, xtab_addr, chunks, grp, c, xform_unit_channel(s_addr + tid * 16u, tl ? mask_tail : 7u));
           mbar_wait(&full[stage], phase);
           xform_span<kHcXformThreads>(s_addr, tid, tl ? units_tail : units_full, k);
           fence_proxy_async();
@@ -616,6 +619,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
     return fail_inval("fused statistics need Np == n_tile == 64, bn == 1, a plain aligned bf16 output and 1 or 2 groups dividing N");
   }
   const int stats_bytes = d->stats_partials != nullptr ? 3072 : 0;
+  const int xtab_bytes = xform ? static_cast<int>(xform_table_bytes(d->pro.groups, d->pro.Cp)) : 0;
   int max_group_taps = 0, seen = 0;
   for (int g = 0; g < d->n_groups; ++g) {
     const cstp_halo_group& gr = d->groups[g];
@@ -669,7 +673,8 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   // shared-memory plan: resident weights when every K-block of this N tile fits beside >= 3 activation stages
   const int bar_bytes = 256;
   const long long res_all = 1LL * d->n_taps * k.tap_bytes;
-  const long long budget = smem_budget() - 1024 - bar_bytes - stats_bytes;
+  const long long budget = smem_budget() - 1024 - bar_bytes - stats_bytes - xtab_bytes;
+  k.xtab_off = static_cast<uint32_t>(bar_bytes + stats_bytes);
   if (d->allow_resident && res_all + (pitch == 8 ? 3LL : 2LL) * k.a_stride <= budget) {
     k.resident = 1;
     k.res_bytes = static_cast<uint32_t>(res_all);
@@ -689,7 +694,8 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   int cols = 32;
   while (cols < 2 * d->n_tile) cols *= 2;
   k.tmem_cols = cols;
-  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) + bar_bytes + stats_bytes;
+  plan->smem_bytes = 1024 + static_cast<int>(k.res_bytes) + stages * static_cast<int>(k.stage_bytes) + bar_bytes + stats_bytes +
+                     xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
   const int n_ntiles = ceil_div(d->Np, d->n_tile);
   const long long m_tiles = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;

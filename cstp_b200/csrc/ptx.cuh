@@ -416,23 +416,70 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // Transforms the units [first, end) of the box at shared address `base` that belong to this thread: first, first + kStep,
-// ...  (kStep = participating threads; kStep * 16 must be a multiple of 1024).  Four independent units in flight.
+// ...  (kStep = participating threads; kStep * 16 must be a multiple of 1024).  Every load of a batch of (up to) four units
+// is issued before the first result is needed -- the loop is latency bound, not throughput bound (ncu: the transform
+// warps of the first version sat on the LDS scoreboard while the issue slots were 35 % busy).
 template <int kStep>
 __device__ __forceinline__ void xform_span(uint32_t base, uint32_t first, uint32_t end, const XformCoef& k) {
   static_assert((kStep * 16) % 1024 == 0, "thread stride must keep the swizzle phase");
+  constexpr uint32_t kB = kStep * 16u;
   uint32_t u = first;
   for (; u + 3 * kStep < end; u += 4 * kStep) {
     const uint32_t a = base + u * 16u;
-    const uint4 v0 = lds128(a), v1 = lds128(a + kStep * 16u), v2 = lds128(a + 2u * kStep * 16u), v3 = lds128(a + 3u * kStep * 16u);
+    const uint4 v0 = lds128(a), v1 = lds128(a + kB), v2 = lds128(a + 2u * kB), v3 = lds128(a + 3u * kB);
     sts128(a, xform_unit(v0, k));
-    sts128(a + kStep * 16u, xform_unit(v1, k));
-    sts128(a + 2u * kStep * 16u, xform_unit(v2, k));
-    sts128(a + 3u * kStep * 16u, xform_unit(v3, k));
+    sts128(a + kB, xform_unit(v1, k));
+    sts128(a + 2u * kB, xform_unit(v2, k));
+    sts128(a + 3u * kB, xform_unit(v3, k));
   }
-  for (; u < end; u += kStep) {
+  if (u < end) {                    // one to three units left: same shape, predicated
     const uint32_t a = base + u * 16u;
-    sts128(a, xform_unit(lds128(a), k));
+    const bool p1 = u + kStep < end, p2 = u + 2 * kStep < end;
+    uint4 v0 = lds128(a), v1 = v0, v2 = v0;
+    if (p1) v1 = lds128(a + kB);
+    if (p2) v2 = lds128(a + 2u * kB);
+    sts128(a, xform_unit(v0, k));
+    if (p1) sts128(a + kB, xform_unit(v1, k));
+    if (p2) sts128(a + 2u * kB, xform_unit(v2, k));
   }
+}
+
+// Coefficient table in shared memory, filled once per CTA by the transform warps: for every statistics group, 64-channel
+// chunk c and 8-channel vector j one record {scale[8], shift[8]} (zeros beyond Cp), so that a thread fetches the
+// coefficients of a staged box with four LDS.128 instead of four L2 round trips per stage.  Records are 80 bytes apart:
+// the eight records of a chunk (the eight vectors the lanes of a warp ask for) then start in eight different 16-byte
+// bank groups and every LDS.128 of the fetch is ONE conflict-free broadcast wavefront (with 64-byte records it was a
+// 4-way conflict, as much shared-memory time as the data of the box itself).
+constexpr uint32_t kXformRec = 80;                                  // bytes per record
+__host__ __device__ __forceinline__ uint32_t xform_table_bytes(int groups, int Cp) {
+  return static_cast<uint32_t>(groups * ((Cp + 63) / 64) * 8) * kXformRec;
+}
+template <int kThreads>
+__device__ __forceinline__ void xform_table_fill(float* tbl, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                 int groups, int Cp, uint32_t tid) {
+  const int chunks = (Cp + 63) / 64;
+  const int total = groups * chunks * 64;
+  for (int i = static_cast<int>(tid); i < total; i += kThreads) {
+    const int g = i / (chunks * 64), ch = i % (chunks * 64);
+    const bool in = ch < Cp;
+    float* rec = tbl + (static_cast<size_t>(g * chunks + ch / 64) * 8 + (ch % 64) / 8) * (kXformRec / 4) + (ch % 8);
+    rec[0] = in ? __ldg(scale + g * Cp + ch) : 0.f;
+    rec[8] = in ? __ldg(shift + g * Cp + ch) : 0.f;
+  }
+}
+// Record of (group g, chunk c, channel offset cj = 8 * j inside the chunk); tbl_addr is the table's shared address.
+__device__ __forceinline__ void xform_load_smem(XformCoef& k, uint32_t tbl_addr, int chunks, int g, int c, int cj) {
+  const uint32_t a = tbl_addr + static_cast<uint32_t>((g * chunks + c) * 8 + (cj >> 3)) * kXformRec;
+  const uint4 s0 = lds128(a), s1 = lds128(a + 16u), b0 = lds128(a + 32u), b1 = lds128(a + 48u);
+  k.s[0] = __uint_as_float(s0.x); k.s[1] = __uint_as_float(s0.y); k.s[2] = __uint_as_float(s0.z); k.s[3] = __uint_as_float(s0.w);
+  k.s[4] = __uint_as_float(s1.x); k.s[5] = __uint_as_float(s1.y); k.s[6] = __uint_as_float(s1.z); k.s[7] = __uint_as_float(s1.w);
+  k.b[0] = __uint_as_float(b0.x); k.b[1] = __uint_as_float(b0.y); k.b[2] = __uint_as_float(b0.z); k.b[3] = __uint_as_float(b0.w);
+  k.b[4] = __uint_as_float(b1.x); k.b[5] = __uint_as_float(b1.y); k.b[6] = __uint_as_float(b1.z); k.b[7] = __uint_as_float(b1.w);
+}
+// Named barrier among the transform warps only (id 2; the statistics epilogue uses id 1).
+template <int kThreads>
+__device__ __forceinline__ void xform_bar_sync() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
 }
 // Smallest u >= lo with u == tid (mod kStep).
 template <int kStep>

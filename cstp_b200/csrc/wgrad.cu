@@ -12,7 +12,7 @@
 namespace cstp {
 
 constexpr int kWgThreads = 256;
-constexpr int kWgXformThreads = 192;   // warps 2..7 run the operand prologue during the main loop
+constexpr int kWgXformThreads = 256;   // warps 8..15: operand prologue (BatchNorm affine + ReLU on the staged X boxes)
 constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // 64 positions x 64 channels
 constexpr int kWgMaxStages = 8;
 constexpr int kWgSmemLimit = 232448;
@@ -34,7 +34,7 @@ struct WgradKParams {
 };
 
 template <bool kXform>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
+__global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = 2 * kBoxBytes;
@@ -76,13 +76,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (kXform && warp >= 2) {
+  if (kXform && warp >= 8) {
     // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU on X in place
-    // Thread t owns the 16-byte units t, t + 192, ... of the (up to) two staged X boxes; box rows run (w, h, t, n): rows of
-    // samples below Nt / 2 take the coefficients of statistics group 0, the others those of group 1.
-    const uint32_t tid = threadIdx.x - 64;
+    // Thread t owns the 16-byte units t, t + 256, ... of the (up to) two staged X boxes (coefficients from a table built
+    // once in shared memory); box rows run (w, h, t, n): rows of samples below Nt / 2 take the coefficients of statistics
+    // group 0, the others those of group 1.
+    const uint32_t tid = threadIdx.x - kWgThreads;
     const uint32_t smem_addr0 = smem_u32(smem);
-    const int Cp = p.pro_cp, stages = p.stages;
+    const int stages = p.stages;
+    const int tchunks = (p.pro_cp + 63) / 64;
+    float* xtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    xform_table_fill<kWgXformThreads>(xtab, p.pro_scale, p.pro_shift, p.pro_groups, p.pro_cp, tid);
+    xform_bar_sync<kWgXformThreads>();
+    const uint32_t xtab_addr = smem_u32(xtab);
     const int rows_per_n = p.bw * p.bh * p.bt;
     const int kb_per_n = p.tiles_w * p.tiles_h * p.tiles_t;
     constexpr uint32_t kUnits = kBoxBytes / 16;
@@ -100,8 +106,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
       const int cj = xform_unit_channel(s_addr + tid * 16u, 7u);
       XformCoef k0[2], k1[2];
       for (int b = 0; b < nchunks; ++b) {
-        if (split > 0) xform_load(k0[b], p.pro_scale, p.pro_shift, c_off[b] + cj, Cp);
-        if (split < kUnits) xform_load(k1[b], p.pro_scale + Cp, p.pro_shift + Cp, c_off[b] + cj, Cp);
+        if (split > 0) xform_load_smem(k0[b], xtab_addr, tchunks, 0, c_off[b] >> 6, cj);
+        if (split < kUnits) xform_load_smem(k1[b], xtab_addr, tchunks, 1, c_off[b] >> 6, cj);
       }
       mbar_wait(&full[stage], phase);
       for (int b = 0; b < nchunks; ++b) {
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4;
     const int row = q * 32 + lane;
     const bool valid = (row >> 6) < nchunks;
@@ -313,7 +319,7 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   k.Nt = d->Nt;
   for (int i = 0; i < d->n_mchunks; ++i) {
     const cstp_mchunk& mc = d->mchunks[i];
-    if (mc.map_id < 0 || mc.map_id >= d->n_amaps || mc.c_off < 0 || mc.c_off % 8 != 0) {
+    if (mc.map_id < 0 || mc.map_id >= d->n_amaps || mc.c_off < 0 || mc.c_off % 8 != 0 || (xform && mc.c_off % 64 != 0)) {
       delete plan;
       return fail_inval("mchunk map_id / c_off out of range");
     }
@@ -321,13 +327,14 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   }
   const uint32_t stage_bytes = (2u + static_cast<uint32_t>(k.n_gboxes)) * kBoxBytes;
   const int bar_bytes = 256;
-  int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(stage_bytes);
+  const int xtab_bytes = xform ? static_cast<int>(xform_table_bytes(d->pro.groups, d->pro.Cp)) : 0;      // prologue coefficient table
+  int stages = (smem_budget() - 1024 - bar_bytes - xtab_bytes) / static_cast<int>(stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   k.stages = stages;
   int cols = 32;
   while (cols < d->n_tile) cols *= 2;
   k.tmem_cols = cols;
-  plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes;
+  plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes + xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
   plan->grid = dim3(static_cast<unsigned>(ceil_div(d->n_mchunks, 2)), static_cast<unsigned>(ceil_div(d->Np, d->n_tile)),
                     static_cast<unsigned>(splits));
@@ -346,7 +353,7 @@ extern "C" int cstp_wgrad_plan_run(const cstp_wgrad_plan* plan, void* stream) {
     attr_set = true;
   }
   if (plan->kp.pro_scale != nullptr)
-    wgrad_gemm_kernel<true><<<plan->grid, kWgThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+    wgrad_gemm_kernel<true><<<plan->grid, kWgThreads + kWgXformThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   else
     wgrad_gemm_kernel<false><<<plan->grid, kWgThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();

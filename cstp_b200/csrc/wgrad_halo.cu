@@ -17,7 +17,7 @@
 namespace cstp {
 
 constexpr int kWhThreads = 256;
-constexpr int kWhXformThreads = 192;   // warps 2..7 run the operand prologue during the main loop (the epilogue warps idle there)
+constexpr int kWhXformThreads = 256;   // warps 8..15: operand prologue (BatchNorm affine + ReLU on the staged X boxes)
 constexpr int kWhMaxStages = 8;
 constexpr int kWhSmemLimit = 232448;
 constexpr int kWhMaxMtiles = 16;
@@ -54,7 +54,7 @@ struct WgradHaloKParams {
 };
 
 template <bool kXform>
-__global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloKParams p) {
+__global__ void __launch_bounds__(kXform ? kWhThreads + kWhXformThreads : kWhThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
@@ -93,28 +93,32 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (kXform && warp >= 2) {
+  if (kXform && warp >= 8) {
     // ------------------------------------------------------------ operand prologue: BatchNorm affine + ReLU on X in place
-    // Thread t owns the 16-byte units t, t + 192, ... of every staged X box (one swizzle phase = one 8-channel vector of
-    // the box's chunk); one K-block is one sample (bn == 1), hence one statistics group.
-    const uint32_t tid = threadIdx.x - 64;
+    // Thread t owns the 16-byte units t, t + 256, ... of every staged X box (one swizzle phase = one 8-channel vector of
+    // the box's chunk; coefficients from a table built once in shared memory); one K-block is one sample (bn == 1),
+    // hence one statistics group.
+    const uint32_t tid = threadIdx.x - kWhThreads;
     const uint32_t smem_addr0 = smem_u32(smem);
-    const int slab = p.tiles_w * p.tiles_h * p.tiles_t, Cp = p.pro_cp, n_xboxes = p.n_xboxes, stages = p.stages;
+    const int slab = p.tiles_w * p.tiles_h * p.tiles_t, n_xboxes = p.n_xboxes, stages = p.stages;
+    const int tchunks = (p.pro_cp + 63) / 64;
+    float* xtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    xform_table_fill<kWhXformThreads>(xtab, p.pro_scale, p.pro_shift, p.pro_groups, p.pro_cp, tid);
+    xform_bar_sync<kWhXformThreads>();
+    const uint32_t xtab_addr = smem_u32(xtab);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       const int n0 = kb / slab;
       const int grp = (p.pro_groups == 2 && 2 * n0 >= p.Nt) ? 1 : 0;
-      const float* sc = p.pro_scale + grp * Cp;
-      const float* sh = p.pro_shift + grp * Cp;
       const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * p.stage_bytes;
       const int cj = xform_unit_channel(s_addr + tid * 16u, 7u);       // boxes are 1024-byte aligned: the same for all
       XformCoef k;
-      xform_load(k, sc, sh, p.xboxes[0].c_off + cj, Cp);
+      xform_load_smem(k, xtab_addr, tchunks, grp, p.xboxes[0].c_off >> 6, cj);
       mbar_wait(&full[stage], phase);
       for (int b = 0; b < n_xboxes; ++b) {
         xform_span<kWhXformThreads>(s_addr + static_cast<uint32_t>(b) * p.xbox_bytes, tid, p.xbox_units, k);
-        if (b + 1 < n_xboxes) xform_load(k, sc, sh, p.xboxes[b + 1].c_off + cj, Cp);
+        if (b + 1 < n_xboxes) xform_load_smem(k, xtab_addr, tchunks, grp, p.xboxes[b + 1].c_off >> 6, cj);
       }
       fence_proxy_async();
       __syncwarp();
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) wgrad_halo_kernel(const __grid_
         phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------ epilogue: TMEM -> fp32 partials
     const int q = warp - 4;
     const int row = q * 32 + lane;
@@ -321,7 +325,7 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   k.xbox_units = static_cast<uint32_t>(xrows) * 8u;
   for (int i = 0; i < d->n_xboxes; ++i) {
     const cstp_xbox& b = d->xboxes[i];
-    if (b.c_off < 0 || b.c_off % 8 != 0) {
+    if (b.c_off < 0 || b.c_off % 8 != 0 || (xform && b.c_off % 64 != 0)) {
       delete plan;
       return fail_inval("xbox c_off");
     }
@@ -343,7 +347,8 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
     k.mtiles[mt] = WhMtile{a, two ? b - a : 0u};
   }
   const int bar_bytes = 256;
-  int stages = (smem_budget() - 1024 - bar_bytes) / static_cast<int>(k.stage_bytes);
+  const int xtab_bytes = xform ? static_cast<int>(xform_table_bytes(d->pro.groups, d->pro.Cp)) : 0;      // prologue coefficient table
+  int stages = (smem_budget() - 1024 - bar_bytes - xtab_bytes) / static_cast<int>(k.stage_bytes);
   if (stages > kWhMaxStages) stages = kWhMaxStages;
   if (stages < 2) {
     delete plan;
@@ -353,7 +358,7 @@ extern "C" int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* d, cstp_w
   int cols = 32;
   while (cols < n_mtiles * d->n_tile) cols *= 2;
   k.tmem_cols = cols;
-  plan->smem_bytes = 1024 + stages * static_cast<int>(k.stage_bytes) + bar_bytes;
+  plan->smem_bytes = 1024 + stages * static_cast<int>(k.stage_bytes) + bar_bytes + xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;   // one CTA per SM (TMEM ownership)
   plan->grid = dim3(static_cast<unsigned>(ceil_div(d->Np, d->n_tile)), static_cast<unsigned>(splits), 1);
   *out_plan = plan;
@@ -371,7 +376,7 @@ extern "C" int cstp_wgrad_halo_plan_run(const cstp_wgrad_halo_plan* plan, void* 
     attr_set = true;
   }
   if (plan->kp.pro_scale != nullptr)
-    wgrad_halo_kernel<true><<<plan->grid, kWhThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
+    wgrad_halo_kernel<true><<<plan->grid, kWhThreads + kWhXformThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   else
     wgrad_halo_kernel<false><<<plan->grid, kWhThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();

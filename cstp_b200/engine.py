@@ -39,6 +39,17 @@ BN_MOMENTUM = 0.1
 # ops.wgrad_plan `prologue`), so the normalised activation is neither written nor re-read.  "0" restores the standalone
 # cstp_bn_apply pass on every edge (same bits either way: tests/test_gpu_step.py).
 FUSE_BN_APPLY = os.environ.get("CSTP_FUSE_BN_APPLY", "1") == "1"
+# ... for activations with at least this many positions per (sample, frame) plane.  Below it (14 x 14 and 7 x 7 planes: conv4 /
+# conv5) the tensors are L2-sized, the standalone apply pass is nearly free, and the 1x3x3 convolutions there re-stage --
+# and would re-transform -- the same box once per filter tap (csrc/conv_gemm.cu).
+FUSE_MIN_POSITIONS = int(os.environ.get("CSTP_FUSE_MIN_POSITIONS") or 28 * 28)
+# Which edges: "all" (default): every conv -> BatchNorm -> ReLU -> conv edge above the size threshold; "auto": networks
+# without a backward pass defer every such edge, the online network only those in front of a 1x3x3 convolution; "none".
+# Background (measured per layer at batch 60, profiles/README.md): the conv kernels of this network are bound by
+# SHARED-MEMORY bandwidth (every tcgen05.mma re-reads its 128-row A slice; N = 64 tiles want 192 B/clk), and the in-place
+# transform adds one read + one write of the staged box: +5 % for a 1x3x3 forward (nine taps per box), +30 % for a 3x1x1
+# forward, +60 % for the weight gradient of a 3x1x1 layer -- against the two HBM passes of cstp_bn_apply each edge drops.
+FUSE_POLICY = os.environ.get("CSTP_FUSE_POLICY") or "all"
 # Storage type of activations, activation gradients and packed weights.  The CUDA kernels only implement bf16; the
 # CPU emulator in tests/ also runs the orchestration in fp32 to separate wiring errors from rounding.
 ACT_DTYPE = torch.bfloat16
@@ -180,7 +191,8 @@ class StepEngine:
     VIEWS = 2          # clips per sample pushed through the backbone = BatchNorm statistics groups
 
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", momentum_ema: float = 0.996,
-                 record: bool = False, overlap: bool = True, bn_sync=None):
+                 record: bool = False, overlap: bool = True, bn_sync=None, fuse_apply: bool | None = None,
+                 ntxent: dict | None = None, fuse_min_positions: int | None = None, fuse_policy: str | None = None):
         if H % 2 or W % 2:
             raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
         self.B, self.T, self.H, self.W = B, T, H, W
@@ -192,6 +204,11 @@ class StepEngine:
         # None: per-GPU BatchNorm statistics (what the reference's --sync_bn actually does);
         # a cstp_b200.parallel.BnSync: statistics over every rank of the data-parallel group (north-star SyncBN)
         self.bn_sync = bn_sync
+        # optional NT-Xent term on the online projector outputs of the two views (north-star extension: the reference
+        # builds NTXentLoss but never calls it): dict(weight, temperature, gather) -- with gather the
+        # embeddings of every rank are all-gathered first, so each rank contrasts against the GLOBAL batch
+        # (loss/NTXent.py:46-62 with batch_size = opts.batch_size, main_byol.py:191-196)
+        self.ntxent = dict(ntxent) if ntxent else None
         # Two-stream schedule (CUDA only): the target network's forward runs beside the online network's, and every
         # weight-gradient GEMM runs beside the BatchNorm-backward streaming kernels of the next unit, so HBM-bound and
         # tensor-bound kernels share the machine.  Results are unchanged (same kernels, same reduction orders).
@@ -201,7 +218,11 @@ class StepEngine:
             self._ev_fwd, self._ev_tgt = torch.cuda.Event(), torch.cuda.Event()
             self._ev_g = [torch.cuda.Event(), torch.cuda.Event()]
             self._ev_wg = [torch.cuda.Event(), torch.cuda.Event()]
-        self.fuse_apply = FUSE_BN_APPLY
+        self.fuse_apply = FUSE_BN_APPLY if fuse_apply is None else bool(fuse_apply)
+        self.fuse_min_positions = FUSE_MIN_POSITIONS if fuse_min_positions is None else int(fuse_min_positions)
+        self.fuse_policy = fuse_policy or FUSE_POLICY
+        if self.fuse_policy not in ("auto", "all", "none"):
+            raise ops.L.CstpError(f"fuse_policy {self.fuse_policy!r}: expected auto, all or none")
         self._pending: dict[int, "ops.BNState"] = {}   # raw tensor address -> BatchNorm state its consumers must apply
         self._pending_act: dict[int, torch.Tensor] = {}   # record mode: the same activations, materialised for the tests
         self.named: dict[str, torch.Tensor] = {}      # name -> activation / gradient tensors (parity tests)
@@ -301,7 +322,9 @@ class StepEngine:
         Cop = pad16(cout)
         raw = self._act(N, To, Ho, Wo, Cop)
         pro = self._pending.get(x.data_ptr())         # x is a raw tensor whose BatchNorm + ReLU we apply on the way in
-        defer = apply and relu and res is None and self.fuse_apply
+        defer = (apply and relu and res is None and self.fuse_apply and self.fuse_policy != "none"
+                 and Ho * Wo >= self.fuse_min_positions
+                 and (self.fuse_policy == "all" or not grads or geom.kernel[0] > 1))
         keep_act = apply and (not defer or self.record)          # parity tests still look at every activation
         act = self._act(N, To, Ho, Wo, Cop) if keep_act else None
         wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
@@ -598,6 +621,10 @@ class StepEngine:
         self.byol_scale = torch.ones(1, **f32)       # d(total)/d(loss_byol) (= loss_weight[0] on the fused path)
         bw = self.bwd
         bw.append(pred["make_backward"](self.dpred, self.byol_scale, self.dproj, False))
+        self.proj_out = proj["out_f32"]
+        if self.ntxent is not None:
+            self._ntxent_setup()
+            bw.append(self._ntxent_backward)
         bw.append(proj["make_backward"](self.dproj, None, self.dfeat, False))
         bw.append(pb["make_backward"](d[2], None, self.dfeat, True))
         bw.append(rot["make_backward"](d[3], None, self.dfeat, True))
@@ -626,6 +653,48 @@ class StepEngine:
         for fn in self._deferred:
             fn()
         self._deferred.clear()
+
+    # ------------------------------------------------------------------------------------------ NT-Xent term
+    def _ntxent_setup(self):
+        import torch.distributed as dist
+        o = self.ntxent
+        o.setdefault("weight", 1.0)
+        o.setdefault("temperature", 0.1)
+        gather = bool(o.get("gather", False)) and dist.is_available() and dist.is_initialized()
+        self._nx_world = dist.get_world_size() if gather else 1
+        self._nx_rank = dist.get_rank() if gather else 0
+        B, W = self.B, self._nx_world
+        f32 = dict(device=self.device, dtype=torch.float32)
+        self._nx_local = torch.zeros(2, B, 512, **f32)           # [zjs = view 2 | zis = view 1] of this rank
+        self._nx_all = torch.zeros(W, 2, B, 512, **f32)
+        self._nx_z = torch.zeros(2 * W * B, 512, **f32)          # cat(zjs of every rank, zis of every rank): NTXent.py:47
+        self._nx_dz = torch.zeros(2 * W * B, 512, **f32)
+        self.ntxent_loss = torch.zeros(1, **f32)
+        self._nx_ws = torch.empty(ops.ntxent_workspace_floats(2 * W * B, 512), **f32)
+
+    def _ntxent_forward(self):
+        """NTXentLoss(zis = projector(view 1), zjs = projector(view 2)) over the (gathered) batch: loss + d(loss)/dz."""
+        B, W = self.B, self._nx_world
+        p = self.proj_out[:, :512]
+        self._nx_local[0].copy_(p[B:])
+        self._nx_local[1].copy_(p[:B])
+        if W > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._nx_all.view(W * 2, B, 512), self._nx_local)
+            self._nx_z.view(2, W, B, 512).copy_(self._nx_all.permute(1, 0, 2, 3))
+        else:
+            self._nx_z.view(2, B, 512).copy_(self._nx_local)
+        ops.ntxent(self._nx_z, float(self.ntxent["temperature"]), True, self.ntxent_loss, self._nx_dz, self._nx_ws)
+
+    def _ntxent_backward(self):
+        """Adds weight * d(NT-Xent)/d(projector output) of this rank's rows to dproj.  Every rank evaluates the same global
+        loss, so the local slice carries a factor `world` that the data-parallel gradient mean removes again
+        (parallel._AllGather)."""
+        B, W, r = self.B, self._nx_world, self._nx_rank
+        dz = self._nx_dz.view(2, W, B, 512)
+        a = float(self.ntxent["weight"]) * W
+        self.dproj[:B, :512].add_(dz[1, r], alpha=a)
+        self.dproj[B:, :512].add_(dz[0, r], alpha=a)
 
     # ------------------------------------------------------------------------------------------ programs
     def _pack_list(self, jobs):
@@ -683,6 +752,8 @@ class StepEngine:
             for op in self.fwd_target:
                 op()
         ops.byol_loss(self.pred, self.tproj, self.B, 512, self.losses[7:8], None, self.dpred)
+        if self.ntxent is not None:
+            self._ntxent_forward()
         for op in self.fwd_heads:
             op()
 

@@ -30,9 +30,11 @@ class FinetuneEngine(StepEngine):
 
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", num_classes: int = 101,
                  cls_bn: bool = True, record: bool = False, overlap: bool = True, backbone_grads: bool = True,
-                 bn_sync=None):
+                 bn_sync=None, fuse_apply: bool | None = None, fuse_min_positions: int | None = None,
+                 fuse_policy: str | None = None):
         self.num_classes, self.cls_bn, self.backbone_grads = num_classes, bool(cls_bn), backbone_grads
-        super().__init__(B, T, H, W, device=device, record=record, overlap=overlap, bn_sync=bn_sync)
+        super().__init__(B, T, H, W, device=device, record=record, overlap=overlap, bn_sync=bn_sync, fuse_apply=fuse_apply,
+                         fuse_min_positions=fuse_min_positions, fuse_policy=fuse_policy)
 
     def _make_stores(self):
         specs = finetune_param_specs(self.num_classes, self.cls_bn)

@@ -357,6 +357,10 @@ def pretext_ce(logits, labels, dlogits, B, n_cls, weights5, losses_out):
     losses_out[6] = tot
 
 
+def ntxent_workspace_floats(rows, d):
+    return 16
+
+
 def ntxent(z, temperature, use_cosine, loss_out, dz, workspace):
     _count()
     zr = z.detach().clone().requires_grad_(True)

@@ -42,7 +42,7 @@ def _worker_collectives(rank, world, path, out):
     dist.destroy_process_group()
 
 
-def _step(batch, rank_slice, grad_sync=None, bn_sync=None):
+def _step(batch, rank_slice, grad_sync=None, bn_sync=None, ntxent=None):
     from cstp_b200 import engine
     from cstp_b200.models.pace.r21d_byol import R21DBYOL
     from tests import emulate_ops
@@ -50,8 +50,11 @@ def _step(batch, rank_slice, grad_sync=None, bn_sync=None):
     engine.ACT_DTYPE = torch.float32
     torch.manual_seed(1)
     m = R21DBYOL(pretrain=True)
+    m.engine_options = {}
     if bn_sync is not None:
-        m.engine_options = {"bn_sync": bn_sync}
+        m.engine_options["bn_sync"] = bn_sync
+    if ntxent is not None:
+        m.engine_options["ntxent"] = ntxent
     lo, hi = rank_slice
     x1, x2, labels = batch
     m.train_step(x1[lo:hi].contiguous(), x2[lo:hi].contiguous(), tuple(l[lo:hi].contiguous() for l in labels), LW, lr=0.03,
@@ -79,6 +82,20 @@ def _worker_syncbn(rank, world, path, out):
     m = _step(batch, P.shard_bounds(GLOBAL_B, rank, world), P.GradSync(), P.BnSync())
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     torch.save({"grad": m._engine.grad.clone(), "losses": m._engine.losses.clone(), "state": sd}, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def _worker_config5(rank, world, path, out):
+    """BASELINE config 5 semantics at toy size: SyncBN over the world + NT-Xent on the all-gathered projector outputs."""
+    from cstp_b200 import parallel as P
+    from oracle import cstp_oracle as O
+    torch.set_num_threads(2)
+    _init(rank, world, path)
+    batch = O.structured_batch(GLOBAL_B, 0, T, S)
+    m = _step(batch, P.shard_bounds(GLOBAL_B, rank, world), P.GradSync(), P.BnSync(),
+              dict(weight=0.7, temperature=0.5, gather=True))
+    torch.save({"grad": m._engine.grad.clone(), "losses": m._engine.losses.clone(), "ntxent": m._engine.ntxent_loss.clone(),
+                "train": m._engine.train.data.clone()}, f"{out}.{rank}")
     dist.destroy_process_group()
 
 
@@ -139,6 +156,28 @@ def test_world_synchronised_batchnorm_equals_global_batch():
             assert torch.allclose(r0["state"][k], v, rtol=1e-4, atol=1e-6), k
     w = "online_net.conv3.block1.conv1.spatial_conv.weight"
     assert ((r0["state"][w] - s1[w]).norm() / s1[w].norm()).item() < 1e-4
+
+
+def test_config5_syncbn_and_gathered_ntxent_equal_global_batch():
+    """Two ranks x 2 samples with world BatchNorm statistics and NT-Xent over the all-gathered embeddings (global
+    negatives) == one process x 4 samples: same NT-Xent loss on every rank, same gradients after the data-parallel mean."""
+    from cstp_b200 import engine
+    from oracle import cstp_oracle as O
+    r0, r1 = _spawn(_worker_config5)
+    assert torch.equal(r0["grad"], r1["grad"]) and torch.equal(r0["train"], r1["train"])
+    assert torch.equal(r0["ntxent"], r1["ntxent"])                 # every rank evaluates the same global loss
+    saved = engine.ops, engine.ACT_DTYPE
+    try:
+        single = _step(O.structured_batch(GLOBAL_B, 0, T, S), (0, GLOBAL_B), ntxent=dict(weight=0.7, temperature=0.5))
+        g1, nx1, l1 = single._engine.grad.clone(), single._engine.ntxent_loss.clone(), single._engine.losses.clone()
+        plain = _step(O.structured_batch(GLOBAL_B, 0, T, S), (0, GLOBAL_B))
+        g0 = plain._engine.grad.clone()
+    finally:
+        engine.ops, engine.ACT_DTYPE = saved
+    assert torch.allclose(r0["ntxent"], nx1, rtol=1e-4, atol=1e-5) and nx1.item() > 0
+    assert torch.allclose((r0["losses"] + r1["losses"]) / 2, l1, rtol=1e-4, atol=1e-5)
+    assert ((r0["grad"] - g1).norm() / g1.norm()).item() < 1e-2
+    assert ((g1 - g0).norm() / g0.norm()).item() > 1e-2             # the NT-Xent term really reaches the backbone gradients
 
 
 @pytest.mark.parametrize("gb,world", [(128, 8), (60, 6), (60, 8), (4, 2)])

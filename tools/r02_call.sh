@@ -1,8 +1,8 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L
-python tools/gpu_kernel_check.py pro_conv2_spatial pro_conv2_temporal pro_stem_temporal pro_conv3_temporal_s2 pro_conv3_spatial pro_conv3_temporal pro_conv4_spatial pro_conv5_spatial pro_conv5_temporal pro_ds_temporal pro_ragged > gpurun_out/r02_pro_check.log 2>&1
-cat gpurun_out/r02_pro_check.log | cut -c1-600
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gputest1.log 2>&1; tail -15 gpurun_out/r02_gputest1.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench1.json 2> gpurun_out/r02_bench1.err; tail -3 gpurun_out/r02_bench1.err; cat gpurun_out/r02_bench1.json | cut -c1-1500
-CSTP_FUSE_BN_APPLY=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench1_nofuse.json 2> gpurun_out/r02_bench1_nofuse.err; cat gpurun_out/r02_bench1_nofuse.json | cut -c1-600
+timeout 600 python -m pytest tests/test_gpu_config3.py -x -q -s -k config4 2>&1 | grep -E "finetune|eval logits|passed|failed|Error" | cut -c1-300
+for rep in 1 2; do for pol in none all auto; do CSTP_FUSE_POLICY=$pol timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$pol', round(d['ms_per_step'],2), round(d['e2e']['ms_per_step'],2), d['clocks']['sm_mhz'], round(d['roofline']['frac'],3), round(d['roofline']['all_tensor_kernels_tflops'],1))
+"; done; done | tee gpurun_out/r02_policy_ab.txt
