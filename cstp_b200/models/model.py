@@ -45,10 +45,17 @@ def generate_model(opts):
     if getattr(opts, "distributed", False):
         # models/model.py:82-103.  The reference's --sync_bn builds a process group holding only the local rank, i.e.
         # per-GPU statistics; the engine's BatchNorm is per-GPU as well, so both flags map to plain DDP.
-        torch.cuda.set_device(opts.local_rank)
-        model.cuda(opts.local_rank)
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[opts.local_rank], output_device=opts.local_rank,
-                                                    find_unused_parameters=(opts.task == "ft_fc"), broadcast_buffers=False)
+        # DDP defaults as in the reference (broadcast_buffers stays True: rank 0's BatchNorm running statistics are what
+        # every rank -- and the checkpoint -- carries).
+        if torch.cuda.is_available():
+            torch.cuda.set_device(opts.local_rank)
+            model.cuda(opts.local_rank)
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[opts.local_rank], output_device=opts.local_rank,
+                                                        find_unused_parameters=(opts.task == "ft_fc"))
+        else:
+            # no GPU in this process: only the host logic can run (tests drive it over a CPU stand-in of the kernel layer;
+            # the engine itself refuses CPU tensors)
+            model = nn.parallel.DistributedDataParallel(model, find_unused_parameters=(opts.task == "ft_fc"))
         wrapped = True
     else:
         model = model.to(opts.device)

@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; echo rc=$?
+tail -5 gpurun_out/r02_bench_n2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench_n2.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e'])
+print(json.dumps(d.get('config5'), indent=1))
+PY
