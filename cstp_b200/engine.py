@@ -39,10 +39,13 @@ BN_MOMENTUM = 0.1
 # ops.wgrad_plan `prologue`), so the normalised activation is neither written nor re-read.  "0" restores the standalone
 # cstp_bn_apply pass on every edge (same bits either way: tests/test_gpu_step.py).
 FUSE_BN_APPLY = os.environ.get("CSTP_FUSE_BN_APPLY", "1") == "1"
-# ... for activations with at least this many positions per (sample, frame) plane.  Below it (14 x 14 and 7 x 7 planes: conv4 /
-# conv5) the tensors are L2-sized, the standalone apply pass is nearly free, and the 1x3x3 convolutions there re-stage --
-# and would re-transform -- the same box once per filter tap (csrc/conv_gemm.cu).
-FUSE_MIN_POSITIONS = int(os.environ.get("CSTP_FUSE_MIN_POSITIONS") or 28 * 28)
+# ... for activations with at least this many positions per (sample, frame) plane: the 56 x 56 planes of the stem and
+# conv2, where the tensors are 0.8-1.7 GB per network at batch 60 and every edge nets -0.3 to -0.4 ms per step (forward
+# of both networks + weight gradient against the two cstp_bn_apply passes saved; profiles/README.md).  On the 28 x 28 planes
+# of conv3 the pass saved is worth 0.07-0.15 ms and the consumers lose more than that (shallow TMA pipelines with
+# non-resident weights cannot hide the extra hop); on 14 x 14 / 7 x 7 planes the tensors are L2-sized and the 1x3x3
+# convolutions re-stage -- and would re-transform -- the same box once per filter tap (csrc/conv_gemm.cu).
+FUSE_MIN_POSITIONS = int(os.environ.get("CSTP_FUSE_MIN_POSITIONS") or 56 * 56)
 # Which edges: "all" (default): every conv -> BatchNorm -> ReLU -> conv edge above the size threshold; "auto": networks
 # without a backward pass defer every such edge, the online network only those in front of a 1x3x3 convolution; "none".
 # Background (measured per layer at batch 60, profiles/README.md): the conv kernels of this network are bound by
@@ -415,6 +418,7 @@ class StepEngine:
                     holder["dx"].zero_()
                 holder["dg"].run()
         bwd.holder = holder
+        bwd.writes = [unit["wname"], unit["bnname"] + ".weight", unit["bnname"] + ".bias"]
         return bwd
 
     @staticmethod
@@ -572,6 +576,8 @@ class StepEngine:
                 holder["wg0"].run(dW0)
                 if pd_x is not None:
                     pd_x.run()
+            bwd.writes = [f"{pre}.{i0}.weight", f"{pre}.{i0}.bias", f"{pre}.{i1}.weight", f"{pre}.{i1}.bias",
+                          f"{pre}.{i3}.weight", f"{pre}.{i3}.bias"]
             return bwd
         res["make_backward"] = make_backward
         return res
@@ -653,6 +659,42 @@ class StepEngine:
         for fn in self._deferred:
             fn()
         self._deferred.clear()
+        self._plan_grad_buckets()
+
+    GRAD_BUCKET_MIN = 3_000_000      # elements (12 MB of fp32): below this an all-reduce is latency, not bandwidth
+
+    def _plan_grad_buckets(self):
+        """Where the data-parallel gradient all-reduce can start before the backward pass has finished.  The flat gradient
+        buffer is laid out in registration order and the backward program runs (roughly) in the reverse order, so after
+        closure i every slot at or above a low-water mark is final: {closure index: (lo, hi)} hands the newly finished
+        tail [lo, hi) to the communication stream whenever it has grown past GRAD_BUCKET_MIN; the last closure sends the
+        rest.  (DDP's bucketed hooks, models/model.py:97-103, on one contiguous buffer.)"""
+        slots = self.train.slots
+        order = sorted(slots.items(), key=lambda kv: kv[1][0])           # (name, (offset, shape)) by offset
+        remaining = {n: 0 for n in slots}
+        for op in self.bwd:
+            for n in getattr(op, "writes", ()):
+                if n in remaining:
+                    remaining[n] += 1
+        never = {n for n, c in remaining.items() if c == 0}              # parameters no closure writes (frozen backbone)
+        self._grad_buckets, sent = {}, self.train.numel
+        for i, op in enumerate(self.bwd):
+            for n in getattr(op, "writes", ()):
+                if n in remaining:
+                    remaining[n] -= 1
+            mark = self.train.numel
+            for n, (off, _) in reversed(order):
+                if remaining[n] > 0 and n not in never:
+                    break
+                mark = off
+            last = i == len(self.bwd) - 1
+            if last:
+                mark = 0
+            if sent - mark >= (1 if last else self.GRAD_BUCKET_MIN):
+                self._grad_buckets[i] = (mark, sent)
+                sent = mark
+        if self.device.type == "cuda":
+            self._bucket_events = {i: torch.cuda.Event() for i in self._grad_buckets}
 
     # ------------------------------------------------------------------------------------------ NT-Xent term
     def _ntxent_setup(self):
@@ -762,13 +804,27 @@ class StepEngine:
         spa, tem, pb, r1, r2 = labels5
         ops.pretext_ce(self.logits6, (spa, tem, pb, pb, r1, r2), self.dlogits6, self.B, 5, self.weights5, self.losses)
 
-    def backward(self):
-        for op in self.bwd:
+    def backward(self, grad_sync=None):
+        """Runs the backward program.  `grad_sync` (a parallel.GradSync): finished tails of the flat gradient buffer are
+        all-reduced on its communication stream while the rest of the backward pass still runs (call grad_sync.finish()
+        before the optimiser); returns True when the buffer was handed over that way."""
+        bucketed = grad_sync is not None and hasattr(grad_sync, "bucket") and self._prof is None
+        side = self.overlap and self._prof is None
+        for i, op in enumerate(self.bwd):
             op()
-        if self.overlap and self._prof is None:
+            if bucketed and i in self._grad_buckets:
+                lo, hi = self._grad_buckets[i]
+                events = []
+                if self.device.type == "cuda":
+                    ev = self._bucket_events[i]
+                    ev.record()
+                    events = [ev] + ([self._ev_wg[0], self._ev_wg[1]] if side else [])
+                grad_sync.bucket(self.grad[lo:hi], events)
+        if side:
             main = torch.cuda.current_stream()
             main.wait_event(self._ev_wg[0])
             main.wait_event(self._ev_wg[1])
+        return bucketed
 
     def optimizer_step(self, lr, momentum=0.9, wd=5e-4, max_norm=18.0, clip=True):
         """clip_grad_norm_ + SGD.step (main_byol.py:88-91,229-232) on the flat buffers, then re-pack the bf16 weights."""

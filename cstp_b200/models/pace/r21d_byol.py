@@ -340,8 +340,9 @@ class R21DBYOL(nn.Module):
         eng.forward(x.contiguous(), repack=self._dirty)
         self._dirty = False
         eng.cross_entropy(labels)
-        eng.backward()
-        if grad_sync is not None:
+        if eng.backward(grad_sync):
+            grad_sync.finish()
+        elif grad_sync is not None:
             grad_sync(eng.grad)
         # parameters frozen by get_fine_tuning_parameters (requires_grad = False) are skipped like optim.SGD skips them
         frozen = frozenset(n for n, p in self.named_parameters() if not p.requires_grad)
@@ -401,8 +402,9 @@ class R21DBYOL(nn.Module):
             self._dirty = False
         eng.forward(x1, x2)
         eng.pretext_losses(labels)
-        eng.backward()
-        if grad_sync is not None:
+        if eng.backward(grad_sync):
+            grad_sync.finish()                   # the all-reduce ran in buckets beside the backward pass
+        elif grad_sync is not None:
             grad_sync(eng.grad)
         eng.optimizer_step(lr, momentum, weight_decay, clip_grad_norm or 0.0, bool(clip_grad_norm))
         self._nbt += self._nbt_inc

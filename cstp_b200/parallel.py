@@ -75,6 +75,15 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.chunks = max(1, chunks)
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._comm = None
+        self._pending = False
+
+    def _reduce(self, piece: torch.Tensor) -> None:
+        if self._avg:
+            dist.all_reduce(piece, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group)
+            piece.mul_(1.0 / self.world)
 
     def __call__(self, flat: torch.Tensor) -> None:
         if self.world == 1:
@@ -82,12 +91,30 @@ class GradSync:
         n = flat.numel()
         step = (n + self.chunks - 1) // self.chunks
         for lo in range(0, n, step):
-            piece = flat[lo:lo + step]
-            if self._avg:
-                dist.all_reduce(piece, op=dist.ReduceOp.AVG, group=self.group)
-            else:
-                dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group)
-                piece.mul_(1.0 / self.world)
+            self._reduce(flat[lo:lo + step])
+
+    def bucket(self, piece: torch.Tensor, events=()) -> None:
+        """All-reduce(mean) of one finished part of the gradient buffer, overlapped with the rest of the backward pass:
+        on CUDA the collective is queued on a communication stream behind `events` (recorded where the part became final);
+        finish() joins it.  Every rank issues the same buckets in the same order (the engine's static backward program)."""
+        if self.world == 1 or piece.numel() == 0:
+            return
+        if not piece.is_cuda:
+            self._reduce(piece)
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=piece.device)
+        with torch.cuda.stream(self._comm):
+            for e in events:
+                self._comm.wait_event(e)
+            self._reduce(piece)
+        self._pending = True
+
+    def finish(self) -> None:
+        """The current stream waits for every bucket queued since the last finish()."""
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self._comm)
+            self._pending = False
 
 
 class BnSync:

@@ -17,7 +17,7 @@ def _model(record=False):
     from cstp_b200.models.pace.r21d_byol import R21DBYOL
     torch.manual_seed(1)
     m = R21DBYOL(pretrain=False, num_classes=101, cls_bn=True)
-    m.engine_options = {"record": record}
+    m.engine_options = {"record": record, "fuse_min_positions": 0}       # every fusable edge, also on small clips
     return m
 
 

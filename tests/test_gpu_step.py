@@ -31,7 +31,9 @@ def _model(record=False):
     from cstp_b200.models.pace.r21d_byol import R21DBYOL
     torch.manual_seed(1)
     m = R21DBYOL(pretrain=True)
-    m.engine_options = {"record": record}
+    # fuse_min_positions 0: every conv -> BatchNorm -> ReLU -> conv edge runs through the operand prologue of the conv /
+    # weight-gradient kernels even on these small clips (the default only fuses 56 x 56 planes and larger)
+    m.engine_options = {"record": record, "fuse_min_positions": 0}
     return m
 
 
