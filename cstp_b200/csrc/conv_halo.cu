@@ -46,6 +46,7 @@ struct ConvHaloKParams {
   int stages, tmem_cols, resident;
   uint32_t a_bytes, b_bytes, stage_bytes, res_bytes, idesc;
   uint32_t a_stride;       // a_bytes rounded up to 1024: where the per-stage weight tiles start (non-resident mode)
+  int group_taps;          // taps per load group (all groups hold the same number)
   int tap_nw;              // regular tap walk of a load group: tap j sits (j % tap_nw) * tap_sw + (j / tap_nw) * tap_sh
   uint32_t tap_sw, tap_sh; // bytes into the staged box (validated against taps[].a_shift when the plan is built)
   uint32_t a_sbo;          // bytes between consecutive 8-row atoms of a tap's rows inside the staged box (128-byte rows)
@@ -107,6 +108,27 @@ __device__ __forceinline__ void stats_flush(float (&acc)[128], float* wsum, floa
   asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+}
+
+// One K-block of one load group with FULL 64-channel chunks (four K steps per tap), for the tap walks this network uses:
+// kTaps taps, kNw of them along w.  Every descriptor is the first tap's plus a compile-time combination of three loop
+// invariants (the 14-bit start-address field never carries: shared addresses stay below 256 KB), so the issuing thread
+// spends two adds per tcgen05.mma.  The generic walk below costs ~35 uniform-datapath instructions per tap, two of them
+// constant-bank loads: the N = 64 layers (32 tensor cycles per MMA) ran at 76 issue cycles per MMA, 42 % tensor-pipe
+// activity (ncu r02_c2s_dgrad_plain).
+template <int kTaps, int kNw>
+__device__ __forceinline__ void issue_group_full(uint32_t d_tmem, uint64_t da0, uint64_t db0, uint64_t sw16, uint64_t sh16,
+                                                 uint64_t bstep16, uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int j = 0; j < kTaps; ++j) {
+    const uint64_t da = da0 + static_cast<uint64_t>(j % kNw) * sw16 + static_cast<uint64_t>(j / kNw) * sh16;
+    const uint64_t db = db0 + static_cast<uint64_t>(j) * bstep16;
+    if (j == 0) umma_bf16_nc(d_tmem, da, db, idesc, first ? 0u : 1u);
+    else umma_bf16_acc_nc(d_tmem, da, db, idesc);
+    umma_bf16_acc_nc(d_tmem, da + 2, db + 2, idesc);
+    umma_bf16_acc_nc(d_tmem, da + 4, db + 4, idesc);
+    umma_bf16_acc_nc(d_tmem, da + 6, db + 6, idesc);
+  }
 }
 
 // kXform: eight more warps (8..15) rewrite every staged activation box in place -- BatchNorm affine + ReLU of the producing
@@ -229,7 +251,10 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     uint32_t idesc;             // pinned in a register: the compiler otherwise re-loads it in front of every tap
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     const int n_groups = p.n_groups, chunks = p.chunks, last_ksteps = p.last_ksteps, stages = p.stages, n_tile = p.n_tile;
-    const int nw = p.tap_nw;
+    // (copied through registers once: the compiler otherwise re-loads them from the constant bank inside the tap loop)
+    int nw, group_taps;
+    asm volatile("mov.u32 %0, %1;" : "=r"(nw) : "r"(p.tap_nw));
+    asm volatile("mov.u32 %0, %1;" : "=r"(group_taps) : "r"(p.group_taps));
     const bool resident = p.resident != 0, has_tail = p.tail != 0;
     const int tail_shift = p.tail == 16 ? 2 : 1;        // shifts are in 128-byte rows; tail rows are 32 / 64 bytes
     const uint32_t sw_full = p.tap_sw, sh_full = p.tap_sh;
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * n_tile);
       uint32_t first = 1;
       for (int g = 0; g < n_groups; ++g) {
-        const int g_first = p.groups[g].first_tap, g_taps = p.groups[g].n_taps;
+        const int g_first = g * group_taps, g_taps = group_taps;        // groups are equal-sized (checked at plan creation)
         for (int c = 0; c < chunks; ++c) {
           mbar_wait(kXform ? &xfull[stage] : &full[stage], phase);
           tc_fence_after();
@@ -270,6 +295,12 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
                                              static_cast<uint32_t>(tl ? full_chunks : c) * b_bytes
                                        : s_addr + a_stride;
             const uint32_t b_step = resident ? tap_bytes : b_bytes;
+            if (ks == 4 && nw == 3 && (g_taps == 9 || g_taps == 3)) {
+              const uint64_t da0 = umma_desc_at(hi_a, s_addr), db0 = umma_desc_at(hi_b, b_addr);
+              if (g_taps == 9) issue_group_full<9, 3>(d_tmem, da0, db0, sw >> 4, sh >> 4, b_step >> 4, idesc, first);
+              else issue_group_full<3, 3>(d_tmem, da0, db0, sw >> 4, sh >> 4, b_step >> 4, idesc, first);
+              first = 0;
+            } else {
             uint32_t a_addr = s_addr, a_row0 = s_addr;       // a_addr walks along w, a_row0 is the start of its h row
             int jw = 0;
             for (int j = 0; j < g_taps; ++j) {
@@ -294,6 +325,7 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
               } else {
                 a_addr += sw;
               }
+            }
             }
             umma_commit(&empty[stage]);
             if (g == n_groups - 1 && c == chunks - 1) umma_commit(&tfull[as]);
@@ -666,6 +698,12 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
       delete plan;
       return fail_inval("tap shifts of a load group must form a regular (w, h) walk starting at 0");
     }
+    for (int g = 0; g < d->n_groups; ++g) regular = regular && d->groups[g].n_taps == d->groups[0].n_taps;
+    if (!regular) {
+      delete plan;
+      return fail_inval("load groups must hold the same number of taps");
+    }
+    k.group_taps = d->groups[0].n_taps;
     k.tap_nw = nw;
     k.tap_sw = sw;
     k.tap_sh = sh;

@@ -31,8 +31,12 @@ gg = torch.randn(N, T, S, S, Cop, device="cuda", generator=g).to(torch.bfloat16)
 part = torch.empty(64 * 1024 * 1024, device="cuda", dtype=torch.float32)
 spec = ops.wgrad_plan(raw, gg, geom, cout, cin, part, prologue=st if fused else None)
 dw = torch.empty_like(w)
+wtp = torch.empty(Cip, geom.taps * ops.pad64(Cop), device="cuda", dtype=torch.bfloat16)
+ops.pack_weight(w, wtp, transpose=True)
+dx = torch.empty(N, T, S, S, Cip, device="cuda", dtype=torch.bfloat16)
+dplans, _ = ops.conv_dgrad_plans(gg, wtp, dx, geom)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for name, fn in (("fwd", plan.run), ("wgrad", lambda: spec.run(dw))):
+for name, fn in (("fwd", plan.run), ("wgrad", lambda: spec.run(dw)), ("dgrad", lambda: [p_.run() for p_ in dplans])):
     for _ in range(2):
         fn()
     e0.record()
@@ -40,4 +44,5 @@ for name, fn in (("fwd", plan.run), ("wgrad", lambda: spec.run(dw))):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    print(case, "fused" if fused else "plain", name, ops.kernel_name(plan if name == "fwd" else spec), f"{e0.elapsed_time(e1) / 5:.4f} ms")
+    kn = ops.kernel_name({"fwd": plan, "wgrad": spec, "dgrad": dplans[0]}[name])
+    print(case, "fused" if fused else "plain", name, kn, f"{e0.elapsed_time(e1) / 5:.4f} ms")
