@@ -582,7 +582,7 @@ extern "C" int cstp_ntxent(const float* z, int rows, int d, float temperature, i
       (reinterpret_cast<uintptr_t>(workspace) % 16) == 0) {
     float* dzn = nullptr;
     float* tc_ws = zn + static_cast<long long>(rows) * d;
-    tc_ws += (4 - (reinterpret_cast<uintptr_t>(tc_ws) / 4) % 4) % 4;        // 16-byte alignment
+    tc_ws += (8 - (reinterpret_cast<uintptr_t>(tc_ws) / 4) % 8) % 8;        // 32-byte alignment (STG.256 of the dZn partials)
     int rc = ntxent_tensor_path(zn, rows, d, temperature, dz != nullptr, row_loss, tc_ws, &dzn, ST(stream));
     if (rc != CSTP_OK) return rc;
     ntxent_loss_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_loss, rows, loss_out);

@@ -353,6 +353,14 @@ __device__ __forceinline__ void epilogue_row_f32(uint32_t taddr, int ncols, floa
 }
 
 
+// 2^x on the special-function unit, one instruction (results below 2^-126 flush to zero; relative error 2^-22).
+// exp2f() without -use_fast_math wraps the same MUFU.EX2 in a denormal-range check (FSETP + 2 FMUL + predicate logic).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------- warpgroup register re-allocation
 // All four warps of a warpgroup must execute these (setmaxnreg is .sync.aligned over the warpgroup).
 template <uint32_t kRegs>

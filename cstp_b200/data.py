@@ -60,3 +60,42 @@ class ClipPrefetcher:
 
     def done(self):
         self.free[self._last].record(torch.cuda.current_stream())
+
+
+class LossReadback:
+    """Device -> host read-back of every step's loss vector without stalling the launch thread.
+
+    The reference reads six `.item()`s per step (main_byol.py:77-84), i.e. it synchronises host and device once per step.
+    Here the copy of step i's vector into one of `depth` pinned host slots is queued on the compute stream right behind
+    the step (so it sees that step's values), and the host only waits for a slot when it comes round again -- `depth`
+    steps later, by which time the copy has long finished -- or in `drain()`.  Every step's vector reaches the host, in
+    order; the launch thread runs up to `depth` steps ahead of the GPU, as it does without any read-back."""
+
+    def __init__(self, n: int = 8, depth: int = 4):
+        self.slots = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.events = [None] * depth
+        self.turn = 0
+        self.values: list[list[float]] = []
+        self.d2h_bytes = 4 * n
+
+    def _collect(self, k: int) -> None:
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+            self.values.append(self.slots[k].tolist())
+            self.events[k] = None
+
+    def push(self, dev_vec: torch.Tensor) -> None:
+        k = self.turn
+        self._collect(k)                                  # the slot's previous occupant (depth steps ago) is consumed first
+        self.slots[k].copy_(dev_vec, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        self.turn = (k + 1) % len(self.slots)
+
+    def drain(self) -> list[list[float]]:
+        """Waits for every outstanding copy and returns all vectors pushed so far, oldest first."""
+        n = len(self.slots)
+        for j in range(n):
+            self._collect((self.turn + j) % n)
+        return self.values
