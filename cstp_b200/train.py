@@ -129,3 +129,105 @@ def pretrain_epochs(model, batches, opts, begin_epoch: int = 1, result_path: str
             save_checkpoint(os.path.join(result_path, f"save_{epoch}.pth"), wrapped, epoch, arch, lr=lr,
                             momentum=opts.momentum, weight_decay=opts.weight_decay, initial_lr=opts.learning_rate)
     return rows
+
+
+# ---------------------------------------------------------------------------------------------- finetune driver
+class PlateauLR:
+    """`optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'min', patience=opts.lr_patience)` of main_ft_mp.py:152 for the
+    scalar learning rate of the fused finetune step: mode 'min', factor 0.1, relative threshold 1e-4, no cooldown,
+    min_lr 0, eps 1e-8 (torch's defaults), stepped with the epoch's mean validation loss (main_ft_mp.py:292)."""
+
+    def __init__(self, lr: float, patience: int = 10, factor: float = 0.1, threshold: float = 1e-4, eps: float = 1e-8):
+        self.lr, self.patience, self.factor, self.threshold, self.eps = float(lr), int(patience), factor, threshold, eps
+        self.best = float("inf")
+        self.num_bad_epochs = 0
+
+    def step(self, metric: float) -> float:
+        metric = float(metric)
+        if metric < self.best * (1.0 - self.threshold):
+            self.best = metric
+            self.num_bad_epochs = 0
+        else:
+            self.num_bad_epochs += 1
+        if self.num_bad_epochs > self.patience:
+            new_lr = max(self.lr * self.factor, 0.0)
+            if self.lr - new_lr > self.eps:
+                self.lr = new_lr
+            self.num_bad_epochs = 0
+        return self.lr
+
+
+FT_TRAIN_COLUMNS = ["epoch", "loss", "acc", "lr"]
+FT_VAL_COLUMNS = ["epoch", "loss", "acc"]
+
+
+def finetune_epochs(model, train_batches, val_batches, opts, begin_epoch: int = 1, result_path: str | None = None,
+                    arch: str = "r21d_byol-1", grad_sync=None, log_train=None, log_val=None):
+    """The epoch loop of main_ft_mp.py:160-170 on the fused finetune step: `train` (:179-244: CrossEntropyLoss, SGD.step,
+    top-1 accuracy, mean loss / accuracy per epoch weighted by batch size) then `validation` (:246-310: model.eval(), mean
+    loss / accuracy, ReduceLROnPlateau on the validation loss, `save_<epoch>_max.pth` whenever the validation accuracy
+    beats the best so far, the previous best file removed).  `train_batches(epoch)` / `val_batches(epoch)` yield
+    (clips, labels) on the device.  Losses and hit counts stay on the device inside an epoch (one read-back per phase
+    instead of two `.item()`s per step).  Returns (train rows, val rows) with the reference's log columns."""
+    model = unwrap(model)
+    task = getattr(opts, "task", "ft_all")
+    sched = PlateauLR(opts.learning_rate, getattr(opts, "lr_patience", 10))
+    best_name, best_acc = next(iter(getattr(opts, "highest_val", {"name": 0}).items()))
+    rows_t, rows_v = [], []
+
+    def fold(acc, loss, hits, n):
+        w = torch.tensor([float(n)], device=loss.device)
+        return (acc[0] + loss.reshape(1) * w, acc[1] + hits.reshape(1).float(), acc[2] + n)
+
+    for epoch in range(begin_epoch, opts.n_epochs + 1):
+        model.train()
+        acc = None
+        for x, labels in train_batches(epoch):
+            loss = model.finetune_step(x, labels, lr=sched.lr, momentum=opts.momentum, weight_decay=opts.weight_decay,
+                                       grad_sync=grad_sync)
+            eng = model._engine
+            hits = (eng.logits[:, :model.num_classes].argmax(1) == labels).sum()          # calculate_accuracy, utils.py:52-65
+            z = torch.zeros(1, device=loss.device)
+            acc = fold(acc or (z, z.clone(), 0), loss.clone(), hits, x.shape[0])
+        if acc is not None:
+            s = torch.cat([acc[0], acc[1]])
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(s[:1])                 # reduce_mean of the loss (main_ft_mp.py:203)
+                s[:1] /= torch.distributed.get_world_size()
+            s = s.cpu()
+            row = dict(zip(FT_TRAIN_COLUMNS, [epoch, s[0].item() / acc[2], s[1].item() / acc[2], float("{:.5f}".format(sched.lr))]))
+            rows_t.append(row)
+            if log_train is not None:
+                log_train(row)
+        # ---- validation (main_ft_mp.py:246-310)
+        model.eval()
+        acc = None
+        with torch.no_grad():
+            for x, labels in val_batches(epoch):
+                model(x, None, o_type=task)                          # eval-mode forward (running statistics)
+                eng = model._engine
+                eng.cross_entropy(labels)
+                hits = (eng.logits[:, :model.num_classes].argmax(1) == labels).sum()
+                z = torch.zeros(1, device=eng.loss.device)
+                acc = fold(acc or (z, z.clone(), 0), eng.loss.clone(), hits, x.shape[0])
+        if acc is None:
+            continue
+        s = torch.cat([acc[0], acc[1]]).cpu()
+        vloss, vacc = s[0].item() / acc[2], s[1].item() / acc[2]
+        sched.step(vloss)
+        row = dict(zip(FT_VAL_COLUMNS, [epoch, vloss, vacc]))
+        rows_v.append(row)
+        if log_val is not None:
+            log_val(row)
+        if vacc > best_acc and result_path is not None:
+            old = os.path.join(result_path, best_name)
+            if os.path.exists(old):
+                os.remove(old)
+            best_name, best_acc = f"save_{epoch}_max.pth", vacc
+            save_checkpoint(os.path.join(result_path, best_name), model, epoch, arch, lr=sched.lr, momentum=opts.momentum,
+                            weight_decay=opts.weight_decay, initial_lr=opts.learning_rate)
+        elif vacc > best_acc:
+            best_name, best_acc = f"save_{epoch}_max.pth", vacc
+    if hasattr(opts, "highest_val"):
+        opts.highest_val = {best_name: best_acc}
+    return rows_t, rows_v

@@ -164,3 +164,57 @@ def test_emulated_fused_step_leaves_frozen_parameters_untouched(emu):
             assert torch.equal(p, before[n]), n               # backbone AND cls_bn: bit-identical
     sa, sb = a.state_dict(), b.state_dict()
     assert max(rel(sa[k], sb[k]) for k in sa if sa[k].dtype.is_floating_point) < 1e-5
+
+
+def test_plateau_lr_matches_torch_reduce_on_plateau():
+    """main_ft_mp.py:152: ReduceLROnPlateau(optimizer, 'min', patience) -- the scalar restatement follows torch's on a
+    sequence with improvements, plateaus longer than the patience and sub-threshold improvements."""
+    from cstp_b200.train import PlateauLR
+    g = torch.Generator().manual_seed(3)
+    seq = [2.0, 1.5, 1.5, 1.49999, 1.6, 1.7, 1.4, 1.4, 1.4, 1.4, 1.4, 1.39, 1.5, 1.5, 1.5, 1.5] + \
+          (1.3 + 0.2 * torch.rand(40, generator=g)).tolist()
+    for patience in (0, 2, 3):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p], lr=0.025)
+        ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "min", patience=patience)
+        mine = PlateauLR(0.025, patience)
+        for v in seq:
+            ref.step(v)
+            assert mine.step(v) == opt.param_groups[0]["lr"], (patience, v)
+
+
+def test_emulated_finetune_epochs_train_validate_and_keep_the_best_checkpoint(emu, tmp_path):
+    """cstp_b200.train.finetune_epochs = the epoch loop of main_ft_mp.py:160-310 on the fused step: log columns, weighted
+    means, eval-mode validation that updates nothing, plateau schedule, save_<epoch>_max.pth replacing the previous best."""
+    import types
+    from cstp_b200 import train as TR
+    B, T, S = 2, 4, 32
+    data = [(O.structured_batch(B, s, T, S)[0], torch.tensor([3 + s, 77 - s])) for s in range(2)]
+    m = _model()
+    opts = types.SimpleNamespace(n_epochs=3, learning_rate=LR, momentum=MOM, weight_decay=WD, lr_patience=0, task="ft_all",
+                                 highest_val={"name": -1.0})
+    seen = []
+    rows_t, rows_v = TR.finetune_epochs(m, lambda e: iter(data), lambda e: iter(data[:1]), opts, result_path=str(tmp_path),
+                                        log_train=seen.append)
+    assert [r["epoch"] for r in rows_t] == [1, 2, 3] == [r["epoch"] for r in rows_v] and seen == rows_t
+    assert list(rows_t[0]) == ["epoch", "loss", "acc", "lr"] and list(rows_v[0]) == ["epoch", "loss", "acc"]
+    assert rows_t[0]["lr"] == LR and all(0.0 <= r["acc"] <= 1.0 for r in rows_t + rows_v)
+    # the first epoch's mean training loss: two steps from the initial weights, restated with the drop-in path
+    ref = _model()
+    ref.train()
+    opt = torch.optim.SGD(ref.parameters(), lr=LR, momentum=MOM, weight_decay=WD)
+    tot = 0.0
+    for x, y in data:
+        loss = torch.nn.CrossEntropyLoss()(ref(x, o_type="ft_all"), y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        tot += loss.item() * B
+    assert abs(rows_t[0]["loss"] - tot / (2 * B)) < 1e-5 * tot
+    # validation ran in eval mode: BatchNorm counters only moved during training (2 steps x 3 epochs)
+    assert m.cls_bn.num_batches_tracked.item() == 6
+    # exactly one best checkpoint is kept, named after the epoch that set the record, in the reference's format
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) == 1 and files[0] == next(iter(opts.highest_val)) and files[0].startswith("save_") and files[0].endswith("_max.pth")
+    ck = torch.load(tmp_path / files[0], weights_only=False)
+    assert set(ck) == {"epoch", "arch", "state_dict", "optimizer"} and all(k.startswith("module.") for k in ck["state_dict"])
