@@ -32,10 +32,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     const int tap = static_cast<int>((i / Kc) % taps);
     const int r = static_cast<int>(i / (static_cast<long long>(Kc) * taps));
     float v = 0.f;
-    if (!transpose) {
+    if (transpose == 0) {
       if (r < cout && c < cin) v = w[(static_cast<long long>(r) * cin + c) * taps + tap];
-    } else {
+    } else if (transpose == 1) {
       if (r < cin && c < cout) v = w[(static_cast<long long>(c) * cin + r) * taps + tap];
+    } else {
+      // stem layout: w is (cout, 3, 1, 7, 7); tap = row pair j, packed column c = hpar*32 + kw*3 + ci (cstp_stem_pack)
+      const int k = c & 31, kh = 2 * tap + (c >> 5) - 1;
+      if (r < cout && c < 64 && k < 21 && kh >= 0 && kh < 7) v = w[((static_cast<long long>(r) * 3 + k % 3) * 7 + kh) * 7 + k / 3];
     }
     packed[i] = __float2bfloat16_rn(v);
   }
@@ -81,10 +85,14 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
       const unsigned tap = q % taps;
       const unsigned r = q / taps;
       float v = 0.f;
-      if (!transpose) {
+      if (transpose == 0) {
         if (r < cout && c < cin) v = w[(static_cast<size_t>(r) * cin + c) * taps + tap];
-      } else {
+      } else if (transpose == 1) {
         if (r < cin && c < cout) v = w[(static_cast<size_t>(c) * cin + r) * taps + tap];
+      } else {                                           // stem layout (see pack_weight_kernel)
+        const unsigned k = c & 31;
+        const int kh = 2 * static_cast<int>(tap) + static_cast<int>(c >> 5) - 1;
+        if (r < cout && c < 64 && k < 21 && kh >= 0 && kh < 7) v = w[((static_cast<size_t>(r) * 3 + k % 3) * 7 + kh) * 7 + k / 3];
       }
       packed[i] = __float2bfloat16_rn(v);
     }
@@ -158,6 +166,48 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
       for (int j = 0; j < 8; ++j) f[j] = offs[j] >= 0 ? flat[offs[j] + 2 * wo] : 0.f;
       dst[wo * nvec + v] = pack8(f);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- stem row packing
+// The 1x7x7 s(1,2,2) p(0,3,3) stem (r21d_byol.py:198) as a FOUR-tap stride-1 convolution over row pairs: the seven kw taps
+// and the three input channels of every output column are packed into a 32-channel vector, and the two frame rows
+// 2*h2, 2*h2 + 1 share one 64-channel pixel,
+//   P[n][t][h2][wo][hpar*32 + kw*3 + ci] = x[n][ci][t][2*h2 + hpar][2*wo + kw - 3]   (0 outside the frame; k >= 21 zero).
+// Output row ho reads frame rows 2*ho - 3 .. 2*ho + 3 = row pairs ho - 2 .. ho + 1: a (1,4,1) stride-1 implicit GEMM over
+// P with padding 2 below / 1 above (TMA zero fill = the h padding), tap j and pixel channel hpar*32 + kw*3 + ci holding
+// w[co][ci][0][kh = 2*j + hpar - 1][kw] (zero for kh = -1).  P holds 64 bytes per (frame row, output column): 0.77 GB per
+// batch of 60 against 1.93 GB for the materialised im2col rows (K = 147 -> 160) it replaces; K grows to 256, which the
+// tensor pipe does not notice on this HBM-bound layer.  One CTA per (n, t, h2): six input rows staged in shared memory.
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int T, int H, int W,
+                                                        uint4* __restrict__ P) {
+  __shared__ float rows[2][3][kStemMaxW + 8];        // [hpar][ci][3 + wi]: three zero columns left, five right
+  const int Wo = W / 2, H2 = H / 2;
+  int b = blockIdx.x;
+  const int h2 = b % H2;
+  b /= H2;
+  const int t = b % T;
+  const int n = b / T;
+  const int Wq = W + 8;
+  for (int i = threadIdx.x; i < 6 * Wq; i += blockDim.x) {
+    const int row = i / Wq, c = i % Wq;              // row = hpar*3 + ci
+    const int hp = row / 3, ci = row % 3;
+    const int wi = c - 3;
+    rows[hp][ci][c] = (wi >= 0 && wi < W)
+        ? __ldg(x + (((static_cast<long long>(n) * 3 + ci) * T + t) * H + 2 * h2 + hp) * W + wi) : 0.f;
+  }
+  __syncthreads();
+  uint4* dst = P + ((static_cast<long long>(n) * T + t) * H2 + h2) * Wo * 8;
+  for (int i = threadIdx.x; i < Wo * 8; i += blockDim.x) {
+    const int wo = i >> 3, hp = (i >> 2) & 1, v = i & 3;   // eight 16-byte vectors (8 channels each) per output column
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;                       // k = kw*3 + ci
+      const int kw = (k * 11) >> 5;                  // k / 3 for k < 32
+      f[j] = k < 21 ? rows[hp][k - 3 * kw][2 * wo + kw] : 0.f;
+    }
+    dst[i] = pack8(f);
   }
 }
 
@@ -661,7 +711,8 @@ using namespace cstp;
 extern "C" int cstp_pack_weight(const float* w, int cout, int cin, int taps, int transpose, void* packed, int Rp, int Kc,
                                 void* stream) {
   CSTP_REQUIRE(w && packed && cout > 0 && cin > 0 && taps > 0 && Rp > 0 && Kc > 0 && Kc % 64 == 0);
-  CSTP_REQUIRE(transpose ? (Rp >= cin && Kc >= cout) : (Rp >= cout && Kc >= cin));
+  CSTP_REQUIRE(transpose == 0 || transpose == 1 || (transpose == 2 && cin == 64 && taps == 4));
+  CSTP_REQUIRE(transpose == 1 ? (Rp >= cin && Kc >= cout) : (Rp >= cout && Kc >= cin));
   const long long total = static_cast<long long>(Rp) * taps * Kc;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, cout, cin, taps, transpose,
                                                                   reinterpret_cast<__nv_bfloat16*>(packed), Rp, Kc);
@@ -688,6 +739,14 @@ extern "C" int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void
   const int threads = (256 / nvec) * nvec >= 64 ? (256 / nvec) * nvec : 256;   // a whole number of vector columns
   stem_im2col_kernel<<<static_cast<unsigned>(blocks), threads, 0, ST(stream)>>>(x, N, T, H, W,
                                                                            reinterpret_cast<__nv_bfloat16*>(col), ldk);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_stem_pack(const float* x, int N, int T, int H, int W, void* P, void* stream) {
+  CSTP_REQUIRE(x && P && N > 0 && T > 0 && H > 0 && W > 0 && W % 2 == 0 && H % 2 == 0 && W <= kStemMaxW);
+  CSTP_REQUIRE((reinterpret_cast<uintptr_t>(P) % 16) == 0);
+  stem_pack_kernel<<<N * T * (H / 2), 256, 0, ST(stream)>>>(x, T, H, W, reinterpret_cast<uint4*>(P));
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

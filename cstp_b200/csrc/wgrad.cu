@@ -212,9 +212,11 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
 }
 
 // dW[(co*cin + ci)*taps + tap] = sum_s P[s][chunk*64 + r][co], ci = c_off(chunk) + r.  One thread per (row, co).
+// layout 1 (stem, cstp_stem_pack): the X channel ci = hpar*32 + kw*3 + c of row pair tap j is w[co][c][0][2*j + hpar - 1][kw]
+// of a (cout, 3, 1, 7, 7) weight; channels / taps without a weight element are skipped.
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partials, int splits, int n_mchunks, int Np,
                                       const int* __restrict__ chunk_tap, const int* __restrict__ chunk_coff, int cout,
-                                      int cin, int taps, float* __restrict__ dw, int accumulate) {
+                                      int cin, int taps, float* __restrict__ dw, int accumulate, int layout) {
   const long long mtot = static_cast<long long>(n_mchunks) * 64;
   const long long total = mtot * cout;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -226,7 +228,14 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partials, int sp
     if (ci >= cin) continue;
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += partials[(static_cast<long long>(s) * mtot + row) * Np + co];
-    const long long o = (static_cast<long long>(co) * cin + ci) * taps + chunk_tap[chunk];
+    long long o;
+    if (layout == 0) {
+      o = (static_cast<long long>(co) * cin + ci) * taps + chunk_tap[chunk];
+    } else {
+      const int k = ci & 31, kh = 2 * chunk_tap[chunk] + (ci >> 5) - 1;
+      if (k >= 21 || kh < 0 || kh > 6) continue;
+      o = ((static_cast<long long>(co) * 3 + k % 3) * 7 + kh) * 7 + k / 3;
+    }
     dw[o] = accumulate ? dw[o] + acc : acc;
   }
 }
@@ -364,15 +373,17 @@ extern "C" void cstp_wgrad_plan_destroy(cstp_wgrad_plan* plan) { delete plan; }
 
 extern "C" int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np, const int32_t* chunk_tap,
                                    const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
-                                   void* stream) {
+                                   int layout, void* stream) {
   CSTP_REQUIRE(partials && chunk_tap && chunk_coff && dw);
+  CSTP_REQUIRE(layout == 0 || (layout == 1 && cin == 64 && taps == 4));
   CSTP_REQUIRE(splits >= 1 && n_mchunks >= 1 && n_mchunks <= CSTP_MAX_MCHUNKS && cout <= Np);
   // chunk_tap / chunk_coff are device pointers (tiny int arrays uploaded once by the host at plan time).
   const long long total = static_cast<long long>(n_mchunks) * 64 * cout;
   int blocks = ceil_div(total, 256);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   wgrad_finalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, n_mchunks, Np, chunk_tap,
-                                                                             chunk_coff, cout, cin, taps, dw, accumulate);
+                                                                             chunk_coff, cout, cin, taps, dw, accumulate,
+                                                                             layout);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -250,8 +250,8 @@ class StepEngine:
         self.bwd: list = []          # executed in order (already reversed while building)
 
         # ---- inputs
-        Ho, Wo = H // 2, W // 2
-        self.col = torch.zeros(self.N * T * Ho * Wo, 160, device=self.device, dtype=ACT_DTYPE)
+        # stem input: the seven kw taps x three channels of every output column, two frame rows per pixel (ops.stem_pack)
+        self.stem_rows = torch.zeros(self.N, T, H // 2, W // 2, ops.STEM_CHANNELS, device=self.device, dtype=ACT_DTYPE)
         self.weights5 = torch.tensor([0.1, 1.0, 1.0, 1.0, 1.0], **f32)
         self.losses = torch.zeros(8, **f32)       # [0..5] CE, [6] weighted CE sum, [7] BYOL loss
         self.norm_out = torch.zeros(2, **f32)
@@ -295,24 +295,26 @@ class StepEngine:
                      store.view(name + ".weight", self.grad) if grads else None,
                      store.view(name + ".bias", self.grad) if grads else None)
 
-    def _packed(self, store: FlatStore, name: str, grads: bool, rows_pad: int | None = None, as_2d: bool = False):
+    def _packed(self, store: FlatStore, name: str, grads: bool, rows_pad: int | None = None, stem: bool = False):
         """bf16 packed forward (and dgrad-transposed) copies of a conv / linear weight; registers the re-pack job.
-        as_2d flattens (Cout, Cin, kT, kH, kW) to (Cout, Cin*taps): the stem runs as a GEMM over im2col rows."""
+        stem: the (Cout, 3, 1, 7, 7) weight in the layout of the packed stem row pairs -- four taps of 64 (hpar, kw, c)
+        channels (include/cstp_b200.h cstp_pack_weight transpose = 2); it has no dgrad copy."""
         w = store.view(name)
-        if as_2d:
-            w = w.view(w.shape[0], -1)
         cout, cin = w.shape[0], w.shape[1]
         taps = w.numel() // (cout * cin)
+        if stem:
+            assert not grads
+            cin, taps = ops.STEM_CHANNELS, 4
         wp = torch.zeros(rows_pad or pad16(cout), taps * pad64(pad16(cin)), device=self.device, dtype=ACT_DTYPE)
         wt = None
         if grads:
             wt = torch.zeros(pad16(cin), taps * pad64(pad16(cout)), device=self.device, dtype=ACT_DTYPE)
-        (self._pack_jobs_online if store is self.train else self._pack_jobs_target).append((w, wp, wt))
+        (self._pack_jobs_online if store is self.train else self._pack_jobs_target).append((w, wp, wt, 2 if stem else 0))
         return wp, wt
 
     # ------------------------------------------------------------------------------------------ conv + BN unit
     def _conv_bn(self, prog, store, grads, x, wname, bnname, geom: ConvGeom, cin, cout, *, relu=True, res=None,
-                 res_site=None, apply=True, tag="", skip_dgrad=False, x_is_col=False):
+                 res_site=None, apply=True, tag="", skip_dgrad=False, stem=False):
         """raw = conv(x); BN statistics; act = [relu](bn(raw) [+ res]).  Returns (raw, act, site, unit); the backward
         closure of the unit is built by _unit_backward.
 
@@ -330,9 +332,9 @@ class StepEngine:
                  and (self.fuse_policy == "all" or not grads or geom.kernel[0] > 1))
         keep_act = apply and (not defer or self.record)          # parity tests still look at every activation
         act = self._act(N, To, Ho, Wo, Cop) if keep_act else None
-        wp, wt = self._packed(store, wname, grads and not skip_dgrad, as_2d=x_is_col)
+        wp, wt = self._packed(store, wname, grads and not skip_dgrad, stem=stem)
         rows = N * To * Ho * Wo
-        flops = 2.0 * rows * cout * cin * (1 if x_is_col else geom.taps)
+        flops = 2.0 * rows * cout * cin * (49 if stem else geom.taps)     # algorithmic: the stem is 3 channels x 1x7x7
         site = self._site(store, grads, bnname, cout, self.VIEWS, rows // self.VIEWS)
         cplan = ops.conv_fwd_plan(x, wp, raw, geom, stats=site.st, prologue=pro)
         plan = _Timed(self, "conv_fwd", flops, [cplan], tag)
@@ -355,7 +357,7 @@ class StepEngine:
             self._rec(tag + ".act", act)
         unit = dict(x=x, raw=raw, act=act, site=site, relu=relu, geom=geom, wname=wname, cin=cin, cout=cout, wt=wt,
                     skip_dgrad=skip_dgrad, tag=tag, flops=flops, bnname=bnname, res=res, res_site=res_site,
-                    x_is_col=x_is_col, grads=grads, pro=pro, deferred=defer,
+                    stem=stem, grads=grads, pro=pro, deferred=defer,
                     # what the tensor cores really consume, as materialised tensors (record mode; parity tests)
                     x_act=self._pending_act.get(x.data_ptr(), x).view(x.shape),
                     res_act=self._pending_act.get(res.data_ptr(), res).view(res.shape) if res is not None else None)
@@ -379,7 +381,8 @@ class StepEngine:
             g = self._gbufs[holder["gbuf"]][:raw.numel()].view(raw.shape)
             holder["g"] = g
             holder["wg"] = _Timed(self, "wgrad", unit["flops"],
-                                  [ops.wgrad_plan(x, g, geom, unit["cout"], unit["cin"], self._wg, prologue=unit["pro"])],
+                                  [ops.wgrad_plan(x, g, geom, unit["cout"], ops.STEM_CHANNELS if unit["stem"] else unit["cin"], self._wg,
+                                                  prologue=unit["pro"], layout=1 if unit["stem"] else 0)],
                                   unit["tag"])
             if not unit["skip_dgrad"]:
                 dx = self._dbuf(x)
@@ -433,14 +436,14 @@ class StepEngine:
         N, T = self.N, self.T
         Ho, Wo = self.H // 2, self.W // 2
         bw: list = []
-        col5 = self.col.view(1, 1, 1, self.col.shape[0], 160)
-        # stem spatial 1x7x7 s(1,2,2): a GEMM over the im2col rows (K = 147 padded to 160)
-        raw5, act5, site, u = self._conv_bn(prog, store, grads, col5, f"{prefix}.conv1.spatial_conv.weight",
-                                            f"{prefix}.conv1.bn", ConvGeom((1, 1, 1)), 147, 83, tag=f"{tag}.conv1.spatial",
-                                            skip_dgrad=True, x_is_col=True)
-        a0 = act5.view(N, T, Ho, Wo, act5.shape[-1])
+        # stem spatial 1x7x7 s(1,2,2) p(0,3,3) (r21d_byol.py:198): a four-tap stride-1 implicit GEMM over packed row pairs,
+        # whose 64 channels hold the (kw, c) taps of every output column for two frame rows -- no im2col matrix in HBM
+        _, a0, site, u = self._conv_bn(prog, store, grads, self.stem_rows, f"{prefix}.conv1.spatial_conv.weight",
+                                       f"{prefix}.conv1.bn", ops.STEM_GEOM, 3, 83, tag=f"{tag}.conv1.spatial",
+                                       skip_dgrad=True, stem=True)
+        assert tuple(a0.shape[:4]) == (N, T, Ho, Wo)
         if grads:
-            bw.append(self._unit_backward(u, self._dbuf(a0).view(act5.shape), act_for_mask=act5))
+            bw.append(self._unit_backward(u, self._dbuf(a0), act_for_mask=a0))
         raw, x, site, u = self._conv_bn(prog, store, grads, a0, f"{prefix}.conv1.temporal_conv.weight", f"{prefix}.bn1",
                                         ConvGeom((3, 1, 1), (1, 1, 1), (1, 0, 0)), 83, 64, tag=f"{tag}.conv1.temporal")
         if grads:
@@ -741,10 +744,10 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------ programs
     def _pack_list(self, jobs):
         flat = []
-        for w, wp, wt in jobs:
-            flat.append((w, wp, False))
+        for w, wp, wt, mode in jobs:
+            flat.append((w, wp, mode))
             if wt is not None:
-                flat.append((w, wt, True))
+                flat.append((w, wt, 1))
         return ops.PackList(flat, self.device)
 
     def pack_online(self):
@@ -759,10 +762,9 @@ class StepEngine:
         self._pl_target.run()
 
     def load_clips(self, x1: torch.Tensor, x2: torch.Tensor):
-        """fp32 NCDHW clips (B,3,T,H,W) -> bf16 im2col rows of the stem (shared by the online and target nets)."""
-        rows = self.col.shape[0] // 2
-        ops.stem_im2col(x1, self.col[:rows])
-        ops.stem_im2col(x2, self.col[rows:])
+        """fp32 NCDHW clips (B,3,T,H,W) -> bf16 packed stem rows (shared by the online and target nets)."""
+        ops.stem_pack(x1, self.stem_rows[:self.B])
+        ops.stem_pack(x2, self.stem_rows[self.B:])
 
     def ema(self):
         """R21DBYOL._update_target_net (r21d_byol.py:331-337) over the flat buffers, then re-pack the target weights."""

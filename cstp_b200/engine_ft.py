@@ -123,7 +123,7 @@ class FinetuneEngine(StepEngine):
 
     # ------------------------------------------------------------------------------------------ programs
     def load_clip(self, x: torch.Tensor):
-        E.ops.stem_im2col(x, self.col)
+        E.ops.stem_pack(x, self.stem_rows)
 
     def forward(self, x, repack: bool = False):
         """logits (device fp32 [B][pad16(num_classes)], the first num_classes columns are valid)."""

@@ -179,10 +179,11 @@ SIGNATURES = {
     "cstp_wgrad_halo_plan_splits": (_i, [_vp]),
     "cstp_wgrad_halo_plan_run": (_i, [_vp, _vp]),
     "cstp_wgrad_halo_plan_destroy": (None, [_vp]),
-    "cstp_wgrad_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "cstp_wgrad_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "cstp_pack_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "cstp_pack_weights_batched": (_i, [_vp, _vp, _i, _i64, _vp]),
     "cstp_stem_im2col": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "cstp_stem_pack": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cstp_bn_stats": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
     "cstp_bn_partials_reduce": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "cstp_bn_finalize": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

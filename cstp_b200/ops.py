@@ -97,6 +97,7 @@ class ConvGeom:
     kernel: tuple[int, int, int]
     stride: tuple[int, int, int] = (1, 1, 1)
     pad: tuple[int, int, int] = (0, 0, 0)
+    pad_hi: tuple[int, int, int] | None = None     # padding at the far end of every axis when it differs from `pad`
 
     @property
     def taps(self) -> int:
@@ -104,7 +105,8 @@ class ConvGeom:
 
     def out_dims(self, T: int, H: int, W: int) -> tuple[int, int, int]:
         (kt, kh, kw), (st, sh, sw), (pt, ph, pw) = self.kernel, self.stride, self.pad
-        return ((T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1)
+        qt, qh, qw = self.pad_hi or self.pad
+        return ((T + pt + qt - kt) // st + 1, (H + ph + qh - kh) // sh + 1, (W + pw + qw - kw) // sw + 1)
 
 
 def fwd_taps(g: ConvGeom):
@@ -482,12 +484,13 @@ class WgradSpec:
     cin: int
     taps: int
     partials: torch.Tensor
+    layout: int = 0              # 1: the stem over cstp_stem_pack rows, dW is the reference's (cout, 3, 1, 7, 7) tensor
 
     def run(self, dw: torch.Tensor, accumulate: bool = False):
         self.plan.run()
         L.check(L.load().cstp_wgrad_finalize(_ptr(self.partials), self.plan.splits, self.n_mchunks, self.Np,
                                              _ptr(self.chunk_tap), _ptr(self.chunk_coff), self.cout, self.cin,
-                                             self.taps, _ptr(dw), int(accumulate), _stream()))
+                                             self.taps, _ptr(dw), int(accumulate), self.layout, _stream()))
 
 
 class WgradHaloPlan(_Plan):
@@ -593,9 +596,11 @@ def wgrad_partials_need(x_shape, g_shape, geom: ConvGeom, sms: int = 148) -> int
 
 
 def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor, *, splits: int | None = None,
-               box=None, sms: int = 148, allow_halo: bool = True, prologue: "BNState | None" = None) -> WgradSpec:
+               box=None, sms: int = 148, allow_halo: bool = True, prologue: "BNState | None" = None,
+               layout: int = 0) -> WgradSpec:
     """dW (cout, cin, kt, kh, kw) from x (N,T,H,W,Cp_in) and g (N,To,Ho,Wo,Cp_out); `partials` is fp32 scratch.
-    With `prologue` x is the raw output of the producing convolution (see conv_fwd_plan)."""
+    With `prologue` x is the raw output of the producing convolution (see conv_fwd_plan).  layout = 1: x holds the stem's
+    packed row pairs (stem_pack), geom is STEM_GEOM, cin = 64 and dW the reference's (cout, 3, 1, 7, 7) weight gradient."""
     _require_cuda(x, g, partials)
     lib = L.load()
     N, T, H, W, Ca = x.shape
@@ -629,7 +634,7 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
         return WgradSpec(plan, len(lay["chunks"]), Np,
                          torch.tensor([c[1] for c in lay["chunks"]], dtype=torch.int32, device=dev),
                          torch.tensor([c[2] for c in lay["chunks"]], dtype=torch.int32, device=dev), cout, cin, geom.taps,
-                         partials)
+                         partials, layout)
     views, taps = _fwd_taps(x, geom)
     nchunk_c = pad64(Ca) // 64
     mch, ctap, ccoff = [], [], []
@@ -668,15 +673,26 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
     plan = WgradPlan(h, lib.cstp_wgrad_plan_destroy, (x, g, partials) + keep)
     plan.splits = lib.cstp_wgrad_plan_splits(h)
     return WgradSpec(plan, len(mch), Np, torch.tensor(ctap, dtype=torch.int32, device=dev),
-                     torch.tensor(ccoff, dtype=torch.int32, device=dev), cout, cin, geom.taps, partials)
+                     torch.tensor(ccoff, dtype=torch.int32, device=dev), cout, cin, geom.taps, partials, layout)
 
 
 # ------------------------------------------------------------------------------------------------ thin wrappers
-def pack_weight(w: torch.Tensor, packed: torch.Tensor, *, transpose: bool = False) -> None:
-    """fp32 (cout, cin, *kernel) -> bf16 packed [Rp][taps*Kc] (forward) or its dgrad transpose."""
-    _require_cuda(w, packed)
+def _pack_dims(w: torch.Tensor, transpose) -> tuple[int, int, int]:
+    """(cout, cin, taps) as the pack kernels index them; transpose = 2 is the stem over packed row pairs: 64 pixel channels
+    (hpar, kw, c), 4 row-pair taps of a (cout, 3, 1, 7, 7) weight."""
+    if int(transpose) == 2:
+        if tuple(w.shape[1:]) != (3, 1, 7, 7):
+            raise L.CstpError(f"stem weight layout expects (cout, 3, 1, 7, 7), got {tuple(w.shape)}")
+        return w.shape[0], STEM_CHANNELS, 4
     cout, cin = w.shape[0], w.shape[1]
-    taps = w.numel() // (cout * cin)
+    return cout, cin, w.numel() // (cout * cin)
+
+
+def pack_weight(w: torch.Tensor, packed: torch.Tensor, *, transpose=False) -> None:
+    """fp32 (cout, cin, *kernel) -> bf16 packed [Rp][taps*Kc] (forward), its dgrad transpose, or (transpose = 2) the stem
+    layout packed[co][kh*Kc + kw*3 + c]."""
+    _require_cuda(w, packed)
+    cout, cin, taps = _pack_dims(w, transpose)
     Rp, Ktot = packed.shape
     L.check(L.load().cstp_pack_weight(_ptr(w), cout, cin, taps, int(transpose), _ptr(packed), Rp, Ktot // taps, _stream()))
 
@@ -688,8 +704,7 @@ class PackList:
         rows, prefix, total = [], [0], 0
         for w, packed, transpose in jobs:
             _require_cuda(w, packed)
-            cout, cin = w.shape[0], w.shape[1]
-            taps = w.numel() // (cout * cin)
+            cout, cin, taps = _pack_dims(w, transpose)
             Rp, Ktot = packed.shape
             rows.append([w.data_ptr(), packed.data_ptr(), cout, cin, taps, int(transpose), Rp, Ktot // taps])
             total += Rp * Ktot
@@ -702,6 +717,22 @@ class PackList:
     def run(self) -> None:
         if self.n:
             L.check(L.load().cstp_pack_weights_batched(_ptr(self.jobs), _ptr(self.prefix), self.n, self.total, _stream()))
+
+
+# The 1x7x7 s(1,2,2) p(0,3,3) stem (r21d_byol.py:198) over stem_pack row pairs: output row ho reads the four row pairs
+# ho - 2 .. ho + 1 (frame rows 2*ho - 4 .. 2*ho + 3; the filter has no element for the first), stride 1.
+STEM_GEOM = ConvGeom((1, 4, 1), (1, 1, 1), (0, 2, 0), (0, 1, 0))
+STEM_CHANNELS = 64          # two frame rows x (21 packed (kw, c) channels zero-padded to 32)
+
+
+def stem_pack(x: torch.Tensor, P: torch.Tensor) -> None:
+    """fp32 NCDHW clips (N,3,T,H,W) -> bf16 P (N,T,H/2,W/2,64),
+    P[n][t][h2][wo][hpar*32 + kw*3 + c] = x[n][c][t][2*h2 + hpar][2*wo + kw - 3]."""
+    _require_cuda(x, P)
+    N, Cc, T, H, W = x.shape
+    assert Cc == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    assert tuple(P.shape) == (N, T, H // 2, W // 2, STEM_CHANNELS) and P.is_contiguous()
+    L.check(L.load().cstp_stem_pack(_ptr(x), N, T, H, W, _ptr(P), _stream()))
 
 
 def stem_im2col(x: torch.Tensor, col: torch.Tensor) -> None:

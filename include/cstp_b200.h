@@ -189,7 +189,10 @@ void cstp_wgrad_plan_destroy(cstp_wgrad_plan* plan);
  * arrays of length n_mchunks (tap index and first input channel of every 64-row chunk). */
 int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np, const int32_t* chunk_tap,
                         const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
-                        void* stream);
+                        int layout, void* stream);
+/* layout 0: dW is (cout, cin, taps) as above.  layout 1 (the stem over cstp_stem_pack row pairs: cin = 64 pixel
+ * channels hpar*32 + kw*3 + c, taps = 4 row pairs j): dW is the reference's (cout, 3, 1, 7, 7) tensor, element
+ * ((co*3 + c)*7 + kh)*7 + kw with kh = 2*j + hpar - 1; channels / taps outside the filter are skipped. */
 
 /* Weight gradient of the wide, shallow stride-1 layers: every CTA computes all taps for its slice of positions.
  * One K-block (box of 64 positions) stages `n_xboxes` boxes of X, each 64 channels wide and extended by
@@ -230,14 +233,22 @@ void cstp_wgrad_halo_plan_destroy(cstp_wgrad_halo_plan* plan);
 
 /* ---- packing / layout -----------------------------------------------------------------------------------
  * fp32 reference-layout weight (rows_out, cin, taps) -> bf16 K-major packed [Rp][taps*Kc].
- * transpose=0: packed[r=co][tap*Kc + ci] (forward);  transpose=1: packed[r=ci][tap*Kc + co] (dgrad). */
+ * transpose=0: packed[r=co][tap*Kc + ci] (forward);  transpose=1: packed[r=ci][tap*Kc + co] (dgrad);
+ * transpose=2: the stem's (cout, 3, 1, 7, 7) weight for cstp_stem_pack row pairs (call with cin = 64, taps = 4):
+ * packed[co][j*Kc + hpar*32 + kw*3 + c] = w[co][c][0][2*j + hpar - 1][kw], zero where no such filter element exists. */
 int cstp_pack_weight(const float* w, int cout, int cin, int taps, int transpose, void* packed, int Rp, int Kc,
                      void* stream);
 /* The same for a whole list of tensors in one launch.  jobs_dev: DEVICE int64 [n_jobs][8] = {w ptr, packed ptr, cout,
  * cin, taps, transpose, Rp, Kc}; prefix_dev: DEVICE int64 [n_jobs + 1], prefix[j] = sum of Rp*taps*Kc of the jobs
  * before j; total = prefix[n_jobs]. */
 int cstp_pack_weights_batched(const int64_t* jobs_dev, const int64_t* prefix_dev, int n_jobs, int64_t total, void* stream);
-/* Stem: fp32 NCDHW clip (N,3,T,H,W) -> bf16 im2col rows [N*T*Ho*Wo][ldk] for the 1x7x7 s(1,2,2) p(0,3,3) conv
+/* Stem, packed row pairs: fp32 NCDHW clip (N,3,T,H,W), H and W even -> bf16 P (N,T,H/2,W/2,64) with
+ * P[n][t][h2][wo][hpar*32 + kw*3 + c] = x[n][c][t][2*h2 + hpar][2*wo + kw - 3] (zero outside the frame, k = 21..31 of
+ * each half zero): the 1x7x7 s(1,2,2) p(0,3,3) convolution (r21d_byol.py:198) becomes a four-tap (1,4,1) stride-1
+ * implicit GEMM over P (row pairs ho-2 .. ho+1) whose packed weights come from cstp_pack_weight(s) with transpose = 2
+ * and whose weight gradient is scattered by cstp_wgrad_finalize layout 1. */
+int cstp_stem_pack(const float* x, int N, int T, int H, int W, void* P, void* stream);
+/* Stem (older form, kept for callers that want the GEMM view): fp32 NCDHW clip (N,3,T,H,W) -> bf16 im2col rows [N*T*Ho*Wo][ldk] for the 1x7x7 s(1,2,2) p(0,3,3) conv
  * (r21d_byol.py:198); column = ci*49 + kh*7 + kw, columns >= 147 are zero. */
 int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void* col, int ldk, void* stream);
 

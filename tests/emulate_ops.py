@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from cstp_b200 import lib as L  # noqa: F401  (engine reaches CstpError through ops.L)
 from cstp_b200 import ops as real
 from cstp_b200.ops import (BNState, ConvGeom, pad16, pad64, fwd_taps, dgrad_classes, bn_nblocks, pick_box,  # noqa: F401
-                           wgrad_partials_need, wgrad_halo_layout)
+                           wgrad_partials_need, wgrad_halo_layout, STEM_GEOM, STEM_CHANNELS)
 
 from .emulate import _gather
 
@@ -133,8 +133,9 @@ def linear_plan(x, w_packed, out, *, out_f32=None, bias=None, accumulate=False):
 
 
 class _WgradSpec:
-    def __init__(self, x, g, geom, cout, cin, prologue=None):
+    def __init__(self, x, g, geom, cout, cin, prologue=None, layout=0):
         self.x, self.g, self.geom, self.cout, self.cin, self.prologue = x, g, geom, cout, cin, prologue
+        self.layout = layout
         self.plan = _Plan(lambda: None)
 
     def run(self, dw, accumulate=False):
@@ -147,15 +148,19 @@ class _WgradSpec:
         for (m, dw_, dh, dt, ti) in taps:
             a = _gather(x, maps[m], geom.stride, (dw_, dh, dt), (Wo, Ho, To, N))
             res[:, :, ti] = (g.reshape(-1, Co).t() @ a.reshape(-1, Ci))[:self.cout, :self.cin]
+        if self.layout == 1:       # stem row pairs: res[co][hpar*32 + kw*3 + c][j] -> dW (cout, 3, 1, 7, 7), kh = 2j + hpar - 1
+            r5 = res.reshape(self.cout, 2, 32, 4)[:, :, :21].reshape(self.cout, 2, 7, 3, 4)      # co, hpar, kw, c, j
+            r5 = r5.permute(0, 3, 4, 1, 2).reshape(self.cout, 3, 8, 7)                           # co, c, 2j + hpar, kw
+            res = r5[:, :, 1:, :]
         res = res.reshape(dw.shape)
         dw.copy_(dw + res if accumulate else res)
 
 
-def wgrad_plan(x, g, geom, cout, cin, partials, *, splits=None, box=None, sms=148, prologue=None):
+def wgrad_plan(x, g, geom, cout, cin, partials, *, splits=None, box=None, sms=148, prologue=None, layout=0):
     need_chunks = geom.taps * (pad64(x.shape[-1]) // 64)
     if need_chunks > L.CSTP_MAX_MCHUNKS:
         raise L.CstpError("too many M chunks")
-    return _WgradSpec(x, g, geom, cout, cin, prologue)
+    return _WgradSpec(x, g, geom, cout, cin, prologue, layout)
 
 
 def pack_weight(w, packed, *, transpose=False):
@@ -163,6 +168,12 @@ def pack_weight(w, packed, *, transpose=False):
     cout, cin = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cin)
     Rp, Ktot = packed.shape
+    if int(transpose) == 2:    # stem: packed[co][j*64 + hpar*32 + kw*3 + c] = w[co][c][0][2j + hpar - 1][kw]
+        packed.zero_()
+        w8 = F.pad(w.reshape(cout, 3, 7, 7), (0, 0, 1, 0))                    # kh' = kh + 1 = 2j + hpar in 0..7
+        w8 = w8.reshape(cout, 3, 4, 2, 7).permute(0, 2, 3, 4, 1).reshape(cout, 4, 2, 21)      # co, j, hpar, kw*3 + c
+        packed.view(Rp, 4, 2, 32)[:cout, :, :, :21] = w8.to(packed.dtype)
+        return
     Kc = Ktot // taps
     w3 = w.reshape(cout, cin, taps)
     packed.zero_()
@@ -180,6 +191,17 @@ class PackList:
     def run(self):
         for w, packed, transpose in self.jobs:
             pack_weight(w, packed, transpose=transpose)
+
+
+def stem_pack(x, P):
+    _count()
+    N, C, T, H, W = x.shape
+    Wo = W // 2
+    xp = F.pad(x, (3, 3))                                    # (N, 3, T, H, W + 6)
+    taps = xp.unfold(4, 7, 2)                                # (N, 3, T, H, Wo, 7): [..., wo, kw] = x[2*wo + kw - 3]
+    P.zero_()
+    rows = taps.permute(0, 2, 3, 4, 5, 1).reshape(N, T, H // 2, 2, Wo, 21)          # n, t, h2, hpar, wo, kw*3 + c
+    P.view(N, T, H // 2, Wo, 2, 32)[..., :21] = rows.permute(0, 1, 2, 4, 3, 5).to(P.dtype)
 
 
 def stem_im2col(x, col):

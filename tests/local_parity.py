@@ -49,16 +49,18 @@ def check_conv_units(eng, params, which="online"):
         W = params[u["wname"]].clone().requires_grad_(u["grads"])
         e: dict = {}
         # ---------------------------------------------------------------- convolution
-        if u["x_is_col"]:
-            rows = u["x"].shape[-2]
-            xin = _f(u["x_act"]).reshape(rows, -1)[:, :cin]
-            raw_r = xin @ W.reshape(cout, -1).t()
-            raw_e = _f(u["raw"]).reshape(rows, -1)[:, :cout]
-            e["conv"] = rel(raw_e, raw_r)
-            # BN over rows: reshape to (N, C, rows/N) per view handled below through a 3-D view
-            N = eng.N
-            raw_e5 = raw_e.reshape(N, rows // N, cout).permute(0, 2, 1).contiguous()
-            to_eng = lambda t: t.permute(0, 2, 1).reshape(rows, cout)              # noqa: E731
+        if u["stem"]:
+            # the engine's operand is the packed stem row pairs P[n][t][h2][wo][hpar*32 + kw*3 + c] =
+            # x[n][c][t][2*h2 + hpar][2*wo + kw - 3]: the bf16 clip is read back from the kw = 3 (even columns) and
+            # kw = 4 (odd columns) taps
+            P = _f(u["x"])
+            Nn, Tt, H2, Wo_, _ = P.shape
+            P = P.reshape(Nn, Tt, H2, Wo_, 2, 32)
+            xin = torch.stack([P[..., 9:12], P[..., 12:15]], 5)          # n, t, h2, wo, hpar, wpar, c
+            xin = xin.permute(0, 6, 1, 2, 4, 3, 5).reshape(Nn, 3, Tt, 2 * H2, 2 * Wo_).contiguous()
+            raw_r = F.conv3d(xin, W, None, (1, 2, 2), (0, 3, 3))
+            raw_e5 = _ncdhw(u["raw"], cout)
+            e["conv"] = rel(raw_e5, raw_r)
         else:
             # (x_act: with the BatchNorm apply fused into this conv's operand path, u["x"] is the producer's raw output and
             # x_act the activation the engine materialised for the tests -- the values the tensor cores consumed)
@@ -66,7 +68,6 @@ def check_conv_units(eng, params, which="online"):
             raw_r = F.conv3d(xin, W, None, geom.stride, geom.pad)
             raw_e5 = _ncdhw(u["raw"], cout)
             e["conv"] = rel(raw_e5, raw_r)
-            to_eng = lambda t: t                                                      # noqa: E731
         # ---------------------------------------------------------------- BatchNorm (+ residual) (+ ReLU)
         gamma = params[u["bnname"] + ".weight"].clone().requires_grad_(u["grads"])
         beta = params[u["bnname"] + ".bias"].clone().requires_grad_(u["grads"])
@@ -83,34 +84,23 @@ def check_conv_units(eng, params, which="online"):
             y = y + r
         act_e = None
         if u["act"] is not None:
-            act_e = _f(u["act"])
-            act_e = act_e.reshape(-1, act_e.shape[-1])[:, :cout] if u["x_is_col"] else _ncdhw(u["act"], cout)
-            e["bn_act"] = rel(act_e, to_eng(F.relu(y) if u["relu"] else y))
+            act_e = _ncdhw(u["act"], cout)
+            e["bn_act"] = rel(act_e, F.relu(y) if u["relu"] else y)
         if u["relu"]:
             # ReLU backward is defined by the sign of the FORWARD OUTPUT (torch: grad * (result > 0)); the engine's own
             # output is used as that result so that exact ties at the kink (fmaf vs mul+add, +-1e-10) cannot flip a mask.
             mask = (act_e > 0).to(y.dtype)
-            if u["x_is_col"]:
-                mask = mask.reshape(eng.N, -1, cout).permute(0, 2, 1)
             y = y * mask
         if not u["grads"]:
             out[tag] = e
             continue
         # ---------------------------------------------------------------- BatchNorm / ReLU backward
         d_out = eng.named[tag + ".d_out"]
-        d5 = _f(d_out)
-        if u["x_is_col"]:
-            d5 = d5.reshape(-1, d5.shape[-1])[:, :cout].reshape(eng.N, -1, cout).permute(0, 2, 1).contiguous()
-        else:
-            d5 = _ncdhw(d_out, cout)
+        d5 = _ncdhw(d_out, cout)
         y.backward(d5)
         g_e = eng.named[tag + ".g"]
-        if u["x_is_col"]:
-            g_e5 = _f(g_e).reshape(-1, g_e.shape[-1])[:, :cout]
-            e["bn_bwd_dx"] = rel(g_e5, to_eng(leaf.grad))
-        else:
-            g_e5 = _ncdhw(g_e, cout)
-            e["bn_bwd_dx"] = rel(g_e5, leaf.grad)
+        g_e5 = _ncdhw(g_e, cout)
+        e["bn_bwd_dx"] = rel(g_e5, leaf.grad)
         e["bn_dgamma"] = rel(eng.train.view(u["bnname"] + ".weight", eng.grad), gamma.grad)
         e["bn_dbeta"] = rel(eng.train.view(u["bnname"] + ".bias", eng.grad), beta.grad)
         # padded channels of the gradient must stay exactly zero (they feed wgrad / dgrad as K columns)

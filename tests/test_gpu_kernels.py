@@ -47,6 +47,8 @@ def test_elementwise_bn_im2col_ema_sgd():
         assert r[f"bn{C}_rm_rel"] < 1e-5 and r[f"bn{C}_rv_rel"] < 1e-5, r
         assert r[f"bn{C}_dgamma_rel"] < 1e-5 and r[f"bn{C}_dbeta_rel"] < 1e-5, r
     assert r["im2col_rel"] < 1e-6 and r["im2col_padzero"]
+    assert r["stem_pack_exact"] and r["stem_fwd_padzero"], r
+    assert r["stem_fwd_rel"] < 4e-3 and r["stem_wgrad_rel"] < 2e-4, r
     assert r["ema_bitexact"]                                       # r21d_byol.py:331-337: exact fp32 arithmetic
     assert r["sgd_rel"] < 1e-6
     assert abs(r["sgd_norm"][0] - r["sgd_norm"][1]) < 1e-4 * r["sgd_norm"][1]

@@ -267,6 +267,34 @@ def case_elementwise():
     got = col[:, :147].float() @ w.view(83, 147).t()
     res["im2col_rel"] = _rel(got, ref)
     res["im2col_padzero"] = bool((col[:, 147:] == 0).all().item())
+    # stem over packed rows (cstp_stem_pack + seven-tap stride-2 implicit GEMM + weight gradient in the stem layout):
+    # odd frame height / partial tiles, against conv3d on the bf16-rounded clip
+    from cstp_b200.ops import STEM_GEOM, STEM_CHANNELS
+    x = torch.rand(3, 3, 2, 22, 36, device=dev, generator=gen) * 2 - 1
+    N_, _, T_, H_, W_ = x.shape
+    P = torch.full((N_, T_, H_ // 2, W_ // 2, STEM_CHANNELS), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.stem_pack(x, P)
+    xb = x.to(torch.bfloat16).float()
+    taps = F.pad(xb, (3, 3)).unfold(4, 7, 2).permute(0, 2, 3, 4, 5, 1).reshape(N_, T_, H_ // 2, 2, W_ // 2, 21)
+    P6 = P.view(N_, T_, H_ // 2, W_ // 2, 2, 32).permute(0, 1, 2, 4, 3, 5)
+    res["stem_pack_exact"] = bool(torch.equal(P6[..., :21].float(), taps) and (P6[..., 21:] == 0).all().item())
+    wb = w.to(torch.bfloat16).float().requires_grad_(True)
+    wp = torch.empty(96, 4 * 64, device=dev, dtype=torch.bfloat16)
+    ops.pack_weight(w, wp, transpose=2)
+    Ho_, Wo_ = H_ // 2, W_ // 2
+    raw = torch.empty(N_, T_, Ho_, Wo_, 96, device=dev, dtype=torch.bfloat16)
+    ops.conv_fwd_plan(P, wp, raw, STEM_GEOM).run()
+    ref = F.conv3d(xb, wb, stride=(1, 2, 2), padding=(0, 3, 3))
+    res["stem_fwd_rel"] = _rel(raw[..., :83].float().permute(0, 4, 1, 2, 3), ref)
+    res["stem_fwd_padzero"] = bool((raw[..., 83:] == 0).all().item())
+    g = torch.zeros_like(raw)
+    g[..., :83] = torch.randn(N_, T_, Ho_, Wo_, 83, device=dev, generator=gen).to(torch.bfloat16)
+    ref.backward(g[..., :83].float().permute(0, 4, 1, 2, 3))
+    scratch = torch.empty(ops.wgrad_partials_need(tuple(P.shape), tuple(g.shape), STEM_GEOM), device=dev)
+    dw = torch.full((83, 3, 1, 7, 7), 9.0, device=dev)
+    ops.wgrad_plan(P, g, STEM_GEOM, 83, STEM_CHANNELS, scratch, layout=1).run(dw)
+    torch.cuda.synchronize()
+    res["stem_wgrad_rel"] = _rel(dw, wb.grad)
     # EMA bit-exactness vs torch CPU semantics, SGD vs torch.optim.SGD
     k = torch.randn(1000003, device=dev, generator=gen)
     q = torch.randn(1000003, device=dev, generator=gen)
