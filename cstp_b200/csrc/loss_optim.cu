@@ -456,7 +456,16 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ mom, long long n, float lr, float momentum,
                                                        float wd, float max_norm, int do_clip, int first_step,
-                                                       const float* __restrict__ partials, float* __restrict__ norm_out) {
+                                                       const float* __restrict__ partials, float* __restrict__ norm_out,
+                                                       const float* __restrict__ hyper) {
+  if (hyper != nullptr) {      // hyper-parameters from device memory: a captured CUDA graph follows the lr schedule
+    lr = hyper[0];
+    momentum = hyper[1];
+    wd = hyper[2];
+    max_norm = hyper[3];
+    do_clip = hyper[4] != 0.f;
+    first_step = hyper[5] != 0.f;
+  }
   __shared__ double red[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < kNormBlocks; i += blockDim.x) acc += static_cast<double>(partials[i]);
@@ -635,7 +644,17 @@ extern "C" int cstp_sgd_clip_step(float* p, const float* g, float* mom, int64_t 
   sumsq_partial_kernel<<<kNormBlocks, 256, 0, ST(stream)>>>(g, n, workspace);
   CSTP_LAUNCHED();
   sgd_step_kernel<<<grid_cap(n, 256), 256, 0, ST(stream)>>>(p, g, mom, n, lr, momentum, wd, max_norm, do_clip, first_step,
-                                                           workspace, norm_out);
+                                                           workspace, norm_out, nullptr);
+  CSTP_LAUNCHED();
+  return CSTP_OK;
+}
+
+extern "C" int cstp_sgd_clip_step_dev(float* p, const float* g, float* mom, int64_t n, const float* hyper, float* norm_out,
+                                      float* workspace, void* stream) {
+  CSTP_REQUIRE(p && g && mom && workspace && hyper && n > 0);
+  sumsq_partial_kernel<<<kNormBlocks, 256, 0, ST(stream)>>>(g, n, workspace);
+  CSTP_LAUNCHED();
+  sgd_step_kernel<<<grid_cap(n, 256), 256, 0, ST(stream)>>>(p, g, mom, n, 0.f, 0.f, 0.f, 0.f, 0, 0, workspace, norm_out, hyper);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

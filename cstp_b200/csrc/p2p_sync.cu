@@ -34,7 +34,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(kSyncThreads) bn_sync_exchange_kernel(const float* __restrict__ row, int n,
                                                                        const uint64_t* __restrict__ peers, int world, int rank,
                                                                        int slots, int row_max, uint32_t seq,
+                                                                       uint32_t* __restrict__ seq_dev,
                                                                        float* __restrict__ out, int* __restrict__ err) {
+  if (seq_dev != nullptr) {      // call counter in device memory (one per buffer set): replayable from a CUDA graph
+    __shared__ uint32_t s_seq;
+    if (threadIdx.x == 0) {
+      s_seq = *seq_dev + 1u;
+      *seq_dev = s_seq;
+    }
+    __syncthreads();
+    seq = s_seq;
+  }
   const int slot = static_cast<int>(seq % static_cast<uint32_t>(slots));
   const size_t flag_off = static_cast<size_t>(slots) * world * row_max * sizeof(float);
   const int n4 = n >> 2;
@@ -89,13 +99,13 @@ extern "C" long long cstp_bn_sync_buffer_bytes(int world, int slots, int row_max
 }
 
 extern "C" int cstp_bn_sync_exchange(const float* row, int n, const uint64_t* peer_buffers, int world, int rank, int slots,
-                                     int row_max, uint32_t seq, float* out, int* err_flag, void* stream) {
+                                     int row_max, uint32_t seq, uint32_t* seq_dev, float* out, int* err_flag, void* stream) {
   CSTP_REQUIRE(row != nullptr && out != nullptr && peer_buffers != nullptr && err_flag != nullptr);
-  CSTP_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && slots >= 2 && seq != 0);
+  CSTP_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && slots >= 2 && ((seq != 0) != (seq_dev != nullptr)));
   CSTP_REQUIRE(n > 0 && n % 4 == 0 && n <= row_max && row_max % 4 == 0);
   CSTP_REQUIRE(reinterpret_cast<uintptr_t>(row) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0);
   bn_sync_exchange_kernel<<<1, kSyncThreads, 0, static_cast<cudaStream_t>(stream)>>>(row, n, peer_buffers, world, rank, slots,
-                                                                                    row_max, seq, out, err_flag);
+                                                                                    row_max, seq, seq_dev, out, err_flag);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

@@ -53,6 +53,10 @@ FUSE_MIN_POSITIONS = int(os.environ.get("CSTP_FUSE_MIN_POSITIONS") or 56 * 56)
 # transform adds one read + one write of the staged box: +5 % for a 1x3x3 forward (nine taps per box), +30 % for a 3x1x1
 # forward, +60 % for the weight gradient of a 3x1x1 layer -- against the two HBM passes of cstp_bn_apply each edge drops.
 FUSE_POLICY = os.environ.get("CSTP_FUSE_POLICY") or "all"
+# The whole step (forward, losses, backward, gradient all-reduce, optimiser, re-pack: ~560 launches on three streams) is
+# captured into ONE CUDA graph after an eager first step and replayed from then on (StepEngine.graphed_step): at 16 samples
+# per GPU the eager step is bound by the host issuing launches through ctypes, not by the GPU.  "0": always eager.
+USE_GRAPH = os.environ.get("CSTP_GRAPH", "1") == "1"
 # Storage type of activations, activation gradients and packed weights.  The CUDA kernels only implement bf16; the
 # CPU emulator in tests/ also runs the orchestration in fp32 to separate wiring errors from rounding.
 ACT_DTYPE = torch.bfloat16
@@ -195,7 +199,8 @@ class StepEngine:
 
     def __init__(self, B: int, T: int = 16, H: int = 112, W: int = 112, device="cuda", momentum_ema: float = 0.996,
                  record: bool = False, overlap: bool = True, bn_sync=None, fuse_apply: bool | None = None,
-                 ntxent: dict | None = None, fuse_min_positions: int | None = None, fuse_policy: str | None = None):
+                 ntxent: dict | None = None, fuse_min_positions: int | None = None, fuse_policy: str | None = None,
+                 graph: bool | None = None):
         if H % 2 or W % 2:
             raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
         self.B, self.T, self.H, self.W = B, T, H, W
@@ -221,6 +226,14 @@ class StepEngine:
             self._ev_fwd, self._ev_tgt = torch.cuda.Event(), torch.cuda.Event()
             self._ev_g = [torch.cuda.Event(), torch.cuda.Event()]
             self._ev_wg = [torch.cuda.Event(), torch.cuda.Event()]
+            if hasattr(bn_sync, "register_side_stream"):
+                bn_sync.register_side_stream(self._s2)
+        self._wg_recorded = [False, False]     # has _ev_wg[b] been recorded during the CURRENT backward pass?
+        self.use_graph = (USE_GRAPH if graph is None else bool(graph)) and self.device.type == "cuda" and not record
+        self._graph = None
+        self._graph_key = None
+        self._graph_launches = 0
+        self._eager_steps = 0
         self.fuse_apply = FUSE_BN_APPLY if fuse_apply is None else bool(fuse_apply)
         self.fuse_min_positions = FUSE_MIN_POSITIONS if fuse_min_positions is None else int(fuse_min_positions)
         self.fuse_policy = fuse_policy or FUSE_POLICY
@@ -256,6 +269,11 @@ class StepEngine:
         self.losses = torch.zeros(8, **f32)       # [0..5] CE, [6] weighted CE sum, [7] BYOL loss
         self.norm_out = torch.zeros(2, **f32)
         self.sgd_ws = torch.zeros(2048, **f32)
+        # static inputs of the captured step: integer labels (spa, tem, pb, rot1, rot2) and the optimiser's hyper-parameters
+        # {lr, momentum, wd, max_norm, do_clip, first_step} (cstp_sgd_clip_step_dev)
+        self.labels_static = tuple(torch.zeros(B, dtype=torch.int64, device=self.device) for _ in range(5))
+        self.hyper = torch.zeros(8, **f32)
+        self._hyper_host = None
 
         self._build()
 
@@ -399,7 +417,7 @@ class StepEngine:
 
         def bwd():
             g = holder["g"]
-            if self.overlap and self._prof is None:
+            if self.overlap and self._prof is None and self._wg_recorded[holder["gbuf"]]:
                 # the weight-gradient GEMM that last read this d(raw) buffer (two units ago) must have finished
                 torch.cuda.current_stream().wait_event(self._ev_wg[holder["gbuf"]])
             ops.bn_backward(d_out, act_for_mask, raw, site.st, site.gamma, site.dgamma, site.dbeta, g, dz=dz,
@@ -414,6 +432,7 @@ class StepEngine:
                     self._s2.wait_event(self._ev_g[b])
                     holder["wg"].run(dw)
                     self._ev_wg[b].record(self._s2)
+                    self._wg_recorded[b] = True
             else:
                 holder["wg"].run(dw)
             if not unit["skip_dgrad"]:
@@ -777,6 +796,10 @@ class StepEngine:
         if repack_online:
             self.pack_online()
         self.load_clips(x1, x2)
+        self._forward_body()
+
+    def _forward_body(self):
+        """Everything of forward() behind the input pass: reads only engine-owned buffers (capturable)."""
         if self.overlap and self._prof is None:
             main = torch.cuda.current_stream()
             self._ev_fwd.record(main)
@@ -812,6 +835,7 @@ class StepEngine:
         before the optimiser); returns True when the buffer was handed over that way."""
         bucketed = grad_sync is not None and hasattr(grad_sync, "bucket") and self._prof is None
         side = self.overlap and self._prof is None
+        self._wg_recorded = [False, False]
         for i, op in enumerate(self.bwd):
             op()
             if bucketed and i in self._grad_buckets:
@@ -820,12 +844,13 @@ class StepEngine:
                 if self.device.type == "cuda":
                     ev = self._bucket_events[i]
                     ev.record()
-                    events = [ev] + ([self._ev_wg[0], self._ev_wg[1]] if side else [])
+                    events = [ev] + ([e for e, r in zip(self._ev_wg, self._wg_recorded) if r] if side else [])
                 grad_sync.bucket(self.grad[lo:hi], events)
         if side:
             main = torch.cuda.current_stream()
-            main.wait_event(self._ev_wg[0])
-            main.wait_event(self._ev_wg[1])
+            for e, r in zip(self._ev_wg, self._wg_recorded):
+                if r:
+                    main.wait_event(e)
         return bucketed
 
     def optimizer_step(self, lr, momentum=0.9, wd=5e-4, max_norm=18.0, clip=True):
@@ -835,6 +860,71 @@ class StepEngine:
                           self.first_step, self.norm_out, self.sgd_ws)
         self.first_step = False
         self.pack_online()
+
+    # ------------------------------------------------------------------------------------------ captured step
+    def set_hyper(self, lr, momentum, wd, max_norm, clip) -> None:
+        """Writes the optimiser's hyper-parameters (and the first-step flag) into device memory when they changed."""
+        h = (float(lr), float(momentum), float(wd), float(max_norm), 1.0 if clip else 0.0, 1.0 if self.first_step else 0.0)
+        if h != self._hyper_host:
+            self.hyper[:6].copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)
+            self._hyper_host = h
+
+    def _step_body(self, grad_sync, after):
+        """forward (behind the input pass) -> pretext losses -> backward (+ gradient all-reduce) -> optimiser -> re-pack,
+        on engine-owned buffers only: the program graphed_step captures."""
+        self._forward_body()
+        self.pretext_losses(self.labels_static)
+        if self.backward(grad_sync):
+            grad_sync.finish()
+        elif grad_sync is not None:
+            grad_sync(self.grad)
+        n = self.train.numel
+        ops.sgd_clip_step_dev(self.train.data[:n], self.grad[:n], self.mom[:n], self.hyper, self.norm_out, self.sgd_ws)
+        self.pack_online()
+        if after is not None:
+            after()
+
+    def graphed_step(self, x1, x2, labels, lr, momentum, wd, max_norm, clip, grad_sync=None, after=None):
+        """One pretraining step with everything behind the input pass replayed from a CUDA graph.  The first call runs the
+        program eagerly (one-time kernel attributes, NCCL / peer-memory channel set-up), the second captures it; inputs
+        (clips -> packed stem rows, labels, hyper-parameters) are written into static buffers in front of the graph.
+        `after` (device-side bookkeeping of the caller, e.g. num_batches_tracked) is part of the program and must be the
+        same callable for the lifetime of a capture; drop_graph() forgets the capture."""
+        self.load_clips(x1, x2)
+        for dst, src in zip(self.labels_static, labels):
+            dst.copy_(src)
+        self.set_hyper(lr, momentum, wd, max_norm, clip)
+        key = id(grad_sync)
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+            ops.note_replayed(self._graph_launches)
+        elif self._eager_steps < 1 or not self.use_graph:
+            self._step_body(grad_sync, after)
+            self._eager_steps += 1
+        else:
+            torch.cuda.synchronize(self.device)
+            before = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            try:
+                # thread_local: NCCL's watchdog thread and the data loader's copy stream keep issuing CUDA calls meanwhile
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._step_body(grad_sync, after)
+            except Exception as e:          # e.g. a collective backend that cannot be captured: stay eager, say so once
+                import warnings
+                warnings.warn(f"cstp_b200: CUDA-graph capture of the step failed ({e!r}); running eagerly")
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
+                self._step_body(grad_sync, after)
+            else:
+                self._graph, self._graph_key = g, key
+                self._graph_launches = ops.launch_count() - before
+                ops.note_replayed(-self._graph_launches)       # the capture pass counted launches that did not run
+                g.replay()
+                ops.note_replayed(self._graph_launches)
+        self.first_step = False
+
+    def drop_graph(self) -> None:
+        self._graph, self._graph_key = None, None
 
     def profile_tensor_launches(self, x1, x2):
         """Runs one forward + backward with CUDA events around every backbone tensor-core launch group.

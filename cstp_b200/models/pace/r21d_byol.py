@@ -258,6 +258,7 @@ class R21DBYOL(nn.Module):
                 for i, m in enumerate(nbt):
                     m._buffers["num_batches_tracked"] = flat[i]
                 self._nbt, self._nbt_inc = flat, torch.tensor(inc, device=x1.device, dtype=flat.dtype)
+            eng.drop_graph()                     # a captured step holds the old num_batches_tracked tensors
             self._alias_ptr = sentinel.data_ptr()
             self._dirty = True
         return eng
@@ -353,6 +354,9 @@ class R21DBYOL(nn.Module):
         self._nbt += self._nbt_inc
         return eng.loss
 
+    def _bump_nbt(self):
+        self._nbt += self._nbt_inc
+
     def mark_weights_dirty(self):
         """Call after changing parameters behind the engine's back (e.g. in-place edits) before a fused train_step."""
         self._dirty = True
@@ -400,6 +404,11 @@ class R21DBYOL(nn.Module):
         if self._dirty:
             eng.pack_online()
             self._dirty = False
+        if eng.use_graph and eng._prof is None:
+            # everything behind the input pass replayed from a CUDA graph (engine.graphed_step)
+            eng.graphed_step(x1, x2, labels, lr, momentum, weight_decay, clip_grad_norm or 0.0, bool(clip_grad_norm),
+                             grad_sync, self._bump_nbt)
+            return eng.losses
         eng.forward(x1, x2)
         eng.pretext_losses(labels)
         if eng.backward(grad_sync):

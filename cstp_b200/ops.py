@@ -923,6 +923,13 @@ def sgd_clip_step(p, g, mom, lr, momentum, wd, max_norm, do_clip, first_step, no
                                         _stream()))
 
 
+def sgd_clip_step_dev(p, g, mom, hyper, norm_out, workspace) -> None:
+    """sgd_clip_step with {lr, momentum, wd, max_norm, do_clip, first_step} read from the device vector `hyper` at run time
+    (the form a captured CUDA graph replays while the host follows the learning-rate schedule)."""
+    L.check(L.load().cstp_sgd_clip_step_dev(_ptr(p), _ptr(g), _ptr(mom), p.numel(), _ptr(hyper), _ptr(norm_out),
+                                            _ptr(workspace), _stream()))
+
+
 def kernel_name(plan) -> str:
     """CUDA kernel a plan object launches (for profiles and the bench roofline)."""
     inner = getattr(plan, "plan", plan)          # WgradSpec wraps its plan
@@ -930,5 +937,15 @@ def kernel_name(plan) -> str:
             WgradPlan: "wgrad_gemm_kernel"}.get(type(inner), type(inner).__name__)
 
 
+_replayed_launches = 0
+
+
+def note_replayed(n: int) -> None:
+    """Kernel launches replayed from a captured CUDA graph (the C-side counter only sees direct launches)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
-    return int(L.load().cstp_launch_count())
+    """Kernels of this library launched so far: direct launches through the C ABI plus launches replayed from CUDA graphs."""
+    return int(L.load().cstp_launch_count()) + _replayed_launches

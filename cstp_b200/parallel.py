@@ -137,8 +137,10 @@ class BnSyncP2P:
     single-CTA kernel (`cstp_bn_sync_exchange`, csrc/p2p_sync.cu) that stores the row into every peer's receive buffer
     (torch symmetric memory), publishes a flag and sums the rows in rank order -- a few microseconds instead of an NCCL
     all-reduce's ~25-30, ~140 times per step.  The sum order is the rank order on every rank, so all ranks hold
-    bit-identical statistics.  One channel (buffer set + sequence counter) per CUDA stream the engine calls it from;
-    channels are created in call order, which is the same on every rank."""
+    bit-identical statistics.  Two channels (buffer set + DEVICE call counter each): one for the stream the step runs on,
+    one for the engine's side stream (register_side_stream) -- keyed by role, not by stream handle, so that the step can be
+    captured into a CUDA graph on torch's capture stream and replayed; channels are created in call order, which is the
+    same on every rank (the first, eager step creates both)."""
 
     def __init__(self, group=None, row_max: int = 4 * 4096, slots: int = 4):
         if not dist.is_initialized():
@@ -147,12 +149,17 @@ class BnSyncP2P:
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.row_max, self.slots = int(row_max), int(slots)
         self._chan = {}
+        self._side = set()
         self.err = None
+
+    def register_side_stream(self, stream) -> None:
+        """Calls issued while `stream` is current use the second channel (the engine's target-network stream)."""
+        self._side.add(stream.cuda_stream)
 
     def _channel(self):
         import torch.distributed._symmetric_memory as symm_mem
         from . import lib as L
-        key = torch.cuda.current_stream().cuda_stream
+        key = 1 if torch.cuda.current_stream().cuda_stream in self._side else 0
         ch = self._chan.get(key)
         if ch is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -164,7 +171,7 @@ class BnSyncP2P:
             dist.barrier(self.group)             # every buffer is zeroed before any peer writes into it
             if self.err is None:
                 self.err = torch.zeros(1, dtype=torch.int32, device=dev)
-            ch = dict(buf=buf, hdl=hdl, peers=int(hdl.buffer_ptrs_dev), seq=0)
+            ch = dict(buf=buf, hdl=hdl, peers=int(hdl.buffer_ptrs_dev), seq_dev=torch.zeros(1, dtype=torch.int32, device=dev))
             self._chan[key] = ch
         return ch
 
@@ -175,9 +182,9 @@ class BnSyncP2P:
         if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
             raise L.CstpError("BnSyncP2P exchanges contiguous fp32 CUDA rows")
         ch = self._channel()
-        ch["seq"] += 1
+        # the call sequence number lives in device memory and is bumped by the kernel (replayable from a CUDA graph)
         L.check(L.load().cstp_bn_sync_exchange(t.data_ptr(), t.numel(), ch["peers"], self.world, self.rank, self.slots,
-                                               self.row_max, ch["seq"], t.data_ptr(), self.err.data_ptr(),
+                                               self.row_max, 0, ch["seq_dev"].data_ptr(), t.data_ptr(), self.err.data_ptr(),
                                                torch.cuda.current_stream().cuda_stream))
 
     def check(self) -> None:

@@ -345,6 +345,11 @@ int cstp_ema_update(float* k, const float* q, int64_t n, float m, float one_minu
 int cstp_sgd_clip_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float wd,
                        float max_norm, int do_clip, int first_step, float* norm_out, float* workspace,
                        void* stream);
+/* The same with the hyper-parameters read from DEVICE memory at run time, hyper = {lr, momentum, wd, max_norm, do_clip,
+ * first_step} (flags: nonzero = set): the launch can sit in a captured CUDA graph while the host follows the per-epoch
+ * learning-rate schedule (scheduler/cosine_anneal.py) by rewriting six floats. */
+int cstp_sgd_clip_step_dev(float* p, const float* g, float* mom, int64_t n, const float* hyper, float* norm_out,
+                           float* workspace, void* stream);
 
 /* ---- pretraining clip pipeline -----------------------------------------------------------
  * Replaces the pixel work of the reference's CPU data pipeline for one batch of pretraining samples:
@@ -390,11 +395,13 @@ int cstp_clip_assemble(const cstp_clip_view* views, int n_views, int T, int S, i
  * stores the local row into every peer's receive buffer, publishes a flag, waits for every peer's flag and sums the rows
  * in rank order (csrc/p2p_sync.cu).  peer_buffers: DEVICE array of `world` pointers to the per-rank buffers
  * (peer-mapped, e.g. torch symmetric memory), each cstp_bn_sync_buffer_bytes(world, slots, row_max) bytes, zeroed before
- * the first call; seq = 1, 2, ... per buffer set, identical on every rank; out may alias row; *err_flag becomes
- * 1 + peer when a peer's flag did not arrive within the spin limit. */
+ * the first call; seq = 1, 2, ... per buffer set, identical on every rank -- either passed by the host (seq != 0,
+ * seq_dev NULL) or kept by the kernel in a DEVICE counter (seq == 0, *seq_dev incremented per call: the launch can then
+ * be replayed from a CUDA graph); out may alias row; *err_flag becomes 1 + peer when a peer's flag did not arrive within
+ * the spin limit. */
 long long cstp_bn_sync_buffer_bytes(int world, int slots, int row_max);
 int cstp_bn_sync_exchange(const float* row, int n, const uint64_t* peer_buffers, int world, int rank, int slots,
-                          int row_max, uint32_t seq, float* out, int* err_flag, void* stream);
+                          int row_max, uint32_t seq, uint32_t* seq_dev, float* out, int* err_flag, void* stream);
 
 #ifdef __cplusplus
 }

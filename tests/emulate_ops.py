@@ -446,6 +446,15 @@ def ema_update(k, q, m):
     k.copy_(k * mf + q * omf)
 
 
+def sgd_clip_step_dev(p, g, mom, hyper, norm_out, workspace):
+    lr, momentum, wd, max_norm, do_clip, first = [float(v) for v in hyper.tolist()]
+    sgd_clip_step(p, g, mom, lr, momentum, wd, max_norm, bool(do_clip), bool(first), norm_out, workspace)
+
+
+def note_replayed(n):
+    _count(n)
+
+
 def sgd_clip_step(p, g, mom, lr, momentum, wd, max_norm, do_clip, first_step, norm_out, workspace):
     _count(2)
     total = g.double().pow(2).sum().sqrt().float()

@@ -65,7 +65,7 @@ def test_bn_sync_exchange_argument_checks():
     lib = L.load()
     assert lib.cstp_bn_sync_buffer_bytes(8, 4, 16384) == 4 * 8 * 16384 * 4 + 4 * 8 * 4
     assert lib.cstp_bn_sync_buffer_bytes(0, 4, 16) == -1
-    assert lib.cstp_bn_sync_exchange(None, 16, None, 2, 0, 4, 64, 1, None, None, None) == -1
+    assert lib.cstp_bn_sync_exchange(None, 16, None, 2, 0, 4, 64, 1, None, None, None, None) == -1
     assert b"invalid argument" in lib.cstp_last_error()
 
 

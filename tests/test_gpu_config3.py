@@ -55,6 +55,33 @@ def test_fused_prologue_is_bit_identical_to_two_pass_batchnorm():
             assert torch.equal(a, b)
 
 
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches():
+    """The captured step (engine.graphed_step: forward, losses, backward on two streams, optimiser with its
+    hyper-parameters in device memory, re-pack, num_batches_tracked) replays the very launches of the eager program: five
+    steps with a learning-rate change in between end in identical bits."""
+    from cstp_b200.models.pace.r21d_byol import R21DBYOL
+    from oracle import cstp_oracle as O
+    batches = [O.structured_batch(3, s, 8, 64) for s in (5, 6)]
+    outs = []
+    for graph in (False, True):
+        torch.manual_seed(1)
+        m = R21DBYOL(pretrain=True)
+        m.engine_options = {"graph": graph}
+        m.cuda()
+        losses = []
+        for i in range(5):
+            x1, x2, lab = batches[i % 2]
+            l = m.train_step(x1.cuda(), x2.cuda(), tuple(t.cuda() for t in lab), LW, lr=0.03 if i < 3 else 0.01)
+            losses.append(l.clone())
+        eng = m._engine
+        assert (eng._graph is not None) == graph
+        outs.append((torch.stack(losses), eng.train.data.clone(), eng.target.data.clone(), eng.bufs.data.clone(),
+                     eng.mom.clone(), m.online_net.bn1.num_batches_tracked.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(outs[1][5]) == 10           # two views per step (r21d_byol.py:362-371 runs the online net twice)
+
+
 def test_config3_batch60_step_against_reference_golden():
     from cstp_b200.models.pace.r21d_byol import R21DBYOL
     from oracle import cstp_oracle as O

@@ -98,11 +98,12 @@ def test_bn_sync_exchange_protocol_on_one_gpu():
     for seq in range(1, 11):
         row = torch.randn(n, device="cuda")
         out = torch.empty_like(row)
-        L.check(lib.cstp_bn_sync_exchange(row.data_ptr(), n, peers.data_ptr(), 1, 0, slots, row_max, seq, out.data_ptr(),
+        L.check(lib.cstp_bn_sync_exchange(row.data_ptr(), n, peers.data_ptr(), 1, 0, slots, row_max, seq, None, out.data_ptr(),
                                           err.data_ptr(), torch.cuda.current_stream().cuda_stream))
         assert torch.equal(out, row)
     bufs, peers = buffers(2)
     s = [torch.cuda.Stream(), torch.cuda.Stream()]
+    counters = torch.full((2,), 6, dtype=torch.int32, device="cuda")      # device-side call counters (CUDA-graph form)
     torch.cuda.synchronize()
     for seq in range(1, 13):
         rows = [torch.randn(n, device="cuda"), torch.randn(n, device="cuda")]
@@ -110,9 +111,12 @@ def test_bn_sync_exchange_protocol_on_one_gpu():
         torch.cuda.synchronize()
         for r in (seq % 2, 1 - seq % 2):                     # alternate which "rank" is launched first
             with torch.cuda.stream(s[r]):
-                L.check(lib.cstp_bn_sync_exchange(rows[r].data_ptr(), n, peers.data_ptr(), 2, r, slots, row_max, seq,
+                host_seq = seq <= 6          # first half: sequence number from the host, second half: device counter
+                L.check(lib.cstp_bn_sync_exchange(rows[r].data_ptr(), n, peers.data_ptr(), 2, r, slots, row_max,
+                                                  seq if host_seq else 0,
+                                                  None if host_seq else counters[r:r + 1].data_ptr(),
                                                   rows[r].data_ptr(), err.data_ptr(), s[r].cuda_stream))     # in place
         torch.cuda.synchronize()
         assert torch.equal(rows[0], rows[1])                 # same order of summation on both ranks: identical bits
         assert torch.equal(rows[0], want)
-    assert int(err.item()) == 0
+    assert int(err.item()) == 0 and counters.tolist() == [12, 12]

@@ -18,8 +18,11 @@ B = int(args[0]) if args else 60
 K = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 8
 torch.manual_seed(1)
 m = R21DBYOL(pretrain=True).cuda()
+m.engine_options = {}
 if "--no-overlap" in sys.argv:
-    m.engine_options = {"overlap": False}
+    m.engine_options["overlap"] = False
+if "--no-graph" in sys.argv:
+    m.engine_options["graph"] = False
 x1, x2, labels = synthetic_batch(B, 0)
 x1, x2 = x1.cuda(), x2.cuda()
 labels = tuple(l.cuda() for l in labels)
