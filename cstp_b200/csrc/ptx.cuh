@@ -68,6 +68,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same for warps that wait for a whole main loop (split-K epilogues): sleep between polls instead of competing with
+// the producer / issuer / transform warps for issue slots (ncu: four spinning epilogue warps executed 19 % of all
+// instructions of a weight-gradient kernel).
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(512);
+    if (++spins > CSTP_SPIN_LIMIT) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -415,6 +426,24 @@ __device__ __forceinline__ uint4 xform_unit(const uint4& v, const XformCoef& k) 
   o.w = xform_pair(v.w, k.s[6], k.b[6], k.s[7], k.b[7]);
   return o;
 }
+// The same map when nothing downstream reads out-of-range elements (no NaN -> 0 rescue needed): ReLU and the bf16 rounding
+// are ONE conversion (cvt.rn.relu.bf16x2.f32: negative results clamp to +0) and the low half is widened on the FMA pipe
+// (IMAD) -- 2 ALU-pipe + 3 FMA-pipe instructions per pair instead of 5 + 2; the ALU pipe (one warp instruction per two
+// cycles and scheduler) is what bounds the transform warps.  Same bits as xform_pair for finite inputs.
+__device__ __forceinline__ uint32_t xform_pair_relu(uint32_t v, float s0, float b0, float s1, float b1) {
+  const float lo = __uint_as_float(v * 65536u), hi = __uint_as_float(v & 0xffff0000u);
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(fmaf(hi, s1, b1)), "f"(fmaf(lo, s0, b0)));
+  return r;
+}
+__device__ __forceinline__ uint4 xform_unit_relu(const uint4& v, const XformCoef& k) {
+  uint4 o;
+  o.x = xform_pair_relu(v.x, k.s[0], k.b[0], k.s[1], k.b[1]);
+  o.y = xform_pair_relu(v.y, k.s[2], k.b[2], k.s[3], k.b[3]);
+  o.z = xform_pair_relu(v.z, k.s[4], k.b[4], k.s[5], k.b[5]);
+  o.w = xform_pair_relu(v.w, k.s[6], k.b[6], k.s[7], k.b[7]);
+  return o;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
@@ -427,18 +456,20 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
 // ...  (kStep = participating threads; kStep * 16 must be a multiple of 1024).  Every load of a batch of (up to) four units
 // is issued before the first result is needed -- the loop is latency bound, not throughput bound (ncu: the transform
 // warps of the first version sat on the LDS scoreboard while the issue slots were 35 % busy).
-template <int kStep>
+// kRelu: the box has no out-of-range element (interior tile, full channel chunk): xform_unit_relu applies.
+template <int kStep, bool kRelu = false>
 __device__ __forceinline__ void xform_span(uint32_t base, uint32_t first, uint32_t end, const XformCoef& k) {
   static_assert((kStep * 16) % 1024 == 0, "thread stride must keep the swizzle phase");
   constexpr uint32_t kB = kStep * 16u;
+  auto f = [&k](const uint4& v) { return kRelu ? xform_unit_relu(v, k) : xform_unit(v, k); };
   uint32_t u = first;
   for (; u + 3 * kStep < end; u += 4 * kStep) {
     const uint32_t a = base + u * 16u;
     const uint4 v0 = lds128(a), v1 = lds128(a + kB), v2 = lds128(a + 2u * kB), v3 = lds128(a + 3u * kB);
-    sts128(a, xform_unit(v0, k));
-    sts128(a + kB, xform_unit(v1, k));
-    sts128(a + 2u * kB, xform_unit(v2, k));
-    sts128(a + 3u * kB, xform_unit(v3, k));
+    sts128(a, f(v0));
+    sts128(a + kB, f(v1));
+    sts128(a + 2u * kB, f(v2));
+    sts128(a + 3u * kB, f(v3));
   }
   if (u < end) {                    // one to three units left: same shape, predicated
     const uint32_t a = base + u * 16u;
@@ -446,9 +477,9 @@ __device__ __forceinline__ void xform_span(uint32_t base, uint32_t first, uint32
     uint4 v0 = lds128(a), v1 = v0, v2 = v0;
     if (p1) v1 = lds128(a + kB);
     if (p2) v2 = lds128(a + 2u * kB);
-    sts128(a, xform_unit(v0, k));
-    if (p1) sts128(a + kB, xform_unit(v1, k));
-    if (p2) sts128(a + 2u * kB, xform_unit(v2, k));
+    sts128(a, f(v0));
+    if (p1) sts128(a + kB, f(v1));
+    if (p2) sts128(a + 2u * kB, f(v2));
   }
 }
 

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
     const int ncols = min(p.n_tile, p.Np - col0);
     const long long mtot = static_cast<long long>(p.n_mchunks) * 64;
     float* dst = p.partials + (static_cast<long long>(split) * mtot + static_cast<long long>(mtile) * 128 + row) * p.Np + col0;
-    mbar_wait(tfull, 0);
+    mbar_wait_idle(tfull, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     epilogue_row_f32(taddr, ncols, dst, valid);     // pipelined TMEM loads, 32-byte stores (ptx.cuh)
@@ -216,20 +216,25 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
 // of a (cout, 3, 1, 7, 7) weight; channels / taps without a weight element are skipped.
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partials, int splits, int n_mchunks, int Np,
                                       const int* __restrict__ chunk_tap, const int* __restrict__ chunk_coff, int cout,
-                                      int cin, int taps, float* __restrict__ dw, int accumulate, int layout) {
+                                      int cin, int taps, float* __restrict__ dw, int accumulate, int layout,
+                                      const int* __restrict__ chunk_splits) {
   const long long mtot = static_cast<long long>(n_mchunks) * 64;
-  const long long total = mtot * cout;
+  // rows carry (tap, row channel), columns the other channel axis: (cin rows, cout columns) -- or, layout 2, the reverse
+  const int ncol = layout == 2 ? cin : cout, nrow = layout == 2 ? cout : cin;
+  const long long total = mtot * ncol;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int co = static_cast<int>(i % cout);
-    const long long row = i / cout;
+    const int col = static_cast<int>(i % ncol);
+    const long long row = i / ncol;
     const int chunk = static_cast<int>(row >> 6);
-    const int ci = chunk_coff[chunk] + static_cast<int>(row & 63);
-    if (ci >= cin) continue;
+    const int rc = chunk_coff[chunk] + static_cast<int>(row & 63);
+    if (rc >= nrow) continue;
+    const int ns = chunk_splits != nullptr ? chunk_splits[chunk] : splits;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partials[(static_cast<long long>(s) * mtot + row) * Np + co];
+    for (int s = 0; s < ns; ++s) acc += partials[(static_cast<long long>(s) * mtot + row) * Np + col];
+    const int co = layout == 2 ? rc : col, ci = layout == 2 ? col : rc;
     long long o;
-    if (layout == 0) {
+    if (layout == 0 || layout == 2) {
       o = (static_cast<long long>(co) * cin + ci) * taps + chunk_tap[chunk];
     } else {
       const int k = ci & 31, kh = 2 * chunk_tap[chunk] + (ci >> 5) - 1;
@@ -373,17 +378,17 @@ extern "C" void cstp_wgrad_plan_destroy(cstp_wgrad_plan* plan) { delete plan; }
 
 extern "C" int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np, const int32_t* chunk_tap,
                                    const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
-                                   int layout, void* stream) {
+                                   int layout, const int32_t* chunk_splits, void* stream) {
   CSTP_REQUIRE(partials && chunk_tap && chunk_coff && dw);
-  CSTP_REQUIRE(layout == 0 || (layout == 1 && cin == 64 && taps == 4));
-  CSTP_REQUIRE(splits >= 1 && n_mchunks >= 1 && n_mchunks <= CSTP_MAX_MCHUNKS && cout <= Np);
+  CSTP_REQUIRE(layout == 0 || layout == 2 || (layout == 1 && cin == 64 && taps == 4));
+  CSTP_REQUIRE(splits >= 1 && n_mchunks >= 1 && n_mchunks <= CSTP_MAX_MCHUNKS && (layout == 2 ? cin : cout) <= Np);
   // chunk_tap / chunk_coff are device pointers (tiny int arrays uploaded once by the host at plan time).
-  const long long total = static_cast<long long>(n_mchunks) * 64 * cout;
+  const long long total = static_cast<long long>(n_mchunks) * 64 * (layout == 2 ? cin : cout);
   int blocks = ceil_div(total, 256);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   wgrad_finalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, splits, n_mchunks, Np, chunk_tap,
                                                                              chunk_coff, cout, cin, taps, dw, accumulate,
-                                                                             layout);
+                                                                             layout, chunk_splits);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

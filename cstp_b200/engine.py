@@ -46,13 +46,15 @@ FUSE_BN_APPLY = os.environ.get("CSTP_FUSE_BN_APPLY", "1") == "1"
 # non-resident weights cannot hide the extra hop); on 14 x 14 / 7 x 7 planes the tensors are L2-sized and the 1x3x3
 # convolutions re-stage -- and would re-transform -- the same box once per filter tap (csrc/conv_gemm.cu).
 FUSE_MIN_POSITIONS = int(os.environ.get("CSTP_FUSE_MIN_POSITIONS") or 56 * 56)
-# Which edges: "all" (default): every conv -> BatchNorm -> ReLU -> conv edge above the size threshold; "auto": networks
-# without a backward pass defer every such edge, the online network only those in front of a 1x3x3 convolution; "none".
-# Background (measured per layer at batch 60, profiles/README.md): the conv kernels of this network are bound by
-# SHARED-MEMORY bandwidth (every tcgen05.mma re-reads its 128-row A slice; N = 64 tiles want 192 B/clk), and the in-place
-# transform adds one read + one write of the staged box: +5 % for a 1x3x3 forward (nine taps per box), +30 % for a 3x1x1
-# forward, +60 % for the weight gradient of a 3x1x1 layer -- against the two HBM passes of cstp_bn_apply each edge drops.
-FUSE_POLICY = os.environ.get("CSTP_FUSE_POLICY") or "all"
+# Which edges: "all": every conv -> BatchNorm -> ReLU -> conv edge above the size threshold; "auto" (default): networks
+# without a backward pass defer every such edge, the online network only those in front of a 3x1x1 convolution; "none".
+# Background (measured per layer at batch 60, profiles/README.md): the in-place transform costs the consumer's forward
+# +1..10 % (1x3x3: nine taps per staged box) to +25 % (3x1x1) and its weight-gradient kernel +35 % (3x1x1, where the
+# transformed operand is the N side of the flipped product) to +45 % (1x3x3, where both M classes transform the same box),
+# against the two HBM passes of cstp_bn_apply the edge drops: 0.56 ms for a 144-channel 56 x 56 tensor (the input of a
+# 3x1x1 layer), 0.25 ms for a 64-channel one (the input of a 1x3x3 layer) -- the latter is less than its weight-gradient
+# kernel loses, so edges in front of a 1x3x3 convolution stay materialised where there is a backward pass.
+FUSE_POLICY = os.environ.get("CSTP_FUSE_POLICY") or "auto"
 # The whole step (forward, losses, backward, gradient all-reduce, optimiser, re-pack: ~560 launches on three streams) is
 # captured into ONE CUDA graph after an eager first step and replayed from then on (StepEngine.graphed_step): at 16 samples
 # per GPU the eager step is bound by the host issuing launches through ctypes, not by the GPU.  "0": always eager.
@@ -347,7 +349,7 @@ class StepEngine:
         pro = self._pending.get(x.data_ptr())         # x is a raw tensor whose BatchNorm + ReLU we apply on the way in
         defer = (apply and relu and res is None and self.fuse_apply and self.fuse_policy != "none"
                  and Ho * Wo >= self.fuse_min_positions
-                 and (self.fuse_policy == "all" or not grads or geom.kernel[0] > 1))
+                 and (self.fuse_policy == "all" or not grads or geom.kernel[0] == 1))
         keep_act = apply and (not defer or self.record)          # parity tests still look at every activation
         act = self._act(N, To, Ho, Wo, Cop) if keep_act else None
         wp, wt = self._packed(store, wname, grads and not skip_dgrad, stem=stem)

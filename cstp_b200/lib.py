@@ -127,6 +127,8 @@ class WgradHaloDesc(C.Structure):
         ("partials", C.c_void_p),
         ("atom_pitch_rows", C.c_int32),
         ("pro", Prologue),
+        ("mt_per_class", C.c_int32),
+        ("pro_on_b", C.c_int32),
     ]
 
 
@@ -179,7 +181,8 @@ SIGNATURES = {
     "cstp_wgrad_halo_plan_splits": (_i, [_vp]),
     "cstp_wgrad_halo_plan_run": (_i, [_vp, _vp]),
     "cstp_wgrad_halo_plan_destroy": (None, [_vp]),
-    "cstp_wgrad_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "cstp_wgrad_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "cstp_wgrad_halo_plan_chunk_splits": (_i, [_vp, _vp, _i]),
     "cstp_pack_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "cstp_pack_weights_batched": (_i, [_vp, _vp, _i, _i64, _vp]),
     "cstp_stem_im2col": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -484,13 +484,16 @@ class WgradSpec:
     cin: int
     taps: int
     partials: torch.Tensor
-    layout: int = 0              # 1: the stem over cstp_stem_pack rows, dW is the reference's (cout, 3, 1, 7, 7) tensor
+    layout: int = 0              # 1: the stem over cstp_stem_pack rows, dW is the reference's (cout, 3, 1, 7, 7) tensor;
+    #                              2: transposed product (rows (tap, cout), columns cin)
+    chunk_splits: torch.Tensor | None = None      # per-chunk number of split-K partials (M classes), None: plan.splits
 
     def run(self, dw: torch.Tensor, accumulate: bool = False):
         self.plan.run()
         L.check(L.load().cstp_wgrad_finalize(_ptr(self.partials), self.plan.splits, self.n_mchunks, self.Np,
                                              _ptr(self.chunk_tap), _ptr(self.chunk_coff), self.cout, self.cin,
-                                             self.taps, _ptr(dw), int(accumulate), self.layout, _stream()))
+                                             self.taps, _ptr(dw), int(accumulate), self.layout, _ptr(self.chunk_splits),
+                                             _stream()))
 
 
 class WgradHaloPlan(_Plan):
@@ -500,33 +503,50 @@ class WgradHaloPlan(_Plan):
         L.check(L.load().cstp_wgrad_halo_plan_run(self.handle, _stream()))
 
 
-def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
-    """Geometry of the all-taps-per-CTA weight-gradient kernel (csrc/wgrad_halo.cu) for a stride-1 1xkxk / kx1x1
-    convolution, or None when the layer does not qualify (then csrc/wgrad.cu is used).  Pure shape arithmetic.
+WGRAD_TRANSPOSE = os.environ.get("CSTP_WGRAD_TRANSPOSE", "1") == "1"
+WGRAD_MCLASSES = os.environ.get("CSTP_WGRAD_MCLASSES", "1") == "1"
 
-    Returns dict(box, halo, xboxes [(c_off, dw, dh, dt)], chunks [(stage byte offset, tap index, c_off)] sorted by
-    offset, xbox_bytes, n_tile, n_ntiles, splits, need (floats of split-K partials))."""
+
+def _wgrad_halo_side(m_channels: int, n_channels: int, dims, geom: ConvGeom, flip: bool, sms: int, xform: bool = False):
+    """One orientation of the all-taps-per-CTA weight-gradient kernel: the operand with `m_channels` carries the taps (staged
+    with a halo, M = (tap, 64-channel chunk)), the other one (`n_channels`, N axis) is staged as plain boxes.  flip: the M
+    side is dL/d(raw) and the N side the activations (the taps then shift the other way).  Returns the layout dict with a
+    `cost` (model cycles per K-block: the larger of tensor time and shared-memory time) or None."""
     (kt, kh, kw), (pt, ph, pw) = geom.kernel, geom.pad
-    if tuple(geom.stride) != (1, 1, 1) or geom.taps == 1 or (kt > 1 and (kh > 1 or kw > 1)):
-        return None
-    N, T, H, W, Ca = x_shape
-    _, To, Ho, Wo, Np = g_shape
-    n_cc = pad64(Ca) // 64
+    N, To, Ho, Wo = dims
+    n_cc = pad64(m_channels) // 64
     n_chunks = geom.taps * n_cc
     if n_chunks > 32:
         return None
     n_mtiles = (n_chunks + 1) // 2
-    n_tile = min(Np, 256, (512 // n_mtiles) // 16 * 16)
-    if n_tile < 16:
-        return None
-    n_ntiles = math.ceil(Np / n_tile)
+    Np = n_channels
+    if WGRAD_MCLASSES:
+        # full-width N tiles (every MMA as wide as the layer allows); the M tiles are dealt to CTA classes that fit TMEM
+        n_ntiles = math.ceil(Np / 256)
+        n_tile = pad16(math.ceil(Np / n_ntiles))
+        if flip and xform and n_ntiles > 1:      # the prologue on the N-side boxes wants N-tile origins on 64-channel chunks
+            n_tile = pad64(n_tile)
+            n_ntiles = math.ceil(Np / n_tile)
+        mt_per_class = min(n_mtiles, 512 // n_tile)
+        n_mclasses = math.ceil(n_mtiles / mt_per_class)
+        mt_per_class = math.ceil(n_mtiles / n_mclasses)          # balanced classes (5 tiles, cap 3 -> 3 + 2)
+        if n_mclasses > 8:
+            return None
+    else:
+        n_tile = min(Np, 256, (512 // n_mtiles) // 16 * 16)
+        if n_tile < 16 or (flip and xform and n_tile < Np and n_tile % 64):
+            return None
+        n_ntiles, mt_per_class, n_mclasses = math.ceil(Np / n_tile), n_mtiles, 1
     temporal = kt > 1
+    # tap a reads the M-side operand at offset (a - pad) from the K-block origin -- or, flipped, at -(a - pad)
+    off = (lambda a, k, p_: (k - 1 - a) if flip else a)
+    org = (lambda k, p_: -(k - 1 - p_) if flip else -p_)
     # 1 x k x k filters, 2-D halo: ONE staged (8 + kw - 1) x (8 + kh - 1) box per 64-channel chunk serves every tap (a tap
-    # is a whole-row shift of it; the 8 positions of a w run are one swizzle atom, atoms one box row apart).  X is then
-    # cheap enough to be re-staged for up to 6 N tiles, which admits layers whose taps x channels need many accumulators.
-    halo_2d = (USE_HALO_2D and not temporal and kw > 1 and kh > 1 and n_ntiles <= 6
+    # is a whole-row shift of it; the 8 positions of a w run are one swizzle atom, atoms one box row apart).  The box is
+    # then cheap enough to be re-staged by several CTA classes.
+    halo_2d = (USE_HALO_2D and not temporal and kw > 1 and kh > 1 and n_ntiles * n_mclasses <= 6
                and math.ceil(Wo / 8) * math.ceil(Ho / 8) * 64 <= 1.35 * Wo * Ho)
-    if n_ntiles > 2 and not halo_2d:          # X is re-staged once per N tile
+    if n_ntiles * n_mclasses > 2 and not halo_2d:          # the M-side boxes are re-staged once per class
         return None
     pitch = 8
     if halo_2d:
@@ -534,8 +554,8 @@ def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
         bw, bh, bt, _ = box
         xrows = (bw + halo[0]) * (bh + halo[1])
         xbox_bytes = (xrows * 128 + 1023) // 1024 * 1024
-        xboxes = [(cc * 64, -pw, -ph, 0) for cc in range(n_cc)]
-        chunks = [(cc * xbox_bytes + (b_ * pitch + c) * 128, b_ * kw + c, cc * 64)
+        xboxes = [(cc * 64, org(kw, pw), org(kh, ph), 0) for cc in range(n_cc)]
+        chunks = [(cc * xbox_bytes + (off(b_, kh, ph) * pitch + off(c, kw, pw)) * 128, b_ * kw + c, cc * 64)
                   for b_ in range(kh) for c in range(kw) for cc in range(n_cc)]
     else:
         best = None
@@ -557,18 +577,18 @@ def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
         xboxes, chunks = [], []
         if temporal:
             for cc in range(n_cc):
-                xboxes.append((cc * 64, 0, 0, -pt))
+                xboxes.append((cc * 64, 0, 0, org(kt, pt)))
             for a in range(kt):
                 for cc in range(n_cc):
-                    chunks.append((cc * xbox_bytes + a * (bw * bh) * 128, a, cc * 64))
+                    chunks.append((cc * xbox_bytes + off(a, kt, pt) * (bw * bh) * 128, a, cc * 64))
         else:
             for c in range(kw):
                 for cc in range(n_cc):
-                    xboxes.append((cc * 64, c - pw, -ph, 0))
+                    xboxes.append((cc * 64, (pw - c) if flip else (c - pw), org(kh, ph), 0))
             for b_ in range(kh):
                 for c in range(kw):
                     for cc in range(n_cc):
-                        chunks.append(((c * n_cc + cc) * xbox_bytes + b_ * bw * 128, b_ * kw + c, cc * 64))
+                        chunks.append(((c * n_cc + cc) * xbox_bytes + off(b_, kh, ph) * bw * 128, b_ * kw + c, cc * 64))
     if len(xboxes) > 16:
         return None
     chunks.sort()
@@ -579,15 +599,42 @@ def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148):
     splits = max(1, sms // n_ntiles)
     kblocks = math.ceil(Wo / bw) * math.ceil(Ho / bh) * math.ceil(To / bt) * N
     splits = min(splits, kblocks)
+    mmas = 4 * n_mtiles * n_ntiles
+    cost = max(mmas * n_tile / 2, mmas * (4096 + 32 * n_tile) / 128)
     return dict(box=box, halo=halo, xboxes=xboxes, chunks=chunks, xbox_bytes=xbox_bytes, n_tile=n_tile,
-                n_ntiles=n_ntiles, splits=splits, need=splits * n_chunks * 64 * Np, pitch=pitch)
+                n_ntiles=n_ntiles, splits=splits, need=splits * n_chunks * 64 * Np, pitch=pitch,
+                mt_per_class=mt_per_class if n_mclasses > 1 else 0, flip=flip, cost=cost)
+
+
+def wgrad_halo_layout(x_shape, g_shape, geom: ConvGeom, sms: int = 148, xform: bool = False):
+    """Geometry of the all-taps-per-CTA weight-gradient kernel (csrc/wgrad_halo.cu) for a stride-1 1xkxk / kx1x1
+    convolution, or None when the layer does not qualify (then csrc/wgrad.cu is used).  Pure shape arithmetic.
+
+    Two orientations are costed (shared-memory bytes and tensor cycles per K-block) and the cheaper one is taken: the taps
+    ride on X (M = (tap, cin chunk), N = cout) or -- `flip`, same-size convolutions only -- on dL/d(raw)
+    (M = (tap, cout chunk), N = cin), which keeps the MMAs wide for the 144 -> 64 3x1x1 layers.
+
+    Returns dict(box, halo, xboxes [(c_off, dw, dh, dt)] of the M-side tensor, chunks [(stage byte offset, tap index,
+    first M-side channel)] sorted by offset, xbox_bytes, n_tile, n_ntiles, mt_per_class, splits, need (floats of split-K
+    partials), flip).  xform: X is read through the operand prologue (constrains the N tiles of the flipped form)."""
+    (kt, kh, kw) = geom.kernel
+    if tuple(geom.stride) != (1, 1, 1) or geom.taps == 1 or (kt > 1 and (kh > 1 or kw > 1)):
+        return None
+    N, T, H, W, Ca = x_shape
+    _, To, Ho, Wo, Np = g_shape
+    lay = _wgrad_halo_side(Ca, Np, (N, To, Ho, Wo), geom, False, sms, xform)
+    if WGRAD_TRANSPOSE and (T, H, W) == (To, Ho, Wo) and geom.pad_hi is None:
+        alt = _wgrad_halo_side(Np, Ca, (N, To, Ho, Wo), geom, True, sms, xform)
+        if alt is not None and (lay is None or alt["cost"] < lay["cost"]):
+            lay = alt
+    return lay
 
 
 def wgrad_partials_need(x_shape, g_shape, geom: ConvGeom, sms: int = 148) -> int:
     """Upper bound (floats) of the split-K scratch wgrad_plan needs for this layer."""
-    lay = wgrad_halo_layout(x_shape, g_shape, geom, sms)
-    if lay is not None:
-        return lay["need"]
+    lays = [wgrad_halo_layout(x_shape, g_shape, geom, sms, xf) for xf in (False, True)]
+    if lays[0] is not None:
+        return max(l["need"] for l in lays if l is not None)
     Ca, Np = x_shape[-1], g_shape[-1]
     nch = geom.taps * (pad64(Ca) // 64)
     n_tile = Np if Np <= 256 else 256
@@ -607,10 +654,18 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
     _, To, Ho, Wo, Np = g.shape
     assert geom.out_dims(T, H, W) == (To, Ho, Wo)
     dev = x.device
-    lay = wgrad_halo_layout(tuple(x.shape), tuple(g.shape), geom, sms) if (allow_halo and splits is None and box is None) else None
+    lay = (wgrad_halo_layout(tuple(x.shape), tuple(g.shape), geom, sms, prologue is not None)
+           if (allow_halo and splits is None and box is None) else None)
     if lay is not None:
+        flip = lay["flip"]
+        if layout != 0 and flip:
+            raise L.CstpError("the stem weight-gradient layout has no transposed form")
         d = L.WgradHaloDesc()
-        d.xmap, d.gmap = _view5(x), _view5(g)
+        d.xmap, d.gmap = (_view5(g), _view5(x)) if flip else (_view5(x), _view5(g))
+        if flip:
+            Np = Ca                       # the N axis (columns of the partials) is cin
+        d.mt_per_class = lay["mt_per_class"]
+        d.pro_on_b = int(flip)
         d.n_xboxes = len(lay["xboxes"])
         for i, xb in enumerate(lay["xboxes"]):
             d.xboxes[i] = L.XBox(*xb)
@@ -631,10 +686,15 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
         L.check(lib.cstp_wgrad_halo_plan_create(C.byref(d), C.byref(h)))
         plan = WgradHaloPlan(h, lib.cstp_wgrad_halo_plan_destroy, (x, g, partials) + keep)
         plan.splits = lib.cstp_wgrad_halo_plan_splits(h)
+        chunk_splits = None
+        if lay["mt_per_class"]:
+            cs = (C.c_int32 * len(lay["chunks"]))()
+            L.check(lib.cstp_wgrad_halo_plan_chunk_splits(h, cs, len(lay["chunks"])))
+            chunk_splits = torch.tensor(list(cs), dtype=torch.int32, device=dev)
         return WgradSpec(plan, len(lay["chunks"]), Np,
                          torch.tensor([c[1] for c in lay["chunks"]], dtype=torch.int32, device=dev),
                          torch.tensor([c[2] for c in lay["chunks"]], dtype=torch.int32, device=dev), cout, cin, geom.taps,
-                         partials, layout)
+                         partials, 2 if flip else layout, chunk_splits)
     views, taps = _fwd_taps(x, geom)
     nchunk_c = pad64(Ca) // 64
     mch, ctap, ccoff = [], [], []

@@ -189,8 +189,11 @@ void cstp_wgrad_plan_destroy(cstp_wgrad_plan* plan);
  * arrays of length n_mchunks (tap index and first input channel of every 64-row chunk). */
 int cstp_wgrad_finalize(const float* partials, int splits, int n_mchunks, int Np, const int32_t* chunk_tap,
                         const int32_t* chunk_coff, int cout, int cin, int taps, float* dw, int accumulate,
-                        int layout, void* stream);
-/* layout 0: dW is (cout, cin, taps) as above.  layout 1 (the stem over cstp_stem_pack row pairs: cin = 64 pixel
+                        int layout, const int32_t* chunk_splits, void* stream);
+/* chunk_splits (DEVICE, may be NULL = `splits` for every chunk): partials of chunk i exist for split < chunk_splits[i].
+ * layout 2: the transposed product -- partial rows are (tap, cout) (chunk_coff = first OUTPUT channel of the chunk), the
+ * Np columns are the input channels; dW is (cout, cin, taps) as for layout 0.
+ * layout 0: dW is (cout, cin, taps) as above.  layout 1 (the stem over cstp_stem_pack row pairs: cin = 64 pixel
  * channels hpar*32 + kw*3 + c, taps = 4 row pairs j): dW is the reference's (cout, 3, 1, 7, 7) tensor, element
  * ((co*3 + c)*7 + kh)*7 + kw with kh = 2*j + hpar - 1; channels / taps outside the filter are skipped. */
 
@@ -223,11 +226,21 @@ typedef struct {
    * chunk; chunk_off in whole 128-byte rows). */
   int32_t atom_pitch_rows;
   cstp_prologue pro;                    /* BatchNorm + ReLU applied to X on the way in (scale NULL: none) */
+  /* M classes: > 0 and < ceil(n_chunks/2): the M tiles are dealt to CTA classes of this many tiles each (the TMEM bound
+   * becomes mt_per_class * n_tile <= 512) and `splits` split-K CTAs per N tile are shared out in proportion to the tiles
+   * of a class; rows of class c exist for split < its split count (cstp_wgrad_halo_plan_chunk_splits). */
+  int32_t mt_per_class;
+  /* Operand roles are symmetric: the caller may pass dL/d(raw) as `xmap` (halo, row-shifted chunks: M = (tap, cout)) and
+   * the activations as `gmap` (N = cin); pro_on_b != 0 then applies the prologue to the gmap boxes (n_tile % 64 == 0 or one
+   * N tile).  The partial rows are then (tap, cout-chunk) and the columns cin: cstp_wgrad_finalize layout 2. */
+  int32_t pro_on_b;
 } cstp_wgrad_halo_desc;
 
 typedef struct cstp_wgrad_halo_plan cstp_wgrad_halo_plan;
 int cstp_wgrad_halo_plan_create(const cstp_wgrad_halo_desc* desc, cstp_wgrad_halo_plan** plan);
-int cstp_wgrad_halo_plan_splits(const cstp_wgrad_halo_plan* plan);
+int cstp_wgrad_halo_plan_splits(const cstp_wgrad_halo_plan* plan);     /* rows of splits in the partials buffer */
+/* out[i] = number of split-K partials that exist for chunk i (differs between M classes). */
+int cstp_wgrad_halo_plan_chunk_splits(const cstp_wgrad_halo_plan* plan, int32_t* out, int n_chunks);
 int cstp_wgrad_halo_plan_run(const cstp_wgrad_halo_plan* plan, void* stream);
 void cstp_wgrad_halo_plan_destroy(cstp_wgrad_halo_plan* plan);
 

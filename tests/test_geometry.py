@@ -123,16 +123,20 @@ def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
                             out[a, b, c, :ce] = t[n0, tt, hh_, ww, c0:c0 + ce]
         return out.reshape(-1, 64)
 
+    # `flip`: the taps ride on dL/d(raw) (M = (tap, cout chunk)) and the activations are the N side (columns = cin)
+    flip = lay["flip"]
+    m_side, n_side = (gr, x) if flip else (x, gr)
+    n_cols = Ca if flip else Np
     n_chunks = len(lay["chunks"])
-    P = torch.zeros(n_chunks * 64, Np)
+    P = torch.zeros(n_chunks * 64, n_cols)
     for n0 in range(N):
         for t0 in range(0, T, bt):
             for h0 in range(0, H, bh):
                 for w0 in range(0, W, bw):
-                    boxes = [fetch(x, c0, w0 + dw, h0 + dh, t0 + dt, n0, bw + hw, bh + hh, bt + ht)
+                    boxes = [fetch(m_side, c0, w0 + dw, h0 + dh, t0 + dt, n0, bw + hw, bh + hh, bt + ht)
                              for (c0, dw, dh, dt) in lay["xboxes"]]
                     staged = torch.cat([torch.cat([b_, torch.zeros(box_rows - b_.shape[0], 64)], 0) for b_ in boxes], 0)
-                    G = torch.cat([fetch(gr, c0, w0, h0, t0, n0, bw, bh, bt) for c0 in range(0, Np, 64)], 1)[:, :Np]
+                    G = torch.cat([fetch(n_side, c0, w0, h0, t0, n0, bw, bh, bt) for c0 in range(0, n_cols, 64)], 1)[:, :n_cols]
                     for i, (off, _, _) in enumerate(lay["chunks"]):
                         idx = [off // 128 + a_ * pitch + j for a_ in range(8) for j in range(8)]
                         rows = staged[idx]
@@ -140,7 +144,9 @@ def test_wgrad_halo_layout_semantics(k, p, shape, cin, cout):
     dw_ = torch.zeros(cout, cin, geom.taps)
     for i, (_, tap, c0) in enumerate(lay["chunks"]):
         for r in range(64):
-            if c0 + r < cin:
+            if flip and c0 + r < cout:
+                dw_[c0 + r, :, tap] = P[i * 64 + r, :cin]
+            elif not flip and c0 + r < cin:
                 dw_[:, c0 + r, tap] = P[i * 64 + r, :cout]
     ref = torch.nn.grad.conv3d_weight(x[..., :cin].permute(0, 4, 1, 2, 3), (cout, cin, *k),
                                       gr[..., :cout].permute(0, 4, 1, 2, 3), stride=1, padding=p)
