@@ -58,9 +58,6 @@ struct ConvHaloKParams {
   const float* pro_scale;  // fp32 [pro_groups][pro_cp]
   const float* pro_shift;
   int pro_groups, pro_cp;
-  int a_w, a_h, a_t;       // extents of the activation view (interior test of the staged boxes)
-  int box_w, box_h, box_t; // extents of a staged box, halo included
-  int dbg;                 // development probe (CSTP_HC_DBG): 4 = never take the cheaper interior transform
   uint32_t xtab_off;       // byte offset (from the mbarrier block) of the prologue's coefficient table in shared memory
   __nv_bfloat16* out;
   float* out_f32;
@@ -363,30 +360,16 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-      int pt = tile;
-      const int w0 = (pt % p.tiles_w) * p.bw;
-      pt /= p.tiles_w;
-      const int h0 = (pt % p.tiles_h) * p.bh;
-      pt /= p.tiles_h;
-      const int t0 = (pt % p.tiles_t) * p.bt;
-      const int n0 = pt / p.tiles_t;
+      const int n0 = tile / slab;
       const int grp = (p.pro_groups == 2 && 2 * n0 >= p.Nt) ? 1 : 0;
       for (int g = 0; g < n_groups; ++g) {
-        // a box that lies inside the tensor has no NaN fill to turn into the padding's zero: cheaper transform
-        const HcGroup gr = p.groups[g];
-        const int bw0 = w0 + gr.dw, bh0 = h0 + gr.dh, bt0 = t0 + gr.dt;
-        const bool inside = bw0 >= 0 && bw0 + p.box_w <= p.a_w && bh0 >= 0 && bh0 + p.box_h <= p.a_h && bt0 >= 0 &&
-                            bt0 + p.box_t <= p.a_t && !(p.dbg & 4);
         for (int c = 0; c < chunks; ++c) {
           const bool tl = has_tail && c == chunks - 1;
           const uint32_t s_addr = stage_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
           XformCoef k;
           xform_load_smem(k, xtab_addr, chunks, grp, c, xform_unit_channel(s_addr + tid * 16u, tl ? mask_tail : 7u));
           mbar_wait(&full[stage], phase);
-          if (inside && (tl || c * 64 + 64 <= p.pro_cp))
-            xform_span<kHcXformThreads, true>(s_addr, tid, tl ? units_tail : units_full, k);
-          else
-            xform_span<kHcXformThreads>(s_addr, tid, tl ? units_tail : units_full, k);
+          xform_span<kHcXformThreads>(s_addr, tid, tl ? units_tail : units_full, k);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&xfull[stage]);
@@ -661,12 +644,6 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.pro_shift = d->pro.shift;
   k.pro_groups = d->pro.groups;
   k.pro_cp = d->pro.Cp;
-  k.a_w = d->amap.dims[1]; k.a_h = d->amap.dims[2]; k.a_t = d->amap.dims[3];
-  k.box_w = d->bw + d->halo_w; k.box_h = d->bh + d->halo_h; k.box_t = d->bt + d->halo_t;
-  {
-    const char* e = getenv("CSTP_HC_DBG");
-    k.dbg = e ? atoi(e) : 0;
-  }
   if (d->stats_partials != nullptr &&
       !(k.fast_store && !d->accumulate && d->Np == 64 && d->n_tile == 64 && d->bn == 1 &&
         (d->stats_groups == 1 || d->stats_groups == 2) && d->Nt % d->stats_groups == 0)) {
