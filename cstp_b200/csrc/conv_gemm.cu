@@ -38,15 +38,28 @@ struct ConvKParams {
   float* out_f32;
   const float* bias;
   long long out_off, osw, osh, ost, osn;
+  int n_classes;                          // tap classes (stride-parity classes of a dgrad) run as one launch
+  int cls_first_tap[8], cls_n_taps[8];
+  long long cls_out_off[8];
   cstp_tap taps[CSTP_MAX_TAPS];
 };
 
 struct TileCoord {
-  int w0, h0, t0, n0, ntile;
+  int w0, h0, t0, n0, ntile, cls;
 };
+
+// Class of a tile.  Class-minor order (the classes of one M tile are neighbours in the tile order and run at the same
+// time on neighbouring CTAs), rotated by the M tile index: with a plain tile % n_classes a persistent CTA (stride = grid
+// size, a multiple of the class count) would see ONE class for ever -- and the classes differ in taps (1, 2, 2, 4 for a
+// stride-2 1x3x3 dgrad: measured 1.78x slower than balanced).
+__device__ __forceinline__ int tile_class(int n_classes, int tile) {
+  return (tile + tile / n_classes) % n_classes;
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
   TileCoord c;
+  c.cls = tile_class(p.n_classes, tile);
+  tile /= p.n_classes;
   c.ntile = tile % p.n_ntiles;
   int pt = tile / p.n_ntiles;
   c.w0 = (pt % p.tiles_w) * p.bw;
@@ -75,7 +88,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.n_ntiles;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.n_ntiles * p.n_classes;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < CSTP_MAX_AMAPS; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -111,7 +124,8 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
-      for (int t = 0; t < p.n_taps; ++t) {
+      const int tap0 = p.cls_first_tap[tc.cls], tap1 = tap0 + p.cls_n_taps[tc.cls];
+      for (int t = tap0; t < tap1; ++t) {
         const cstp_tap tap = p.taps[t];
         for (int c = 0; c < p.chunks_per_tap; ++c) {
           mbar_wait(&empty[stage], phase ^ 1u);
@@ -138,9 +152,8 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     int it = 0;
     // loop-invariant parameters live in registers and the MMAs are issued without a compiler memory clobber (see
     // conv_halo.cu: otherwise every UTCHMMA waits for a fresh LDCU of the kernel parameters)
-    const int n_taps = p.n_taps, chunks_per_tap = p.chunks_per_tap, last_ksteps = p.last_ksteps, stages = p.stages;
-    const int n_tile = p.n_tile;
-    const int kblocks = n_taps * chunks_per_tap;
+    const int chunks_per_tap = p.chunks_per_tap, last_ksteps = p.last_ksteps, stages = p.stages;
+    const int n_tile = p.n_tile, n_classes = p.n_classes;
     uint32_t idesc;
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     const uint32_t smem_addr0 = smem_u32(smem);
@@ -151,6 +164,8 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
       mbar_wait(&tempty[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * n_tile);
+      const int n_taps = p.cls_n_taps[tile_class(n_classes, tile)];
+      const int kblocks = n_taps * chunks_per_tap;
       int kb = 0;
       for (int t = 0; t < n_taps; ++t) {
         for (int c = 0; c < chunks_per_tap; ++c, ++kb) {
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     // below Nt / 2 take the coefficients of statistics group 0, the others those of group 1.
     const uint32_t tid = threadIdx.x - kConvThreads;
     const uint32_t smem_addr0 = smem_u32(smem);
-    const int n_taps = p.n_taps, chunks_per_tap = p.chunks_per_tap, stages = p.stages;
+    const int chunks_per_tap = p.chunks_per_tap, stages = p.stages;
     float* xtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     xform_table_fill<kConvXformThreads>(xtab, p.pro_scale, p.pro_shift, p.pro_groups, p.pro_cp, tid);
     xform_bar_sync<kConvXformThreads>();
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
         const int rb = (p.Nt / 2 - tc.n0) * rows_per_n;
         split = rb <= 0 ? 0u : (rb >= 128 ? kUnits : static_cast<uint32_t>(rb) * 8u);
       }
+      const int n_taps = p.cls_n_taps[tc.cls];
       for (int t = 0; t < n_taps; ++t) {
         for (int c = 0; c < chunks_per_tap; ++c) {
           const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
       const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
       const int col0 = tc.ntile * p.n_tile;
       const int ncols = min(p.n_tile, p.Np - col0);
-      const long long off = p.out_off + w * p.osw + h * p.osh + t * p.ost + n * p.osn + col0;
+      const long long off = p.cls_out_off[tc.cls] + w * p.osw + h * p.osh + t * p.ost + n * p.osn + col0;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
@@ -352,6 +368,16 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   CSTP_REQUIRE(d->w_packed != nullptr);
   CSTP_REQUIRE(d->out_bf16 != nullptr || d->out_f32 != nullptr);
   CSTP_REQUIRE(d->osw % 8 == 0 && d->osh % 8 == 0 && d->ost % 8 == 0 && d->osn % 8 == 0 && d->out_off % 8 == 0);
+  const int n_classes = d->n_classes > 1 ? d->n_classes : 1;
+  CSTP_REQUIRE(n_classes <= 8);
+  if (n_classes > 1) {
+    int covered = 0;
+    for (int c = 0; c < n_classes; ++c) {
+      CSTP_REQUIRE(d->cls_first_tap[c] == covered && d->cls_n_taps[c] >= 1 && d->cls_out_off[c] % 8 == 0);
+      covered += d->cls_n_taps[c];
+    }
+    CSTP_REQUIRE(covered == d->n_taps);
+  }
   const bool xform = d->pro.scale != nullptr;
   if (xform) {
     CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
@@ -405,8 +431,16 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   k.out_f32 = d->out_f32;
   k.bias = d->bias;
   k.out_off = d->out_off; k.osw = d->osw; k.osh = d->osh; k.ost = d->ost; k.osn = d->osn;
+  k.n_classes = n_classes;
+  bool offs16 = true;
+  for (int c = 0; c < n_classes; ++c) {
+    k.cls_first_tap[c] = n_classes > 1 ? d->cls_first_tap[c] : 0;
+    k.cls_n_taps[c] = n_classes > 1 ? d->cls_n_taps[c] : d->n_taps;
+    k.cls_out_off[c] = n_classes > 1 ? d->cls_out_off[c] : d->out_off;
+    offs16 = offs16 && k.cls_out_off[c] % 16 == 0;
+  }
   k.fast_store = d->out_bf16 != nullptr && d->out_f32 == nullptr && d->bias == nullptr &&
-                 reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && d->out_off % 16 == 0 && d->osw % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(d->out_bf16) % 32 == 0 && offs16 && d->osw % 16 == 0 &&
                  d->osh % 16 == 0 && d->ost % 16 == 0 && d->osn % 16 == 0 && d->n_tile % 16 == 0;
   k.pro_scale = d->pro.scale;
   k.pro_shift = d->pro.shift;
@@ -436,7 +470,7 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   k.tmem_cols = cols;
   plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes + xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
-  const long long total = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n * k.n_ntiles;
+  const long long total = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n * k.n_ntiles * n_classes;
   const int sms = num_sms();
   plan->grid = static_cast<int>(total < sms ? total : sms);
   *out_plan = plan;

@@ -48,6 +48,10 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p),
         ("accumulate", C.c_int32),
         ("pro", Prologue),
+        ("n_classes", C.c_int32),
+        ("cls_first_tap", C.c_int32 * 8),
+        ("cls_n_taps", C.c_int32 * 8),
+        ("cls_out_off", C.c_int64 * 8),
     ]
 
 

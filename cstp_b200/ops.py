@@ -217,9 +217,15 @@ def _set_prologue(d, prologue: "BNState | None", a_channels: int) -> tuple:
 
 
 def _make_conv_plan(views, taps, a_channels, w_packed, Np, tile_space, box, out, out_f32, out_off, ostrides, bias,
-                    accumulate, n_tile, keep, prologue=None) -> ConvPlan:
+                    accumulate, n_tile, keep, prologue=None, classes=None) -> ConvPlan:
+    """classes: [(first tap, number of taps, output element offset)] -- several tap classes with the same tile space run
+    as one launch (the stride-parity classes of a strided dgrad)."""
     lib = L.load()
     d = L.ConvDesc()
+    if classes and len(classes) > 1:
+        d.n_classes = len(classes)
+        for i, (t0, nt, off) in enumerate(classes):
+            d.cls_first_tap[i], d.cls_n_taps[i], d.cls_out_off[i] = t0, nt, off
     keep = keep + _set_prologue(d, prologue, a_channels)
     d.n_amaps = len(views)
     for i, v in enumerate(views):
@@ -393,6 +399,10 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
 # The first attempt (shuffle butterfly per 16-column chunk, all tile widths) removed 2.3 ms of bn_reduce passes at batch 60
 # but cost 3-5 ms in the conv kernels and was taken out (profiles/README.md).
 FUSE_BN_STATS = os.environ.get("CSTP_FUSE_BN_STATS", "1") == "1"
+DGRAD_ONE_LAUNCH = os.environ.get("CSTP_DGRAD_ONE_LAUNCH", "1") == "1"
+# (measured at batch 60: conv3.block1.conv1.spatial dgrad 0.89 ms as one conv_gemm launch, 0.99 ms with its 2- and 4-tap
+# classes on the halo kernel -- kept as a knob, off)
+DGRAD_STRIDED_HALO = os.environ.get("CSTP_DGRAD_STRIDED_HALO", "0") == "1"
 USE_TAIL_BOXES = os.environ.get("CSTP_TAIL_BOXES", "1") == "1"
 USE_HALO_2D = os.environ.get("CSTP_HALO_2D", "1") == "1"
 HALO_MIN_POSITIONS = 28 * 28      # per (t, n) slab: smaller extents cannot fill 128-row single-slab tiles
@@ -443,22 +453,40 @@ def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False, allo
     Kc = pad64(Co)
     assert wt_packed.shape[0] >= Ci and wt_packed.shape[1] == geom.taps * Kc
     gview = _view5(g)
-    plans, covers_all = [], True
-    for cl in dgrad_classes(tuple(dx.shape), geom):
-        if not cl["taps"]:
-            covers_all = False
-            continue
+    plans = []
+    classes = dgrad_classes(tuple(dx.shape), geom)
+    live = [cl for cl in classes if cl["taps"]]
+    rest = []
+    for cl in live:
         taps = [(0, dw_, dh_, dt_, ti * Kc) for (dw_, dh_, dt_, ti) in cl["taps"]]
-        if allow_halo and tuple(geom.stride) == (1, 1, 1) and H * W >= HALO_MIN_POSITIONS:
+        # every class is a stride-1 convolution over g with its own taps and a strided output: the halo kernel applies to
+        # the classes whose taps form a 1-D / 2-D neighbourhood (stride-2 1x3x3: the 2- and 4-tap classes)
+        if allow_halo and cl["space"][0] * cl["space"][1] >= HALO_MIN_POSITIONS and (
+                tuple(geom.stride) == (1, 1, 1) or DGRAD_STRIDED_HALO):
             lay = conv_halo_layout(cl["space"], [t[1:] for t in taps], Co, Ci)
             if lay is not None:
                 plans.append(_make_conv_halo_plan(gview, lay, Co, wt_packed, Ci, cl["space"], dx, None, cl["off"],
                                                   cl["ostrides"], None, accumulate, (g, wt_packed, dx)))
                 continue
-        box = pick_box(*cl["space"], 128)
-        plans.append(_make_conv_plan([gview], taps, Co, wt_packed, Ci, cl["space"], box, dx, None, cl["off"],
-                                     cl["ostrides"], None, accumulate, None, (g, wt_packed, dx)))
-    return plans, covers_all
+        rest.append((cl, taps))
+    if (DGRAD_ONE_LAUNCH and 1 < len(rest) <= 8
+            and all(cl["space"] == rest[0][0]["space"] and cl["ostrides"] == rest[0][0]["ostrides"] for cl, _ in rest)
+            and sum(len(t) for _, t in rest) <= L.CSTP_MAX_TAPS):
+        # stride-parity classes that share their tile space (even extents): ONE launch, class-minor tile order -- the
+        # classes of one tile read the same boxes of g at the same time
+        taps, cls, t0 = [], [], 0
+        for cl, tp in rest:
+            taps += tp
+            cls.append((t0, len(tp), cl["off"]))
+            t0 += len(tp)
+        cl0 = rest[0][0]
+        plans.append(_make_conv_plan([gview], taps, Co, wt_packed, Ci, cl0["space"], pick_box(*cl0["space"], 128), dx, None,
+                                     cl0["off"], cl0["ostrides"], None, accumulate, None, (g, wt_packed, dx), classes=cls))
+    else:
+        for cl, taps in rest:
+            plans.append(_make_conv_plan([gview], taps, Co, wt_packed, Ci, cl["space"], pick_box(*cl["space"], 128), dx, None,
+                                         cl["off"], cl["ostrides"], None, accumulate, None, (g, wt_packed, dx)))
+    return plans, len(live) == len(classes)
 
 
 def linear_plan(x, w_packed, out, *, out_f32=None, bias=None, accumulate=False) -> ConvPlan:

@@ -89,6 +89,15 @@ typedef struct {
   const float* bias;            /* fp32 [Np] or NULL */
   int32_t accumulate;           /* 1: out += D (read-modify-write) */
   cstp_prologue pro;            /* BatchNorm + ReLU applied to A on the way in (scale NULL: none) */
+  /* Tap classes (0 or 1: one class holding every tap).  A strided convolution's dgrad is one implicit GEMM per
+   * stride-parity class of dx, each with its own taps and output origin but the same tile space: n_classes > 1 runs them
+   * as ONE launch -- class c covers taps [cls_first_tap[c], + cls_n_taps[c]) and writes at cls_out_off[c] (out_off is
+   * ignored); the classes of one M tile run on neighbouring CTAs at the same time, so the activation boxes they share
+   * come from L2 once. */
+  int32_t n_classes;
+  int32_t cls_first_tap[8];
+  int32_t cls_n_taps[8];
+  int64_t cls_out_off[8];
 } cstp_conv_desc;
 
 typedef struct cstp_conv_plan cstp_conv_plan;

@@ -3,8 +3,8 @@ per-kernel-name totals, shares of one step and (when captured) DRAM traffic and 
 
     python tools/summarize_launches.py gpurun_out/launches.csv [first_id last_id] > profiles/rNN_launches_summary.txt
 
-Without an id window the last complete step is the span between the last two launches of the stem im2col kernel pair
-(the first kernels of every step)."""
+Without an id window the last complete step is the span between the last two launches of the stem input kernel pair
+(the first kernels of every step; stem_pack since round 2)."""
 from __future__ import annotations
 
 import collections
@@ -41,7 +41,7 @@ def main():
     if len(sys.argv) >= 4:
         lo, hi = int(sys.argv[2]), int(sys.argv[3])
     else:
-        stems = [i for i in ids if by[i]["name"].startswith("stem_im2col")]
+        stems = [i for i in ids if by[i]["name"].startswith(("stem_im2col", "stem_pack"))]
         starts = [s for k, s in enumerate(stems) if k == 0 or s - stems[k - 1] > 1]
         lo, hi = starts[-2], starts[-1]
     step = [by[i] for i in ids if lo <= i < hi]
