@@ -179,33 +179,40 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 // w[co][ci][0][kh = 2*j + hpar - 1][kw] (zero for kh = -1).  P holds 64 bytes per (frame row, output column): 0.77 GB per
 // batch of 60 against 1.93 GB for the materialised im2col rows (K = 147 -> 160) it replaces; K grows to 256, which the
 // tensor pipe does not notice on this HBM-bound layer.  One CTA per (n, t, h2): six input rows staged in shared memory.
+constexpr int kStemRowPairs = 4;     // row pairs per CTA: 24 input rows staged with float4 loads, 28 KB written per CTA
 __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int T, int H, int W,
                                                         uint4* __restrict__ P) {
-  __shared__ float rows[2][3][kStemMaxW + 8];        // [hpar][ci][3 + wi]: three zero columns left, five right
+  __shared__ __align__(16) float rows[kStemRowPairs][2][3][kStemMaxW + 8];   // [pair][hpar][ci][4 + wi]: zero columns around
   const int Wo = W / 2, H2 = H / 2;
+  const int groups = (H2 + kStemRowPairs - 1) / kStemRowPairs;
   int b = blockIdx.x;
-  const int h2 = b % H2;
-  b /= H2;
+  const int h2_0 = (b % groups) * kStemRowPairs;
+  b /= groups;
   const int t = b % T;
   const int n = b / T;
-  const int Wq = W + 8;
-  for (int i = threadIdx.x; i < 6 * Wq; i += blockDim.x) {
-    const int row = i / Wq, c = i % Wq;              // row = hpar*3 + ci
-    const int hp = row / 3, ci = row % 3;
-    const int wi = c - 3;
-    rows[hp][ci][c] = (wi >= 0 && wi < W)
-        ? __ldg(x + (((static_cast<long long>(n) * 3 + ci) * T + t) * H + 2 * h2 + hp) * W + wi) : 0.f;
+  const int np = min(kStemRowPairs, H2 - h2_0);
+  // (column c of a staged row holds x[wi = c - 4]: the float4 loads stay 16-byte aligned; columns 0..3 and W+4.. are zero)
+  const int W4 = W / 4;
+  for (int i = threadIdx.x; i < np * 6 * (W4 + 2); i += blockDim.x) {
+    const int q = i % (W4 + 2), row = i / (W4 + 2);          // row = (pair*2 + hpar)*3 + ci
+    const int ci = row % 3, hp = (row / 3) & 1, pr = row / 6;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q >= 1 && q <= W4)
+      v = __ldg(reinterpret_cast<const float4*>(
+                    x + (((static_cast<long long>(n) * 3 + ci) * T + t) * H + 2 * (h2_0 + pr) + hp) * W) + (q - 1));
+    *reinterpret_cast<float4*>(&rows[pr][hp][ci][4 * q]) = v;
   }
   __syncthreads();
-  uint4* dst = P + ((static_cast<long long>(n) * T + t) * H2 + h2) * Wo * 8;
-  for (int i = threadIdx.x; i < Wo * 8; i += blockDim.x) {
-    const int wo = i >> 3, hp = (i >> 2) & 1, v = i & 3;   // eight 16-byte vectors (8 channels each) per output column
+  uint4* dst = P + (((static_cast<long long>(n) * T + t) * H2 + h2_0) * Wo) * 8;
+  for (int i = threadIdx.x; i < np * Wo * 8; i += blockDim.x) {
+    const int v = i & 3, hp = (i >> 2) & 1;          // eight 16-byte vectors (8 channels each) per output column
+    const int wo = (i >> 3) % Wo, pr = (i >> 3) / Wo;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = v * 8 + j;                       // k = kw*3 + ci
       const int kw = (k * 11) >> 5;                  // k / 3 for k < 32
-      f[j] = k < 21 ? rows[hp][k - 3 * kw][2 * wo + kw] : 0.f;
+      f[j] = k < 21 ? rows[pr][hp][k - 3 * kw][2 * wo + kw + 1] : 0.f;      // x[2*wo + kw - 3] sits in column 2*wo + kw + 1
     }
     dst[i] = pack8(f);
   }
@@ -744,9 +751,10 @@ extern "C" int cstp_stem_im2col(const float* x, int N, int T, int H, int W, void
 }
 
 extern "C" int cstp_stem_pack(const float* x, int N, int T, int H, int W, void* P, void* stream) {
-  CSTP_REQUIRE(x && P && N > 0 && T > 0 && H > 0 && W > 0 && W % 2 == 0 && H % 2 == 0 && W <= kStemMaxW);
-  CSTP_REQUIRE((reinterpret_cast<uintptr_t>(P) % 16) == 0);
-  stem_pack_kernel<<<N * T * (H / 2), 256, 0, ST(stream)>>>(x, T, H, W, reinterpret_cast<uint4*>(P));
+  CSTP_REQUIRE(x && P && N > 0 && T > 0 && H > 0 && W > 0 && W % 4 == 0 && H % 2 == 0 && W <= kStemMaxW);
+  CSTP_REQUIRE((reinterpret_cast<uintptr_t>(P) % 16) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0);
+  const int groups = (H / 2 + kStemRowPairs - 1) / kStemRowPairs;
+  stem_pack_kernel<<<N * T * groups, 256, 0, ST(stream)>>>(x, T, H, W, reinterpret_cast<uint4*>(P));
   CSTP_LAUNCHED();
   return CSTP_OK;
 }

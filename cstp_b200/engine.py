@@ -203,8 +203,8 @@ class StepEngine:
                  record: bool = False, overlap: bool = True, bn_sync=None, fuse_apply: bool | None = None,
                  ntxent: dict | None = None, fuse_min_positions: int | None = None, fuse_policy: str | None = None,
                  graph: bool | None = None):
-        if H % 2 or W % 2:
-            raise ops.L.CstpError("clip height/width must be even (1x7x7 stride-2 stem)")
+        if H % 2 or W % 4:
+            raise ops.L.CstpError("clip height must be even and its width a multiple of 4 (1x7x7 stride-2 stem over packed rows)")
         self.B, self.T, self.H, self.W = B, T, H, W
         self.N = self.VIEWS * B
         self.device = torch.device(device)
