@@ -227,19 +227,22 @@ def config5_record(args, rank: int, world: int) -> dict | None:
     # ---- parity: one GPU steps the whole global batch once
     parity = None
     if rank == 0:
-        whole = make({"ntxent": dict(nx)})
-        w = step(whole, gx1.cuda(), gx2.cuda(), tuple(l.cuda() for l in glab), None).cpu()
-        wnx = whole._engine.ntxent_loss.item()
-        mf = mean_first.cpu()
-        tot = lambda v, n: LOSS_WEIGHT[0] * v[7].item() + v[6].item() + nx["weight"] * n     # noqa: E731
-        parity = {"what": f"first step from the seeded init: {world} ranks x {b} samples vs ONE GPU x {GB} samples "
-                          "(same clips, labels and weights)",
-                  "loss_total_dp": tot(mf, first_nx.item()), "loss_total_one_gpu": tot(w, wnx),
-                  "loss_total_rel": abs(tot(mf, first_nx.item()) - tot(w, wnx)) / abs(tot(w, wnx)),
-                  "loss_byol_dp": mf[7].item(), "loss_byol_one_gpu": w[7].item(),
-                  "ntxent_dp": first_nx.item(), "ntxent_one_gpu": wnx,
-                  "ce_rel_max": max(abs(mf[i].item() - w[i].item()) / abs(w[i].item()) for i in range(6))}
-        del whole
+        try:                          # (rank 0 alone: a failure here must not desynchronise the barrier below)
+            whole = make({"ntxent": dict(nx)})
+            w = step(whole, gx1.cuda(), gx2.cuda(), tuple(l.cuda() for l in glab), None).cpu()
+            wnx = whole._engine.ntxent_loss.item()
+            mf = mean_first.cpu()
+            tot = lambda v, n: LOSS_WEIGHT[0] * v[7].item() + v[6].item() + nx["weight"] * n     # noqa: E731
+            parity = {"what": f"first step from the seeded init: {world} ranks x {b} samples vs ONE GPU x {GB} samples "
+                              "(same clips, labels and weights)",
+                      "loss_total_dp": tot(mf, first_nx.item()), "loss_total_one_gpu": tot(w, wnx),
+                      "loss_total_rel": abs(tot(mf, first_nx.item()) - tot(w, wnx)) / abs(tot(w, wnx)),
+                      "loss_byol_dp": mf[7].item(), "loss_byol_one_gpu": w[7].item(),
+                      "ntxent_dp": first_nx.item(), "ntxent_one_gpu": wnx,
+                      "ce_rel_max": max(abs(mf[i].item() - w[i].item()) / abs(w[i].item()) for i in range(6))}
+            del whole
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": f"{type(e).__name__}: {e}"}
         gc.collect()
         torch.cuda.empty_cache()
     dist.barrier()
@@ -446,7 +449,12 @@ def main():
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        c5 = config5_record(args, rank, world)
+        try:
+            c5 = config5_record(args, rank, world)
+        except Exception as e:  # noqa: BLE001   the batch-60 line above is already measured: report, do not lose it
+            import traceback
+            traceback.print_exc()
+            c5 = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
     if world > 1:
         dist.barrier()
     if rank != 0:

@@ -3,7 +3,10 @@
 // Both operands come straight out of NDHWC activations, so both are "MN-major" for the tensor core: the
 // reduction (K) axis is the position axis, channels are contiguous.  One K-block is a TMA box of 64 positions;
 // the M tile (128 rows) is two 64-channel chunks of X, each with its own tap shift, so that 3x3 / 3x1x1 taps of
-// narrow layers (Cin = 64) still fill the 128-row MMA.  Split-K over position tiles; fp32 partials are reduced in
+// narrow layers (Cin = 64) still fill the 128-row MMA.  A CTA owns up to four such M tiles (mt_per_cta, one TMEM
+// accumulator each) that share ONE staged G tile per K-block: the kernel is bound by the L2 -> SM feed of its operands
+// (a 128 x 256 tile re-loads 48 KB per 64 positions), and every extra M tile per CTA removes one re-load of G.
+// Split-K over position tiles; fp32 partials are reduced in
 // fixed order by cstp_wgrad_finalize, which also scatters into the reference (Cout, Cin, kT, kH, kW) layout.
 // Replaces cuDNN conv3d wgrad / cuBLAS addmm wgrad behind main_byol.py:87.
 #include "common.h"
@@ -16,6 +19,7 @@ constexpr int kWgXformThreads = 256;   // warps 8..15: operand prologue (BatchNo
 constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // 64 positions x 64 channels
 constexpr int kWgMaxStages = 8;
 constexpr int kWgSmemLimit = 232448;
+constexpr int kWgMaxMt = 4;            // M tiles per CTA: n_mt * n_tile <= 512 TMEM columns
 
 struct WgradKParams {
   CUtensorMap amap[CSTP_MAX_AMAPS];
@@ -23,6 +27,7 @@ struct WgradKParams {
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int bw, bh, bt, bn;
   int n_mchunks, Np, n_tile, n_gboxes;
+  int n_mt;                // M tiles (128 rows = two chunks) per CTA, 1..kWgMaxMt
   int total_kblocks, kblocks_per_split;
   int stages, tmem_cols;
   uint32_t idesc;
@@ -37,7 +42,7 @@ template <bool kXform>
 __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = 2 * kBoxBytes;
+  const uint32_t a_bytes = 2u * static_cast<uint32_t>(p.n_mt) * kBoxBytes;
   const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.n_gboxes) * kBoxBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
   uint64_t* full = bars;
@@ -49,8 +54,9 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int mtile = blockIdx.x, ntile = blockIdx.y, split = blockIdx.z;
-  const int chunk0 = mtile * 2;
-  const int nchunks = min(2, p.n_mchunks - chunk0);
+  const int chunk0 = mtile * 2 * p.n_mt;
+  const int nchunks = min(2 * p.n_mt, p.n_mchunks - chunk0);       // (the prologue variant runs with n_mt == 1)
+  const int mts = (nchunks + 1) >> 1;                              // M tiles of this CTA that hold at least one chunk
   const int kb_begin = split * p.kblocks_per_split;
   const int kb_end = min(p.total_kblocks, kb_begin + p.kblocks_per_split);
 
@@ -105,12 +111,16 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
       const uint32_t s_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
       const int cj = xform_unit_channel(s_addr + tid * 16u, 7u);
       XformCoef k0[2], k1[2];
-      for (int b = 0; b < nchunks; ++b) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (b >= nchunks) break;
         if (split > 0) xform_load_smem(k0[b], xtab_addr, tchunks, 0, c_off[b] >> 6, cj);
         if (split < kUnits) xform_load_smem(k1[b], xtab_addr, tchunks, 1, c_off[b] >> 6, cj);
       }
       mbar_wait(&full[stage], phase);
-      for (int b = 0; b < nchunks; ++b) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (b >= nchunks) break;
         const uint32_t box = s_addr + static_cast<uint32_t>(b) * kBoxBytes;
         if (split > 0) xform_span<kWgXformThreads>(box, tid, split, k0[b]);
         if (split < kUnits) xform_span<kWgXformThreads>(box, xform_first<kWgXformThreads>(split, tid), kUnits, k1[b]);
@@ -130,8 +140,6 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    const cstp_mchunk mc0 = p.mchunks[chunk0];
-    const cstp_mchunk mc1 = p.mchunks[nchunks > 1 ? chunk0 + 1 : chunk0];
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       int pt = kb;
       const int w0 = (pt % p.tiles_w) * p.bw;
@@ -145,10 +153,11 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
       if (leader) {
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         mbar_expect_tx(&full[stage], static_cast<uint32_t>(nchunks + p.n_gboxes) * kBoxBytes);
-        tma_load_5d(sa, &p.amap[mc0.map_id], &full[stage], mc0.c_off, w0 + mc0.dw, h0 + mc0.dh, t0 + mc0.dt, n0);
-        if (nchunks > 1)
-          tma_load_5d(sa + kBoxBytes, &p.amap[mc1.map_id], &full[stage], mc1.c_off, w0 + mc1.dw, h0 + mc1.dh,
-                      t0 + mc1.dt, n0);
+        for (int b = 0; b < nchunks; ++b) {
+          const cstp_mchunk mc = p.mchunks[chunk0 + b];
+          tma_load_5d(sa + static_cast<uint32_t>(b) * kBoxBytes, &p.amap[mc.map_id], &full[stage], mc.c_off, w0 + mc.dw,
+                      h0 + mc.dh, t0 + mc.dt, n0);
+        }
         for (int j = 0; j < p.n_gboxes; ++j)
           tma_load_5d(sa + a_bytes + j * kBoxBytes, &p.gmap, &full[stage], ntile * p.n_tile + j * 64, w0, h0, t0, n0);
       }
@@ -165,6 +174,7 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
     const uint32_t smem_addr0 = smem_u32(smem);
     const uint64_t dhi = umma_desc_hi(kBoxBytes, 1024);
     const int stages = p.stages;        // loop invariants in registers, clobber-free MMA issue (see conv_halo.cu)
+    const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
     uint32_t idesc;
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -173,13 +183,17 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
       if (leader) {
         const uint32_t a_addr = smem_addr0 + static_cast<uint32_t>(stage) * stage_bytes;
         // MN-major, 128B swizzle: 16 K-rows per step = 2048 B (+128 in the address field); LBO = next 64-channel
-        // chunk, SBO = next 8 K-rows.
-        const uint64_t da = umma_desc_at(dhi, a_addr);
+        // chunk, SBO = next 8 K-rows.  M tile mt: its two X boxes, accumulator mt (n_tile columns each), the shared G tile
+        // (a tile whose second chunk does not exist multiplies stale rows that the epilogue never stores).
         const uint64_t db = umma_desc_at(dhi, a_addr + a_bytes);
-        umma_bf16_nc(tmem_base, da, db, idesc, kb > kb_begin ? 1u : 0u);
-        umma_bf16_acc_nc(tmem_base, da + 128, db + 128, idesc);
-        umma_bf16_acc_nc(tmem_base, da + 256, db + 256, idesc);
-        umma_bf16_acc_nc(tmem_base, da + 384, db + 384, idesc);
+        for (int mt = 0; mt < mts; ++mt) {
+          const uint64_t da = umma_desc_at(dhi, a_addr + static_cast<uint32_t>(mt) * 2u * kBoxBytes);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(mt) * n_tile;
+          umma_bf16_nc(d_tmem, da, db, idesc, kb > kb_begin ? 1u : 0u);
+          umma_bf16_acc_nc(d_tmem, da + 128, db + 128, idesc);
+          umma_bf16_acc_nc(d_tmem, da + 256, db + 256, idesc);
+          umma_bf16_acc_nc(d_tmem, da + 384, db + 384, idesc);
+        }
         umma_commit(&empty[stage]);
         if (kb == kb_end - 1) umma_commit(tfull);
       }
@@ -192,15 +206,18 @@ __global__ void __launch_bounds__(kXform ? kWgThreads + kWgXformThreads : kWgThr
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4;
     const int row = q * 32 + lane;
-    const bool valid = (row >> 6) < nchunks;
     const int col0 = ntile * p.n_tile;
     const int ncols = min(p.n_tile, p.Np - col0);
     const long long mtot = static_cast<long long>(p.n_mchunks) * 64;
-    float* dst = p.partials + (static_cast<long long>(split) * mtot + static_cast<long long>(mtile) * 128 + row) * p.Np + col0;
     mbar_wait_idle(tfull, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    epilogue_row_f32(taddr, ncols, dst, valid);     // pipelined TMEM loads, 32-byte stores (ptx.cuh)
+    for (int mt = 0; mt < mts; ++mt) {
+      const bool valid = (2 * mt + (row >> 6)) < nchunks;
+      float* dst = p.partials +
+                   (static_cast<long long>(split) * mtot + (static_cast<long long>(mtile) * p.n_mt + mt) * 128 + row) * p.Np + col0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * p.n_tile);
+      epilogue_row_f32(taddr, ncols, dst, valid);     // pipelined TMEM loads, 32-byte stores (ptx.cuh)
+    }
   }
 
   tc_fence_before();
@@ -282,6 +299,8 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   CSTP_REQUIRE(d->Wt >= 1 && d->Ht >= 1 && d->Tt >= 1 && d->Nt >= 1);
   CSTP_REQUIRE(d->splits >= 1 && d->partials != nullptr && reinterpret_cast<uintptr_t>(d->partials) % 32 == 0);   // 32-byte stores
   const bool xform = d->pro.scale != nullptr;
+  const int n_mt = d->mt_per_cta > 0 ? d->mt_per_cta : 1;
+  CSTP_REQUIRE(n_mt <= kWgMaxMt && n_mt * d->n_tile <= 512 && (!xform || n_mt == 1));
   if (xform) {
     CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
     CSTP_REQUIRE(d->pro.Cp == d->amap[0].dims[0]);
@@ -319,6 +338,7 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
   k.Np = d->Np;
   k.n_tile = d->n_tile;
   k.n_gboxes = ceil_div(d->n_tile, 64);
+  k.n_mt = n_mt;
   k.total_kblocks = k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
   int splits = d->splits < k.total_kblocks ? d->splits : k.total_kblocks;
   k.kblocks_per_split = ceil_div(k.total_kblocks, splits);
@@ -339,18 +359,22 @@ extern "C" int cstp_wgrad_plan_create(const cstp_wgrad_desc* d, cstp_wgrad_plan*
     }
     k.mchunks[i] = mc;
   }
-  const uint32_t stage_bytes = (2u + static_cast<uint32_t>(k.n_gboxes)) * kBoxBytes;
+  const uint32_t stage_bytes = (2u * static_cast<uint32_t>(n_mt) + static_cast<uint32_t>(k.n_gboxes)) * kBoxBytes;
   const int bar_bytes = 256;
   const int xtab_bytes = xform ? static_cast<int>(xform_table_bytes(d->pro.groups, d->pro.Cp)) : 0;      // prologue coefficient table
   int stages = (smem_budget() - 1024 - bar_bytes - xtab_bytes) / static_cast<int>(stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
+  if (stages < 2) {
+    delete plan;
+    return fail_inval("wgrad stage (mt_per_cta X boxes + the G tile) too large for a two-stage shared-memory pipeline");
+  }
   k.stages = stages;
   int cols = 32;
-  while (cols < d->n_tile) cols *= 2;
+  while (cols < n_mt * d->n_tile) cols *= 2;
   k.tmem_cols = cols;
   plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes + xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
-  plan->grid = dim3(static_cast<unsigned>(ceil_div(d->n_mchunks, 2)), static_cast<unsigned>(ceil_div(d->Np, d->n_tile)),
+  plan->grid = dim3(static_cast<unsigned>(ceil_div(d->n_mchunks, 2 * n_mt)), static_cast<unsigned>(ceil_div(d->Np, d->n_tile)),
                     static_cast<unsigned>(splits));
   *out_plan = plan;
   return CSTP_OK;

@@ -73,6 +73,7 @@ class WgradDesc(C.Structure):
         ("splits", C.c_int32),
         ("partials", C.c_void_p),
         ("pro", Prologue),
+        ("mt_per_cta", C.c_int32),
     ]
 
 

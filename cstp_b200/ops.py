@@ -665,9 +665,46 @@ def wgrad_partials_need(x_shape, g_shape, geom: ConvGeom, sms: int = 148) -> int
         return max(l["need"] for l in lays if l is not None)
     Ca, Np = x_shape[-1], g_shape[-1]
     nch = geom.taps * (pad64(Ca) // 64)
-    n_tile = Np if Np <= 256 else 256
-    base = math.ceil(nch / 2) * math.ceil(Np / n_tile)
-    return max(1, math.ceil(2 * sms / base)) * nch * 64 * Np
+    To, Ho, Wo = g_shape[1:4]
+    box = pick_box(Wo, Ho, To, g_shape[0], 64)
+    kblocks = math.ceil(Wo / box[0]) * math.ceil(Ho / box[1]) * math.ceil(To / box[2]) * math.ceil(g_shape[0] / box[3])
+    return max(_wgrad_gemm_shape(nch, Np, kblocks, sms, xf)[2] for xf in (False, True)) * nch * 64 * Np
+
+
+WGRAD_MT = int(os.environ.get("CSTP_WGRAD_MT", "4"))      # upper bound of M tiles per CTA in csrc/wgrad.cu (1: round-1 shape)
+
+
+def _wgrad_gemm_shape(nch: int, Np: int, kblocks: int, sms: int = 148, xform: bool = False) -> tuple[int, int, int]:
+    """(n_tile, mt_per_cta, splits) of csrc/wgrad.cu for `nch` 64-row M chunks, Np columns and `kblocks` 64-position K-blocks.
+    The kernel is bound by the L2 -> SM feed: a CTA stages 2 * mt X boxes and n_tile / 64 G boxes of 8 KB per K-block, so
+      * the N tile is the multiple of 64 that needs the fewest tiles, then the fewest padded columns (576 -> 3 x 192, not
+        256 + 256 + 64 with every MMA 256 wide);
+      * a CTA takes as many 128-row M tiles as TMEM (mt * n_tile <= 512 columns) and a three-stage pipeline allow: they
+        share one staged G tile (no prologue variant: its transform keeps the coefficients of two boxes in registers);
+      * the split-K factor minimises waves x K-blocks per split + the cost of writing and re-reading one more partial."""
+    if WGRAD_MT <= 1:
+        n_tile = Np if Np <= 256 else 256
+        base = math.ceil(nch / 2) * math.ceil(Np / n_tile)
+        return n_tile, 1, max(1, min(math.ceil(2 * sms / base), max(1, kblocks // 4)))
+    if Np <= 256:
+        n_tile = Np
+    else:
+        n_tile = min((256, 192, 128), key=lambda c: (math.ceil(Np / c), math.ceil(Np / c) * c, -c))
+    ngb = math.ceil(n_tile / 64)
+    mt = 1
+    if not xform:
+        for m in range(2, min(WGRAD_MT, 4) + 1):
+            if m * n_tile <= 512 and 3 * (2 * m + ngb) * 8192 <= SMEM_BUDGET and m <= math.ceil(nch / 2):
+                mt = m
+    base = math.ceil(nch / (2 * mt)) * math.ceil(Np / n_tile)
+    t_kb = (2 * mt + ngb) * 195.0 / 1.7e9                        # seconds per K-block and CTA at the L2 fair share
+    t_part = 2.0 * nch * 64 * Np * 4 / 5e12                      # one more partial: written here, read by the finalize pass
+    best = None
+    for sp in range(1, max(1, min(kblocks // 4, math.ceil(4 * sms / base))) + 1):
+        cost = math.ceil(base * sp / sms) * math.ceil(kblocks / sp) * t_kb + sp * t_part
+        if best is None or cost < best[0] - 1e-12:
+            best = (cost, sp)
+    return n_tile, mt, best[1]
 
 
 def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor, *, splits: int | None = None,
@@ -734,11 +771,10 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
     if len(mch) > L.CSTP_MAX_MCHUNKS:
         raise L.CstpError(f"wgrad needs {len(mch)} M chunks > {L.CSTP_MAX_MCHUNKS}")
     box = box or pick_box(Wo, Ho, To, N, 64)
-    n_tile = Np if Np <= 256 else 256
     kblocks = math.ceil(Wo / box[0]) * math.ceil(Ho / box[1]) * math.ceil(To / box[2]) * math.ceil(N / box[3])
-    base_ctas = math.ceil(len(mch) / 2) * math.ceil(Np / n_tile)
+    n_tile, n_mt, auto_splits = _wgrad_gemm_shape(len(mch), Np, kblocks, sms, prologue is not None)
     if splits is None:
-        splits = max(1, min(math.ceil(2 * sms / base_ctas), max(1, kblocks // 4)))
+        splits = auto_splits
     d = L.WgradDesc()
     d.n_amaps = len(views)
     for i, v in enumerate(views):
@@ -747,7 +783,7 @@ def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor
     for i, mc in enumerate(mch):
         d.mchunks[i] = L.MChunk(*mc)
     d.gmap = _view5(g)
-    d.Np, d.n_tile = Np, n_tile
+    d.Np, d.n_tile, d.mt_per_cta = Np, n_tile, n_mt
     d.Wt, d.Ht, d.Tt, d.Nt = Wo, Ho, To, N
     d.bw, d.bh, d.bt, d.bn = box
     d.splits = splits

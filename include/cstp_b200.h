@@ -187,6 +187,8 @@ typedef struct {
   int32_t splits;                       /* requested split-K factor (>=1) */
   float* partials;                      /* fp32 [splits_eff][n_mchunks*64][Np] */
   cstp_prologue pro;                    /* BatchNorm + ReLU applied to X on the way in (scale NULL: none) */
+  int32_t mt_per_cta;                   /* 128-row M tiles per CTA sharing one staged G tile (0 / 1 .. 4; mt_per_cta * n_tile
+                                           <= 512 TMEM columns; 1 with a prologue): fewer re-loads of G through L2 */
 } cstp_wgrad_desc;
 
 typedef struct cstp_wgrad_plan cstp_wgrad_plan;
