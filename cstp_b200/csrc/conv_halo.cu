@@ -8,6 +8,12 @@
 //     atom aligned);
 //   * when all weight K-blocks of one N tile fit next to the activation pipeline they are loaded ONCE per CTA
 //     ("resident B"); every CTA then keeps its N tile for its whole life (blockIdx.y) and walks M tiles only.
+//   * "slab mode" (64-column layers): a tcgen05.mma of 128 x 64 x 16 cannot be fed faster than one per ~76 cycles
+//     (its 4 KB A slice comes out of shared memory at 64 B/clk) while the tensor pipe needs 32.  So G consecutive output
+//     slabs along the tap axis share one accumulator of G x 64 columns: every INPUT slab is staged once and multiplied,
+//     in ONE MMA of up to 3 x 64 columns, with the stacked weights [tap +1 | tap 0 | tap -1] of the output slabs it
+//     feeds (a row offset into the resident weight block picks the sub-range at the tile's borders).  36 tap units
+//     of a 1x3x3 tile with G = 4 take 18 MMA series instead of 36, and every A slice is read once instead of three times.
 // Same math, epilogue and output layout as conv_gemm.cu.
 // Replaces cuDNN conv3d fwd/dgrad behind models/pace/r21d_byol.py:81-97 (main_byol.py:87 for the dgrad).
 #include "common.h"
@@ -21,6 +27,7 @@ constexpr int kHcMaxStages = 8;
 constexpr int kHcSmemLimit = 232448;
 constexpr int kHcMaxGroups = 4;
 constexpr int kHcMaxTaps = 16;
+constexpr int kHcMaxSlabs = 8;           // staged input slabs per tile in slab mode (G + taps along the slab axis - 1)
 
 struct HcGroup {
   int dw, dh, dt;       // origin offset of the staged (halo) box from the tile origin
@@ -63,6 +70,18 @@ struct ConvHaloKParams {
   float* out_f32;
   const float* bias;
   long long out_off, osw, osh, ost, osn;
+  int step_h, step_t;      // tile step along h / t (bh / bt, or G along the slab axis in slab mode)
+  // slab mode (slab_g > 1): G output slabs of slab_cols columns each on the accumulator's N axis
+  int slab_g, slab_axis;   // axis 1: h, 2: t
+  int slab_in;             // staged input slabs per tile
+  int slab_nslots;         // taps along the slab axis (weights of one w tap: nslots stacked blocks of slab_cols rows)
+  int slab_cols;
+  uint32_t res_tap_stride, res_chunk_stride, res_tail_base, res_tail_tap_stride;     // resident weight block layout
+  int slab_order[kHcMaxSlabs];    // load / issue order of the input slabs (the first MMA of an accumulator column range
+  int slab_init[kHcMaxSlabs];     // must overwrite: slabs flagged `init` come first and cover disjoint column ranges)
+  int slab_doff[kHcMaxSlabs];     // first accumulator column this input slab feeds
+  int slab_brow[kHcMaxSlabs];     // first row of the stacked weight block it multiplies with
+  uint32_t slab_idesc[kHcMaxSlabs];
   HcGroup groups[kHcMaxGroups];
   HcTap taps[kHcMaxTaps];
 };
@@ -196,27 +215,35 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     if (p.resident && leader) {
       mbar_expect_tx(bfull, p.res_bytes);
       for (int t = 0; t < p.n_taps; ++t) {
-        uint8_t* tb = smem + static_cast<size_t>(t) * p.tap_bytes;
+        uint8_t* tb = smem + static_cast<size_t>(t) * p.res_tap_stride;
         for (int c = 0; c < full_chunks; ++c)
-          tma_load_2d(tb + static_cast<size_t>(c) * p.b_bytes, &p.bmap, bfull, p.taps[t].k_off + c * 64, ntile * p.n_tile);
+          tma_load_2d(tb + static_cast<size_t>(c) * p.res_chunk_stride, &p.bmap, bfull, p.taps[t].k_off + c * 64,
+                      ntile * p.n_tile);
         if (p.tail)
-          tma_load_2d(tb + static_cast<size_t>(full_chunks) * p.b_bytes, &p.bmap_tail, bfull,
+          tma_load_2d(smem + p.res_tail_base + static_cast<size_t>(t) * p.res_tail_tap_stride, &p.bmap_tail, bfull,
                       p.taps[t].k_off + full_chunks * 64, ntile * p.n_tile);
       }
     }
     int stage = 0;
     uint32_t phase = 0;
+    const int pslab = (kXform || kStats) ? 0 : p.slab_g;
+    const int n_loads = pslab ? p.slab_in : p.n_groups;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       int pt = tile;
       const int w0 = (pt % p.tiles_w) * p.bw;
       pt /= p.tiles_w;
-      const int h0 = (pt % p.tiles_h) * p.bh;
+      const int h0 = (pt % p.tiles_h) * p.step_h;
       pt /= p.tiles_h;
-      const int t0 = (pt % p.tiles_t) * p.bt;
+      const int t0 = (pt % p.tiles_t) * p.step_t;
       pt /= p.tiles_t;
       const int n0 = pt * p.bn;
-      for (int g = 0; g < p.n_groups; ++g) {
-        const HcGroup gr = p.groups[g];
+      for (int g = 0; g < n_loads; ++g) {
+        HcGroup gr = p.groups[pslab ? 0 : g];
+        if (pslab) {               // input slab s of the tile: the first slab's origin moved s steps along the slab axis
+          const int sl = p.slab_order[g];
+          gr.dh += p.slab_axis == 1 ? sl : 0;
+          gr.dt += p.slab_axis == 2 ? sl : 0;
+        }
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1u);
           if (leader) {
@@ -250,7 +277,9 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     const uint32_t stage_bytes = p.stage_bytes, a_stride = p.a_stride, b_bytes = p.b_bytes, tap_bytes = p.tap_bytes;
     uint32_t idesc;             // pinned in a register: the compiler otherwise re-loads it in front of every tap
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
-    const int n_groups = p.n_groups, chunks = p.chunks, last_ksteps = p.last_ksteps, stages = p.stages, n_tile = p.n_tile;
+    const int slab_g = (kXform || kStats) ? 0 : p.slab_g;      // (slab mode exists in the plain instantiation only)
+    const int n_groups = slab_g ? p.slab_in : p.n_groups, chunks = p.chunks, last_ksteps = p.last_ksteps, stages = p.stages,
+              n_tile = p.n_tile;
     // (copied through registers once: the compiler otherwise re-loads them from the constant bank inside the tap loop)
     int nw, group_taps;
     asm volatile("mov.u32 %0, %1;" : "=r"(nw) : "r"(p.tap_nw));
@@ -291,6 +320,27 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
             const int ks = (c == chunks - 1) ? last_ksteps : 4;
             const uint64_t hi_a = tl ? dhi_tail_a : dhi_a, hi_b = tl ? dhi_tail_b : dhi_b;
             const uint32_t sw = tl ? sw_full >> tail_shift : sw_full, sh = tl ? sh_full >> tail_shift : sh_full;
+            if (slab_g) {
+              // slab mode: this stage holds ONE input slab; w tap j multiplies it with the stacked weight blocks of the
+              // output slabs it feeds (brow rows into the [nslots x slab_cols]-row block of tap j), ncols wide, into the
+              // accumulator columns doff .. doff + ncols
+              const uint32_t rowb = tl ? static_cast<uint32_t>(p.tail) * 2u : 128u;
+              const uint32_t blk = static_cast<uint32_t>(p.slab_nslots) * (tl ? p.res_tail_tap_stride : p.res_tap_stride);
+              const uint32_t b0 = res_addr + (tl ? p.res_tail_base : static_cast<uint32_t>(c) * p.res_chunk_stride) +
+                                  static_cast<uint32_t>(p.slab_brow[g]) * rowb;
+              const uint32_t sidesc = p.slab_idesc[g];
+              const uint32_t dcol = d_tmem + static_cast<uint32_t>(p.slab_doff[g]);
+              uint32_t acc = (p.slab_init[g] && c == 0) ? 0u : 1u;
+              for (int j = 0; j < nw; ++j) {
+                const uint64_t da = umma_desc_at(hi_a, s_addr + static_cast<uint32_t>(j) * sw);
+                const uint64_t db = umma_desc_at(hi_b, b0 + static_cast<uint32_t>(j) * blk);
+                umma_bf16_nc(dcol, da, db, sidesc, acc);
+                acc = 1u;
+                for (int k = 1; k < ks; ++k) umma_bf16_acc_nc(dcol, da + 2 * k, db + 2 * k, sidesc);
+              }
+              umma_commit(&empty[stage]);
+              if (g == n_groups - 1 && c == chunks - 1) umma_commit(&tfull[as]);
+            } else {
             uint32_t b_addr = resident ? res_addr + static_cast<uint32_t>(g_first) * tap_bytes +
                                              static_cast<uint32_t>(tl ? full_chunks : c) * b_bytes
                                        : s_addr + a_stride;
@@ -329,6 +379,7 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
             }
             umma_commit(&empty[stage]);
             if (g == n_groups - 1 && c == chunks - 1) umma_commit(&tfull[as]);
+            }
           }
           first = 0;
           __syncwarp();
@@ -409,9 +460,9 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
       int pt = tile;
       const int w = (pt % p.tiles_w) * p.bw + rw;
       pt /= p.tiles_w;
-      const int h = (pt % p.tiles_h) * p.bh + rh;
+      const int h = (pt % p.tiles_h) * p.step_h + rh;
       pt /= p.tiles_h;
-      const int t = (pt % p.tiles_t) * p.bt + rt;
+      const int t = (pt % p.tiles_t) * p.step_t + rt;
       pt /= p.tiles_t;
       const int n = pt * p.bn + rn;
       const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
@@ -442,6 +493,16 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
         stats_chunk<32>(va, dst, valid, acc);
         tmem_ld_wait();
         stats_chunk<48>(vb, dst, valid, acc);
+      } else if (!kXform && p.slab_g) {
+        // slab mode: column block o of the accumulator is output slab o along the slab axis (plain bf16 rows)
+        const long long ostep = p.slab_axis == 1 ? p.osh : p.ost;
+        const int pos = p.slab_axis == 1 ? h : t, lim = p.slab_axis == 1 ? p.Ht : p.Tt;
+        for (int o = 0; o < p.slab_g; ++o) {
+          const bool ok = valid && pos + o < lim;
+          const uint32_t ta = taddr + static_cast<uint32_t>(o * p.slab_cols);
+          if (p.accumulate) epilogue_row_bf16<true>(ta, p.slab_cols, p.out + off + o * ostep, ok);
+          else epilogue_row_bf16<false>(ta, p.slab_cols, p.out + off + o * ostep, ok);
+        }
       } else if (p.fast_store) {
         // plain bf16 output (optionally accumulated into what is there): pipelined, one 32-byte store per 16 columns.
         // (The row-per-thread layout makes every 16-byte store a half-written sector; with nine serial
@@ -554,6 +615,17 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   CSTP_REQUIRE(pitch >= 8 && pitch <= 64);
   CSTP_REQUIRE(d->halo_w == 0 ? (pitch == 8 && xrows % 8 == 0) : (d->bw == 8 && pitch == d->bw + d->halo_w));
   const bool xform = d->pro.scale != nullptr;
+  const int G = d->slabs.n_slabs > 1 ? d->slabs.n_slabs : 0;
+  if (G) {
+    // slab mode: taps[] lists, for every w tap j, the nslots stacked weight blocks (tap offset along the slab axis
+    // DEscending); groups[0] is the origin of the first input slab; one tile = 128 positions x G output slabs
+    const cstp_halo_slabs& sl = d->slabs;
+    CSTP_REQUIRE((sl.axis == 1 || sl.axis == 2) && sl.nslots >= 1 && sl.nslots <= 4 && d->n_taps % sl.nslots == 0);
+    CSTP_REQUIRE(G + sl.nslots - 1 <= kHcMaxSlabs && d->n_groups == 1 && d->groups[0].n_taps == d->n_taps);
+    CSTP_REQUIRE(d->Np % 16 == 0 && d->n_tile == G * d->Np && d->n_tile <= 256 && sl.nslots * d->Np <= 256);
+    CSTP_REQUIRE((sl.axis == 1 ? d->bh : d->bt) == 1 && (sl.axis == 1 ? d->halo_h : d->halo_t) == 0);
+    CSTP_REQUIRE(!xform && d->stats_partials == nullptr && d->allow_resident && d->bias == nullptr && d->out_f32 == nullptr);
+  }
   if (xform) {
     // the prologue picks its coefficient row per tile: one sample per tile, the statistics groups split the N axis evenly
     CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
@@ -585,7 +657,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
     if (rc == CSTP_OK) {
       const uint64_t bdims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
       const uint64_t bstr[1] = {(uint64_t)d->Ktot * 2};
-      const uint32_t bbox[2] = {64u, (uint32_t)d->n_tile};
+      const uint32_t bbox[2] = {64u, (uint32_t)(G ? d->Np : d->n_tile)};
       rc = encode_tmap_bf16(&k.bmap, d->w_packed, 2, bdims, bstr, bbox);
     }
     // channel tail: exactly 16 or 32 channels beyond a multiple of 64 get their own narrow (32 / 64-byte row) boxes
@@ -597,7 +669,7 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
       if (rc == CSTP_OK) {
         const uint64_t bdims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Np};
         const uint64_t bstr[1] = {(uint64_t)d->Ktot * 2};
-        const uint32_t bbox_t[2] = {(uint32_t)k.tail, (uint32_t)d->n_tile};
+        const uint32_t bbox_t[2] = {(uint32_t)k.tail, (uint32_t)(G ? d->Np : d->n_tile)};
         rc = encode_tmap_bf16(&k.bmap_tail, d->w_packed, 2, bdims, bstr, bbox_t, k.tail * 2);
       }
     } else if (rc == CSTP_OK) {
@@ -609,9 +681,11 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
       return rc;
     }
   }
+  k.step_h = (G && d->slabs.axis == 1) ? G : d->bh;
+  k.step_t = (G && d->slabs.axis == 2) ? G : d->bt;
   k.tiles_w = ceil_div(d->Wt, d->bw);
-  k.tiles_h = ceil_div(d->Ht, d->bh);
-  k.tiles_t = ceil_div(d->Tt, d->bt);
+  k.tiles_h = ceil_div(d->Ht, k.step_h);
+  k.tiles_t = ceil_div(d->Tt, k.step_t);
   k.tiles_n = ceil_div(d->Nt, d->bn);
   k.bw = d->bw; k.bh = d->bh; k.bt = d->bt; k.bn = d->bn;
   k.Wt = d->Wt; k.Ht = d->Ht; k.Tt = d->Tt; k.Nt = d->Nt;
@@ -624,11 +698,66 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.a_bytes = static_cast<uint32_t>(xrows) * 128u;
   k.a_stride = (k.a_bytes + 1023u) & ~1023u;
   k.a_sbo = static_cast<uint32_t>(pitch) * 128u;
-  k.b_bytes = static_cast<uint32_t>(d->n_tile) * 128u;
+  const uint32_t b_rows = static_cast<uint32_t>(G ? d->Np : d->n_tile);      // rows of one staged weight block
+  k.b_bytes = b_rows * 128u;
   k.a_bytes_tail = static_cast<uint32_t>(xrows) * static_cast<uint32_t>(k.tail) * 2u;
-  k.b_bytes_tail = static_cast<uint32_t>(d->n_tile) * static_cast<uint32_t>(k.tail) * 2u;
+  k.b_bytes_tail = b_rows * static_cast<uint32_t>(k.tail) * 2u;
   k.tap_bytes = k.tail ? static_cast<uint32_t>(k.chunks - 1) * k.b_bytes + k.b_bytes_tail
                        : static_cast<uint32_t>(k.chunks) * k.b_bytes;
+  {
+    // resident weight blocks: classic [tap][chunk], slab mode [chunk][w tap][slot] (the stacked blocks of one w tap are
+    // consecutive rows of ONE K-major operand)
+    const uint32_t full_chunks = static_cast<uint32_t>(k.tail ? k.chunks - 1 : k.chunks);
+    if (G) {
+      k.res_tap_stride = k.b_bytes;
+      k.res_chunk_stride = static_cast<uint32_t>(d->n_taps) * k.b_bytes;
+      k.res_tail_base = full_chunks * k.res_chunk_stride;
+      k.res_tail_tap_stride = k.b_bytes_tail;
+    } else {
+      k.res_tap_stride = k.tap_bytes;
+      k.res_chunk_stride = k.b_bytes;
+      k.res_tail_base = full_chunks * k.b_bytes;
+      k.res_tail_tap_stride = k.tap_bytes;
+    }
+  }
+  if (G) {
+    const cstp_halo_slabs& sl = d->slabs;
+    const int span = sl.nslots - 1, n_in = G + span;
+    k.slab_g = G;
+    k.slab_axis = sl.axis;
+    k.slab_in = n_in;
+    k.slab_nslots = sl.nslots;
+    k.slab_cols = d->Np;
+    // input slab s feeds the output slabs o = max(0, s - span) .. min(G - 1, s) with the taps s - o (descending):
+    // stacked blocks (span - s + o_lo) ..; the slabs that cover disjoint column ranges and together all G x Np columns
+    // (s = span, span + nslots, ...) go first and overwrite the accumulator
+    int order[kHcMaxSlabs], n_ord = 0, covered = 0;
+    bool used[kHcMaxSlabs] = {false};
+    while (covered < G) {
+      int s = covered + span;                         // its lowest output slab is `covered`
+      if (s > n_in - 1) s = n_in - 1;
+      int o_lo = s - span > 0 ? s - span : 0;
+      if (o_lo != covered) {                          // cannot happen: s - span == covered unless clamped to the last slab
+        delete plan;
+        return fail_inval("slab mode: no overwrite cover of the accumulator");
+      }
+      order[n_ord++] = s;
+      used[s] = true;
+      covered = (s < G - 1 ? s : G - 1) + 1;
+    }
+    const int n_init = n_ord;
+    for (int s = 0; s < n_in; ++s)
+      if (!used[s]) order[n_ord++] = s;
+    for (int i = 0; i < n_in; ++i) {
+      const int s = order[i];
+      const int o_lo = s - span > 0 ? s - span : 0, o_hi = s < G - 1 ? s : G - 1;
+      k.slab_order[i] = s;
+      k.slab_init[i] = i < n_init ? 1 : 0;
+      k.slab_doff[i] = o_lo * d->Np;
+      k.slab_brow[i] = (span - s + o_lo) * d->Np;
+      k.slab_idesc[i] = umma_idesc_bf16(128, static_cast<uint32_t>((o_hi - o_lo + 1) * d->Np), 0, 0);
+    }
+  }
   k.idesc = umma_idesc_bf16(128, static_cast<uint32_t>(d->n_tile), 0, 0);
   k.accumulate = d->accumulate;
   k.out = reinterpret_cast<__nv_bfloat16*>(d->out_bf16);
@@ -677,6 +806,21 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
     }
     k.taps[t] = HcTap{tp.a_shift, tp.k_off};
   }
+  if (G) {
+    // slab mode: taps[j * nslots + slot] share the w shift j * sw (whole rows of the staged box)
+    const int ns = d->slabs.nslots, nwt = d->n_taps / ns;
+    const uint32_t sw = nwt > 1 ? d->taps[ns].a_shift : 0u;
+    bool ok = k.fast_store != 0;
+    for (int t = 0; t < d->n_taps; ++t) ok = ok && d->taps[t].a_shift == static_cast<uint32_t>(t / ns) * sw;
+    if (!ok) {
+      delete plan;
+      return fail_inval("slab mode: taps must be listed w tap by w tap (equal shifts within one w tap), plain aligned bf16 output");
+    }
+    k.group_taps = d->n_taps;
+    k.tap_nw = nwt;
+    k.tap_sw = sw;
+    k.tap_sh = 0;
+  } else
   // the issuer walks the taps of a group arithmetically: derive (nw, sw, sh) from the first group and hold every group to it
   {
     const cstp_halo_group& g0 = d->groups[0];
@@ -727,6 +871,10 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   if (stages < 2) {
     delete plan;
     return fail_inval("stage too large for the shared-memory pipeline");
+  }
+  if (G && !k.resident) {
+    delete plan;
+    return fail_inval("slab mode needs the weights resident in shared memory");
   }
   k.stages = stages;
   int cols = 32;

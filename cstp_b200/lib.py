@@ -85,6 +85,10 @@ class HaloTap(C.Structure):
     _fields_ = [("a_shift", C.c_uint32), ("k_off", C.c_int32)]
 
 
+class HaloSlabs(C.Structure):
+    _fields_ = [("n_slabs", C.c_int32), ("axis", C.c_int32), ("nslots", C.c_int32)]
+
+
 class ConvHaloDesc(C.Structure):
     _fields_ = [
         ("amap", Tensor5),
@@ -110,6 +114,7 @@ class ConvHaloDesc(C.Structure):
         ("stats_groups", C.c_int32),
         ("stats_partials", C.c_void_p),
         ("pro", Prologue),
+        ("slabs", HaloSlabs),
     ]
 
 

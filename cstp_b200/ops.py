@@ -354,6 +354,79 @@ def _conv_halo_layout(tile_space, taps, a_channels: int, Np: int, halo_2d: bool)
                 tail=tail, pitch=pitch)
 
 
+USE_SLABS = os.environ.get("CSTP_SLABS", "1") == "1"
+SLAB_G = int(os.environ.get("CSTP_SLAB_G", "4"))
+
+
+def slab_tables(G: int, nslots: int, Np: int):
+    """The per-input-slab tables of csrc/conv_halo.cu's slab mode, in issue order: [(input slab s, overwrite?, first
+    accumulator column, first row of the stacked weight block, MMA width)] -- restated here for the CPU layout
+    interpreter (tests/test_geometry.py); cstp_conv_halo_plan_create derives the same."""
+    span, n_in = nslots - 1, G + nslots - 1
+    order, covered = [], 0
+    while covered < G:
+        s = min(covered + span, n_in - 1)
+        order.append(s)
+        covered = min(s, G - 1) + 1
+    n_init = len(order)
+    order += [s for s in range(n_in) if s not in order]
+    out = []
+    for i, s in enumerate(order):
+        o_lo, o_hi = max(0, s - span), min(G - 1, s)
+        out.append((s, i < n_init, o_lo * Np, (span - s + o_lo) * Np, (o_hi - o_lo + 1) * Np))
+    return out
+
+
+def conv_slab_layout(tile_space, taps, a_channels: int, Np: int, G: int | None = None):
+    """Slab-mode geometry of csrc/conv_halo.cu (include/cstp_b200.h cstp_halo_slabs) for a stride-1 tap list
+    [(dw, dh, dt, k_off)] of a layer with Np == 64 output columns, or None.  1 x k x k taps: G output rows per tile (slab
+    axis h), every input row staged as ONE box with a halo along w (the w taps are row shifts of it); k x 1 x 1 taps: G
+    output frames per tile (slab axis t), plain boxes.  Same dict as conv_halo_layout plus `slabs` = (G, axis, nslots);
+    taps are listed w tap by w tap, the taps along the slab axis in DEscending offset order."""
+    Wt, Ht, Tt, Nt = tile_space
+    G = G or SLAB_G
+    if not USE_SLABS or Np != 64 or G < 2 or G * Np > 256 or len(taps) < 2 or len(taps) > 16:
+        return None
+    dws, dhs, dts = sorted({t[0] for t in taps}), sorted({t[1] for t in taps}), sorted({t[2] for t in taps})
+    consecutive = lambda v: v == list(range(v[0], v[-1] + 1))      # noqa: E731
+    if len(dts) == 1 and len(dhs) > 1 and consecutive(dws) and consecutive(dhs) and len(taps) == len(dws) * len(dhs):
+        axis, along, wspan, extent = 1, dhs, dws[-1] - dws[0], Ht
+    elif len(dws) == 1 and len(dhs) == 1 and len(dts) > 1 and consecutive(dts) and dws[0] == 0 and dhs[0] == 0:
+        axis, along, wspan, extent = 2, dts, 0, Tt
+    else:
+        return None
+    nslots = len(along)
+    if nslots > 4 or nslots * Np > 256 or extent < G:
+        return None
+    # 128 positions with extent 1 along the slab axis, 8 along w (one swizzle atom per run when the box has a w halo)
+    best = None
+    for b1 in (16, 8, 4, 2, 1):                  # extent along the other spatial / temporal axis, the rest along n
+        bn = 16 // b1
+        other = Tt if axis == 1 else Ht
+        key = (math.ceil(other / b1) * math.ceil(Nt / bn), bn)
+        if best is None or key < best[0]:
+            best = (key, b1, bn)
+    _, b1, bn = best
+    box = (8, 1, b1, bn) if axis == 1 else (8, b1, 1, bn)
+    rows = (8 + wspan) * b1 * bn
+    pitch = 8 + wspan if wspan else 8
+    a_bytes = (rows * 128 + 1023) // 1024 * 1024
+    chunks = pad64(a_channels) // 64
+    tail = a_channels % 64 if (USE_TAIL_BOXES and a_channels > 64 and a_channels % 64 in (16, 32)) else 0
+    k_bytes_per_row = ((chunks - 1) * 128 + tail * 2) if tail else chunks * 128
+    if len(taps) * k_bytes_per_row * Np + 2 * a_bytes > SMEM_BUDGET:
+        return None
+    by_off = {(t[0], t[1], t[2]): t[3] for t in taps}
+    out_taps = []
+    for dw in dws:
+        for da in reversed(along):
+            key = (dw, da, dts[0]) if axis == 1 else (dw, dhs[0], da)
+            out_taps.append(((dw - dws[0]) * 128, by_off[key]))
+    groups = [(dws[0], dhs[0], dts[0], 0, len(taps))]
+    return dict(box=box, halo=(wspan, 0, 0), groups=groups, taps=out_taps, n_tile=G * Np, a_bytes=a_bytes, resident=True,
+                tail=tail, pitch=pitch, slabs=(G, axis, nslots))
+
+
 def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, out_f32, out_off, ostrides, bias,
                          accumulate, keep, stats=None, prologue=None) -> ConvHaloPlan:
     lib = L.load()
@@ -381,6 +454,8 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     d.allow_resident = int(lay["resident"])
     d.use_tail_boxes = int(bool(lay.get("tail", 0)))
     d.atom_pitch_rows = lay.get("pitch", 8)
+    if lay.get("slabs"):
+        d.slabs.n_slabs, d.slabs.axis, d.slabs.nslots = lay["slabs"]
     d.stats_partials = 0 if stats is None else stats.partials.data_ptr()
     d.stats_groups = 0 if stats is None else stats.groups
     h = C.c_void_p()
@@ -463,7 +538,11 @@ def conv_dgrad_plans(g, wt_packed, dx, geom: ConvGeom, *, accumulate=False, allo
         # the classes whose taps form a 1-D / 2-D neighbourhood (stride-2 1x3x3: the 2- and 4-tap classes)
         if allow_halo and cl["space"][0] * cl["space"][1] >= HALO_MIN_POSITIONS and (
                 tuple(geom.stride) == (1, 1, 1) or DGRAD_STRIDED_HALO):
-            lay = conv_halo_layout(cl["space"], [t[1:] for t in taps], Co, Ci)
+            lay = None
+            if tuple(geom.stride) == (1, 1, 1):
+                lay = conv_slab_layout(cl["space"], [t[1:] for t in taps], Co, Ci)
+            if lay is None:
+                lay = conv_halo_layout(cl["space"], [t[1:] for t in taps], Co, Ci)
             if lay is not None:
                 plans.append(_make_conv_halo_plan(gview, lay, Co, wt_packed, Ci, cl["space"], dx, None, cl["off"],
                                                   cl["ostrides"], None, accumulate, (g, wt_packed, dx)))

@@ -119,6 +119,19 @@ typedef struct {
   int32_t k_off;
 } cstp_halo_tap;
 
+/* "Slab mode" for layers with few output channels (Np <= 64): n_slabs = G > 1 consecutive output slabs along `axis`
+ * (1: h, 2: t) share one accumulator of n_tile = G * Np columns.  Every input slab of the tile (G + nslots - 1 of them, the
+ * first at the origin groups[0]) is staged once and multiplied, per w tap, with the stacked weight blocks of the output
+ * slabs it feeds: a 128 x 64 x 16 tcgen05.mma is bound by the shared-memory read of its A slice, an MMA of 2 - 3 x 64
+ * columns is not.  taps[] then lists, w tap by w tap, the nslots taps along `axis` in DEscending offset order; the tile
+ * covers bw*bh*bt*bn == 128 positions with extent 1 along `axis`.  Needs resident weights, a plain bf16 output, no
+ * prologue / statistics. */
+typedef struct {
+  int32_t n_slabs;              /* 0 / 1: off */
+  int32_t axis;
+  int32_t nslots;
+} cstp_halo_slabs;
+
 typedef struct {
   cstp_tensor5 amap;
   int32_t a_channels;
@@ -153,6 +166,7 @@ typedef struct {
   int32_t stats_groups;
   float* stats_partials;
   cstp_prologue pro;            /* BatchNorm + ReLU applied to A on the way in (scale NULL: none) */
+  cstp_halo_slabs slabs;        /* n_slabs <= 1: classic tiles */
 } cstp_conv_halo_desc;
 
 typedef struct cstp_conv_halo_plan cstp_conv_halo_plan;

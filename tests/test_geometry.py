@@ -225,3 +225,95 @@ def test_conv_halo_layout_semantics(k, p, shape, cin, cout, dgrad):
     else:
         ref = torch.nn.grad.conv3d_input((N, cin, T, H, W), w, x5, stride=1, padding=p)
     assert torch.allclose(out.permute(0, 4, 1, 2, 3), ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("k,p,shape,cin,cout,dgrad,G", [
+    ((1, 3, 3), (0, 1, 1), (1, 2, 12, 12), 64, 144, True, 4),      # dgrad of the 64 -> 144 1x3x3 layers (conv2.*.spatial): slab axis h
+    ((1, 3, 3), (0, 1, 1), (2, 3, 10, 20), 64, 144, True, 4),      # partial slab group along h, partial tiles along w / t
+    ((3, 1, 1), (1, 0, 0), (1, 8, 16, 8), 144, 64, False, 4),      # temporal forward 144 -> 64: slab axis t
+    ((3, 1, 1), (1, 0, 0), (2, 6, 8, 8), 80, 64, False, 2),        # two output frames per tile, ragged T
+    ((1, 3, 3), (0, 1, 1), (1, 1, 9, 8), 64, 64, False, 3),
+])
+def test_conv_slab_layout_semantics(k, p, shape, cin, cout, dgrad, G):
+    """Interprets ops.conv_slab_layout + ops.slab_tables exactly as csrc/conv_halo.cu's slab mode does: every input slab
+    of a tile is staged once (w halo box, zero OOB fill) and multiplied, per w tap, with `width` stacked weight rows
+    starting at `brow` into the accumulator columns `doff`..; the slabs flagged `init` overwrite.  Compared with torch
+    conv3d / its input gradient."""
+    import torch.nn.functional as F
+    from cstp_b200.ops import conv_slab_layout, slab_tables, dgrad_classes, pad16, pad64
+    N, T, H, W = shape
+    geom = ConvGeom(k, (1, 1, 1), p)
+    gen = torch.Generator().manual_seed(7)
+    w = torch.randn(cout, cin, *k, generator=gen)
+    if not dgrad:
+        a_c, n_c = cin, cout
+        _, taps = fwd_taps(geom)
+        taps = [(dw, dh, dt, ti) for (_, dw, dh, dt, ti) in taps]
+        wmat = lambda ti: w.reshape(cout, cin, -1)[:, :, ti]                     # [n][c]   # noqa: E731
+    else:
+        a_c, n_c = cout, cin
+        (cl,) = dgrad_classes((N, T, H, W, pad16(cin)), geom)
+        taps = cl["taps"]
+        wmat = lambda ti: w.reshape(cout, cin, -1)[:, :, ti].t()                 # [n = ci][c = co]  # noqa: E731
+    Ca, Np = pad16(a_c), pad16(n_c)
+    assert Np == 64
+    a = torch.zeros(N, T, H, W, Ca)
+    a[..., :a_c] = torch.randn(N, T, H, W, a_c, generator=gen)
+    lay = conv_slab_layout((W, H, T, N), [(dw, dh, dt, ti * pad64(Ca)) for (dw, dh, dt, ti) in taps], Ca, Np, G)
+    assert lay is not None and lay["slabs"][0] == G
+    _, axis, nslots = lay["slabs"]
+    bw, bh, bt, bn = lay["box"]
+    hw = lay["halo"][0]
+    pitch = lay["pitch"]
+    assert bw * bh * bt * bn == 128 and (bh if axis == 1 else bt) == 1 and lay["n_tile"] == G * Np
+    (gdw, gdh, gdt, _, _), = lay["groups"]
+    tap_of_koff = {ti * pad64(Ca): ti for (_, _, _, ti) in taps}
+    nw = len(lay["taps"]) // nslots
+    # stacked weight block of w tap j: [nslots * Np rows][Ca]
+    stack = [torch.cat([torch.nn.functional.pad(wmat(tap_of_koff[lay["taps"][j * nslots + sl][1]]), (0, Ca - a_c, 0, Np - n_c))
+                        for sl in range(nslots)]) for j in range(nw)]
+    assert all(lay["taps"][j * nslots + sl][0] == j * 128 * (1 if hw else 0) for j in range(nw) for sl in range(nslots))
+    table = slab_tables(G, nslots, Np)
+
+    def fetch(w0, h0, t0, n0):          # the staged box: rows (n, t, h, w) with w fastest, bw + hw wide
+        box = torch.zeros(bn, bt, bh, bw + hw, Ca)
+        for nn in range(bn):
+            for aa in range(bt):
+                for bb in range(bh):
+                    for cc in range(bw + hw):
+                        n_, tt, hh_, ww = n0 + nn, t0 + aa, h0 + bb, w0 + cc
+                        if n_ < N and 0 <= tt < T and 0 <= hh_ < H and 0 <= ww < W:
+                            box[nn, aa, bb, cc] = a[n_, tt, hh_, ww]
+        return box.reshape(-1, Ca)
+
+    out = torch.zeros(N, T, H, W, n_c)
+    step_h, step_t = (G if axis == 1 else bh), (G if axis == 2 else bt)
+    for n0 in range(0, N, bn):
+        for t0 in range(0, T, step_t):
+            for h0 in range(0, H, step_h):
+                for w0 in range(0, W, bw):
+                    acc = torch.full((128, G * Np), float("nan"))        # stale accumulator: the init slabs must overwrite
+                    for (s, init, doff, brow, width) in table:
+                        staged = fetch(w0 + gdw, h0 + gdh + (s if axis == 1 else 0), t0 + gdt + (s if axis == 2 else 0), n0)
+                        first = init
+                        for j in range(nw):
+                            rows = staged[[j + a_ * pitch + r for a_ in range(16) for r in range(8)]]
+                            prod = rows @ stack[j][brow:brow + width].t()
+                            acc[:, doff:doff + width] = prod if first else acc[:, doff:doff + width] + prod
+                            first = False
+                    assert not torch.isnan(acc).any()
+                    for r in range(128):
+                        ww, hh_, tt, n_ = w0 + r % bw, h0 + (r // bw) % bh, t0 + (r // (bw * bh)) % bt, n0 + r // (bw * bh * bt)
+                        for o in range(G):
+                            pos = (hh_ if axis == 1 else tt) + o
+                            if ww < W and n_ < N and (pos < H if axis == 1 else pos < T) and hh_ < H and tt < T:
+                                if axis == 1:
+                                    out[n_, tt, pos, ww] = acc[r, o * Np:o * Np + n_c]
+                                else:
+                                    out[n_, pos, hh_, ww] = acc[r, o * Np:o * Np + n_c]
+    x5 = a[..., :a_c].permute(0, 4, 1, 2, 3)
+    if not dgrad:
+        ref = F.conv3d(x5, w, None, 1, p)
+    else:
+        ref = torch.nn.grad.conv3d_input((N, cin, T, H, W), w, x5, stride=1, padding=p)
+    assert torch.allclose(out.permute(0, 4, 1, 2, 3), ref, rtol=1e-4, atol=1e-3)

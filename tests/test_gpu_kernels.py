@@ -73,7 +73,10 @@ def test_ragged_and_tiny_geometries():
                dict(N=1, T=1, H=2, W=2, cin=16, cout=16, kernel=(1, 1, 1), stride=(1, 1, 1), pad=(0, 0, 0)),
                # 2-D halo layouts (conv fwd / dgrad with a 16-channel tail / wgrad) with partial tiles along h and w
                dict(N=1, T=2, H=40, W=36, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1)),
-               dict(N=2, T=1, H=36, W=28, cin=128, cout=240, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))):
+               dict(N=2, T=1, H=36, W=28, cin=128, cout=240, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1)),
+               # slab mode (dgrad of 64 -> 144 1x3x3: four dx rows per tile): rows / columns / frames that do not fill the tiles
+               dict(N=3, T=5, H=30, W=36, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1)),
+               dict(N=2, T=16, H=28, W=28, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))):
         r = case_conv(**kw)
         assert r["fwd_nan"] == 0 and r["fwd_pad_zero"] and r["fwd_rel"] < 4e-3, (kw, r)
         assert r["dgrad_nan"] == 0 and r["dgrad_rel"] < 4e-3, (kw, r)
