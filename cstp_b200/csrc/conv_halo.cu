@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
   // the producer / issuer warpgroup and the transform warpgroup hand registers to the epilogue warpgroup (setmaxnreg at
   // the head of each warpgroup's branch, where ptxas can see which code runs under which budget).
   constexpr bool kRealloc = kStats && kXform;
+  // slab mode is compiled into every instantiation but the prologue-without-statistics one (no layer needs it there, and its
+  // 128-register budget spills with the extra paths)
+  constexpr bool kSlabOk = !(kXform && !kStats);
 
   // Roles run WARP-CONVERGED: all 32 lanes walk the loops and poll the mbarriers, one elected lane issues the TMA /
   // tcgen05 instructions.  (With a single-lane branch the compiler cannot keep descriptors and addresses in uniform
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     }
     int stage = 0;
     uint32_t phase = 0;
-    const int pslab = (kXform || kStats) ? 0 : p.slab_g;
+    const int pslab = kSlabOk ? p.slab_g : 0;
     const int n_loads = pslab ? p.slab_in : p.n_groups;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       int pt = tile;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     const uint32_t stage_bytes = p.stage_bytes, a_stride = p.a_stride, b_bytes = p.b_bytes, tap_bytes = p.tap_bytes;
     uint32_t idesc;             // pinned in a register: the compiler otherwise re-loads it in front of every tap
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
-    const int slab_g = (kXform || kStats) ? 0 : p.slab_g;      // (slab mode exists in the plain instantiation only)
+    const int slab_g = kSlabOk ? p.slab_g : 0;
     const int n_groups = slab_g ? p.slab_in : p.n_groups, chunks = p.chunks, last_ksteps = p.last_ksteps, stages = p.stages,
               n_tile = p.n_tile;
     // (copied through registers once: the compiler otherwise re-loads them from the constant bank inside the tap loop)
@@ -403,15 +406,15 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
     const uint32_t xtab_addr = smem_u32(xtab);
     const uint32_t stage_addr0 = smem_u32(stage0);
     const uint32_t stage_bytes = p.stage_bytes;
-    const int n_groups = p.n_groups, chunks = p.chunks, stages = p.stages;
+    const int n_groups = (kSlabOk && p.slab_g) ? p.slab_in : p.n_groups, chunks = p.chunks, stages = p.stages;
     const bool has_tail = p.tail != 0;
     const uint32_t units_full = p.a_bytes >> 4, units_tail = p.a_bytes_tail >> 4;
     const uint32_t mask_tail = p.tail == 16 ? 1u : 3u;
-    const int slab = p.tiles_w * p.tiles_h * p.tiles_t;        // tiles per sample (bn == 1)
+    const int slab = p.tiles_w * p.tiles_h * p.tiles_t;        // tiles per bn samples (all of one statistics group)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-      const int n0 = tile / slab;
+      const int n0 = (tile / slab) * p.bn;
       const int grp = (p.pro_groups == 2 && 2 * n0 >= p.Nt) ? 1 : 0;
       for (int g = 0; g < n_groups; ++g) {
         for (int c = 0; c < chunks; ++c) {
@@ -464,7 +467,8 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
       pt /= p.tiles_h;
       const int t = (pt % p.tiles_t) * p.step_t + rt;
       pt /= p.tiles_t;
-      const int n = pt * p.bn + rn;
+      const int n_first = pt * p.bn;                          // first sample of the tile
+      const int n = n_first + rn;
       const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
       const long long off = p.out_off + w * p.osw + h * p.osh + t * p.ost + n * p.osn + col0;
       mbar_wait(&tfull[as], aphase);
@@ -474,26 +478,34 @@ __global__ void __launch_bounds__(kXform ? kHcThreads + kHcXformThreads : kHcThr
         // 64-column tile, plain bf16 output, bn == 1: the whole tile belongs to ONE statistics group (the halves of the N
         // axis are the two views); the accumulators are flushed when the group changes (at most once per CTA) and at
         // the end -- no shuffle and no shared memory per tile, two FMAs per element
-        const int g = (p.stats_groups == 2 && 2 * n >= p.Nt) ? 1 : 0;       // n: this tile's sample (rn == 0)
+        const int g = (p.stats_groups == 2 && 2 * n_first >= p.Nt) ? 1 : 0;  // all bn samples of a tile share the group
         if (g != cur_group) {
           if (cur_group >= 0) stats_flush(acc, wsum, tot + cur_group * 128, q, lane);
           cur_group = g;
         }
-        __nv_bfloat16* dst = p.out + off;
-        uint32_t va[16], vb[16];
-        tmem_ld16(taddr, va);
-        tmem_ld_wait();
-        tmem_ld16(taddr + 16, vb);
-        stats_chunk<0>(va, dst, valid, acc);
-        tmem_ld_wait();
-        tmem_ld16(taddr + 32, va);
-        stats_chunk<16>(vb, dst, valid, acc);
-        tmem_ld_wait();
-        tmem_ld16(taddr + 48, vb);
-        stats_chunk<32>(va, dst, valid, acc);
-        tmem_ld_wait();
-        stats_chunk<48>(vb, dst, valid, acc);
-      } else if (!kXform && p.slab_g) {
+        // slab mode: G column blocks of 64 = G output slabs along the slab axis, all of them feed the same 64 channel sums
+        const int n_os = p.slab_g ? p.slab_g : 1;
+        const long long ostep = p.slab_axis == 1 ? p.osh : p.ost;
+        const int pos = p.slab_axis == 1 ? h : t, lim = p.slab_g ? (p.slab_axis == 1 ? p.Ht : p.Tt) : 0x7fffffff;
+        for (int o = 0; o < n_os; ++o) {
+          const bool ok = valid && pos + o < lim;
+          __nv_bfloat16* dst = p.out + off + o * ostep;
+          const uint32_t ta = taddr + static_cast<uint32_t>(o * 64);
+          uint32_t va[16], vb[16];
+          tmem_ld16(ta, va);
+          tmem_ld_wait();
+          tmem_ld16(ta + 16, vb);
+          stats_chunk<0>(va, dst, ok, acc);
+          tmem_ld_wait();
+          tmem_ld16(ta + 32, va);
+          stats_chunk<16>(vb, dst, ok, acc);
+          tmem_ld_wait();
+          tmem_ld16(ta + 48, vb);
+          stats_chunk<32>(va, dst, ok, acc);
+          tmem_ld_wait();
+          stats_chunk<48>(vb, dst, ok, acc);
+        }
+      } else if (kSlabOk && p.slab_g) {
         // slab mode: column block o of the accumulator is output slab o along the slab axis (plain bf16 rows)
         const long long ostep = p.slab_axis == 1 ? p.osh : p.ost;
         const int pos = p.slab_axis == 1 ? h : t, lim = p.slab_axis == 1 ? p.Ht : p.Tt;
@@ -624,12 +636,12 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
     CSTP_REQUIRE(G + sl.nslots - 1 <= kHcMaxSlabs && d->n_groups == 1 && d->groups[0].n_taps == d->n_taps);
     CSTP_REQUIRE(d->Np % 16 == 0 && d->n_tile == G * d->Np && d->n_tile <= 256 && sl.nslots * d->Np <= 256);
     CSTP_REQUIRE((sl.axis == 1 ? d->bh : d->bt) == 1 && (sl.axis == 1 ? d->halo_h : d->halo_t) == 0);
-    CSTP_REQUIRE(!xform && d->stats_partials == nullptr && d->allow_resident && d->bias == nullptr && d->out_f32 == nullptr);
+    CSTP_REQUIRE((!xform || d->stats_partials != nullptr) && d->allow_resident && d->bias == nullptr && d->out_f32 == nullptr);
   }
   if (xform) {
     // the prologue picks its coefficient row per tile: one sample per tile, the statistics groups split the N axis evenly
     CSTP_REQUIRE(d->pro.shift != nullptr && (d->pro.groups == 1 || d->pro.groups == 2) && d->Nt % d->pro.groups == 0);
-    CSTP_REQUIRE(d->pro.Cp == d->a_channels && d->bn == 1);
+    CSTP_REQUIRE(d->pro.Cp == d->a_channels && (d->Nt / d->pro.groups) % d->bn == 0);    // a tile's samples share one group
     CSTP_REQUIRE(reinterpret_cast<uintptr_t>(d->pro.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(d->pro.shift) % 16 == 0);
   }
 
@@ -774,10 +786,12 @@ extern "C" int cstp_conv_halo_plan_create(const cstp_conv_halo_desc* d, cstp_con
   k.pro_groups = d->pro.groups;
   k.pro_cp = d->pro.Cp;
   if (d->stats_partials != nullptr &&
-      !(k.fast_store && !d->accumulate && d->Np == 64 && d->n_tile == 64 && d->bn == 1 &&
-        (d->stats_groups == 1 || d->stats_groups == 2) && d->Nt % d->stats_groups == 0)) {
+      !(k.fast_store && !d->accumulate && d->Np == 64 && d->n_tile == (G ? G * 64 : 64) &&
+        (d->stats_groups == 1 || d->stats_groups == 2) && d->Nt % d->stats_groups == 0 &&
+        (d->Nt / d->stats_groups) % d->bn == 0)) {
     delete plan;
-    return fail_inval("fused statistics need Np == n_tile == 64, bn == 1, a plain aligned bf16 output and 1 or 2 groups dividing N");
+    return fail_inval("fused statistics need Np == 64 (one 64-column tile, or slab mode), a plain aligned bf16 output and 1 or 2 "
+                      "groups dividing N into multiples of bn");
   }
   const int stats_bytes = d->stats_partials != nullptr ? 3072 : 0;
   const int xtab_bytes = xform ? static_cast<int>(xform_table_bytes(d->pro.groups, d->pro.Cp)) : 0;

@@ -356,6 +356,11 @@ def _conv_halo_layout(tile_space, taps, a_channels: int, Np: int, halo_2d: bool)
 
 USE_SLABS = os.environ.get("CSTP_SLABS", "1") == "1"
 SLAB_G = int(os.environ.get("CSTP_SLAB_G", "4"))
+# slab mode for the forward 64-column layers (conv1.temporal, conv2.*.temporal) as well: built and tested (prologue + fused
+# statistics run in slab mode), but OFF by default -- behind the operand prologue those launches are bound by the staging
+# pipeline, not by the MMA issue rate, and slab mode stages 6 input frames per 4 output frames instead of 18 per 16
+# (measured at batch 60: 0.82 - 0.86 ms against 0.775 ms per launch)
+SLABS_FWD = os.environ.get("CSTP_SLABS_FWD", "0") == "1"
 
 
 def slab_tables(G: int, nslots: int, Np: int):
@@ -377,7 +382,7 @@ def slab_tables(G: int, nslots: int, Np: int):
     return out
 
 
-def conv_slab_layout(tile_space, taps, a_channels: int, Np: int, G: int | None = None):
+def conv_slab_layout(tile_space, taps, a_channels: int, Np: int, G: int | None = None, n_div: int = 0):
     """Slab-mode geometry of csrc/conv_halo.cu (include/cstp_b200.h cstp_halo_slabs) for a stride-1 tap list
     [(dw, dh, dt, k_off)] of a layer with Np == 64 output columns, or None.  1 x k x k taps: G output rows per tile (slab
     axis h), every input row staged as ONE box with a halo along w (the w taps are row shifts of it); k x 1 x 1 taps: G
@@ -402,10 +407,14 @@ def conv_slab_layout(tile_space, taps, a_channels: int, Np: int, G: int | None =
     best = None
     for b1 in (16, 8, 4, 2, 1):                  # extent along the other spatial / temporal axis, the rest along n
         bn = 16 // b1
+        if n_div and n_div % bn:                 # the samples of a tile must share one BatchNorm statistics group
+            continue
         other = Tt if axis == 1 else Ht
         key = (math.ceil(other / b1) * math.ceil(Nt / bn), bn)
         if best is None or key < best[0]:
             best = (key, b1, bn)
+    if best is None:
+        return None
     _, b1, bn = best
     box = (8, 1, b1, bn) if axis == 1 else (8, b1, 1, bn)
     rows = (8 + wspan) * b1 * bn
@@ -462,6 +471,7 @@ def _make_conv_halo_plan(view, lay, a_channels, w_packed, Np, tile_space, out, o
     L.check(lib.cstp_conv_halo_plan_create(C.byref(d), C.byref(h)))
     plan = ConvHaloPlan(h, lib.cstp_conv_halo_plan_destroy, keep + ((stats.partials,) if stats is not None else ()))
     plan.resident = bool(lib.cstp_conv_halo_plan_resident(h))
+    plan.slab = bool(lay.get("slabs"))
     if stats is not None:
         plan.stat_blocks = lib.cstp_conv_halo_plan_stat_blocks(h)
         if plan.stat_blocks * stats.groups * 2 * stats.Cp > stats.partials.numel():
@@ -503,6 +513,16 @@ def conv_fwd_plan(x, w_packed, out, geom: ConvGeom, *, out_f32=None, bias=None, 
     taps = [(m, dw, dh, dt, ti * Kc) for (m, dw, dh, dt, ti) in taps]
     ostr = (Np, Wo * Np, Ho * Wo * Np, To * Ho * Wo * Np)
     if allow_halo and box is None and n_tile is None and len(views) == 1 and Ho * Wo >= HALO_MIN_POSITIONS:
+        if SLABS_FWD and out is not None and out_f32 is None and bias is None:
+            # 64-column layers (conv1.temporal, conv2.*.temporal): G output frames per tile on the accumulator's N axis
+            groups = stats.groups if stats is not None else (prologue.groups if prologue is not None else 1)
+            lay = conv_slab_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np, n_div=N // groups) if N % groups == 0 else None
+            if lay is not None:
+                fuse = FUSE_BN_STATS and stats is not None and stats.groups in (1, 2) and not accumulate
+                if fuse or prologue is None:        # (the kernel has no prologue-without-statistics slab instantiation)
+                    return _make_conv_halo_plan(views[0], lay, Ca, w_packed, Np, (Wo, Ho, To, N), out, None, 0, ostr, None,
+                                                accumulate, (x, w_packed, out), stats=stats if fuse else None,
+                                                prologue=prologue)
         lay = conv_halo_layout((Wo, Ho, To, N), [t[1:] for t in taps], Ca, Np)
         if lay is not None:
             fuse = (FUSE_BN_STATS and stats is not None and stats.groups in (1, 2) and N % stats.groups == 0

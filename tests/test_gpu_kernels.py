@@ -32,6 +32,20 @@ def test_conv_forward_dgrad_wgrad(name):
     assert r["wgrad_nan"] == 0 and r["wgrad_rel"] < 2e-4, r      # fp32 output, deterministic split-K
 
 
+@pytest.mark.parametrize("name", _cases("prologue"))
+def test_operand_prologue_and_fused_statistics(name):
+    """conv forward / weight gradient reading the producer's RAW output (BatchNorm affine + ReLU applied to the staged
+    tiles in shared memory) against cstp_bn_apply followed by the plain kernels: same bf16 operands in the same order, so
+    the results -- and the BatchNorm statistics fused into the epilogue -- must be bit-identical.  The 64-column temporal
+    layers run in slab mode (four output frames per accumulator)."""
+    from tools.gpu_kernel_check import run_case
+    r = run_case(name)
+    assert r["fwd_nan"] == 0 and r["fwd_equal"], r
+    assert r.get("stats_equal", True), r
+    # (wgrad_gemm with a prologue keeps one M tile per CTA and its own split-K factor: same products, another fp32 sum order)
+    assert r["wgrad_nan"] == 0 and (r["wgrad_equal"] or r["wgrad_rel"] < 2e-6), r
+
+
 @pytest.mark.parametrize("name", _cases("linear"))
 def test_linear(name):
     from tools.gpu_kernel_check import run_case

@@ -111,13 +111,21 @@ def case_conv(N, T, H, W, cin, cout, kernel, stride, pad, check_dgrad=True, chec
     return res
 
 
-def case_prologue(N, T, H, W, cin, cout, kernel, stride, pad, with_stats=False, iters=10):
+def case_prologue(N, T, H, W, cin, cout, kernel, stride, pad, with_stats=False, iters=10, slabs_fwd=False):
     """Operand prologue (cstp_prologue): conv forward and weight gradient reading the producer's RAW output and applying
     its BatchNorm affine + ReLU in shared memory, against the two-pass path (cstp_bn_apply, then the plain kernels).
     Both feed the tensor cores the same bf16 values in the same order, so outputs must be bit-identical."""
     import torch
     from cstp_b200 import ops
 
+    if slabs_fwd:                       # the forward slab layouts are off by default (ops.SLABS_FWD): switch them on for this case
+        old_flag, ops.SLABS_FWD = ops.SLABS_FWD, True
+        try:
+            res = case_prologue(N, T, H, W, cin, cout, kernel, stride, pad, with_stats, iters)
+        finally:
+            ops.SLABS_FWD = old_flag
+        assert res["slab"], "the case did not take the slab layout"
+        return res
     geom = ops.ConvGeom(tuple(kernel), tuple(stride), tuple(pad))
     Cip, Cop = ops.pad16(cin), ops.pad16(cout)
     raw = _mk_act(N, T, H, W, cin, Cip, 1)
@@ -152,6 +160,7 @@ def case_prologue(N, T, H, W, cin, cout, kernel, stride, pad, with_stats=False, 
         plans.append(plan)
     torch.cuda.synchronize()
     res["kernel"] = ops.kernel_name(plans[1])
+    res["slab"] = bool(getattr(plans[1], "slab", False))
     res["fwd_nan"] = int(torch.isnan(outs[1].float()).sum().item())
     res["fwd_equal"] = bool(torch.equal(outs[0], outs[1]))
     res["fwd_rel"] = _rel(outs[1], outs[0])
@@ -400,6 +409,10 @@ CASES = {
     "pro_conv2_spatial": ("prologue", dict(N=2, T=4, H=56, W=56, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
     "pro_conv2_temporal": ("prologue", dict(N=2, T=8, H=56, W=56, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True)),
     "pro_stem_temporal": ("prologue", dict(N=2, T=8, H=56, W=56, cin=83, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True)),
+    # slab mode (four output frames per accumulator) with the prologue and the fused statistics: two samples per tile
+    "pro_conv2_temporal_slab": ("prologue", dict(N=4, T=8, H=56, W=56, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True, slabs_fwd=True)),
+    "pro_stem_temporal_slab": ("prologue", dict(N=4, T=16, H=56, W=56, cin=83, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True, slabs_fwd=True)),
+    "pro_temporal_slab_ragged": ("prologue", dict(N=4, T=6, H=36, W=28, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True, slabs_fwd=True)),
     "pro_conv3_temporal_s2": ("prologue", dict(N=2, T=8, H=28, W=28, cin=230, cout=128, kernel=(3, 1, 1), stride=(2, 1, 1), pad=(1, 0, 0))),
     "pro_conv3_spatial": ("prologue", dict(N=2, T=4, H=28, W=28, cin=128, cout=288, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
     "pro_conv3_temporal": ("prologue", dict(N=2, T=4, H=28, W=28, cin=288, cout=128, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0))),
