@@ -86,6 +86,11 @@ int smem_budget() {
   return b;
 }
 
+int conv_cluster() {
+  static int c = env_int("CSTP_CONV_CLUSTER", 1, 0, 1);
+  return c;
+}
+
 int stream_ctas_per_sm() {
   static int c = env_int("CSTP_STREAM_CTAS_PER_SM", 8, 1, 16);
   return c;

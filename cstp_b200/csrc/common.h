@@ -57,6 +57,7 @@ int num_sms();
 // CSTP_SMEM_KB / CSTP_STREAM_CTAS_PER_SM (read once).
 int smem_budget();
 int stream_ctas_per_sm();
+int conv_cluster();          // CSTP_CONV_CLUSTER (default 1): conv_gemm as CTA pairs with the weight tile multicast
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 

@@ -7,6 +7,10 @@
 //   warp 1 (one lane)  tcgen05.mma issuer: D[128 x n_tile] fp32 in TMEM, double-buffered across tiles.
 //   warp 2             TMEM allocator.
 //   warps 4..7         epilogue: tcgen05.ld -> (+bias, +previous) -> bf16 / fp32 rows to global.
+// CTA pairs (thread-block clusters of two, launched with the cluster attribute): the two CTAs take neighbouring M tiles of
+// the SAME N tile in lockstep; each loads half of the weight tile and multicasts it into both shared memories, and a stage
+// is released by the MMA commits of both (multicast arrive).  The kernel is bound by the L2 -> SM feed on the deep layers
+// (16 KB of activations + 24-32 KB of weights per 64-channel K-block): the pair reads every weight tile from L2 once.
 // Replaces cuDNN conv3d fwd/dgrad and cuBLAS addmm behind models/pace/r21d_byol.py:81-97,236-253.
 #include "common.h"
 #include "ptx.cuh"
@@ -22,6 +26,7 @@ constexpr int kSmemLimit = 232448;  // 227 KB
 struct ConvKParams {
   CUtensorMap amap[CSTP_MAX_AMAPS];
   CUtensorMap bmap;
+  CUtensorMap bmap_half;   // boxes of n_tile / 2 rows: what one CTA of a pair loads (and multicasts)
   int tiles_w, tiles_h, tiles_t, tiles_n, n_ntiles;
   int bw, bh, bt, bn;
   int Wt, Ht, Tt, Nt;
@@ -56,12 +61,14 @@ __device__ __forceinline__ int tile_class(int n_classes, int tile) {
   return (tile + tile / n_classes) % n_classes;
 }
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+// (csize, crank): CTAs per cluster and this CTA's rank -- a "tile" of a pair is two neighbouring M tiles (the second one
+// may lie beyond the tile space: its loads are zero-filled, its rows fail the validity test of the epilogue).
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile, int csize = 1, int crank = 0) {
   TileCoord c;
   c.cls = tile_class(p.n_classes, tile);
   tile /= p.n_classes;
   c.ntile = tile % p.n_ntiles;
-  int pt = tile / p.n_ntiles;
+  int pt = (tile / p.n_ntiles) * csize + crank;
   c.w0 = (pt % p.tiles_w) * p.bw;
   pt /= p.tiles_w;
   c.h0 = (pt % p.tiles_h) * p.bh;
@@ -88,7 +95,11 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.n_ntiles * p.n_classes;
+  const int csize = kXform ? 1 : static_cast<int>(cluster_nctarank());      // 1, or 2: CTA pair
+  const int crank = kXform ? 0 : static_cast<int>(cluster_ctarank());
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n;
+  const int total_tiles = ((m_tiles + csize - 1) / csize) * p.n_ntiles * p.n_classes;
+  const int tile0 = static_cast<int>(blockIdx.x) / csize, tile_step = static_cast<int>(gridDim.x) / csize;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < CSTP_MAX_AMAPS; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], static_cast<uint32_t>(csize));        // released by the MMA commits of every CTA of the pair
       if constexpr (kXform) mbar_init(&xfull[s], kConvXformThreads / 32);
     }
     for (int a = 0; a < 2; ++a) {
@@ -112,6 +123,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (!kXform) cluster_sync_all();      // the peer's mbarriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -122,8 +134,8 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile(p, tile, csize, crank);
       const int tap0 = p.cls_first_tap[tc.cls], tap1 = tap0 + p.cls_n_taps[tc.cls];
       for (int t = tap0; t < tap1; ++t) {
         const cstp_tap tap = p.taps[t];
@@ -134,7 +146,12 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
             mbar_expect_tx(&full[stage], kABytes + p.b_bytes);
             tma_load_5d(sa, &p.amap[tap.map_id], &full[stage], c * 64, tc.w0 + tap.dw, tc.h0 + tap.dh, tc.t0 + tap.dt,
                         tc.n0);
-            tma_load_2d(sa + kABytes, &p.bmap, &full[stage], tap.k_off + c * 64, tc.ntile * p.n_tile);
+            if (csize == 1) {
+              tma_load_2d(sa + kABytes, &p.bmap, &full[stage], tap.k_off + c * 64, tc.ntile * p.n_tile);
+            } else {          // my half of the weight tile, into both CTAs (the peer sends the other half)
+              tma_load_2d_mc(sa + kABytes + static_cast<uint32_t>(crank) * (p.b_bytes >> 1), &p.bmap_half, &full[stage],
+                             tap.k_off + c * 64, tc.ntile * p.n_tile + crank * (p.n_tile >> 1), 0x3);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -158,7 +175,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     asm volatile("mov.u32 %0, %1;" : "=r"(idesc) : "r"(p.idesc));
     const uint32_t smem_addr0 = smem_u32(smem);
     const uint64_t dhi = umma_desc_hi(16, 1024);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1u);
@@ -183,7 +200,8 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
             } else {
               for (int k = 1; k < last_ksteps; ++k) umma_bf16_acc_nc(d_tmem, da + 2 * k, db + 2 * k, idesc);
             }
-            umma_commit(&empty[stage]);
+            if (csize == 1) umma_commit(&empty[stage]);
+            else umma_commit_mc(&empty[stage], 0x3);
             if (kb == kblocks - 1) umma_commit(&tfull[as]);
           }
           __syncwarp();
@@ -210,8 +228,8 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     constexpr uint32_t kUnits = kABytes / 16;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile(p, tile, csize, crank);
       uint32_t split = kUnits;                     // units below `split` belong to group 0
       if (p.pro_groups == 2) {
         const int rb = (p.Nt / 2 - tc.n0) * rows_per_n;
@@ -247,10 +265,10 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
     const int rt = (row / (p.bw * p.bh)) % p.bt;
     const int rn = row / (p.bw * p.bh * p.bt);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const TileCoord tc = decode_tile(p, tile);
+      const TileCoord tc = decode_tile(p, tile, csize, crank);
       const int w = tc.w0 + rw, h = tc.h0 + rh, t = tc.t0 + rt, n = tc.n0 + rn;
       const bool valid = (w < p.Wt) && (h < p.Ht) && (t < p.Tt) && (n < p.Nt);
       const int col0 = tc.ntile * p.n_tile;
@@ -323,6 +341,7 @@ __global__ void __launch_bounds__(kXform ? kConvThreads + kConvXformThreads : kC
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (!kXform) cluster_sync_all();      // no CTA leaves while its peer may still signal its mbarriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -335,6 +354,7 @@ struct cstp_conv_plan {
   cstp::ConvKParams kp;
   int grid;
   int smem_bytes;
+  int cluster;      // CTAs per cluster: 1, or 2 (grid is then even)
 };
 
 using namespace cstp;
@@ -407,6 +427,10 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
     const uint64_t strides[1] = {(uint64_t)d->Ktot * 2};
     const uint32_t box[2] = {64u, (uint32_t)d->n_tile};
     int rc = encode_tmap_bf16(&k.bmap, d->w_packed, 2, dims, strides, box);
+    if (rc == CSTP_OK) {
+      const uint32_t half[2] = {64u, (uint32_t)(d->n_tile / 2 >= 8 ? d->n_tile / 2 : 8)};
+      rc = encode_tmap_bf16(&k.bmap_half, d->w_packed, 2, dims, strides, half);
+    }
     if (rc != CSTP_OK) {
       delete plan;
       return rc;
@@ -470,12 +494,46 @@ extern "C" int cstp_conv_plan_create(const cstp_conv_desc* d, cstp_conv_plan** o
   k.tmem_cols = cols;
   plan->smem_bytes = 1024 + stages * static_cast<int>(stage_bytes) + bar_bytes + xtab_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // keep one CTA per SM (TMEM ownership)
-  const long long total = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n * k.n_ntiles * n_classes;
+  const long long m_tiles = 1LL * k.tiles_w * k.tiles_h * k.tiles_t * k.tiles_n;
+  const long long total = m_tiles * k.n_ntiles * n_classes;
   const int sms = num_sms();
   plan->grid = static_cast<int>(total < sms ? total : sms);
+  plan->cluster = 1;
+  // CTA pairs when the persistent grid is full anyway (deep layers: many tiles, weight tiles of 16-32 KB per K-block)
+  if (conv_cluster() && !xform && total >= 2LL * sms && m_tiles >= 2 && d->n_tile % 16 == 0 && d->n_tile >= 32) {
+    static int max_pairs = -1;        // co-resident clusters of two with this kernel's footprint (one CTA per SM)
+    if (max_pairs < 0) {
+      max_pairs = 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(sms & ~1), 1, 1);
+      cfg.blockDim = dim3(kConvThreads, 1, 1);
+      cfg.dynamicSmemBytes = kSmemLimit;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) == cudaSuccess &&
+          cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<false>, &cfg) == cudaSuccess)
+        max_pairs = n;
+      else
+        (void)cudaGetLastError();
+    }
+    const long long pair_tiles = ((m_tiles + 1) / 2) * k.n_ntiles * n_classes;
+    long long pairs = max_pairs < pair_tiles ? max_pairs : pair_tiles;
+    if (pairs >= (sms * 9) / 20) {        // (a machine that cannot hold ~all SMs in pairs keeps single CTAs)
+      plan->cluster = 2;
+      plan->grid = static_cast<int>(2 * pairs);
+    }
+  }
   *out_plan = plan;
   return CSTP_OK;
 }
+
+extern "C" int cstp_conv_plan_cluster(const cstp_conv_plan* plan) { return plan ? plan->cluster : CSTP_EINVAL; }
 
 extern "C" int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream) {
   CSTP_REQUIRE(plan != nullptr);
@@ -487,7 +545,21 @@ extern "C" int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream) {
   }
   if (plan->kp.pro_scale != nullptr)
     conv_gemm_kernel<true><<<plan->grid, kConvThreads + kConvXformThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
-  else
+  else if (plan->cluster > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(plan->grid), 1, 1);
+    cfg.blockDim = dim3(kConvThreads, 1, 1);
+    cfg.dynamicSmemBytes = static_cast<size_t>(plan->smem_bytes);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = static_cast<unsigned>(plan->cluster);
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CSTP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, plan->kp));
+  } else
     conv_gemm_kernel<false><<<plan->grid, kConvThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(plan->kp);
   CSTP_LAUNCHED();
   return CSTP_OK;

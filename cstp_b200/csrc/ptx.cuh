@@ -109,6 +109,32 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* desc, ui
       : "memory");
 }
 
+// The multicast form: the box lands at the same shared-memory offset of every CTA in `mask` (bits = ranks in the cluster)
+// and completes `bytes` on the mbarrier at the same offset in each of them.  One L2 read feeds two SMs.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// Every thread of every CTA of the cluster (a cluster of one when the kernel was launched without the attribute).
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 // Allocation is warp-collective (.sync.aligned): call from one full warp.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -161,6 +187,15 @@ __device__ __forceinline__ void umma_bf16_acc_nc(uint32_t tmem_d, uint64_t desc_
 // Make all previously issued MMAs arrive on an mbarrier when they retire. Issued by ONE thread.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// The same arrival on the mbarrier at this offset in EVERY CTA of `mask`: a stage that was filled by multicast loads may only
+// be overwritten once the MMAs of all the CTAs that received it have read it.
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 

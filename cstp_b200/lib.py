@@ -177,6 +177,7 @@ SIGNATURES = {
     "cstp_launch_count": (C.c_longlong, []),
     "cstp_conv_plan_create": (_i, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
     "cstp_conv_plan_run": (_i, [_vp, _vp]),
+    "cstp_conv_plan_cluster": (_i, [_vp]),
     "cstp_conv_plan_destroy": (None, [_vp]),
     "cstp_conv_halo_plan_create": (_i, [C.POINTER(ConvHaloDesc), C.POINTER(_vp)]),
     "cstp_conv_halo_plan_resident": (_i, [_vp]),

@@ -188,6 +188,11 @@ class ConvPlan(_Plan):
     def run(self):
         L.check(L.load().cstp_conv_plan_run(self.handle, _stream()))
 
+    @property
+    def cluster(self) -> int:
+        """CTAs per cluster of the launch (2: CTA pairs with multicast weight tiles)."""
+        return int(L.load().cstp_conv_plan_cluster(self.handle))
+
 
 class WgradPlan(_Plan):
     splits: int = 1

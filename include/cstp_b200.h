@@ -103,6 +103,9 @@ typedef struct {
 typedef struct cstp_conv_plan cstp_conv_plan;
 int cstp_conv_plan_create(const cstp_conv_desc* desc, cstp_conv_plan** plan);
 int cstp_conv_plan_run(const cstp_conv_plan* plan, void* stream);
+/* CTAs per thread-block cluster the plan launches with: 1, or 2 (CTA pairs, each weight tile multicast into both shared
+ * memories; chosen when the persistent grid is full and CSTP_CONV_CLUSTER != 0). */
+int cstp_conv_plan_cluster(const cstp_conv_plan* plan);
 void cstp_conv_plan_destroy(cstp_conv_plan* plan);
 
 /* Stride-1 1xkxk / kx1x1 convolutions with a large spatial extent: the activation box is staged once per "load group"

@@ -51,7 +51,7 @@ def case_conv(N, T, H, W, cin, cout, kernel, stride, pad, check_dgrad=True, chec
     xr = x[..., :cin].float().permute(0, 4, 1, 2, 3)
     wr = w.to(torch.bfloat16).float()
     ref = F.conv3d(xr, wr, bias=None if b is None else b[:cout], stride=stride, padding=pad).permute(0, 2, 3, 4, 1)
-    res = {"fwd_rel": _rel(out[..., :cout], ref), "fwd_pad_zero": bool((out[..., cout:].float() == 0).all().item()) if not bias else True,
+    res = {"fwd_cluster": getattr(plan, "cluster", 0), "fwd_rel": _rel(out[..., :cout], ref), "fwd_pad_zero": bool((out[..., cout:].float() == 0).all().item()) if not bias else True,
            "fwd_nan": int(torch.isnan(out.float()).sum().item())}
     # timing
     for _ in range(3):
@@ -82,6 +82,7 @@ def case_conv(N, T, H, W, cin, cout, kernel, stride, pad, check_dgrad=True, chec
         res["dgrad_rel"] = _rel(dx[..., :cin], dref)
         res["dgrad_nan"] = int(torch.isnan(dx.float()).sum().item())
         res["dgrad_plans"] = len(plans)
+        res["dgrad_cluster"] = max(getattr(p, "cluster", 0) for p in plans)
         e0.record()
         for _ in range(5):
             for p in plans:
@@ -405,6 +406,12 @@ CASES = {
     "conv2_spatial_big": ("conv", dict(N=8, T=16, H=56, W=56, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
     "conv2_temporal_big": ("conv", dict(N=8, T=16, H=56, W=56, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0))),
     "conv3_spatial_big": ("conv", dict(N=8, T=8, H=28, W=28, cin=128, cout=288, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    # enough tiles for conv_gemm's CTA pairs (clusters of two, weight tiles multicast); odd M-tile counts leave the last pair
+    # with one CTA beyond the tile space
+    "conv4_spatial_pairs": ("conv", dict(N=24, T=4, H=14, W=14, cin=256, cout=576, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
+    "conv5_temporal_pairs": ("conv", dict(N=61, T=2, H=7, W=7, cin=1152, cout=512, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0))),
+    "conv4_spatial_s2_pairs": ("conv", dict(N=15, T=8, H=28, W=28, cin=128, cout=460, kernel=(1, 3, 3), stride=(1, 2, 2), pad=(0, 1, 1))),
+    "conv3_temporal_s2_pairs": ("conv", dict(N=21, T=8, H=28, W=28, cin=230, cout=128, kernel=(3, 1, 1), stride=(2, 1, 1), pad=(1, 0, 0))),
     # operand prologue (BatchNorm + ReLU applied to the staged operand): every kernel / layout that carries it
     "pro_conv2_spatial": ("prologue", dict(N=2, T=4, H=56, W=56, cin=64, cout=144, kernel=(1, 3, 3), stride=(1, 1, 1), pad=(0, 1, 1))),
     "pro_conv2_temporal": ("prologue", dict(N=2, T=8, H=56, W=56, cin=144, cout=64, kernel=(3, 1, 1), stride=(1, 1, 1), pad=(1, 0, 0), with_stats=True)),
