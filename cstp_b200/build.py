@@ -5,6 +5,7 @@ The shared library links the CUDA runtime statically and resolves the one driver
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -44,13 +45,30 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def is_stale() -> bool:
+    """True when the library was built here from other sources than the ones in the tree (a library that arrived without
+    its stamp -- a snapshot of built artefacts -- is taken as it is)."""
+    stamp = OBJ_DIR / "stamp"
+    return LIB_PATH.exists() and stamp.exists() and stamp.read_text() != _digest()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu for sm_100a and link libcstp_b200.so. Skips work when sources are unchanged."""
+    """Compile every .cu for sm_100a and link libcstp_b200.so. Skips work when sources are unchanged.  Serialised over
+    processes by a file lock (ranks of one torchrun launch), the library is moved into place atomically."""
+    OBJ_DIR.mkdir(exist_ok=True)
+    with open(OBJ_DIR / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     stamp = OBJ_DIR / "stamp"
     digest = _digest()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB_PATH
-    OBJ_DIR.mkdir(exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src: str) -> tuple[str, str]:
@@ -67,10 +85,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *[o for o, _ in results]]
+    tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *[o for o, _ in results]]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     stamp.write_text(digest)
     return LIB_PATH
 

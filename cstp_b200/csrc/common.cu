@@ -91,6 +91,16 @@ int conv_cluster() {
   return c;
 }
 
+int bn_bwd_rows() {
+  static int c = env_int("CSTP_BN_BWD_ROWS", 4, 2, 4);
+  return c;
+}
+
+int bn_apply_rows() {
+  static int c = env_int("CSTP_BN_APPLY_ROWS", 2, 2, 4);
+  return c;
+}
+
 int stream_ctas_per_sm() {
   static int c = env_int("CSTP_STREAM_CTAS_PER_SM", 8, 1, 16);
   return c;

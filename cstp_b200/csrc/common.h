@@ -57,6 +57,8 @@ int num_sms();
 // CSTP_SMEM_KB / CSTP_STREAM_CTAS_PER_SM (read once).
 int smem_budget();
 int stream_ctas_per_sm();
+int bn_bwd_rows();           // CSTP_BN_BWD_ROWS (2 or 4, default 4): rows per trip of bn_bwd_apply_kernel
+int bn_apply_rows();         // CSTP_BN_APPLY_ROWS (2 or 4, default 2: 4 measured neutral): rows per trip of bn_apply_kernel without a second coefficient set
 int conv_cluster();          // CSTP_CONV_CLUSTER (default 1): conv_gemm as CTA pairs with the weight tile multicast
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }

@@ -462,8 +462,8 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, float (&f)[8]
 // out = act(raw*scale + shift + residual).  Two rows per trip with every load issued before the first use (one 16-byte
 // load in flight per thread and four CTAs per SM keep 16 KB per SM in the air: 4.7 TB/s; the HBM pipe wants ~3x that).
 // kCoef2: the residual carries its own BatchNorm coefficients (res_mode 2 / 3): 32 more registers, three CTAs per SM.
-template <bool kCoef2>
-__global__ void __launch_bounds__(256, kCoef2 ? 3 : 4) bn_apply_kernel(const uint4* __restrict__ raw, int Cp, long long rows_per_group,
+template <bool kCoef2, int kRows>
+__global__ void __launch_bounds__(256, (kCoef2 || kRows > 2) ? 3 : 4) bn_apply_kernel(const uint4* __restrict__ raw, int Cp, long long rows_per_group,
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                           int relu, int res_mode, const uint4* __restrict__ res,
                                                           const float* __restrict__ scale2, const float* __restrict__ shift2,
@@ -509,18 +509,20 @@ __global__ void __launch_bounds__(256, kCoef2 ? 3 : 4) bn_apply_kernel(const uin
   const long long base = static_cast<long long>(t.g) * rows_per_group;
   const long long rstep = static_cast<long long>(gridDim.x) * t.rows_per_pass;
   long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl;
-  for (; r + rstep < rows_per_group; r += 2 * rstep) {
-    const long long i0 = (base + r) * nvec + t.cvec, i1 = i0 + rstep * nvec;
-    const uint4 a0 = raw[i0], a1 = raw[i1];
-    uint4 q0 = a0, q1 = a1;
-    if (res_mode != 0) {
-      q0 = res[i0];
-      q1 = res[i1];
+  for (; r + (kRows - 1) * rstep < rows_per_group; r += kRows * rstep) {
+    long long i[kRows];
+    uint4 a[kRows], q[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      i[k] = (base + r + k * rstep) * nvec + t.cvec;
+      a[k] = raw[i[k]];
     }
-    out[i0] = apply(a0, q0);
-    out[i1] = apply(a1, q1);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) q[k] = res_mode != 0 ? res[i[k]] : a[k];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) out[i[k]] = apply(a[k], q[k]);
   }
-  if (r < rows_per_group) {
+  for (; r < rows_per_group; r += rstep) {
     const long long i = (base + r) * nvec + t.cvec;
     const uint4 a = raw[i];
     uint4 q = a;
@@ -570,6 +572,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 //   act != NULL            mask = act > 0            (block outputs: the pre-activation includes the residual)
 //   mscale != NULL         mask = raw*mscale + mshift > 0, the same fmaf the forward apply evaluated (saves the act read)
 //   neither                no ReLU behind this BatchNorm
+template <int kRows>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act,
                                                            const uint4* __restrict__ raw, int Cp, long long rows_per_group,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -622,19 +625,24 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const uint4* __res
     gout[i] = pack8(o);
   };
   long long r = static_cast<long long>(blockIdx.x) * t.rows_per_pass + t.rl;
-  // two rows per trip with every load issued before the first use: 4 (6 with act) independent 16-byte loads in flight
-  for (; r + rstep < rows_per_group; r += 2 * rstep) {
-    const long long i0 = (base + r) * nvec + t.cvec, i1 = (base + r + rstep) * nvec + t.cvec;
-    const uint4 d0 = d[i0], x0 = raw[i0], d1 = d[i1], x1 = raw[i1];
-    uint4 y0 = make_uint4(0, 0, 0, 0), y1 = y0;
-    if (act != nullptr) {
-      y0 = act[i0];
-      y1 = act[i1];
+  // kRows rows per trip with every load issued before the first use: 2 (3 with act) independent 16-byte loads per row.
+  // Four rows (120 registers, two CTAs per SM: 64 KB in flight per SM) against two: 144-channel pass 5.5 -> 6.4 TB/s,
+  // batch-60 step -0.4 ms (profiles/r02f_bn_rows_ab.txt)
+  for (; r + (kRows - 1) * rstep < rows_per_group; r += kRows * rstep) {
+    long long i[kRows];
+    uint4 vd[kRows], vx[kRows], vy[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      i[k] = (base + r + k * rstep) * nvec + t.cvec;
+      vd[k] = d[i[k]];
+      vx[k] = raw[i[k]];
     }
-    row(i0, d0, x0, y0);
-    row(i1, d1, x1, y1);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) vy[k] = act != nullptr ? act[i[k]] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) row(i[k], vd[k], vx[k], vy[k]);
   }
-  if (r < rows_per_group) {
+  for (; r < rows_per_group; r += rstep) {
     const long long i = (base + r) * nvec + t.cvec;
     row(i, d[i], raw[i], act != nullptr ? act[i] : make_uint4(0, 0, 0, 0));
   }
@@ -815,14 +823,10 @@ extern "C" int cstp_bn_apply(const void* raw, int64_t rows, int Cp, int groups, 
   CSTP_REQUIRE(raw && out && scale && shift && rows > 0 && groups > 0 && rows % groups == 0 && Cp % 16 == 0);
   CSTP_REQUIRE(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || res != nullptr));
   CSTP_REQUIRE(res_mode < 2 || (scale2 && shift2));
-  if (res_mode >= 2)
-    bn_apply_kernel<true><<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
-        reinterpret_cast<const uint4*>(raw), Cp, rows / groups, scale, shift, relu, res_mode,
-        reinterpret_cast<const uint4*>(res), scale2, shift2, reinterpret_cast<uint4*>(out));
-  else
-    bn_apply_kernel<false><<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
-        reinterpret_cast<const uint4*>(raw), Cp, rows / groups, scale, shift, relu, res_mode,
-        reinterpret_cast<const uint4*>(res), scale2, shift2, reinterpret_cast<uint4*>(out));
+  auto kernel = res_mode >= 2 ? bn_apply_kernel<true, 2> : (bn_apply_rows() == 4 ? bn_apply_kernel<false, 4> : bn_apply_kernel<false, 2>);
+  kernel<<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(raw), Cp, rows / groups, scale, shift, relu, res_mode,
+      reinterpret_cast<const uint4*>(res), scale2, shift2, reinterpret_cast<uint4*>(out));
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
@@ -859,7 +863,8 @@ extern "C" int cstp_bn_bwd_apply(const void* d, const void* act, const void* raw
   CSTP_REQUIRE((mask_scale == nullptr) == (mask_shift == nullptr));
   CSTP_REQUIRE(act == nullptr || mask_scale == nullptr);
   // (64 registers / 4 CTAs per SM was measured: it spills and is 7 % slower than 80 registers / 3 CTAs)
-  bn_bwd_apply_kernel<<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
+  auto kernel = bn_bwd_rows() == 4 ? bn_bwd_apply_kernel<4> : bn_bwd_apply_kernel<2>;
+  kernel<<<bn_grid(rows / groups, Cp, groups), 256, 0, ST(stream)>>>(
       reinterpret_cast<const uint4*>(d), reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint4*>(raw), Cp,
       rows / groups, mean, invstd, coef, mask_scale, mask_shift, reinterpret_cast<uint4*>(g),
       reinterpret_cast<uint4*>(dz));

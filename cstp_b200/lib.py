@@ -246,6 +246,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         if not build_if_missing:
             raise CstpError(f"{path} is missing: run `python -m cstp_b200.build` (there is no CPU fallback)")
         _build.build()
+    elif build_if_missing and _build.is_stale():      # sources edited since the library was built here
+        _build.build()
     lib = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -784,7 +784,8 @@ def _wgrad_gemm_shape(nch: int, Np: int, kblocks: int, sms: int = 148, xform: bo
       * the N tile is the multiple of 64 that needs the fewest tiles, then the fewest padded columns (576 -> 3 x 192, not
         256 + 256 + 64 with every MMA 256 wide);
       * a CTA takes as many 128-row M tiles as TMEM (mt * n_tile <= 512 columns) and a three-stage pipeline allow: they
-        share one staged G tile (no prologue variant: its transform keeps the coefficients of two boxes in registers);
+        share one staged G tile (the prologue variant takes one: its transform keeps the coefficients of two boxes in
+        registers);
       * the split-K factor minimises waves x K-blocks per split + the cost of writing and re-reading one more partial."""
     if WGRAD_MT <= 1:
         n_tile = Np if Np <= 256 else 256
@@ -796,10 +797,11 @@ def _wgrad_gemm_shape(nch: int, Np: int, kblocks: int, sms: int = 148, xform: bo
         n_tile = min((256, 192, 128), key=lambda c: (math.ceil(Np / c), math.ceil(Np / c) * c, -c))
     ngb = math.ceil(n_tile / 64)
     mt = 1
-    if not xform:
-        for m in range(2, min(WGRAD_MT, 4) + 1):
-            if m * n_tile <= 512 and 3 * (2 * m + ngb) * 8192 <= SMEM_BUDGET and m <= math.ceil(nch / 2):
-                mt = m
+    for m in range(2, min(WGRAD_MT, 4) + 1):
+        if m * n_tile <= 512 and 3 * (2 * m + ngb) * 8192 <= SMEM_BUDGET and m <= math.ceil(nch / 2):
+            mt = m
+    # (the split-K factor is the plain kernel's also behind the prologue, which runs one M tile per CTA: the same K ranges
+    # summed in the same order keep the fused edge bit-identical to bn_apply followed by the plain kernel)
     base = math.ceil(nch / (2 * mt)) * math.ceil(Np / n_tile)
     t_kb = (2 * mt + ngb) * 195.0 / 1.7e9                        # seconds per K-block and CTA at the L2 fair share
     t_part = 2.0 * nch * 64 * Np * 4 / 5e12                      # one more partial: written here, read by the finalize pass
@@ -808,7 +810,7 @@ def _wgrad_gemm_shape(nch: int, Np: int, kblocks: int, sms: int = 148, xform: bo
         cost = math.ceil(base * sp / sms) * math.ceil(kblocks / sp) * t_kb + sp * t_part
         if best is None or cost < best[0] - 1e-12:
             best = (cost, sp)
-    return n_tile, mt, best[1]
+    return n_tile, 1 if xform else mt, best[1]
 
 
 def wgrad_plan(x, g, geom: ConvGeom, cout: int, cin: int, partials: torch.Tensor, *, splits: int | None = None,

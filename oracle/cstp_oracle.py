@@ -147,11 +147,6 @@ def ema_update(target: dict, online: dict, momentum: float = 0.996) -> None:
         target[k] = target[k] * momentum + online[k] * (1. - momentum)
 
 
-def split_state(state: dict):
-    """Splits a (module.-free) R21DBYOL state_dict into online/target/other sub-dicts with their prefixes kept."""
-    return state
-
-
 def loss_com_forward(state: dict, x1, x2, momentum=0.996, tape: Tape | None = None):
     """R21DBYOL.forward(x1, x2, o_type="loss_com") -- r21d_byol.py:357-382.
 

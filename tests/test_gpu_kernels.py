@@ -42,8 +42,8 @@ def test_operand_prologue_and_fused_statistics(name):
     r = run_case(name)
     assert r["fwd_nan"] == 0 and r["fwd_equal"], r
     assert r.get("stats_equal", True), r
-    # (wgrad_gemm with a prologue keeps one M tile per CTA and its own split-K factor: same products, another fp32 sum order)
-    assert r["wgrad_nan"] == 0 and (r["wgrad_equal"] or r["wgrad_rel"] < 2e-6), r
+    # (wgrad_gemm with a prologue keeps one M tile per CTA but the plain kernel's split-K factor: same K ranges, same sum order)
+    assert r["wgrad_nan"] == 0 and r["wgrad_equal"], r
 
 
 @pytest.mark.parametrize("name", _cases("linear"))
