@@ -429,6 +429,23 @@ def main():
             del k["flops"]
         dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
         ach = kern[dom]["tflops"]
+        # the dominant kernel's launches by layer family: its average mixes tensor-bound launches (64 -> 144 1x3x3) with
+        # launches that are HBM-bound by their operands (3x1x1 on 144-channel tensors, the 3- / 45-channel stem) or carry
+        # the BatchNorm + ReLU operand prologue of the pass they replace
+        fam: dict = {}
+        for kind, tag, t_ms, fl, n, name in eng.last_profile:
+            if name != dom:
+                continue
+            layer = tag.split(".", 1)[1] if "." in tag else tag
+            group = kind + (" stem" if layer.startswith("conv1.") else " 1x3x3" if layer.endswith("spatial") else " 3x1x1")
+            f = fam.setdefault(group, {"ms_per_step": 0.0, "flops": 0.0, "launches_per_step": 0})
+            f["ms_per_step"] += t_ms
+            f["flops"] += fl
+            f["launches_per_step"] += n
+        for f in fam.values():
+            f["tflops"] = f["flops"] / (f["ms_per_step"] * 1e-3) / 1e12 if f["ms_per_step"] > 0 else 0.0
+            f["frac_of_peak"] = f["tflops"] / pk["tf_sustained"]
+            del f["flops"]
         tensor_ms = sum(k["ms_per_step"] for k in kern.values())
         traffic, traffic_src = ncu_traffic(dom, B)
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -439,7 +456,7 @@ def main():
                 "peak_source": pk["src"] + " sustained bf16 cuBLAS matmul (kernel timed inside a long step)",
                 "how": "CUDA events on the launching stream around every launch of the kernel in one extra instrumented "
                        "step; achieved = sum over its launches of 2*M*N*K (true channel counts) / sum of durations",
-                "kernels": kern,
+                "kernels": kern, "dominant_by_layer_family": fam,
                 "all_tensor_kernels_tflops": B * FLOPS_PER_SAMPLE / (tensor_ms * 1e-3) / 1e12,
                 "step_tflops": B * FLOPS_PER_SAMPLE / (ms_step * 1e-3) / 1e12}
     c5 = None
