@@ -326,75 +326,115 @@ __global__ void __launch_bounds__(256, 4) bn_reduce_kernel(const uint4* __restri
   }
 }
 
-// Deterministic tree over the per-block partials: 8 warps x 32 channels per CTA; warp w owns blocks w, w+8, ... and
-// keeps 8 independent loads of both quantities in flight (the loop is latency bound: a serial version of it cost
-// 130 us per launch), the 8 warp sums are then combined in fixed order in double.  partials: [nblocks][groups][2][Cp].
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nblocks, int groups, int g, int Cp,
-                                                int c, bool active, double (*red)[2][32], double& s, double& ss) {
+// Deterministic tree over the per-block partials: kRedWarps warps x 32 channels per CTA; warp w owns blocks w, w + kRedWarps,
+// ... and adds them in that order, the warp sums are then combined in fixed order in double.  The loop is latency bound (a
+// serial version of it cost 130 us per launch; 8 warps with 8 + a serial tail of loads in flight 11 us): 32 warps, kG
+// statistics groups at a time, four blocks x both quantities per trip (296 blocks: 3 trips per warp).
+// partials: [nblocks][groups][2][Cp].
+constexpr int kRedWarps = 32;
+constexpr int kRedThreads = kRedWarps * 32;
+template <int kG>
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nblocks, int groups, int g0, int Cp,
+                                                int c, bool active, double (*red)[4][32], double (&s)[kG], double (&ss)[kG]) {
+  constexpr int kU = 4;
   const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
-  double a0 = 0.0, a1 = 0.0;
+  double a0[kG], a1[kG];
+#pragma unroll
+  for (int q = 0; q < kG; ++q) a0[q] = a1[q] = 0.0;
   if (active) {
     const long long bstride = static_cast<long long>(groups) * 2 * Cp;
-    const float* base = partials + static_cast<long long>(g) * 2 * Cp + c;
+    const float* base = partials + static_cast<long long>(g0) * 2 * Cp + c;
     int b = ty;
-    for (; b + 56 < nblocks; b += 64) {
-      float v0[8], v1[8];
+    for (; b + (kU - 1) * kRedWarps < nblocks; b += kU * kRedWarps) {
+      float v0[kG][kU], v1[kG][kU];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float* p = base + (b + 8 * j) * bstride;
-        v0[j] = __ldg(p);
-        v1[j] = __ldg(p + Cp);
+      for (int j = 0; j < kU; ++j) {
+        const float* p = base + (b + kRedWarps * j) * bstride;
+#pragma unroll
+        for (int q = 0; q < kG; ++q) {
+          v0[q][j] = __ldg(p + q * 2 * Cp);
+          v1[q][j] = __ldg(p + q * 2 * Cp + Cp);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a0 += static_cast<double>(v0[j]);
-        a1 += static_cast<double>(v1[j]);
+      for (int j = 0; j < kU; ++j) {
+#pragma unroll
+        for (int q = 0; q < kG; ++q) {
+          a0[q] += static_cast<double>(v0[q][j]);
+          a1[q] += static_cast<double>(v1[q][j]);
+        }
       }
     }
-    for (; b < nblocks; b += 8) {
+    for (; b < nblocks; b += kRedWarps) {
       const float* p = base + b * bstride;
-      a0 += static_cast<double>(__ldg(p));
-      a1 += static_cast<double>(__ldg(p + Cp));
+#pragma unroll
+      for (int q = 0; q < kG; ++q) {
+        a0[q] += static_cast<double>(__ldg(p + q * 2 * Cp));
+        a1[q] += static_cast<double>(__ldg(p + q * 2 * Cp + Cp));
+      }
     }
   }
   __syncthreads();
-  red[ty][0][tx] = a0;
-  red[ty][1][tx] = a1;
-  __syncthreads();
-  s = 0.0;
-  ss = 0.0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    s += red[w][0][tx];
-    ss += red[w][1][tx];
+  for (int q = 0; q < kG; ++q) {
+    red[ty][2 * q][tx] = a0[q];
+    red[ty][2 * q + 1][tx] = a1[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kG; ++q) {
+    s[q] = 0.0;
+    ss[q] = 0.0;
+    if (ty == 0) {          // (only the leading warp uses the sums)
+      for (int w = 0; w < kRedWarps; ++w) {
+        s[q] += red[w][2 * q][tx];
+        ss[q] += red[w][2 * q + 1][tx];
+      }
+    }
+  }
+}
+
+// f(g, sum, sum2) for every statistics group in ascending order; the groups are reduced two at a time.
+template <class F>
+__device__ __forceinline__ void for_each_group_sum(const float* __restrict__ partials, int nblocks, int groups, int Cp, int c,
+                                                   bool active, double (*red)[4][32], F f) {
+  int g = 0;
+  for (; g + 1 < groups; g += 2) {
+    double s[2], ss[2];
+    reduce_partials<2>(partials, nblocks, groups, g, Cp, c, active, red, s, ss);
+    f(g, s[0], ss[0]);
+    f(g + 1, s[1], ss[1]);
+  }
+  if (g < groups) {
+    double s[1], ss[1];
+    reduce_partials<1>(partials, nblocks, groups, g, Cp, c, active, red, s, ss);
+    f(g, s[0], ss[0]);
   }
 }
 
 // Collapses the per-block partials to one row [groups][2][Cp] (fp32): the payload of the cross-rank statistics
 // all-reduce in world-synchronised BatchNorm (SyncBN); the finalize kernels then run with nblocks = 1.
-__global__ void __launch_bounds__(256) bn_partials_reduce_kernel(const float* __restrict__ partials, int nblocks, int groups,
+__global__ void __launch_bounds__(kRedThreads) bn_partials_reduce_kernel(const float* __restrict__ partials, int nblocks, int groups,
                                                                  int Cp, float* __restrict__ out) {
-  __shared__ double red[8][2][32];
+  __shared__ double red[kRedWarps][4][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool lead = (threadIdx.x >> 5) == 0 && c < Cp;
-  for (int g = 0; g < groups; ++g) {
-    double s, ss;
-    reduce_partials(partials, nblocks, groups, g, Cp, c, c < Cp, red, s, ss);
+  for_each_group_sum(partials, nblocks, groups, Cp, c, c < Cp, red, [&](int g, double s, double ss) {
     if (lead) {
       out[(g * 2 + 0) * Cp + c] = static_cast<float>(s);
       out[(g * 2 + 1) * Cp + c] = static_cast<float>(ss);
     }
-  }
+  });
 }
 
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
+__global__ void __launch_bounds__(kRedThreads) bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
                                                           long long rows_per_group, int C, int Cp,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, float momentum, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var, float* __restrict__ scale,
                                                           float* __restrict__ shift, float* __restrict__ mean_out,
                                                           float* __restrict__ invstd_out) {
-  __shared__ double red[8][2][32];
+  __shared__ double red[kRedWarps][4][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool lead = (threadIdx.x >> 5) == 0 && c < Cp;
   float rm = 0.f, rv = 0.f;
@@ -402,16 +442,14 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
     rm = running_mean[c];
     rv = running_var[c];
   }
-  for (int g = 0; g < groups; ++g) {
-    double s, ss;
-    reduce_partials(partials, nblocks, groups, g, Cp, c, c < C, red, s, ss);
-    if (!lead) continue;
+  for_each_group_sum(partials, nblocks, groups, Cp, c, c < C, red, [&](int g, double s, double ss) {
+    if (!lead) return;
     if (c >= C) {
       scale[g * Cp + c] = 0.f;
       shift[g * Cp + c] = 0.f;
       mean_out[g * Cp + c] = 0.f;
       invstd_out[g * Cp + c] = 0.f;
-      continue;
+      return;
     }
     const double n = static_cast<double>(rows_per_group);
     const double mu = s / n;
@@ -427,7 +465,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
     const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
     rm = (1.f - momentum) * rm + momentum * static_cast<float>(mu);
     rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
-  }
+  });
   if (lead && c < C && running_mean != nullptr) {
     running_mean[c] = rm;
     running_var[c] = rv;
@@ -531,27 +569,25 @@ __global__ void __launch_bounds__(256, (kCoef2 || kRows > 2) ? 3 : 4) bn_apply_k
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int groups,
                                                               long long rows_per_group, int C, int Cp,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, int accumulate,
                                                               float* __restrict__ coef) {
-  __shared__ double red[8][2][32];
+  __shared__ double red[kRedWarps][4][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool lead = (threadIdx.x >> 5) == 0 && c < Cp;
   double dg = 0.0, db = 0.0;
-  for (int g = 0; g < groups; ++g) {
-    double s, sx;
-    reduce_partials(partials, nblocks, groups, g, Cp, c, c < C, red, s, sx);
-    if (!lead) continue;
+  for_each_group_sum(partials, nblocks, groups, Cp, c, c < C, red, [&](int g, double s, double sx) {
+    if (!lead) return;
     float* cf = coef + static_cast<long long>(g) * 3 * Cp;
     if (c >= C) {
       cf[c] = 0.f;
       cf[Cp + c] = 0.f;
       cf[2 * Cp + c] = 0.f;
-      continue;
+      return;
     }
     // partials hold sum(dy * x) over raw x: sum(dy * xhat) = invstd * (sum(dy*x) - mean * sum(dy))
     sx = static_cast<double>(invstd[g * Cp + c]) * (sx - static_cast<double>(mean[g * Cp + c]) * s);
@@ -561,7 +597,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     cf[2 * Cp + c] = static_cast<float>(sx / n);
     db += s;
     dg += sx;
-  }
+  });
   if (lead && c < C && dgamma != nullptr) {
     dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(dg) : static_cast<float>(dg);
     dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(db) : static_cast<float>(db);
@@ -800,7 +836,7 @@ extern "C" int cstp_bn_stats(const void* raw, int64_t rows, int Cp, int groups, 
 
 extern "C" int cstp_bn_partials_reduce(const float* partials, int nblocks, int groups, int Cp, float* out, void* stream) {
   CSTP_REQUIRE(partials && out && nblocks > 0 && groups > 0 && Cp % 16 == 0);
-  bn_partials_reduce_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, Cp, out);
+  bn_partials_reduce_kernel<<<ceil_div(Cp, 32), kRedThreads, 0, ST(stream)>>>(partials, nblocks, groups, Cp, out);
   CSTP_LAUNCHED();
   return CSTP_OK;
 }
@@ -810,7 +846,7 @@ extern "C" int cstp_bn_finalize(const float* partials, int nblocks, int groups, 
                                 float* running_var, float* scale, float* shift, float* mean, float* invstd,
                                 void* stream) {
   CSTP_REQUIRE(partials && gamma && beta && scale && shift && mean && invstd && C <= Cp);
-  bn_finalize_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma, beta,
+  bn_finalize_kernel<<<ceil_div(Cp, 32), kRedThreads, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma, beta,
                                                                eps, momentum, running_mean, running_var, scale, shift,
                                                                mean, invstd);
   CSTP_LAUNCHED();
@@ -850,7 +886,7 @@ extern "C" int cstp_bn_bwd_finalize(const float* partials, int nblocks, int grou
                                     int Cp, const float* gamma, const float* mean, const float* invstd, float* dgamma,
                                     float* dbeta, int accumulate, float* coef, void* stream) {
   CSTP_REQUIRE(partials && gamma && mean && invstd && coef && C <= Cp);
-  bn_bwd_finalize_kernel<<<ceil_div(Cp, 32), 256, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma,
+  bn_bwd_finalize_kernel<<<ceil_div(Cp, 32), kRedThreads, 0, ST(stream)>>>(partials, nblocks, groups, rows_per_group, C, Cp, gamma,
                                                                   mean, invstd, dgamma, dbeta, accumulate, coef);
   CSTP_LAUNCHED();
   return CSTP_OK;

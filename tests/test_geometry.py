@@ -317,3 +317,25 @@ def test_conv_slab_layout_semantics(k, p, shape, cin, cout, dgrad, G):
     else:
         ref = torch.nn.grad.conv3d_input((N, cin, T, H, W), w, x5, stride=1, padding=p)
     assert torch.allclose(out.permute(0, 4, 1, 2, 3), ref, rtol=1e-4, atol=1e-3)
+
+
+def test_wgrad_gemm_shape_keeps_the_split_factor_behind_the_prologue():
+    """csrc/wgrad.cu behind the operand prologue runs one M tile per CTA, but with the plain kernel's N tile and split-K
+    factor: the same K ranges are summed in the same order, so a fused conv -> BN -> ReLU -> conv edge stays bit-identical
+    to cstp_bn_apply followed by the plain kernel (tests/test_gpu_config3.py checks the bits on the GPU)."""
+    for nch in (1, 2, 4, 9, 18, 27, 36, 72):
+        for Np in (64, 128, 144, 256, 288, 512, 576, 1152):
+            for kblocks in (4, 49, 368, 1470, 5880):
+                plain = ops._wgrad_gemm_shape(nch, Np, kblocks, 148, False)
+                fused = ops._wgrad_gemm_shape(nch, Np, kblocks, 148, True)
+                assert fused[0] == plain[0] and fused[2] == plain[2], (nch, Np, kblocks, plain, fused)
+                assert fused[1] == 1 and 1 <= plain[1] <= 4 and plain[1] * plain[0] <= 512
+                assert 1 <= plain[2] <= max(1, kblocks // 4)
+
+
+def test_library_is_not_stale_after_build():
+    """lib.load() rebuilds when the sources changed since the library was built here (build.is_stale), never silently loads
+    an old one; a fresh build is not stale."""
+    from cstp_b200 import build
+    build.build()
+    assert build.LIB_PATH.exists() and not build.is_stale()
