@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
     }
     __syncthreads();
     int lo = job0;
-    for (int e = threadIdx.x; e < kPackSpan; e += 256) {
+    // eight consecutive K columns per thread: one 16-byte store, eight independent loads (a job's size and every row of
+    // Kc columns are multiples of 64 elements, so a group of eight never straddles a row, a tap or a job)
+    for (int e = threadIdx.x * 8; e < kPackSpan; e += 256 * 8) {
       const long long g = base + e;
       if (g >= total) break;
       while (lo + 1 < n_jobs && prefix[lo + 1] <= g) ++lo;
@@ -80,21 +82,27 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const long lo
       const int transpose = static_cast<int>(jb[5]);
       const unsigned Kc = static_cast<unsigned>(jb[7]);
       const unsigned i = static_cast<unsigned>(g - prefix[lo]);          // a job holds < 2^32 elements
-      const unsigned c = i % Kc;
+      const unsigned c0 = i % Kc;
       const unsigned q = i / Kc;
       const unsigned tap = q % taps;
       const unsigned r = q / taps;
-      float v = 0.f;
-      if (transpose == 0) {
-        if (r < cout && c < cin) v = w[(static_cast<size_t>(r) * cin + c) * taps + tap];
-      } else if (transpose == 1) {
-        if (r < cin && c < cout) v = w[(static_cast<size_t>(c) * cin + r) * taps + tap];
-      } else {                                           // stem layout (see pack_weight_kernel)
-        const unsigned k = c & 31;
-        const int kh = 2 * static_cast<int>(tap) + static_cast<int>(c >> 5) - 1;
-        if (r < cout && c < 64 && k < 21 && kh >= 0 && kh < 7) v = w[((static_cast<size_t>(r) * 3 + k % 3) * 7 + kh) * 7 + k / 3];
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned c = c0 + j;
+        v[j] = 0.f;
+        if (transpose == 0) {
+          if (r < cout && c < cin) v[j] = __ldg(w + (static_cast<size_t>(r) * cin + c) * taps + tap);
+        } else if (transpose == 1) {
+          if (r < cin && c < cout) v[j] = __ldg(w + (static_cast<size_t>(c) * cin + r) * taps + tap);
+        } else {                                           // stem layout (see pack_weight_kernel)
+          const unsigned k = c & 31;
+          const int kh = 2 * static_cast<int>(tap) + static_cast<int>(c >> 5) - 1;
+          if (r < cout && c < 64 && k < 21 && kh >= 0 && kh < 7)
+            v[j] = __ldg(w + ((static_cast<size_t>(r) * 3 + k % 3) * 7 + kh) * 7 + k / 3);
+        }
       }
-      packed[i] = __float2bfloat16_rn(v);
+      *reinterpret_cast<uint4*>(packed + i) = pack8(v);
     }
   }
 }

@@ -936,6 +936,9 @@ class PackList:
             _require_cuda(w, packed)
             cout, cin, taps = _pack_dims(w, transpose)
             Rp, Ktot = packed.shape
+            # (the kernel writes eight K columns per 16-byte store)
+            if (Ktot // taps) % 8 or Ktot % taps or packed.data_ptr() % 16 or not packed.is_contiguous():
+                raise L.CstpError(f"packed weight {tuple(packed.shape)} / {taps} taps: K rows must be 16-byte aligned multiples of 8")
             rows.append([w.data_ptr(), packed.data_ptr(), cout, cin, taps, int(transpose), Rp, Ktot // taps])
             total += Rp * Ktot
             prefix.append(total)

@@ -137,3 +137,30 @@ def test_bn_sync_exchange_protocol_on_one_gpu():
         assert torch.equal(rows[0], rows[1])                 # same order of summation on both ranks: identical bits
         assert torch.equal(rows[0], want)
     assert int(err.item()) == 0 and counters.tolist() == [12, 12]
+
+
+def test_batched_weight_pack_equals_the_per_tensor_pack():
+    """cstp_pack_weights_batched (one launch for every weight of a network, eight K columns per 16-byte store) writes the
+    very bytes of cstp_pack_weight job by job: forward layout, dgrad transpose, stem row-pair layout, ragged channel counts
+    (padding rows and columns exactly zero)."""
+    from cstp_b200 import ops
+    from cstp_b200.ops import pad64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    jobs, refs = [], []
+    for (cout, cin, k, tr) in ((144, 64, (1, 3, 3), 0), (144, 64, (1, 3, 3), 1), (64, 144, (3, 1, 1), 0), (64, 144, (3, 1, 1), 1),
+                               (83, 45, (3, 1, 1), 0), (83, 45, (3, 1, 1), 1), (45, 3, (1, 7, 7), 2), (512, 1152, (3, 1, 1), 1),
+                               (4096, 512, (), 0), (5, 4096, (), 0)):
+        w = torch.randn((cout, cin) + k, device="cuda", generator=g)
+        co, ci, taps = ops._pack_dims(w, tr)
+        rows, cols = (ci, co) if tr == 1 else (co, ci)
+        Rp = (rows + 15) // 16 * 16
+        shape = (Rp, taps * pad64(cols))
+        a = torch.full(shape, 7.0, device="cuda", dtype=torch.bfloat16)
+        b = torch.full(shape, 9.0, device="cuda", dtype=torch.bfloat16)
+        ops.pack_weight(w, b, transpose=tr)
+        jobs.append((w, a, tr))
+        refs.append(b)
+    ops.PackList(jobs, "cuda").run()
+    torch.cuda.synchronize()
+    for (w, a, tr), b in zip(jobs, refs):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (tuple(w.shape), tr)
