@@ -294,11 +294,18 @@ def ncu_traffic(kernel: str, B: int):
         return None, None
     total, ids = 0.0, set()
     with open(paths[-1]) as f:
+        head = f.readline()
+        if head.startswith("#"):          # provenance line of the capture (commit, command)
+            note = head[1:].strip()
+        else:
+            note = None
+            f.seek(0)
         for r in csv.reader(f):
             if len(r) > 10 and r[0].isdigit() and r[-3].startswith("dram__bytes_"):
                 total += float(r[-1].replace(",", ""))
                 ids.add(r[0])
-    return (total / len(ids) if ids else None), os.path.relpath(paths[-1], os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.relpath(paths[-1], os.path.dirname(os.path.abspath(__file__)))
+    return (total / len(ids) if ids else None), (src + (" [" + note + "]" if note else ""))
 
 
 def main():
