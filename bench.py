@@ -318,6 +318,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the BASELINE config 5 sub-record")
+    ap.add_argument("--config5-timeout", type=float, default=240.0, help="seconds before a hung config 5 sub-record is cut off")
     ap.add_argument("--bn-sync", default="local", choices=["local", "world", "world-p2p"],
                     help="local: per-GPU BatchNorm statistics (the reference's behaviour); world: SyncBN over all ranks")
     args = ap.parse_args()
@@ -466,43 +467,60 @@ def main():
                 "kernels": kern, "dominant_by_layer_family": fam,
                 "all_tensor_kernels_tflops": B * FLOPS_PER_SAMPLE / (tensor_ms * 1e-3) / 1e12,
                 "step_tflops": B * FLOPS_PER_SAMPLE / (ms_step * 1e-3) / 1e12}
+    value = world * B / (ms_step * 1e-3)
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": value, "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {**workload_config(B, world, "per-GPU (reference semantics)" if args.bn_sync == "local" or world == 1
+                                         else ("world-synchronised (SyncBN all-reduce per BatchNorm call)" if args.bn_sync == "world" else
+                                               "world-synchronised (SyncBN rows exchanged over NVLink peer memory, one kernel per call)")),
+                       "l2_policy": "inputs and activations far larger than the 126 MB L2 (clips alone 2x%.0f MB)" % (x1.numel() * 4 / 1e6),
+                       "views_per_s": 2 * value, "schedule": "two streams (target fwd || online fwd, wgrad || BN backward)"},
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": None,
+            "losses_last_step": {"byol": final[7], "ce": final[:6]},
+        }
     c5 = None
     if world > 1 and not args.no_config5:
         eng = None                        # (rank 0's handle from the roofline block) the batch-60 engine must go first
         del model
         import gc
+        import threading
         gc.collect()
         torch.cuda.empty_cache()
+
+        # the batch-60 line above is already measured: a sub-record that raises is reported, one that HANGS (a lost peer in
+        # an exchange) is cut off by a watchdog thread on every rank -- rank 0 prints the line with the error, all exit 0
+        def bail():
+            if rank == 0:
+                line["config5"] = {"error": f"config-5 sub-record did not finish within {args.config5_timeout} s"}
+                emit(line)
+            sys.stdout.flush()
+            os._exit(0)
+        dog = threading.Timer(args.config5_timeout, bail)
+        dog.daemon = True
+        dog.start()
         try:
             c5 = config5_record(args, rank, world)
-        except Exception as e:  # noqa: BLE001   the batch-60 line above is already measured: report, do not lose it
+        except Exception as e:  # noqa: BLE001
             import traceback
             traceback.print_exc()
             c5 = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
-    if world > 1:
+        if world > 1:
+            dist.barrier()
+        dog.cancel()
+    elif world > 1:
         dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
-    value = world * B / (ms_step * 1e-3)
-    line = {
-        "metric": "clips/sec, r21d_byol pretrain step, 16x112x112", "value": value, "unit": "clips/s", "n_gpus": world,
-        "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {**workload_config(B, world, "per-GPU (reference semantics)" if args.bn_sync == "local" or world == 1
-                                     else ("world-synchronised (SyncBN all-reduce per BatchNorm call)" if args.bn_sync == "world" else
-                                           "world-synchronised (SyncBN rows exchanged over NVLink peer memory, one kernel per call)")),
-                   "l2_policy": "inputs and activations far larger than the 126 MB L2 (clips alone 2x%.0f MB)" % (x1.numel() * 4 / 1e6),
-                   "views_per_s": 2 * value, "schedule": "two streams (target fwd || online fwd, wgrad || BN backward)"},
-        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                "ms_per_step": ms_e2e},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-        "losses_last_step": {"byol": final[7], "ce": final[:6]},
-    }
+        line["cpu_baseline"] = cpu_baseline()
     if c5 is not None:
         line["config5"] = c5
     emit(line)
