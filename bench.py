@@ -280,6 +280,29 @@ def emit(line: dict) -> None:
     _JSON_OUT.flush()
 
 
+def run_with_watchdog(seconds: float, fn, on_timeout):
+    """fn() under a watchdog THREAD (the main thread may sit in a CUDA or NCCL call that never returns, where a signal
+    handler would not run): on_timeout() is called from the timer thread if fn has not returned after `seconds`."""
+    import threading
+    dog = threading.Timer(seconds, on_timeout)
+    dog.daemon = True
+    dog.start()
+    try:
+        return fn()
+    finally:
+        dog.cancel()
+
+
+def bail_out(line: dict | None, key: str, message: str) -> None:
+    """Ends the process with exit code 0 from a watchdog: the rank that holds the measured line prints it with the error
+    recorded under `key` first (the other ranks pass None)."""
+    if line is not None:
+        line[key] = {"error": message}
+        emit(line)
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def ncu_traffic(kernel: str, B: int):
     """(bytes, source): average DRAM bytes (read + write) per launch of `kernel` from the newest committed ncu capture of
     this command at the same per-GPU batch (profiles/rNN_ncu_<kernel>_b<B>_dram.csv: dram__bytes_read.sum +
@@ -489,30 +512,22 @@ def main():
         eng = None                        # (rank 0's handle from the roofline block) the batch-60 engine must go first
         del model
         import gc
-        import threading
         gc.collect()
         torch.cuda.empty_cache()
 
         # the batch-60 line above is already measured: a sub-record that raises is reported, one that HANGS (a lost peer in
         # an exchange) is cut off by a watchdog thread on every rank -- rank 0 prints the line with the error, all exit 0
-        def bail():
-            if rank == 0:
-                line["config5"] = {"error": f"config-5 sub-record did not finish within {args.config5_timeout} s"}
-                emit(line)
-            sys.stdout.flush()
-            os._exit(0)
-        dog = threading.Timer(args.config5_timeout, bail)
-        dog.daemon = True
-        dog.start()
-        try:
-            c5 = config5_record(args, rank, world)
-        except Exception as e:  # noqa: BLE001
-            import traceback
-            traceback.print_exc()
-            c5 = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
-        if world > 1:
+        def sub_record():
+            try:
+                c = config5_record(args, rank, world)
+            except Exception as e:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                c = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
             dist.barrier()
-        dog.cancel()
+            return c
+        c5 = run_with_watchdog(args.config5_timeout, sub_record, lambda: bail_out(
+            line, "config5", f"config-5 sub-record did not finish within {args.config5_timeout} s"))
     elif world > 1:
         dist.barrier()
     if rank != 0:

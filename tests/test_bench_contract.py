@@ -30,3 +30,19 @@ def test_roofline_traffic_comes_from_a_committed_capture_with_its_provenance():
     assert src.startswith("profiles/r02_ncu_conv_halo_b60_dram.csv") and "commit" in src
     assert 1.5e9 < per_launch < 2.5e9          # ~1.88 GB per launch = the algorithmic bytes of the layers it runs
     assert bench.ncu_traffic("conv_halo_kernel", 7) == (None, None)
+
+
+def test_watchdog_prints_the_measured_line_when_a_sub_record_hangs():
+    """bench.py at N > 1: a config-5 sub-record that never returns (a lost peer) must not lose the batch-60 line."""
+    code = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+            "line = {'metric': 'm', 'value': 1.0}\n"
+            "bench.run_with_watchdog(0.3, lambda: time.sleep(30), lambda: bench.bail_out(line, 'config5', 'too slow'))\n"
+            "print('not reached')\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "m", "value": 1.0, "config5": {"error": "too slow"}}
+    # and a sub-record that returns in time passes its result through, the timer cancelled
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.run_with_watchdog(5.0, lambda: {"ok": 1}, lambda: (_ for _ in ()).throw(AssertionError("fired"))) == {"ok": 1}
